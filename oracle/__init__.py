@@ -1,0 +1,234 @@
+"""Python face of the CPU oracle (oracle/cvo_oracle.c).
+
+TEST INFRASTRUCTURE ONLY — PARITY UNPINNED (see oracle/cvo_oracle.h).  Only
+tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this package.  The product (unified_cvo_b200) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from unified_cvo_b200._abi import AlignInfo, IterTrace, Params  # type definitions only
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libcvo_oracle.so")
+_BASE_SO = os.path.join(_HERE, "_build", "libcvo_cpu_baseline.so")
+
+
+def build(force: bool = False) -> None:
+    """gcc-compile the C restatement (no reference sources involved)."""
+    if force:
+        subprocess.run(["make", "-C", _HERE, "clean"], check=True, capture_output=True)
+    subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+
+
+class _Cloud(C.Structure):
+    _fields_ = [
+        ("n", C.c_int),
+        ("F", C.c_int),
+        ("C", C.c_int),
+        ("xyz", C.POINTER(C.c_float)),
+        ("feat", C.POINTER(C.c_float)),
+        ("labels", C.POINTER(C.c_float)),
+        ("geotype", C.POINTER(C.c_float)),
+    ]
+
+
+class _Sparse(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int),
+        ("stride", C.c_int),
+        ("mat", C.POINTER(C.c_float)),
+        ("ind", C.POINTER(C.c_int)),
+        ("nonzeros", C.POINTER(C.c_uint)),
+        ("capacity", C.c_int),
+        ("nonzero_sum", C.c_ulonglong),
+    ]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        f32p = C.POINTER(C.c_float)
+        L.oracle_sparse_new.restype = C.POINTER(_Sparse)
+        L.oracle_sparse_new.argtypes = [C.c_int, C.c_int]
+        L.oracle_sparse_free.argtypes = [C.POINTER(_Sparse)]
+        L.oracle_align.restype = C.c_int
+        L.oracle_align.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
+                                   f32p, C.POINTER(AlignInfo), C.POINTER(IterTrace), C.c_int]
+        L.oracle_iterate.restype = None
+        L.oracle_iterate.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
+                                     f32p, C.c_float, C.c_int, C.POINTER(IterTrace),
+                                     C.POINTER(_Sparse)]
+        L.oracle_inner_product.restype = C.c_float
+        L.oracle_inner_product.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud),
+                                           f32p, C.c_float, f32p, C.POINTER(_Sparse)]
+        L.oracle_function_angle.restype = C.c_float
+        L.oracle_function_angle.argtypes = [C.POINTER(Params), C.POINTER(_Cloud),
+                                            C.POINTER(_Cloud), f32p, C.c_float, C.c_int]
+        L.oracle_cubic_roots.restype = C.c_int
+        L.oracle_cubic_roots.argtypes = [C.POINTER(C.c_double)] * 3
+        L.oracle_exp_sek3.restype = None
+        L.oracle_exp_sek3.argtypes = [f32p, C.c_float, f32p]
+        L.oracle_se3_log_norm.restype = C.c_double
+        L.oracle_se3_log_norm.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.oracle_update_tf.restype = None
+        L.oracle_update_tf.argtypes = [f32p] * 5
+        L.oracle_transform.restype = None
+        L.oracle_transform.argtypes = [f32p, f32p, f32p, C.c_int, f32p]
+        L.oracle_num_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+class Cloud:
+    """Host cloud in the C-ABI's layout (row-major features / labels)."""
+
+    def __init__(self, xyz, features=None, labels=None, geotype=None):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        n = self.xyz.shape[0]
+        self.features = (None if features is None or np.size(features) == 0
+                         else np.ascontiguousarray(features, dtype=np.float32).reshape(n, -1))
+        self.labels = (None if labels is None or np.size(labels) == 0
+                       else np.ascontiguousarray(labels, dtype=np.float32).reshape(n, -1))
+        self.geotype = (None if geotype is None
+                        else np.ascontiguousarray(geotype, dtype=np.float32).reshape(n, 2))
+
+    @property
+    def n(self):
+        return self.xyz.shape[0]
+
+    @property
+    def F(self):
+        return 0 if self.features is None else self.features.shape[1]
+
+    @property
+    def C(self):
+        return 0 if self.labels is None else self.labels.shape[1]
+
+    def c_struct(self) -> _Cloud:
+        return _Cloud(self.n, self.F, self.C, _fp(self.xyz), _fp(self.features),
+                      _fp(self.labels), _fp(self.geotype))
+
+
+def _sparse_to_numpy(sp) -> dict:
+    s = sp.contents
+    rows, stride = s.rows, s.stride
+    nz = np.ctypeslib.as_array(s.nonzeros, shape=(max(rows, 1),))[:rows].copy()
+    if rows * stride > 0:
+        mat = np.ctypeslib.as_array(s.mat, shape=(rows * stride,)).reshape(rows, stride).copy()
+        ind = np.ctypeslib.as_array(s.ind, shape=(rows * stride,)).reshape(rows, stride).copy()
+    else:
+        mat = np.zeros((rows, 0), np.float32)
+        ind = np.zeros((rows, 0), np.int32)
+    return {"nonzeros": nz, "mat": mat, "ind": ind, "stride": stride,
+            "nonzero_sum": int(s.nonzero_sum)}
+
+
+def sparse_to_csr(sp: dict):
+    """(row_ptr, cols, vals) in the reference's row order."""
+    nz = sp["nonzeros"].astype(np.int64)
+    row_ptr = np.zeros(len(nz) + 1, np.int64)
+    np.cumsum(nz, out=row_ptr[1:])
+    cols = np.concatenate([sp["ind"][i, : nz[i]] for i in range(len(nz))] or [np.zeros(0, np.int32)])
+    vals = np.concatenate([sp["mat"][i, : nz[i]] for i in range(len(nz))] or [np.zeros(0, np.float32)])
+    return row_ptr, cols.astype(np.int32), vals.astype(np.float32)
+
+
+def iterate(params: Params, src: Cloud, tgt: Cloud, R, T, ell: float, num_neighbors: int,
+            want_matrix: bool = False):
+    L = lib()
+    R = np.ascontiguousarray(R, np.float32).reshape(9)
+    T = np.ascontiguousarray(T, np.float32).reshape(3)
+    tr = IterTrace()
+    cs, ct = src.c_struct(), tgt.c_struct()
+    sp = L.oracle_sparse_new(src.n, max(int(num_neighbors), 1)) if want_matrix else None
+    L.oracle_iterate(C.byref(params), C.byref(cs), C.byref(ct), _fp(R), _fp(T), C.c_float(ell),
+                     int(num_neighbors), C.byref(tr), sp)
+    if want_matrix:
+        out = _sparse_to_numpy(sp)
+        L.oracle_sparse_free(sp)
+        return tr, out
+    return tr
+
+
+def align(params: Params, src: Cloud, tgt: Cloud, T_init=None, trace_cap: int = 0):
+    L = lib()
+    Ti = np.eye(4, dtype=np.float32) if T_init is None else np.asarray(T_init, np.float32)
+    Ti = np.ascontiguousarray(Ti.T).reshape(16)  # column-major
+    To = np.zeros(16, np.float32)
+    info = AlignInfo()
+    trace = (IterTrace * trace_cap)() if trace_cap > 0 else None
+    cs, ct = src.c_struct(), tgt.c_struct()
+    ret = L.oracle_align(C.byref(params), C.byref(cs), C.byref(ct), _fp(Ti), _fp(To),
+                         C.byref(info), trace, trace_cap)
+    executed = info.iterations + (0 if info.stop_reason == 8 else 1)  # 8 = STOP_MAX_ITER
+    n_rec = min(trace_cap, executed) if trace_cap else 0
+    return ret, To.reshape(4, 4).T.copy(), info, ([trace[i] for i in range(n_rec)] if trace else [])
+
+
+def inner_product(params: Params, src: Cloud, tgt: Cloud, T, ell: float, kernel3x3=None,
+                  want_matrix: bool = False):
+    L = lib()
+    T16 = np.ascontiguousarray(np.asarray(T, np.float32).T).reshape(16)
+    K = None if kernel3x3 is None else np.ascontiguousarray(np.asarray(kernel3x3, np.float32).T).reshape(9)
+    cs, ct = src.c_struct(), tgt.c_struct()
+    sp = L.oracle_sparse_new(src.n, max(int(params.nearest_neighbors_max), 1)) if want_matrix else None
+    val = L.oracle_inner_product(C.byref(params), C.byref(cs), C.byref(ct), _fp(T16),
+                                 C.c_float(ell), _fp(K), sp)
+    if want_matrix:
+        out = _sparse_to_numpy(sp)
+        L.oracle_sparse_free(sp)
+        return float(val), out
+    return float(val)
+
+
+def function_angle(params: Params, src: Cloud, tgt: Cloud, T, ell: float, is_approximate=True):
+    L = lib()
+    T16 = np.ascontiguousarray(np.asarray(T, np.float32).T).reshape(16)
+    cs, ct = src.c_struct(), tgt.c_struct()
+    return float(L.oracle_function_angle(C.byref(params), C.byref(cs), C.byref(ct), _fp(T16),
+                                         C.c_float(ell), int(bool(is_approximate))))
+
+
+def cubic_roots(coef):
+    L = lib()
+    c = (C.c_double * 4)(*[float(x) for x in coef])
+    re = (C.c_double * 3)()
+    im = (C.c_double * 3)()
+    rc = L.oracle_cubic_roots(c, re, im)
+    return rc, np.array(re[:]) + 1j * np.array(im[:])
+
+
+def exp_sek3(xi, dt):
+    L = lib()
+    x = np.ascontiguousarray(xi, np.float32).reshape(6)
+    out = np.zeros(12, np.float32)
+    L.oracle_exp_sek3(_fp(x), C.c_float(dt), _fp(out))
+    return out.reshape(4, 3).T.copy()  # 3x4
+
+
+def se3_log_norm(dR, dT):
+    L = lib()
+    r = np.ascontiguousarray(np.asarray(dR, np.float64).T).reshape(9)
+    t = np.ascontiguousarray(dT, np.float64).reshape(3)
+    return float(L.oracle_se3_log_norm(r.ctypes.data_as(C.POINTER(C.c_double)),
+                                       t.ctypes.data_as(C.POINTER(C.c_double))))
+
+
+def num_threads() -> int:
+    return int(lib().oracle_num_threads())

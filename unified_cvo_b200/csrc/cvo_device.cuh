@@ -1,0 +1,128 @@
+// cvo_device.cuh — device-side state and launch arguments of the CVO hot path.
+//
+// Data layout in HBM (all SoA; the reference's 192-byte AoS CvoPoint,
+// utils/PointSegmentedDistribution.hpp:147-229, is NOT used on the device):
+//   source cloud (the rows of the kernel matrix, N points)
+//     src_xyz   float4[N]      exact coordinates (x,y,z,0)
+//     src_rowA  float4[N]      prefilter record (-2(x-c), dist_to_sensor); c = source centroid
+//     src_feat  float [N*Fp]   row-major, Fp = F rounded up to 4, zero padded
+//     src_lab   float [N*Cp]   row-major label distributions
+//     src_geo   float2[N]      geometric type
+//   target cloud (the moving cloud, M points): tgt_xyz / tgt_feat / tgt_lab / tgt_geo
+//     plus, rewritten every iteration by prep_kernel:
+//     tgt_moved float4[M]      y' = Rinv*y + Tinv, exact reference arithmetic
+//     px,py,pz,pw float[M]     y'-c and |y'-c|^2: the streamed operand of the pair kernel
+//   candidate cells  uint32[N * nchunks * L] + uint32 counts[N * nchunks]
+//   kernel matrix    ELL: ell_idx uint32[N*cap_max], ell_val float[N*cap_max], row_nnz[N]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/cvo_b200.h"
+
+namespace cvo_b200 {
+
+constexpr int kTileRows = 64;          // source rows staged per warp tile
+constexpr int kJQ = 8;                 // targets held per lane
+constexpr int kJBlock = 32 * kJQ;      // targets per warp sweep
+constexpr int kPairWarps = 8;          // warps per CTA of the pair kernel
+constexpr int kSparseThreads = 256;    // CTA size of the sparse kernels
+constexpr int kQueueCap = 1024;        // max indicator_window_size supported
+
+struct FlowPartial {
+  double omega[3];
+  double v[3];
+  double a_sum;
+  unsigned long long nnz;
+  unsigned int max_row;
+  unsigned int pad;
+};
+struct StepPartial {
+  double b, c, d, e;
+};
+
+// Device-resident controller state: everything align_impl keeps in host
+// variables (CvoGPU.cu:1363-1386) lives here so the loop needs no host round trip.
+struct DevState {
+  float R[9], T[3];         // current T_target_to_source blocks (column-major R)
+  float Rinv[9], Tinv[3];   // update_tf output; Rinv/Tinv are also the final transform
+  float ell;
+  int num_neighbors;
+  int iter;
+  int done;
+  int ret;
+  int stop_reason;
+  int max_iter;
+  int controller_on;        // 1: align loop; 0: single iterate() call (queues/ell/cap untouched);
+                            // 2: fixed-state timing loop (pose restored, runs to max_iter)
+  // flow
+  float omega[3], v[3];
+  double omega_sum[3], v_sum[3];
+  double a_sum;
+  unsigned long long nnz;
+  unsigned int max_row_nnz;
+  // step
+  double B, C, D, E;
+  float step;
+  double dist;
+  // indicator queues (CvoGPU.cu:1377-1380)
+  float q_start[kQueueCap];
+  float q_end[kQueueCap];
+  int qs_head, qs_size, qe_head, qe_size;
+  float start_sum, end_sum;
+  // scheduling scratch
+  unsigned int work_counter;
+  unsigned int flow_blocks_done;
+  unsigned int step_blocks_done;
+  unsigned int ymax2_bits;  // max_j |y'_j - c|^2 as float bits
+  // trace
+  cvo_b200_iter_trace* trace;
+  int trace_cap;
+  int pad0;
+  // multi-GPU: totals of the LOCAL row shard, written before the collective
+  double local_flow[9];     // omega[3], v[3], a_sum, (double)nnz, (double)max_row_nnz
+  double local_step[4];
+};
+
+struct IterArgs {
+  const cvo_b200_params* params;  // device copy (the reference's params_gpu)
+  DevState* st;
+  // source shard
+  const float4* src_xyz;
+  const float4* src_rowA;
+  const float* src_feat;
+  const float* src_lab;
+  const float2* src_geo;
+  int row_begin;   // first global source row of this shard
+  int n_rows;      // rows in this shard
+  int n_src_total; // N (all shards) — the indicator uses N*M
+  // target
+  const float4* tgt_xyz;
+  float4* tgt_moved;
+  float* px; float* py; float* pz; float* pw;
+  const float* tgt_feat;
+  const float* tgt_lab;
+  const float2* tgt_geo;
+  int M;
+  int Fp, Cp;      // padded feature / class dims (same for both clouds)
+  float cx, cy, cz;
+  // candidate cells
+  uint32_t* cand;
+  uint32_t* cand_cnt;
+  int nchunks, chunk_len, L;
+  // ELL kernel matrix
+  uint32_t* ell_idx;
+  float* ell_val;
+  uint32_t* row_nnz;
+  int cap_max;
+  // partial sums
+  FlowPartial* flow_part;
+  StepPartial* step_part;
+  // kernel variant
+  int mode;        // 0 isotropic (fill_in_A_mat_gpu), 1 Mahalanobis (.._dense_mat_kernel)
+  float kinv[9];   // column-major inverse kernel for mode 1
+  int world;       // >1: tails only publish local totals, finalize kernels run after the collective
+  int n_items;     // pair-kernel work items = row_tiles * nchunks
+};
+
+}  // namespace cvo_b200

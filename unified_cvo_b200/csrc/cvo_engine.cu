@@ -1,0 +1,952 @@
+// cvo_engine.cu — host side of the C-ABI (include/cvo_b200.h): handle, device
+// buffers, the iteration launcher, the device-resident align loop, inner product,
+// association export, timing helpers and the optional NCCL plumbing.
+//
+// Replaces, on the host side: CvoGPU ctor/dtor/write_params (CvoGPU.cu:64-83),
+// CvoPointCloud_to_gpu (CvoGPU_impl.cu:206-285), CvoState ctor/dtor (CvoState.cu:22-125),
+// the loop skeleton of align_impl (CvoGPU.cu:1338-1572), inner_product_impl
+// (:1719-1778), gpu_association_to_cpu (CvoGPU_impl.cu:366-427).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cvo_device.cuh"
+
+namespace cvo_b200 {
+void launch_prep(const IterArgs& A, int blocks, cudaStream_t s);
+void launch_pair(const IterArgs& A, int blocks, cudaStream_t s);
+void launch_flow(const IterArgs& A, int blocks, cudaStream_t s);
+void launch_step(const IterArgs& A, int blocks, cudaStream_t s);
+void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride, cudaStream_t s);
+void launch_finalize_step(const IterArgs& A, const double* gathered, int stride, cudaStream_t s);
+void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s);
+int pair_kernel_max_blocks_per_sm();
+}  // namespace cvo_b200
+
+using namespace cvo_b200;
+
+namespace {
+thread_local std::string g_error;
+
+// ---- NCCL through dlopen: the single-GPU path has no NCCL dependency at all ------
+typedef struct ncclComm* ncclComm_t;
+struct UniqueId {  // ncclUniqueId: 128 opaque bytes, passed BY VALUE to ncclCommInitRank
+  char internal[128];
+};
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, UniqueId, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+const int kNcclFloat64 = 8;  // ncclDouble
+
+bool load_nccl(std::string& err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) {
+    err = std::string("dlopen(libnccl.so.2) failed: ") + dlerror();
+    return false;
+  }
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank =
+      (int (*)(ncclComm_t*, int, UniqueId, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(
+      g_nccl.lib, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+    err = "libnccl is missing a required symbol";
+    return false;
+  }
+  return true;
+}
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;  // elements
+  cudaError_t ensure(size_t n) {
+    if (n <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n < 16 ? 16 : n;
+    cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct CloudDev {
+  int n = 0, F = 0, C = 0;
+  bool has_geo = false;
+  DevBuf<float4> xyz;
+  DevBuf<float4> rowA;  // prefilter records (any cloud can play the source role)
+  DevBuf<float> feat;   // n * Fp
+  DevBuf<float> lab;    // n * Cp
+  DevBuf<float2> geo;
+  int Fp = 0, Cp = 0;   // strides the buffers were packed with
+  float cx = 0, cy = 0, cz = 0;
+  bool set = false;
+};
+}  // namespace
+
+struct cvo_b200_handle {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  cvo_b200_params params;
+  cvo_b200_params* d_params = nullptr;
+  DevState* d_state = nullptr;
+  CloudDev src, tgt;
+  // per-iteration workspace
+  DevBuf<float4> tgt_moved;
+  DevBuf<float> px, py, pz, pw;
+  DevBuf<uint32_t> cand, cand_cnt, ell_idx, row_nnz;
+  DevBuf<float> ell_val;
+  DevBuf<FlowPartial> flow_part;
+  DevBuf<StepPartial> step_part;
+  DevBuf<float> zeros_f;    // stand-in for absent features / labels
+  DevBuf<float2> zeros_g;   // stand-in for absent geometric types
+  DevBuf<cvo_b200_iter_trace> d_trace;
+  DevBuf<double> gathered;  // multi-GPU all-gather receive buffer
+  int row_begin = 0, row_end = -1;
+  // launch geometry
+  int prep_blocks = 1, pair_blocks = 1, sparse_blocks = 1;
+  // graph cache for the align loop
+  cudaGraphExec_t graph_exec = nullptr;
+  IterArgs graph_args;
+  int graph_batch = 0;
+  bool use_graph = true;
+  // host poll buffer (pinned)
+  int* h_poll = nullptr;
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  std::string err;
+  uint64_t launches = 0;
+};
+
+namespace {
+#define CVO_CUDA(h, expr)                                                               \
+  do {                                                                                  \
+    cudaError_t e__ = (expr);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e__);                   \
+      return CVO_B200_ERR_CUDA;                                                         \
+    }                                                                                   \
+  } while (0)
+
+int fail(cvo_b200_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  g_error = msg;
+  return code;
+}
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// Pick the work decomposition of the pair kernel and size every buffer.
+int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const CloudDev* S = nullptr,
+            const CloudDev* Tg = nullptr, bool sharded = true) {
+  if (!h->src.set || !h->tgt.set) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
+  const CloudDev& cs = S ? *S : h->src;
+  const CloudDev& ct = Tg ? *Tg : h->tgt;
+  const int N = cs.n, M = ct.n;
+  const int rb = sharded ? h->row_begin : 0;
+  const int re = (!sharded || h->row_end < 0 || h->row_end > N) ? N : h->row_end;
+  if (rb < 0 || rb > re) return fail(h, CVO_B200_ERR_INVALID, "bad row range");
+  const int n_rows = re - rb;
+  const int Fp = std::max(cs.Fp, ct.Fp);
+  const int Cp = std::max(cs.Cp, ct.Cp);
+  if ((cs.Fp && ct.Fp && cs.Fp != ct.Fp) || (cs.Cp && ct.Cp && cs.Cp != ct.Cp))
+    return fail(h, CVO_B200_ERR_INVALID, "source and target feature/class dimensions differ");
+  const int cap_max = std::max(1, h->params.nearest_neighbors_max);
+
+  // ---- chunking: enough (row tile, target chunk) items to fill the machine a few times
+  const int row_tiles = std::max(1, (n_rows + kTileRows - 1) / kTileRows);
+  const int target_items = h->num_sms * 32;
+  int nchunks = std::max(1, (target_items + row_tiles - 1) / row_tiles);
+  const int max_chunks = std::max(1, (M + kJBlock - 1) / kJBlock);
+  nchunks = std::min(nchunks, max_chunks);
+  int chunk_len = round_up(std::max(1, (M + nchunks - 1) / nchunks), kJBlock);
+  nchunks = std::max(1, (M + chunk_len - 1) / chunk_len);
+  int L = std::min(chunk_len, std::max(64, 2 * cap_max));
+  // keep the candidate cells within ~8 GiB
+  while ((size_t)std::max(n_rows, 1) * nchunks * L * 4 > ((size_t)8 << 30) && L > 64) L /= 2;
+
+  const size_t n_zero = (size_t)std::max(N, M) * (size_t)std::max(std::max(Fp, Cp), 1);
+  CVO_CUDA(h, h->tgt_moved.ensure((size_t)M));
+  CVO_CUDA(h, h->px.ensure((size_t)M));
+  CVO_CUDA(h, h->py.ensure((size_t)M));
+  CVO_CUDA(h, h->pz.ensure((size_t)M));
+  CVO_CUDA(h, h->pw.ensure((size_t)M));
+  CVO_CUDA(h, h->cand.ensure((size_t)std::max(n_rows, 1) * nchunks * L));
+  CVO_CUDA(h, h->cand_cnt.ensure((size_t)std::max(n_rows, 1) * nchunks));
+  CVO_CUDA(h, h->ell_idx.ensure((size_t)std::max(n_rows, 1) * cap_max));
+  CVO_CUDA(h, h->ell_val.ensure((size_t)std::max(n_rows, 1) * cap_max));
+  CVO_CUDA(h, h->row_nnz.ensure((size_t)std::max(n_rows, 1)));
+  if (h->zeros_f.cap < n_zero) {
+    CVO_CUDA(h, h->zeros_f.ensure(n_zero));
+    CVO_CUDA(h, cudaMemsetAsync(h->zeros_f.p, 0, h->zeros_f.cap * sizeof(float), h->stream));
+  }
+  if (h->zeros_g.cap < (size_t)std::max(N, M)) {
+    CVO_CUDA(h, h->zeros_g.ensure((size_t)std::max(N, M)));
+    CVO_CUDA(h, cudaMemsetAsync(h->zeros_g.p, 0, h->zeros_g.cap * sizeof(float2), h->stream));
+  }
+
+  // ---- launch geometry (fixed grids; kernels are grid-stride / work-stealing)
+  int occ = pair_kernel_max_blocks_per_sm();
+  if (occ < 1) occ = 1;
+  const int n_items = row_tiles * nchunks;
+  h->pair_blocks = std::max(1, std::min(h->num_sms * occ, (n_items + kPairWarps - 1) / kPairWarps));
+  h->prep_blocks = std::max(1, std::min(h->num_sms * 4, (M + 255) / 256));
+  const int warps_per_block = kSparseThreads / 32;
+  h->sparse_blocks =
+      std::max(1, std::min(h->num_sms * 4, (n_rows + warps_per_block - 1) / warps_per_block));
+  CVO_CUDA(h, h->flow_part.ensure((size_t)h->sparse_blocks));
+  CVO_CUDA(h, h->step_part.ensure((size_t)h->sparse_blocks));
+
+  std::memset(&A, 0, sizeof(A));
+  A.params = h->d_params;
+  A.st = h->d_state;
+  A.src_xyz = cs.xyz.p;
+  A.src_rowA = cs.rowA.p;
+  A.src_feat = cs.Fp ? cs.feat.p : h->zeros_f.p;
+  A.src_lab = cs.Cp ? cs.lab.p : h->zeros_f.p;
+  A.src_geo = cs.has_geo ? cs.geo.p : h->zeros_g.p;
+  A.row_begin = rb;
+  A.n_rows = n_rows;
+  A.n_src_total = N;
+  A.tgt_xyz = ct.xyz.p;
+  A.tgt_moved = h->tgt_moved.p;
+  A.px = h->px.p; A.py = h->py.p; A.pz = h->pz.p; A.pw = h->pw.p;
+  A.tgt_feat = ct.Fp ? ct.feat.p : h->zeros_f.p;
+  A.tgt_lab = ct.Cp ? ct.lab.p : h->zeros_f.p;
+  A.tgt_geo = ct.has_geo ? ct.geo.p : h->zeros_g.p;
+  A.M = M;
+  A.Fp = Fp;
+  A.Cp = Cp;
+  A.cx = cs.cx; A.cy = cs.cy; A.cz = cs.cz;
+  A.cand = h->cand.p;
+  A.cand_cnt = h->cand_cnt.p;
+  A.nchunks = nchunks;
+  A.chunk_len = chunk_len;
+  A.L = L;
+  A.ell_idx = h->ell_idx.p;
+  A.ell_val = h->ell_val.p;
+  A.row_nnz = h->row_nnz.p;
+  A.cap_max = cap_max;
+  A.flow_part = h->flow_part.p;
+  A.step_part = h->step_part.p;
+  A.mode = mode;
+  if (kinv)
+    for (int k = 0; k < 9; k++) A.kinv[k] = kinv[k];
+  A.world = sharded ? h->world : 1;
+  A.n_items = n_items;
+  if (h->world > 1) CVO_CUDA(h, h->gathered.ensure((size_t)h->world * 16));
+  return CVO_B200_OK;
+}
+
+// One iteration's worth of launches.  `stage`: 3 = everything, 2 = stop after flow.
+int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEvent_t pair_begin,
+                      cudaEvent_t pair_end) {
+  cudaStream_t s = h->stream;
+  launch_prep(A, h->prep_blocks, s);
+  if (pair_begin) cudaEventRecord(pair_begin, s);
+  launch_pair(A, h->pair_blocks, s);
+  if (pair_end) cudaEventRecord(pair_end, s);
+  launch_flow(A, h->sparse_blocks, s);
+  h->launches += 3;
+  if (A.world > 1) {
+    DevState* st = h->d_state;
+    int rc = g_nccl.AllGather(&st->local_flow[0], h->gathered.p, 9, kNcclFloat64, h->comm, s);
+    if (rc != 0) return fail(h, CVO_B200_ERR_NCCL, "ncclAllGather(flow) failed");
+    launch_finalize_flow(A, h->gathered.p, 9, s);
+    h->launches += 1;
+  }
+  if (stage >= 3) {
+    launch_step(A, h->sparse_blocks, s);
+    h->launches += 1;
+    if (A.world > 1) {
+      DevState* st = h->d_state;
+      int rc = g_nccl.AllGather(&st->local_step[0], h->gathered.p, 4, kNcclFloat64, h->comm, s);
+      if (rc != 0) return fail(h, CVO_B200_ERR_NCCL, "ncclAllGather(step) failed");
+      launch_finalize_step(A, h->gathered.p, 4, s);
+      h->launches += 1;
+    }
+  }
+  return CVO_B200_OK;
+}
+
+void host_update_tf(const float R[9], const float T[3], float Rinv[9], float Tinv[3]) {
+  // CvoGPU.cu:94-112 on the host, for the initial pose only (same arithmetic as the
+  // device controller: -R^T applied with c0 + (c1 + c2)).
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) Rinv[3 * j + i] = R[3 * i + j];
+  for (int i = 0; i < 3; i++) {
+    volatile float c0 = (-Rinv[i]) * T[0];
+    volatile float c1 = (-Rinv[3 + i]) * T[1];
+    volatile float c2 = (-Rinv[6 + i]) * T[2];
+    volatile float s12 = c1 + c2;
+    Tinv[i] = c0 + s12;
+  }
+}
+
+int init_state(cvo_b200_handle* h, const float R[9], const float T[3], float ell, int cap,
+               int controller_on, int max_iter, cvo_b200_iter_trace* d_trace, int trace_cap) {
+  static thread_local DevState hs;  // ~8.5 KB; keep it off the stack of small callers
+  std::memset(&hs, 0, sizeof(hs));
+  std::memcpy(hs.R, R, sizeof(hs.R));
+  std::memcpy(hs.T, T, sizeof(hs.T));
+  host_update_tf(R, T, hs.Rinv, hs.Tinv);
+  hs.ell = ell;
+  hs.num_neighbors = cap;
+  hs.max_iter = max_iter;
+  hs.controller_on = controller_on;
+  hs.trace = d_trace;
+  hs.trace_cap = trace_cap;
+  CVO_CUDA(h, cudaMemcpyAsync(h->d_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
+  // the source of an async copy from pageable memory is staged before the call returns
+  return CVO_B200_OK;
+}
+
+void split_pose(const float T16[16], float R[9], float T[3]) {
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) R[3 * j + i] = T16[4 * j + i];
+  for (int i = 0; i < 3; i++) T[i] = T16[12 + i];
+}
+
+void destroy_graph(cvo_b200_handle* h) {
+  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+  h->graph_exec = nullptr;
+  h->graph_batch = 0;
+}
+
+// Capture `batch` iterations into one graph.  All per-iteration values (pose, ell, cap,
+// flags) live in DevState, so the graph is parameter-free and is rebuilt only when the
+// buffers or the decomposition change.
+int ensure_graph(cvo_b200_handle* h, const IterArgs& A, int batch) {
+  if (h->graph_exec && h->graph_batch == batch && std::memcmp(&h->graph_args, &A, sizeof(A)) == 0)
+    return CVO_B200_OK;
+  destroy_graph(h);
+  cudaGraph_t graph = nullptr;
+  CVO_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  const uint64_t before = h->launches;
+  int rc = CVO_B200_OK;
+  for (int b = 0; b < batch && rc == CVO_B200_OK; b++) rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
+  h->launches = before;  // counted when the graph is launched
+  cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+  if (rc != CVO_B200_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(h, CVO_B200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+  e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    h->graph_exec = nullptr;
+    return fail(h, CVO_B200_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+  }
+  h->graph_args = A;
+  h->graph_batch = batch;
+  return CVO_B200_OK;
+}
+
+int launches_per_iteration(const cvo_b200_handle* h) { return h->world > 1 ? 6 : 4; }
+
+int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F,
+                 const float* features, int C, const float* labels, const float* geotype) {
+  if (n < 0 || F < 0 || C < 0 || (n > 0 && !xyz)) return fail(h, CVO_B200_ERR_INVALID, "bad cloud arguments");
+  c.n = n;
+  c.F = features ? F : 0;
+  c.C = labels ? C : 0;
+  c.Fp = round_up(c.F, 4);
+  c.Cp = round_up(c.C, 4);
+  c.has_geo = geotype != nullptr;
+  c.set = true;
+  if (n == 0) return CVO_B200_OK;
+  std::vector<float4> buf((size_t)n);
+  double mx = 0, my = 0, mz = 0;
+  size_t n_finite = 0;
+  for (int i = 0; i < n; i++) {
+    const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+    buf[i] = make_float4(x, y, z, 0.f);
+    if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
+      mx += x; my += y; mz += z;
+      n_finite++;
+    }
+  }
+  CVO_CUDA(h, c.xyz.ensure((size_t)n));
+  CVO_CUDA(h, cudaMemcpyAsync(c.xyz.p, buf.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+  CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  {
+    // prefilter records: a = -2 (x - c) and the reference's a_to_sensor (CvoGPU.cu:506)
+    c.cx = n_finite ? (float)(mx / (double)n_finite) : 0.f;
+    c.cy = n_finite ? (float)(my / (double)n_finite) : 0.f;
+    c.cz = n_finite ? (float)(mz / (double)n_finite) : 0.f;
+    for (int i = 0; i < n; i++) {
+      const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
+      volatile float xx = x * x, yy = y * y, zz = z * z;
+      volatile float sxy = xx + yy;
+      const float dist = sqrtf(sxy + zz);
+      buf[i] = make_float4(-2.f * (x - c.cx), -2.f * (y - c.cy), -2.f * (z - c.cz), dist);
+    }
+    CVO_CUDA(h, c.rowA.ensure((size_t)n));
+    CVO_CUDA(h, cudaMemcpyAsync(c.rowA.p, buf.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (c.F > 0) {
+    std::vector<float> fb((size_t)n * c.Fp, 0.f);
+    for (int i = 0; i < n; i++)
+      std::memcpy(&fb[(size_t)i * c.Fp], features + (size_t)i * c.F, sizeof(float) * c.F);
+    CVO_CUDA(h, c.feat.ensure(fb.size()));
+    CVO_CUDA(h, cudaMemcpyAsync(c.feat.p, fb.data(), fb.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (c.C > 0) {
+    std::vector<float> lb((size_t)n * c.Cp, 0.f);
+    for (int i = 0; i < n; i++)
+      std::memcpy(&lb[(size_t)i * c.Cp], labels + (size_t)i * c.C, sizeof(float) * c.C);
+    CVO_CUDA(h, c.lab.ensure(lb.size()));
+    CVO_CUDA(h, cudaMemcpyAsync(c.lab.p, lb.data(), lb.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  if (geotype) {
+    CVO_CUDA(h, c.geo.ensure((size_t)n));
+    CVO_CUDA(h, cudaMemcpyAsync(c.geo.p, geotype, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  }
+  return CVO_B200_OK;
+}
+
+// Runs the device-resident loop to completion.  Returns when DevState.done is set.
+int run_loop(cvo_b200_handle* h, const IterArgs& A, int max_iter) {
+  const int batch = 32;
+  int rc;
+  if (h->use_graph) {
+    rc = ensure_graph(h, A, batch);
+    if (rc != CVO_B200_OK) return rc;
+  }
+  int launched_iters = 0;
+  while (true) {
+    if (h->use_graph) {
+      CVO_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+      h->launches += (uint64_t)batch * launches_per_iteration(h);
+    } else {
+      for (int b = 0; b < batch; b++) {
+        rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
+        if (rc != CVO_B200_OK) return rc;
+      }
+    }
+    launched_iters += batch;
+    CVO_CUDA(h, cudaMemcpyAsync(h->h_poll, &h->d_state->iter, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->h_poll[1] /*done*/) break;
+    if (launched_iters > max_iter + batch) return fail(h, CVO_B200_ERR_STATE, "align loop did not terminate");
+  }
+  return CVO_B200_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C-ABI
+extern "C" {
+
+int cvo_b200_abi_version(void) { return CVO_B200_ABI_VERSION; }
+
+int cvo_b200_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    g_error = cudaGetErrorString(e);
+    cudaGetLastError();
+    return CVO_B200_ERR_CUDA;
+  }
+  return n;
+}
+
+const char* cvo_b200_global_error(void) { return g_error.c_str(); }
+
+int cvo_b200_create(const cvo_b200_params* p, int device, cvo_b200_handle** out) {
+  if (!p || !out) return fail(nullptr, CVO_B200_ERR_INVALID, "null argument");
+  *out = nullptr;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, CVO_B200_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+  cvo_b200_handle* h = new (std::nothrow) cvo_b200_handle();
+  if (!h) return fail(nullptr, CVO_B200_ERR_NOMEM, "out of host memory");
+  h->device = device;
+  h->params = *p;
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+    delete h;
+    return fail(nullptr, CVO_B200_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+  }
+  h->num_sms = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    delete h;
+    return fail(nullptr, CVO_B200_ERR_CUDA,
+                "this library is built for sm_100a (B200) only; device is sm_" +
+                    std::to_string(prop.major) + std::to_string(prop.minor));
+  }
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_params, sizeof(cvo_b200_params)) != cudaSuccess ||
+      cudaMalloc((void**)&h->d_state, sizeof(DevState)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_poll, 16 * sizeof(int)) != cudaSuccess) {
+    std::string msg = std::string("handle allocation: ") + cudaGetErrorString(cudaGetLastError());
+    cvo_b200_destroy(h);
+    return fail(nullptr, CVO_B200_ERR_CUDA, msg);
+  }
+  cudaMemcpy(h->d_params, p, sizeof(*p), cudaMemcpyHostToDevice);
+  cudaMemset(h->d_state, 0, sizeof(DevState));
+  const char* ng = getenv("CVO_B200_NO_GRAPH");
+  h->use_graph = !(ng && ng[0] == '1');
+  *out = h;
+  return CVO_B200_OK;
+}
+
+void cvo_b200_destroy(cvo_b200_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  destroy_graph(h);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (CloudDev* c : {&h->src, &h->tgt}) {
+    c->xyz.release(); c->rowA.release(); c->feat.release(); c->lab.release(); c->geo.release();
+  }
+  h->tgt_moved.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
+  h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
+  h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
+  h->zeros_g.release(); h->d_trace.release(); h->gathered.release();
+  if (h->d_params) cudaFree(h->d_params);
+  if (h->d_state) cudaFree(h->d_state);
+  if (h->h_poll) cudaFreeHost(h->h_poll);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int cvo_b200_write_params(cvo_b200_handle* h, const cvo_b200_params* p) {
+  if (!h || !p) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  // The reference keeps a host copy (read by the controller) and a device copy (read by
+  // the kernels) that drivers sync by hand (CvoGPU.cu:73-77); here one call updates both.
+  h->params = *p;
+  CVO_CUDA(h, cudaMemcpyAsync(h->d_params, &h->params, sizeof(*p), cudaMemcpyHostToDevice, h->stream));
+  CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  return CVO_B200_OK;
+}
+
+int cvo_b200_get_params(const cvo_b200_handle* h, cvo_b200_params* out) {
+  if (!h || !out) return CVO_B200_ERR_INVALID;
+  *out = h->params;
+  return CVO_B200_OK;
+}
+
+const char* cvo_b200_last_error(const cvo_b200_handle* h) { return h ? h->err.c_str() : g_error.c_str(); }
+
+int cvo_b200_set_cloud(cvo_b200_handle* h, int which, int n, const float* xyz, int F,
+                       const float* features, int C, const float* labels, const float* geotype) {
+  if (!h || (which != 0 && which != 1)) return fail(h, CVO_B200_ERR_INVALID, "bad handle / which");
+  cudaSetDevice(h->device);
+  return upload_cloud(h, which == 0 ? h->src : h->tgt, n, xyz, F, features, C, labels, geotype);
+}
+
+int cvo_b200_set_row_range(cvo_b200_handle* h, int row_begin, int row_end) {
+  if (!h || row_begin < 0 || (row_end >= 0 && row_end < row_begin)) return fail(h, CVO_B200_ERR_INVALID, "bad row range");
+  h->row_begin = row_begin;
+  h->row_end = row_end;
+  return CVO_B200_OK;
+}
+
+int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], float ell,
+                     int num_neighbors, cvo_b200_iter_trace* trace) {
+  if (!h || !R || !T || !trace) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  IterArgs A;
+  int rc = prepare(h, A, 0, nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
+  if (num_neighbors > A.cap_max) return fail(h, CVO_B200_ERR_INVALID, "num_neighbors exceeds nearest_neighbors_max");
+  CVO_CUDA(h, h->d_trace.ensure(1));
+  rc = init_state(h, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
+  if (rc != CVO_B200_OK) return rc;
+  rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  CVO_CUDA(h, cudaMemcpyAsync(trace, h->d_trace.p, sizeof(*trace), cudaMemcpyDeviceToHost, h->stream));
+  CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  CVO_CUDA(h, cudaGetLastError());
+  return CVO_B200_OK;
+}
+
+int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
+                   cvo_b200_align_info* info, cvo_b200_iter_trace* trace, int trace_cap) {
+  if (!h || !T_init || !T_out) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  if (info) std::memset(info, 0, sizeof(*info));
+  if (!h->src.set || !h->tgt.set) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
+  // CvoGPU.cu:1614-1617: empty input -> return 0, output untouched
+  if (h->src.n == 0 || h->tgt.n == 0) return CVO_B200_OK;
+  if (h->params.is_using_kdtree) return fail(h, CVO_B200_ERR_INVALID, "is_using_kdtree is not supported (off in every shipped yaml)");
+  if (h->params.indicator_window_size > kQueueCap - 2)
+    return fail(h, CVO_B200_ERR_INVALID, "indicator_window_size too large");
+  IterArgs A;
+  int rc = prepare(h, A, 0, nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  float R[9], T[3];
+  split_pose(T_init, R, T);
+  if (trace_cap < 0) trace_cap = 0;
+  if (!trace) trace_cap = 0;
+  if (trace_cap > 0) CVO_CUDA(h, h->d_trace.ensure((size_t)trace_cap));
+  const int max_iter = h->params.MAX_ITER;
+  if (max_iter <= 0) {  // loop body never runs: transform = update_tf(init)
+    float Rinv[9], Tinv[3];
+    host_update_tf(R, T, Rinv, Tinv);
+    for (int j = 0; j < 3; j++) {
+      for (int i = 0; i < 3; i++) T_out[4 * j + i] = Rinv[3 * j + i];
+      T_out[4 * j + 3] = 0.f;
+    }
+    T_out[12] = Tinv[0]; T_out[13] = Tinv[1]; T_out[14] = Tinv[2]; T_out[15] = 1.f;
+    if (info) info->stop_reason = CVO_B200_STOP_MAX_ITER;
+    return CVO_B200_OK;
+  }
+  rc = init_state(h, R, T, h->params.ell_init, h->params.nearest_neighbors_max, 1, max_iter,
+                  trace_cap > 0 ? h->d_trace.p : nullptr, trace_cap);
+  if (rc != CVO_B200_OK) return rc;
+  cudaEvent_t ev0, ev1;
+  CVO_CUDA(h, cudaEventCreate(&ev0));
+  CVO_CUDA(h, cudaEventCreate(&ev1));
+  if (h->use_graph) {
+    rc = ensure_graph(h, A, 32);
+    if (rc != CVO_B200_OK) return rc;
+  }
+  cudaEventRecord(ev0, h->stream);
+  rc = run_loop(h, A, max_iter);
+  cudaEventRecord(ev1, h->stream);
+  if (rc != CVO_B200_OK) {
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    return rc;
+  }
+  static thread_local DevState hs;
+  CVO_CUDA(h, cudaMemcpyAsync(&hs, h->d_state, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
+  CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev0, ev1);
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  CVO_CUDA(h, cudaGetLastError());
+  for (int j = 0; j < 3; j++) {
+    for (int i = 0; i < 3; i++) T_out[4 * j + i] = hs.Rinv[3 * j + i];
+    T_out[4 * j + 3] = 0.f;
+  }
+  T_out[12] = hs.Tinv[0]; T_out[13] = hs.Tinv[1]; T_out[14] = hs.Tinv[2]; T_out[15] = 1.f;
+  const int executed = (hs.stop_reason == CVO_B200_STOP_MAX_ITER) ? hs.iter : hs.iter + 1;
+  if (info) {
+    info->ret = hs.ret;
+    info->iterations = hs.iter;
+    info->stop_reason = hs.stop_reason;
+    info->final_num_neighbors = hs.num_neighbors;
+    info->final_ell = hs.ell;
+    info->registration_seconds = (double)ms / 1000.0;
+    info->pairs_tested = (uint64_t)h->src.n * (uint64_t)h->tgt.n * (uint64_t)executed;
+  }
+  if (trace_cap > 0) {
+    const int nrec = std::min(trace_cap, executed);
+    CVO_CUDA(h, cudaMemcpy(trace, h->d_trace.p, sizeof(cvo_b200_iter_trace) * (size_t)nrec, cudaMemcpyDeviceToHost));
+  }
+  return CVO_B200_OK;
+}
+
+int cvo_b200_align_host(cvo_b200_handle* h, int n_src, const float* src_xyz, int F,
+                        const float* src_feat, int C, const float* src_labels,
+                        const float* src_geotype, int n_tgt, const float* tgt_xyz,
+                        const float* tgt_feat, const float* tgt_labels,
+                        const float* tgt_geotype, const float T_init[16], float T_out[16],
+                        cvo_b200_align_info* info) {
+  if (!h) return CVO_B200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  cudaEvent_t e0, e1;
+  CVO_CUDA(h, cudaEventCreate(&e0));
+  CVO_CUDA(h, cudaEventCreate(&e1));
+  cudaEventRecord(e0, h->stream);
+  int rc = upload_cloud(h, h->src, n_src, src_xyz, F, src_feat, C, src_labels, src_geotype);
+  if (rc == CVO_B200_OK) rc = upload_cloud(h, h->tgt, n_tgt, tgt_xyz, F, tgt_feat, C, tgt_labels, tgt_geotype);
+  cudaEventRecord(e1, h->stream);
+  if (rc != CVO_B200_OK) {
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+  }
+  rc = cvo_b200_align(h, T_init, T_out, info, nullptr, 0);
+  float ms = 0.f;
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (info) info->upload_seconds = (double)ms / 1000.0;
+  return rc;
+}
+
+static int inner_product_common(cvo_b200_handle* h, const float T16[16], float ell,
+                                const float* kernel3x3, double* a_sum, IterArgs* A_out,
+                                const CloudDev* S = nullptr, const CloudDev* Tg = nullptr) {
+  IterArgs A;
+  float kinv[9];
+  int mode = 0;
+  if (kernel3x3) {
+    // Matrix3f::inverse() for fixed size 3: cofactors / determinant, float (CvoGPU.cu:1946)
+    const float* m = kernel3x3;
+#define CVO_K(i, j) m[3 * (j) + (i)]
+    volatile float c00 = CVO_K(1, 1) * CVO_K(2, 2) - CVO_K(1, 2) * CVO_K(2, 1);
+    volatile float c10 = CVO_K(1, 2) * CVO_K(2, 0) - CVO_K(1, 0) * CVO_K(2, 2);
+    volatile float c20 = CVO_K(1, 0) * CVO_K(2, 1) - CVO_K(1, 1) * CVO_K(2, 0);
+    volatile float t1 = CVO_K(0, 1) * c10, t2 = CVO_K(0, 2) * c20;
+    volatile float t12 = t1 + t2;
+    const float det = CVO_K(0, 0) * c00 + t12;
+    const float invdet = 1.0f / det;
+    kinv[0] = c00 * invdet;
+    kinv[1] = c10 * invdet;
+    kinv[2] = c20 * invdet;
+    kinv[3] = (CVO_K(0, 2) * CVO_K(2, 1) - CVO_K(0, 1) * CVO_K(2, 2)) * invdet;
+    kinv[4] = (CVO_K(0, 0) * CVO_K(2, 2) - CVO_K(0, 2) * CVO_K(2, 0)) * invdet;
+    kinv[5] = (CVO_K(2, 0) * CVO_K(0, 1) - CVO_K(0, 0) * CVO_K(2, 1)) * invdet;
+    kinv[6] = (CVO_K(0, 1) * CVO_K(1, 2) - CVO_K(0, 2) * CVO_K(1, 1)) * invdet;
+    kinv[7] = (CVO_K(1, 0) * CVO_K(0, 2) - CVO_K(0, 0) * CVO_K(1, 2)) * invdet;
+    kinv[8] = (CVO_K(0, 0) * CVO_K(1, 1) - CVO_K(1, 0) * CVO_K(0, 1)) * invdet;
+#undef CVO_K
+    mode = 1;
+  }
+  // inner products / associations are never sharded: every rank computes all rows
+  int rc = prepare(h, A, mode, kernel3x3 ? kinv : nullptr, S, Tg, false);
+  if (rc != CVO_B200_OK) return rc;
+  float R[9], T[3];
+  split_pose(T16, R, T);
+  // inner_product_impl uses num_neighbors = nearest_neighbors_max (CvoGPU.cu:1752-1754)
+  rc = init_state(h, R, T, ell, A.cap_max, 0, 1, nullptr, 0);
+  if (rc != CVO_B200_OK) return rc;
+  rc = enqueue_iteration(h, A, 2, nullptr, nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  double s = 0.0;
+  CVO_CUDA(h, cudaMemcpyAsync(&s, &h->d_state->a_sum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  CVO_CUDA(h, cudaGetLastError());
+  *a_sum = s;
+  if (A_out) *A_out = A;
+  return CVO_B200_OK;
+}
+
+int cvo_b200_inner_product(cvo_b200_handle* h, const float T[16], float ell, float* out) {
+  if (!h || !T || !out) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  if (!h->src.set || !h->tgt.set) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
+  if (h->src.n == 0 || h->tgt.n == 0) {
+    *out = 0.f;
+    return CVO_B200_OK;
+  }
+  double s = 0.0;
+  int rc = inner_product_common(h, T, ell, nullptr, &s, nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  *out = (float)s;
+  return CVO_B200_OK;
+}
+
+int cvo_b200_function_angle(cvo_b200_handle* h, const float T[16], float ell, int is_approximate,
+                            float* out) {
+  if (!h || !T || !out) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  if (!h->src.set || !h->tgt.set) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
+  // CvoGPU.cu:1821-1823
+  if (h->src.n == 0 || h->tgt.n == 0) {
+    *out = 0.f;
+    return CVO_B200_OK;
+  }
+  float fxfz = 0.f;
+  int rc = cvo_b200_inner_product(h, T, ell, &fxfz);
+  if (rc != CVO_B200_OK) return rc;
+  float fx_norm, fz_norm;
+  if (is_approximate) {  // :1831-1833
+    fx_norm = std::sqrt((double)h->src.n);
+    fz_norm = std::sqrt((double)h->tgt.n);
+  } else {               // :1835-1837: self inner products at the identity
+    const float I16[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    double sxx = 0.0, szz = 0.0;
+    rc = inner_product_common(h, I16, ell, nullptr, &sxx, nullptr, &h->src, &h->src);
+    if (rc != CVO_B200_OK) return rc;
+    rc = inner_product_common(h, I16, ell, nullptr, &szz, nullptr, &h->tgt, &h->tgt);
+    if (rc != CVO_B200_OK) return rc;
+    fx_norm = std::sqrt((float)sxx);
+    fz_norm = std::sqrt((float)szz);
+  }
+  *out = fxfz / (fx_norm * fz_norm);
+  return CVO_B200_OK;
+}
+
+int cvo_b200_association(cvo_b200_handle* h, const float T[16], float ell, const float* kernel3x3,
+                         int64_t* nnz, int32_t* row_ptr, int32_t* cols, float* vals) {
+  if (!h || !T || !nnz) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  if (!h->src.set || !h->tgt.set) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
+  *nnz = 0;
+  if (h->src.n == 0 || h->tgt.n == 0) return CVO_B200_OK;  // CvoGPU.cu:1884-1885
+  double s = 0.0;
+  IterArgs A;
+  int rc = inner_product_common(h, T, ell, kernel3x3, &s, &A);
+  if (rc != CVO_B200_OK) return rc;
+  const int n_rows = A.n_rows;
+  std::vector<uint32_t> cnt((size_t)n_rows);
+  CVO_CUDA(h, cudaMemcpy(cnt.data(), A.row_nnz, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost));
+  int64_t total = 0;
+  if (row_ptr) row_ptr[0] = 0;
+  for (int i = 0; i < n_rows; i++) {
+    total += cnt[i];
+    if (row_ptr) row_ptr[i + 1] = (int32_t)total;
+  }
+  *nnz = total;
+  if (!cols || !vals || total == 0) return CVO_B200_OK;
+  std::vector<uint32_t> idx((size_t)n_rows * A.cap_max);
+  std::vector<float> val((size_t)n_rows * A.cap_max);
+  CVO_CUDA(h, cudaMemcpy(idx.data(), A.ell_idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CVO_CUDA(h, cudaMemcpy(val.data(), A.ell_val, val.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  int64_t o = 0;
+  for (int i = 0; i < n_rows; i++)
+    for (uint32_t k = 0; k < cnt[i]; k++, o++) {
+      cols[o] = (int32_t)idx[(size_t)i * A.cap_max + k];
+      vals[o] = val[(size_t)i * A.cap_max + k];
+    }
+  return CVO_B200_OK;
+}
+
+int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T[3], float ell,
+                             int num_neighbors, int iters, float* ms_total, float* ms_pair_kernel) {
+  if (!h || !R || !T || iters <= 0) return fail(h, CVO_B200_ERR_INVALID, "bad argument");
+  cudaSetDevice(h->device);
+  IterArgs A;
+  int rc = prepare(h, A, 0, nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
+  if (num_neighbors > A.cap_max) num_neighbors = A.cap_max;
+  rc = init_state(h, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
+  if (rc != CVO_B200_OK) return rc;
+  const int n_ev = ms_pair_kernel ? iters : 0;
+  std::vector<cudaEvent_t> ea((size_t)n_ev), eb((size_t)n_ev);
+  for (int i = 0; i < n_ev; i++) {
+    cudaEventCreate(&ea[i]);
+    cudaEventCreate(&eb[i]);
+  }
+  cudaEvent_t e0, e1;
+  CVO_CUDA(h, cudaEventCreate(&e0));
+  CVO_CUDA(h, cudaEventCreate(&e1));
+  cudaEventRecord(e0, h->stream);
+  for (int i = 0; i < iters && rc == CVO_B200_OK; i++)
+    rc = enqueue_iteration(h, A, 3, n_ev ? ea[i] : nullptr, n_ev ? eb[i] : nullptr);
+  cudaEventRecord(e1, h->stream);
+  cudaError_t se = cudaStreamSynchronize(h->stream);
+  float ms = 0.f, msp = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  for (int i = 0; i < n_ev; i++) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, ea[i], eb[i]);
+    msp += t;
+    cudaEventDestroy(ea[i]);
+    cudaEventDestroy(eb[i]);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc != CVO_B200_OK) return rc;
+  CVO_CUDA(h, se);
+  CVO_CUDA(h, cudaGetLastError());
+  if (ms_total) *ms_total = ms;
+  if (ms_pair_kernel) *ms_pair_kernel = msp;
+  return CVO_B200_OK;
+}
+
+uint64_t cvo_b200_launch_count(const cvo_b200_handle* h) { return h ? h->launches : 0; }
+void* cvo_b200_stream(const cvo_b200_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int cvo_b200_fma_peak(cvo_b200_handle* h, int kind, int iters, double* fma_per_s) {
+  if (!h || !fma_per_s || iters <= 0) return fail(h, CVO_B200_ERR_INVALID, "bad argument");
+  cudaSetDevice(h->device);
+  CVO_CUDA(h, h->zeros_f.ensure(64));
+  const int blocks = h->num_sms * 8;
+  launch_fma_peak(kind, iters / 8 + 1, blocks, h->zeros_f.p, h->stream);  // warm-up
+  cudaEvent_t e0, e1;
+  CVO_CUDA(h, cudaEventCreate(&e0));
+  CVO_CUDA(h, cudaEventCreate(&e1));
+  cudaEventRecord(e0, h->stream);
+  launch_fma_peak(kind, iters, blocks, h->zeros_f.p, h->stream);
+  cudaEventRecord(e1, h->stream);
+  h->launches += 2;
+  CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  CVO_CUDA(h, cudaGetLastError());
+  const double fmas = (double)blocks * 256.0 * (double)iters * 16.0 * (kind == 1 ? 2.0 : 1.0);
+  *fma_per_s = fmas / ((double)ms * 1e-3);
+  return CVO_B200_OK;
+}
+
+int cvo_b200_comm_unique_id(char id[128]) {
+  std::string err;
+  if (!load_nccl(err)) return fail(nullptr, CVO_B200_ERR_NCCL, err);
+  UniqueId u;
+  int rc = g_nccl.GetUniqueId(&u);
+  if (rc != 0) return fail(nullptr, CVO_B200_ERR_NCCL, "ncclGetUniqueId failed");
+  std::memcpy(id, u.internal, 128);
+  return CVO_B200_OK;
+}
+
+int cvo_b200_comm_init(cvo_b200_handle* h, int rank, int world, const char id[128]) {
+  if (!h || world < 1 || rank < 0 || rank >= world) return fail(h, CVO_B200_ERR_INVALID, "bad rank/world");
+  cudaSetDevice(h->device);
+  if (world == 1) {
+    h->rank = 0;
+    h->world = 1;
+    return CVO_B200_OK;
+  }
+  std::string err;
+  if (!load_nccl(err)) return fail(h, CVO_B200_ERR_NCCL, err);
+  UniqueId u;
+  std::memcpy(u.internal, id, 128);
+  int rc = g_nccl.CommInitRank(&h->comm, world, u, rank);
+  if (rc != 0)
+    return fail(h, CVO_B200_ERR_NCCL,
+                std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+  h->rank = rank;
+  h->world = world;
+  destroy_graph(h);
+  return CVO_B200_OK;
+}
+
+int cvo_b200_comm_destroy(cvo_b200_handle* h) {
+  if (!h) return CVO_B200_ERR_INVALID;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  destroy_graph(h);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  h->comm = nullptr;
+  h->world = 1;
+  h->rank = 0;
+  return CVO_B200_OK;
+}
+
+}  // extern "C"
