@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native CVO hot path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Metric (BASELINE.json): point-pairs/s per CVO iteration = N_src * M_tgt * iterations / time.
+A "step" is one full registration (CvoGPU::align) of one synthetic frame pair:
+  N=1  -> workload C2  (BASELINE configs[1]: N=M=10 000, geometric kernel)
+  N>1  -> workload C4  (BASELINE configs[3]: N=M=200 000, geometry + 5-dim colour, MAX_ITER
+          capped at 50), SOURCE rows sharded across ranks, two 72/32-byte NCCL all-gathers per
+          iteration (strong scaling: the job is fixed, per-GPU work shrinks).
+`value` times the loop with the clouds already resident in HBM (CUDA events on the launching
+stream, inside libcvo_b200); `e2e` times the reference-facing call with HOST buffers (upload,
+loop, pose read-back) by wall clock.  `--impl reference` times the CPU restatement of the
+reference's algorithm (oracle/, OpenMP on all host cores) on a bounded number of iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "point_pairs_per_s"
+UNIT = "pairs/s"
+DATA = os.path.join(ROOT, "tests", "data")
+
+WORKLOADS = {
+    # name: (synthetic config, yaml, overrides, description)
+    "C2": ("C2", "cvo_outdoor_params.yaml",
+           dict(is_using_intensity=0, is_using_geometric_type=0, ell_init=0.95),
+           "synthetic N=M=10000 geometric kernel (BASELINE configs[1]); cvo_outdoor_params.yaml "
+           "with intensity/geometric-type off, ell_init=0.95; one step = one full align()"),
+    "KITTI05": ("KITTI05", "cvo_intensity_params_img_gpu0.yaml", dict(),
+                "synthetic KITTI-05-sized N=M=16384, geometry+5-dim colour; one step = one align()"),
+    "C4": ("C4", "cvo_intensity_params_img_gpu0.yaml", dict(MAX_ITER=50),
+           "synthetic N=M=200000 geometry+5-dim colour (BASELINE configs[3]), MAX_ITER=50; "
+           "one step = one align() of 50 iterations"),
+}
+
+
+def load_workload(name):
+    import unified_cvo_b200 as u
+    from unified_cvo_b200 import synthetic
+
+    cfg, yaml, over, desc = WORKLOADS[name]
+    d = synthetic.make_config(cfg)
+    p = u.read_params_yaml(os.path.join(DATA, yaml))
+    for k, v in over.items():
+        setattr(p, k, v)
+
+    def cloud(c):
+        return u.CvoPointCloud(c["xyz"], c["features"], c["labels"], c["geotype"])
+
+    return cloud(d["source"]), cloud(d["target"]), p, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": reasons}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def algorithmic_bytes_per_iteration(N, M, F, C):
+    """compulsory traffic of one iteration = (N+M)(16+4F+4C) + 256 bytes."""
+    return (N + M) * (16 + 4 * F + 4 * C) + 256
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle's align (restated reference algorithm, OpenMP) on a bounded sample."""
+    if rank != 0:
+        return
+    import oracle
+
+    name = args.workload or ("C2" if world == 1 else "C4")
+    src, tgt, p, desc = load_workload(name)
+    N, M = src.num_points(), tgt.num_points()
+    # bounded sample: a fixed number of leading iterations of the same registration
+    per_iter_pairs = N * M
+    sample_iters = max(2, int(min(p.MAX_ITER, 4e9 // per_iter_pairs, 60)))
+    p = p.copy()
+    p.MAX_ITER = sample_iters
+    cs = oracle.Cloud(src.positions_, src.features_, src.labels_, src.geometric_types_)
+    ct = oracle.Cloud(tgt.positions_, tgt.features_, tgt.labels_, tgt.geometric_types_)
+    for _ in range(min(args.warmup, 1)):
+        q = p.copy()
+        q.MAX_ITER = 2
+        oracle.align(q, cs, ct)
+    times, pairs = [], 0
+    for _ in range(args.steps):
+        t0 = time.perf_counter()
+        _, _, info, _ = oracle.align(p, cs, ct)
+        times.append(time.perf_counter() - t0)
+        pairs += info.pairs_tested
+    total = sum(times)
+    value = pairs / total
+    cores = oracle.num_threads()
+    sample = f"first {sample_iters} iterations of the {name} registration per step, {args.steps} steps"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{name}: {desc}", "N": N, "M": M},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import unified_cvo_b200 as u
+
+    name = args.workload or ("C2" if world == 1 else "C4")
+    src, tgt, p, desc = load_workload(name)
+    N, M, F, C = src.num_points(), tgt.num_points(), src.feature_dimensions(), src.num_classes()
+    torch.cuda.set_device(local_rank)
+    g = u.CvoGPU(p, device=local_rank)
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)  # control plane only
+        uid = [u.CvoGPU.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        g.comm_init(rank, world, uid[0])
+        per = (N + world - 1) // world
+        g.set_row_range(rank * per, min(N, (rank + 1) * per))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+
+    g.set_cloud(0, src)
+    g.set_cloud(1, tgt)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+
+    # ---- warm-up (also ramps the clocks: at least ~0.5 s of work)
+    t_warm = time.perf_counter()
+    w = 0
+    while w < args.warmup or time.perf_counter() - t_warm < 0.5:
+        g.align(src, tgt, resident=True)
+        w += 1
+        if w > args.warmup + 50:
+            break
+
+    # ---- timed region: K resident steps, device time per step, L2 flushed between steps
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = g.launch_count()
+    dev_s, pairs, iters = 0.0, 0, 0
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        _, _, info = g.align(src, tgt, resident=True)
+        dev_s += info.registration_seconds
+        pairs += info.pairs_tested
+        iters += info.iterations + (0 if info.stop_reason == 8 else 1)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = g.launch_count() - launches0
+    clocks = sampler.stop()
+
+    # ---- end to end: host buffers in, pose out, through the reference-facing call
+    e2e_s, e2e_pairs = 0.0, 0
+    if world == 1:
+        for _ in range(max(1, min(args.steps, 5))):
+            t0 = time.perf_counter()
+            _, _, info = g.align_host(src, tgt)
+            e2e_s += time.perf_counter() - t0
+            e2e_pairs += info.pairs_tested
+        e2e_steps = max(1, min(args.steps, 5))
+    else:
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            g.set_cloud(0, src)
+            g.set_cloud(1, tgt)
+            _, _, info = g.align(src, tgt, resident=True)
+            e2e_s += time.perf_counter() - t0
+            e2e_pairs += info.pairs_tested
+
+    # max over ranks of the device time
+    if dist is not None:
+        t = torch.tensor([dev_s, e2e_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_s, e2e_s = float(t[0]), float(t[1])
+
+    # ---- roofline of the dominant kernel (pair_kernel), measured live with CUDA events
+    roof, fp32 = None, None
+    peaks, peak_src = measured_peaks()
+    ms_tot, ms_pair = g.time_iterations(np.eye(3), np.zeros(3), p.ell_init, p.nearest_neighbors_max, 40)
+    rows_local = N if world == 1 else (min(N, (rank + 1) * ((N + world - 1) // world)) - rank * ((N + world - 1) // world))
+    t_pair = ms_pair / 40 * 1e-3
+    alg_bytes = algorithmic_bytes_per_iteration(rows_local, M, F, C)
+    achieved = alg_bytes / t_pair / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+            "kernel": "pair_kernel", "kernel_us": t_pair * 1e6, "kernel_share_of_iteration": ms_pair / ms_tot,
+            "note": "the path is fp32-pipe bound, not HBM bound (SURVEY.md §8d): see fp32"}
+    fma = g.fma_peak(1, 8192)
+    pair_rate = rows_local * M / t_pair
+    fp32 = {"pair_tests_per_s": pair_rate, "fma_peak_per_s": fma, "fma_per_pair": 3,
+            "peak_pair_tests_per_s": fma / 3.0, "frac": pair_rate / (fma / 3.0)}
+
+    if rank != 0:
+        return
+    value = pairs / dev_s
+    h2d = (N + M) * (32 + 4 * ((F + 3) // 4 * 4) + 4 * ((C + 3) // 4 * 4) + 8) + 9000
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{name}: {desc}", "N": N, "M": M, "F": F, "C": C,
+                   "iterations_per_step": iters / args.steps, "l2_flush_between_steps": True,
+                   "parallelism": "single GPU" if world == 1 else f"source rows sharded x{world}, NCCL all-gather",
+                   "timing": "CUDA events on the launching stream inside cvo_b200_align, summed over steps"},
+        "e2e": {"value": e2e_pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 8800, "steps": e2e_steps,
+                "note": "wall clock around cvo_b200_align_host: upload, loop, pose read-back"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "fp32": fp32,
+        "wall_ms_per_step": 1e3 * wall / args.steps,
+        "frame_pairs_per_s": args.steps / dev_s,
+    }
+    # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same registration
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        q = p.copy()
+        q.MAX_ITER = max(2, int(min(p.MAX_ITER, 2.5e10 // (N * M), 400)))
+        cs = oracle.Cloud(src.positions_, src.features_, src.labels_, src.geometric_types_)
+        ct = oracle.Cloud(tgt.positions_, tgt.features_, tgt.labels_, tgt.geometric_types_)
+        t0 = time.perf_counter()
+        _, _, info, _ = oracle.align(q, cs, ct)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": info.pairs_tested / dt, "unit": UNIT, "cores": oracle.num_threads(),
+                                "kind": "port",
+                                "sample": f"first {q.MAX_ITER} iterations of the same {name} registration "
+                                          f"(oracle/cvo_oracle.c, OpenMP), {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    g.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29531")
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})"}))
+        sys.exit(2)
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

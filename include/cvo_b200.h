@@ -115,7 +115,7 @@ typedef struct cvo_b200_params {
 #define CVO_B200_ELL_DECAYED 16      /* ell was decayed at the end of this iteration  */
 
 /* One CVO iteration, as the reference's debug log would describe it
- * (CvoGPU.cu:1387-1533).  Doubles as the parity probe. 256 bytes. */
+ * (CvoGPU.cu:1387-1533).  Doubles as the parity probe. 232 bytes. */
 typedef struct cvo_b200_iter_trace {
   int32_t iter;
   int32_t num_neighbors;     /* row cap used by this iteration                      */
@@ -156,6 +156,9 @@ typedef struct cvo_b200_handle cvo_b200_handle;
 int cvo_b200_abi_version(void);
 /* number of CUDA devices visible, or a negative error code */
 int cvo_b200_device_count(void);
+/* sizeof of the ABI structs as compiled into the library, for binding self-checks:
+ * which = 0 cvo_b200_params, 1 cvo_b200_iter_trace, 2 cvo_b200_align_info; -1 otherwise */
+int cvo_b200_sizeof(int which);
 /* thread-local message of the last failing call without a handle */
 const char* cvo_b200_global_error(void);
 

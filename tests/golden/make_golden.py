@@ -1,0 +1,77 @@
+"""Generates the committed golden fixtures from the ORACLE (oracle/cvo_oracle.c).
+
+The reference ships no golden vectors for this path and cannot be built here
+(SURVEY.md §4, §8c), so these fixtures freeze the oracle's outputs: they guard the
+oracle against regressions and give the GPU parity tests inputs/outputs that do not need
+the oracle at run time.  Regenerate with:  python tests/golden/make_golden.py
+Each fixture holds teacher-forced single iterations: the state (R, T, ell, cap) taken
+from the oracle's own align() trajectory and the iteration's outputs at that state.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import oracle  # noqa: E402
+from helpers import (demo_clouds, demo_params, geometric_params, synthetic_pair,  # noqa: E402
+                     to_oracle_cloud)
+
+CASES = {
+    "demo_color": dict(kind="demo", color=True, sample=[0, 1, 2, 10, 100, 500, 1000, 3000, 6000]),
+    "demo_geometric": dict(kind="demo", color=False, sample=[0, 1, 2, 10, 100, 500, 1000, 3000]),
+    "synthetic_2k": dict(kind="synthetic", P=2500, N=2000, M=2000, seed=20002,
+                         sample=[0, 1, 2, 5, 10, 50, 100, 200, 400]),
+}
+
+
+def case_inputs(c):
+    if c["kind"] == "demo":
+        src, tgt = demo_clouds(c["color"])
+        return src, tgt, demo_params(src, tgt, c["color"])
+    src, tgt, _ = synthetic_pair(c["P"], c["N"], c["M"], c["seed"])
+    return src, tgt, geometric_params()
+
+
+def run_case(c):
+    src, tgt, p = case_inputs(c)
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    n = max(c["sample"]) + 1
+    ret, T, info, tr = oracle.align(p, cs, ct, None, trace_cap=n)
+    out = []
+    for k in c["sample"]:
+        if k >= len(tr):
+            continue
+        if k == 0:
+            R, Tt = np.eye(3, dtype=np.float32).reshape(9), np.zeros(3, np.float32)
+        else:
+            R, Tt = np.array(list(tr[k - 1].R), np.float32), np.array(list(tr[k - 1].T), np.float32)
+        ell, cap = float(tr[k].ell), int(tr[k].num_neighbors)
+        r = oracle.iterate(p, cs, ct, R, Tt, ell, cap)
+        out.append(dict(k=k, R=[float(x) for x in R], T=[float(x) for x in Tt], ell=ell, cap=cap,
+                        nnz=int(r.nnz), max_row_nnz=int(r.max_row_nnz),
+                        twist=[float(x) for x in list(r.omega) + list(r.v)],
+                        omega_sum=list(r.omega_sum), v_sum=list(r.v_sum),
+                        BCDE=[r.B, r.C, r.D, r.E], step=float(r.step), a_sum=r.a_sum, dist=r.dist,
+                        R_next=[float(x) for x in r.R], T_next=[float(x) for x in r.T]))
+    return dict(iters=out, ret=ret, iterations=info.iterations, transform=[[float(x) for x in row] for row in T])
+
+
+def main():
+    for name, c in CASES.items():
+        res = run_case(c)
+        with open(os.path.join(HERE, f"{name}_iters.json"), "w") as fh:
+            json.dump(dict(case=name, iters=res["iters"]), fh, indent=0)
+        if name == "demo_color":
+            with open(os.path.join(HERE, "demo_color_align.json"), "w") as fh:
+                json.dump(dict(case=name, ret=res["ret"], iterations=res["iterations"],
+                               transform=res["transform"]), fh, indent=0)
+        print(name, len(res["iters"]), "records; align iterations", res["iterations"])
+
+
+if __name__ == "__main__":
+    main()

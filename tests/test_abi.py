@@ -1,0 +1,89 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads without a GPU, exports every
+symbol include/cvo_b200.h declares, its structs match the ctypes mirror, the parameter
+reader behaves like read_CvoParams_yaml, and GPU entry points fail loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import unified_cvo_b200 as u
+from unified_cvo_b200 import _abi
+from helpers import DATA, ROOT
+
+
+def test_header_symbols_all_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "cvo_b200.h")).read()
+    declared = set(re.findall(r"\b(cvo_b200_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"cvo_b200_handle"}
+    assert declared == set(_abi.SYMBOLS), declared ^ set(_abi.SYMBOLS)
+    lib = _abi.load_library()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.cvo_b200_abi_version() == 1
+
+
+def test_struct_sizes_match_the_compiled_library():
+    lib = _abi.load_library()
+    assert lib.cvo_b200_sizeof(0) == C.sizeof(_abi.Params)
+    assert lib.cvo_b200_sizeof(1) == C.sizeof(_abi.IterTrace) == 232
+    assert lib.cvo_b200_sizeof(2) == C.sizeof(_abi.AlignInfo)
+    assert lib.cvo_b200_sizeof(99) == -1
+
+
+def test_param_defaults_follow_the_reference_constructor():
+    p = u.default_params()  # CvoParams.hpp:75-126
+    assert p.ell_init == pytest.approx(0.5) and p.ell_min == pytest.approx(0.05)
+    assert p.sigma == pytest.approx(0.1) and p.sp_thres == pytest.approx(0.0006)
+    assert p.c == 7.0 and p.d == 7.0 and p.MAX_ITER == 10000
+    assert p.nearest_neighbors_max == 512 and p.indicator_window_size == 15
+    assert p.is_using_geometry == 1 and p.is_using_intensity == 0 and p.is_using_kdtree == 0
+    assert p.multiframe_least_squares_num_threads == 24
+
+
+def test_yaml_reader_matches_shipped_files_and_first_duplicate_wins():
+    p = u.read_params_yaml(os.path.join(DATA, "cvo_outdoor_params.yaml"))
+    assert p.ell_init == pytest.approx(0.2) and p.sp_thres == pytest.approx(0.007)
+    assert p.MAX_ITER == 100000 and p.max_step == pytest.approx(0.01)
+    assert p.nearest_neighbors_max == 256 and p.is_using_geometric_type == 1
+    assert p.ell_decay_rate == pytest.approx(0.8) and p.indicator_window_size == 10
+    assert p.multiframe_ell_init == pytest.approx(4.0)  # "4  #2.5" -> comment stripped
+    q = u.read_params_yaml(os.path.join(DATA, "cvo_intensity_params_img_gpu0.yaml"))
+    assert q.nearest_neighbors_max == 256  # duplicate key (256 then 512): first occurrence wins
+    assert q.c_ell == pytest.approx(0.05) and q.is_using_intensity == 1
+    r = u.read_params_yaml(os.path.join(DATA, "cvo_rgbd_params.yaml"))
+    assert r.max_step == pytest.approx(0.8) and r.MAX_ITER == 2000 and r.c_sigma == pytest.approx(0.6)
+    with pytest.raises(u.CvoError):
+        u.read_params_yaml(os.path.join(DATA, "does_not_exist.yaml"))
+
+
+def test_pcd_reader_and_xyzrgb_constructor():
+    pc = u.CvoPointCloud.from_pcd(os.path.join(DATA, "source.pcd"))
+    assert pc.num_points() == 523 and pc.feature_dimensions() == 5 and pc.num_classes() == 0
+    # first point: rgb 4290691523 = 0xFFBEC1C3 -> (190,193,195)/255  (CvoPointCloud.cpp:583-587)
+    np.testing.assert_allclose(pc.features_[0], [190 / 255, 193 / 255, 195 / 255, 0, 0], rtol=1e-6)
+    assert np.all(pc.geometric_types_ == [0, 1])
+    xyz_only = u.CvoPointCloud.from_pcd(os.path.join(DATA, "target.pcd"), use_color=False)
+    assert xyz_only.num_points() == 1080 and xyz_only.feature_dimensions() == 0
+    assert np.all(xyz_only.geometric_types_ == [1, 0])
+    moved = u.CvoPointCloud.transform(np.eye(4), pc)
+    assert np.array_equal(moved.positions_, pc.positions_)
+    assert (pc + xyz_only).num_points() == 1603
+
+
+def test_no_cpu_fallback_without_a_gpu():
+    lib = _abi.load_library()
+    if lib.cvo_b200_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(u.CvoError):
+        u.CvoGPU(u.default_params())
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "unified_cvo_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(base, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "cvo_oracle" not in txt, f

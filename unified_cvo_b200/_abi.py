@@ -133,6 +133,7 @@ _i32p = C.POINTER(C.c_int32)
 SYMBOLS = {
     "cvo_b200_abi_version": (C.c_int, []),
     "cvo_b200_device_count": (C.c_int, []),
+    "cvo_b200_sizeof": (C.c_int, [C.c_int]),
     "cvo_b200_global_error": (C.c_char_p, []),
     "cvo_b200_params_default": (None, [C.POINTER(Params)]),
     "cvo_b200_params_read_yaml": (C.c_int, [C.c_char_p, C.POINTER(Params)]),

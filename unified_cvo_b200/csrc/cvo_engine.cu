@@ -473,6 +473,15 @@ extern "C" {
 
 int cvo_b200_abi_version(void) { return CVO_B200_ABI_VERSION; }
 
+int cvo_b200_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(cvo_b200_params);
+    case 1: return (int)sizeof(cvo_b200_iter_trace);
+    case 2: return (int)sizeof(cvo_b200_align_info);
+    default: return -1;
+  }
+}
+
 int cvo_b200_device_count(void) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);

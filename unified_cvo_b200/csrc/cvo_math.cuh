@@ -87,7 +87,21 @@ __device__ inline bool cubic_roots(const double coef[4], double re[3], double im
     x1 = 2.0 * sqrt(-q) * cos(th / 3.0) - a2 / 3.0;
   }
   x1 = poly3_polish(a2, a1, a0, x1);
-  double b = a2 + x1, c = a1 + x1 * b;
+  /* deflate to u^2 + b u + c with the numerically safer of two formulas each:
+   * c = product of the other two roots = -a0/x1 (no cancellation), and
+   * b = -(their sum) = a2 + x1  or  (c - a1)/x1, whichever cancels less. */
+  double b, c;
+  if (x1 != 0.0) {
+    c = -a0 / x1;
+    double b1 = a2 + x1, b2 = (c - a1) / x1;
+    double r1 = fabs(b1) / (fabs(a2) + fabs(x1));
+    double den2 = fabs(c) + fabs(a1);
+    double r2 = den2 > 0.0 ? fabs(c - a1) / den2 : 0.0;
+    b = (r1 >= r2) ? b1 : b2;
+  } else {
+    b = a2;
+    c = a1;
+  }
   double d2 = b * b - 4.0 * c;
   double r2re, r2im, r3re, r3im;
   if (d2 >= 0.0) {

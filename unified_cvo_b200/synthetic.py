@@ -52,7 +52,8 @@ def gt_transform() -> np.ndarray:
 def make_pair(P: int, N: int, M: int, seed: int, F: int = 0, C: int = 0, overlap: float = 0.8,
               with_geotype: bool = False):
     """Returns dict(source=..., target=..., T_gt=...), each cloud a dict of float32 arrays."""
-    assert P >= N + int(round((1.0 - overlap) * M)), "base scene too small for the overlap"
+    n_ov = min(int(round(overlap * M)), N)
+    assert P >= N + (M - n_ov), "base scene too small for the requested overlap"
     bx = uniform01(seed, 1, P) * 20.0 - 10.0
     by = uniform01(seed, 2, P) * 4.0 - 2.0
     bz = uniform01(seed, 3, P) * 28.0 + 2.0
@@ -70,7 +71,6 @@ def make_pair(P: int, N: int, M: int, seed: int, F: int = 0, C: int = 0, overlap
         lab[np.arange(P), cls] = 0.9
     perm = np.argsort(uniform01(seed, 40, P), kind="stable")
     src_idx = perm[:N]
-    n_ov = int(round(overlap * M))
     tgt_idx = np.concatenate([src_idx[:n_ov], perm[N:N + (M - n_ov)]])
     tgt_idx = tgt_idx[np.argsort(uniform01(seed, 41, M), kind="stable")]
 
