@@ -245,4 +245,4 @@ def test_demo_alignment_golden_pose():
     ret, T, info, _ = oracle.align(p, to_oracle_cloud(src), to_oracle_cloud(tgt))
     assert ret == g["ret"]
     # chaotic trajectory, contracting end point: pose pinned loosely, iteration count not at all
-    np.testing.assert_allclose(T, np.array(g["transform"]), atol=5e-3)
+    np.testing.assert_allclose(T, np.array(g["transform"]), atol=1e-5)  # same code, same machine class

@@ -29,13 +29,18 @@ constexpr int kPairWarps = 8;          // warps per CTA of the pair kernel
 constexpr int kSparseThreads = 256;    // CTA size of the sparse kernels
 constexpr int kQueueCap = 1024;        // max indicator_window_size supported
 
+// per-block partial sums of the flow pass: omega[3], v[3], a_sum, nnz, max_row (all as doubles:
+// nnz and max_row are exact integers < 2^53)
 struct FlowPartial {
-  double omega[3];
-  double v[3];
-  double a_sum;
-  unsigned long long nnz;
-  unsigned int max_row;
-  unsigned int pad;
+  double v[9];
+};
+// The scalar prologue of fill_in_A_mat_gpu (CvoGPU.cu:495-515), evaluated once per
+// write_params on the host (same float arithmetic) instead of once per thread.
+struct KernConsts {
+  float sigma2, c2, c_sigma2, s_ell, s_sigma2, s_ell_square, sp_thres;
+  float log_geo;      // logf(sp_thres / sigma2)
+  float d2_c_thres, d2_s_thres, d2_s_thres_dense;
+  int use_geo_type, use_geometry, use_intensity, use_semantics;
 };
 struct StepPartial {
   double b, c, d, e;
@@ -74,7 +79,10 @@ struct DevState {
   unsigned int work_counter;
   unsigned int flow_blocks_done;
   unsigned int step_blocks_done;
-  unsigned int ymax2_bits;  // max_j |y'_j - c|^2 as float bits
+  float ymax2_bound;        // upper bound of max_j |y'_j - c|^2 for the CURRENT Rinv/Tinv
+  // constants and per-iteration matrices shared by all threads
+  KernConsts kc;
+  float W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];  // omega_hat powers (CvoGPU.cu:970-980)
   // trace
   cvo_b200_iter_trace* trace;
   int trace_cap;
@@ -105,7 +113,12 @@ struct IterArgs {
   const float2* tgt_geo;
   int M;
   int Fp, Cp;      // padded feature / class dims (same for both clouds)
-  float cx, cy, cz;
+  float cx, cy, cz;        // prefilter centre (source centroid)
+  float tcx, tcy, tcz;     // target centroid and radius max_j |y_j - tc| (static per cloud)
+  float trad;
+  int M_pad;               // M rounded up to kJBlock: px..pw are padded with (0,0,0,+inf)
+  float4* rowrec;          // [n_rows][2]: (ax,ax,ay,ay) (az,az,t,t), rewritten every iteration
+  float2* row_lt;          // [n_rows]: (l_i, d2_thres_i) of the exact test
   // candidate cells
   uint32_t* cand;
   uint32_t* cand_cnt;

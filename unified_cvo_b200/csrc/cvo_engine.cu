@@ -26,8 +26,10 @@ void launch_flow(const IterArgs& A, int blocks, cudaStream_t s);
 void launch_step(const IterArgs& A, int blocks, cudaStream_t s);
 void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride, cudaStream_t s);
 void launch_finalize_step(const IterArgs& A, const double* gathered, int stride, cudaStream_t s);
+void launch_init_bound(const IterArgs& A, cudaStream_t s);
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s);
 int pair_kernel_max_blocks_per_sm();
+int sparse_kernel_max_blocks_per_sm();
 }  // namespace cvo_b200
 
 using namespace cvo_b200;
@@ -106,7 +108,8 @@ struct CloudDev {
   DevBuf<float> lab;    // n * Cp
   DevBuf<float2> geo;
   int Fp = 0, Cp = 0;   // strides the buffers were packed with
-  float cx = 0, cy = 0, cz = 0;
+  float cx = 0, cy = 0, cz = 0;  // centroid (float)
+  float radius = 0;              // max_i |x_i - centroid| (rounded up)
   bool set = false;
 };
 }  // namespace
@@ -122,6 +125,8 @@ struct cvo_b200_handle {
   // per-iteration workspace
   DevBuf<float4> tgt_moved;
   DevBuf<float> px, py, pz, pw;
+  DevBuf<float4> rowrec;
+  DevBuf<float2> row_lt;
   DevBuf<uint32_t> cand, cand_cnt, ell_idx, row_nnz;
   DevBuf<float> ell_val;
   DevBuf<FlowPartial> flow_part;
@@ -183,22 +188,26 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
 
   // ---- chunking: enough (row tile, target chunk) items to fill the machine a few times
   const int row_tiles = std::max(1, (n_rows + kTileRows - 1) / kTileRows);
-  const int target_items = h->num_sms * 32;
+  const int target_items = h->num_sms * 96;
   int nchunks = std::max(1, (target_items + row_tiles - 1) / row_tiles);
   const int max_chunks = std::max(1, (M + kJBlock - 1) / kJBlock);
   nchunks = std::min(nchunks, max_chunks);
   int chunk_len = round_up(std::max(1, (M + nchunks - 1) / nchunks), kJBlock);
   nchunks = std::max(1, (M + chunk_len - 1) / chunk_len);
-  int L = std::min(chunk_len, std::max(64, 2 * cap_max));
+  // cell capacity in candidate WORDS (one word = one lane's 8 consecutive targets)
+  int L = std::min(chunk_len / 8, std::max(64, 2 * cap_max));
   // keep the candidate cells within ~8 GiB
-  while ((size_t)std::max(n_rows, 1) * nchunks * L * 4 > ((size_t)8 << 30) && L > 64) L /= 2;
+  while ((size_t)std::max(n_rows, 1) * nchunks * L * 4 > ((size_t)8 << 30) && L > 32) L /= 2;
+  const int M_pad = round_up(std::max(M, 1), kJBlock);
 
   const size_t n_zero = (size_t)std::max(N, M) * (size_t)std::max(std::max(Fp, Cp), 1);
   CVO_CUDA(h, h->tgt_moved.ensure((size_t)M));
-  CVO_CUDA(h, h->px.ensure((size_t)M));
-  CVO_CUDA(h, h->py.ensure((size_t)M));
-  CVO_CUDA(h, h->pz.ensure((size_t)M));
-  CVO_CUDA(h, h->pw.ensure((size_t)M));
+  CVO_CUDA(h, h->px.ensure((size_t)M_pad));
+  CVO_CUDA(h, h->py.ensure((size_t)M_pad));
+  CVO_CUDA(h, h->pz.ensure((size_t)M_pad));
+  CVO_CUDA(h, h->pw.ensure((size_t)M_pad));
+  CVO_CUDA(h, h->rowrec.ensure((size_t)std::max(n_rows, 1) * 2));
+  CVO_CUDA(h, h->row_lt.ensure((size_t)std::max(n_rows, 1)));
   CVO_CUDA(h, h->cand.ensure((size_t)std::max(n_rows, 1) * nchunks * L));
   CVO_CUDA(h, h->cand_cnt.ensure((size_t)std::max(n_rows, 1) * nchunks));
   CVO_CUDA(h, h->ell_idx.ensure((size_t)std::max(n_rows, 1) * cap_max));
@@ -218,10 +227,13 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   if (occ < 1) occ = 1;
   const int n_items = row_tiles * nchunks;
   h->pair_blocks = std::max(1, std::min(h->num_sms * occ, (n_items + kPairWarps - 1) / kPairWarps));
-  h->prep_blocks = std::max(1, std::min(h->num_sms * 4, (M + 255) / 256));
+  h->prep_blocks = std::max(1, std::min(h->num_sms * 4, (std::max(M_pad, n_rows) + 255) / 256));
   const int warps_per_block = kSparseThreads / 32;
+  int socc = sparse_kernel_max_blocks_per_sm();
+  if (socc < 1) socc = 1;
+  // one warp per source row while the rows fit in one resident wave, grid-stride beyond
   h->sparse_blocks =
-      std::max(1, std::min(h->num_sms * 4, (n_rows + warps_per_block - 1) / warps_per_block));
+      std::max(1, std::min(h->num_sms * socc, (n_rows + warps_per_block - 1) / warps_per_block));
   CVO_CUDA(h, h->flow_part.ensure((size_t)h->sparse_blocks));
   CVO_CUDA(h, h->step_part.ensure((size_t)h->sparse_blocks));
 
@@ -246,6 +258,11 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.Fp = Fp;
   A.Cp = Cp;
   A.cx = cs.cx; A.cy = cs.cy; A.cz = cs.cz;
+  A.tcx = ct.cx; A.tcy = ct.cy; A.tcz = ct.cz;
+  A.trad = ct.radius;
+  A.M_pad = M_pad;
+  A.rowrec = h->rowrec.p;
+  A.row_lt = h->row_lt.p;
   A.cand = h->cand.p;
   A.cand_cnt = h->cand_cnt.p;
   A.nchunks = nchunks;
@@ -311,8 +328,44 @@ void host_update_tf(const float R[9], const float T[3], float Rinv[9], float Tin
   }
 }
 
-int init_state(cvo_b200_handle* h, const float R[9], const float T[3], float ell, int cap,
-               int controller_on, int max_iter, cvo_b200_iter_trace* d_trace, int trace_cap) {
+// fill_in_A_mat_gpu's scalar prologue (CvoGPU.cu:495-515, and :235-254 for the dense-kernel
+// variant), in the same float arithmetic, once per call instead of once per thread
+KernConsts make_consts(const cvo_b200_params& p) {
+  KernConsts k;
+  std::memset(&k, 0, sizeof(k));
+  volatile float sigma2 = p.sigma * p.sigma;
+  volatile float c2 = p.c_ell * p.c_ell;
+  volatile float c_sigma2 = p.c_sigma * p.c_sigma;
+  volatile float s_sigma2 = p.s_sigma * p.s_sigma;
+  volatile float s_ell_square = p.s_ell * p.s_ell;
+  k.sigma2 = sigma2; k.c2 = c2; k.c_sigma2 = c_sigma2; k.s_ell = p.s_ell; k.s_sigma2 = s_sigma2;
+  k.s_ell_square = s_ell_square;
+  k.sp_thres = p.sp_thres;
+  k.use_geo_type = p.is_using_geometric_type;
+  k.use_geometry = p.is_using_geometry;
+  k.use_intensity = p.is_using_intensity;
+  k.use_semantics = p.is_using_semantics;
+  volatile float q_geo = p.sp_thres / sigma2;
+  k.log_geo = logf(q_geo);
+  k.d2_c_thres = 1.f;
+  k.d2_s_thres = 1.f;
+  k.d2_s_thres_dense = 1.f;
+  if (k.use_intensity) {
+    volatile float q = p.sp_thres / c_sigma2;
+    k.d2_c_thres = (float)(-2.0 * (double)c2 * (double)logf(q));
+  }
+  if (k.use_semantics) {
+    volatile float q = p.sp_thres / s_sigma2;
+    const double lg = (double)logf(q);
+    k.d2_s_thres = (float)(-2.0 * (double)p.s_ell * (double)p.s_ell * lg);
+    k.d2_s_thres_dense = (float)(-2.0 * (double)s_ell_square * lg);
+  }
+  return k;
+}
+
+int init_state(cvo_b200_handle* h, const IterArgs& A, const float R[9], const float T[3], float ell,
+               int cap, int controller_on, int max_iter, cvo_b200_iter_trace* d_trace,
+               int trace_cap) {
   static thread_local DevState hs;  // ~8.5 KB; keep it off the stack of small callers
   std::memset(&hs, 0, sizeof(hs));
   std::memcpy(hs.R, R, sizeof(hs.R));
@@ -324,8 +377,11 @@ int init_state(cvo_b200_handle* h, const float R[9], const float T[3], float ell
   hs.controller_on = controller_on;
   hs.trace = d_trace;
   hs.trace_cap = trace_cap;
+  hs.kc = make_consts(h->params);
   CVO_CUDA(h, cudaMemcpyAsync(h->d_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
   // the source of an async copy from pageable memory is staged before the call returns
+  launch_init_bound(A, h->stream);  // Rinv/Tinv + the |y'-c| bound, same code as the controller
+  h->launches += 1;
   return CVO_B200_OK;
 }
 
@@ -403,6 +459,14 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
     c.cx = n_finite ? (float)(mx / (double)n_finite) : 0.f;
     c.cy = n_finite ? (float)(my / (double)n_finite) : 0.f;
     c.cz = n_finite ? (float)(mz / (double)n_finite) : 0.f;
+    double r2max = 0.0;
+    for (int i = 0; i < n; i++) {
+      const double dx = (double)xyz[3 * (size_t)i] - c.cx, dy = (double)xyz[3 * (size_t)i + 1] - c.cy,
+                   dz = (double)xyz[3 * (size_t)i + 2] - c.cz;
+      const double r2 = dx * dx + dy * dy + dz * dz;
+      if (r2 > r2max) r2max = r2;  // NaN compares false; +inf propagates (every pair a candidate)
+    }
+    c.radius = (float)(std::sqrt(r2max) * (1.0 + 1e-6)) + 1e-6f;
     for (int i = 0; i < n; i++) {
       const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
       volatile float xx = x * x, yy = y * y, zz = z * z;
@@ -542,6 +606,7 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
     c->xyz.release(); c->rowA.release(); c->feat.release(); c->lab.release(); c->geo.release();
   }
   h->tgt_moved.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
+  h->rowrec.release(); h->row_lt.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
   h->zeros_g.release(); h->d_trace.release(); h->gathered.release();
@@ -595,7 +660,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) return fail(h, CVO_B200_ERR_INVALID, "num_neighbors exceeds nearest_neighbors_max");
   CVO_CUDA(h, h->d_trace.ensure(1));
-  rc = init_state(h, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
+  rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
   rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
   if (rc != CVO_B200_OK) return rc;
@@ -636,7 +701,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
     if (info) info->stop_reason = CVO_B200_STOP_MAX_ITER;
     return CVO_B200_OK;
   }
-  rc = init_state(h, R, T, h->params.ell_init, h->params.nearest_neighbors_max, 1, max_iter,
+  rc = init_state(h, A, R, T, h->params.ell_init, h->params.nearest_neighbors_max, 1, max_iter,
                   trace_cap > 0 ? h->d_trace.p : nullptr, trace_cap);
   if (rc != CVO_B200_OK) return rc;
   cudaEvent_t ev0, ev1;
@@ -749,7 +814,7 @@ static int inner_product_common(cvo_b200_handle* h, const float T16[16], float e
   float R[9], T[3];
   split_pose(T16, R, T);
   // inner_product_impl uses num_neighbors = nearest_neighbors_max (CvoGPU.cu:1752-1754)
-  rc = init_state(h, R, T, ell, A.cap_max, 0, 1, nullptr, 0);
+  rc = init_state(h, A, R, T, ell, A.cap_max, 0, 1, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
   rc = enqueue_iteration(h, A, 2, nullptr, nullptr);
   if (rc != CVO_B200_OK) return rc;
@@ -852,7 +917,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   if (rc != CVO_B200_OK) return rc;
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) num_neighbors = A.cap_max;
-  rc = init_state(h, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
+  rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
   const int n_ev = ms_pair_kernel ? iters : 0;
   std::vector<cudaEvent_t> ea((size_t)n_ev), eb((size_t)n_ev);

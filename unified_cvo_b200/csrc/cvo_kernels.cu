@@ -2,13 +2,13 @@
 //
 // Per iteration (reference call stack: align_impl, CvoGPU.cu:1387-1533):
 //   prep_kernel      update_tf + transform_pointcloud_thrust (CvoGPU.cu:94-112,
-//                    CvoGPU_impl.cu:31-82,164-173): y' = Rinv*y + Tinv, plus the
-//                    centred SoA operand of the pair kernel.
+//                    CvoGPU_impl.cu:31-82,164-173): y' = Rinv*y + Tinv, the centred SoA
+//                    operand of the pair kernel, and the per-row prefilter records.
 //   pair_kernel      the dense N x M part of fill_in_A_mat_gpu (CvoGPU.cu:477-593):
 //                    a conservative fp32 prefilter |x-y'|^2 < thres_i on packed
 //                    f32x2 FMAs that emits, per (row, target chunk), the ORDERED
 //                    list of candidate targets.  Source tiles are TMA-staged into
-//                    shared memory, targets are streamed into registers.
+//                    shared memory (double buffered), targets are streamed into registers.
 //   flow_kernel      the exact per-pair arithmetic of fill_in_A_mat_gpu on the
 //                    candidates (row cap = first num_neighbors survivors in target
 //                    order), the ELL kernel matrix, compute_flow_gpu_no_eigen
@@ -20,7 +20,7 @@
 // This file is compiled with --fmad=false: all C++ float/double expressions are
 // evaluated uncontracted, in the reference's mixed precision.  The only fused
 // arithmetic is the explicit fma.rn.f32x2 of the prefilter, whose rounding error is
-// covered by the candidate margin (see expand_rows()).
+// covered by the candidate margin (see prefilter_threshold()).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -87,40 +87,6 @@ __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
-// ------------------------------------------------------------------ per-launch constants
-// The scalar prologue of fill_in_A_mat_gpu (CvoGPU.cu:495-515), hoisted.
-struct KernConsts {
-  float sigma2, c2, c_sigma2, s_ell, s_sigma2, s_ell_square, sp_thres;
-  float log_geo;      // logf(sp_thres / sigma2)
-  float d2_c_thres, d2_s_thres;
-  int use_geo_type, use_geometry, use_intensity, use_semantics;
-};
-__device__ __forceinline__ KernConsts make_consts(const cvo_b200_params* p, int mode) {
-  KernConsts k;
-  k.sigma2 = p->sigma * p->sigma;
-  k.c2 = p->c_ell * p->c_ell;
-  k.c_sigma2 = p->c_sigma * p->c_sigma;
-  k.s_ell = p->s_ell;
-  k.s_sigma2 = p->s_sigma * p->s_sigma;
-  k.s_ell_square = p->s_ell * p->s_ell;
-  k.sp_thres = p->sp_thres;
-  k.use_geo_type = p->is_using_geometric_type;
-  k.use_geometry = p->is_using_geometry;
-  k.use_intensity = p->is_using_intensity;
-  k.use_semantics = p->is_using_semantics;
-  k.log_geo = logf(p->sp_thres / k.sigma2);
-  k.d2_c_thres = 1.f;
-  k.d2_s_thres = 1.f;
-  if (k.use_intensity) k.d2_c_thres = -2.0 * k.c2 * logf(p->sp_thres / k.c_sigma2);
-  if (k.use_semantics) {
-    if (mode == 1)
-      k.d2_s_thres = -2.0 * k.s_ell_square * logf(p->sp_thres / k.s_sigma2);
-    else
-      k.d2_s_thres = -2.0 * k.s_ell * k.s_ell * logf(p->sp_thres / k.s_sigma2);
-  }
-  if (mode == 1) k.use_geo_type = 0;  // CvoGPU.cu:1948-1949
-  return k;
-}
 // CvoGPU.cu:86-90 compute_range_ell
 __device__ __forceinline__ float range_ell(float curr_ell, float dist_to_sensor) {
   float final_ell = ((dist_to_sensor) / 500.0 + 1.0) * curr_ell;
@@ -128,205 +94,266 @@ __device__ __forceinline__ float range_ell(float curr_ell, float dist_to_sensor)
 }
 
 // ================================================================== prep_kernel
+// Prefilter identity: |x~ - y~|^2 = |y~|^2 - 2 x~.y~ + |x~|^2 with x~ = x - c, y~ = y' - c.
+// pair_kernel evaluates s = w + ax*yx + ay*yy + az*yz (a = -2 x~, w = |y~|^2) with three packed
+// FMAs per TWO pairs and tests s < t_i, t_i = thres_i - |x~_i|^2 + margin_i.  margin_i bounds
+// every rounding error between s and the reference's float d2 (gpu_utils.cuh:73-78):
+//   * centring x~ = fl(x-c), y~ = fl(y'-c): distance error <= u(|x~|+|y~|)
+//   * w = fl(|y~|^2) and the three FMAs: <= 6u(|x~|+|y~|)^2
+//   * the reference's own d2 rounding: <= 5u*thres
+// (u = 2^-24) with a 2x safety factor, so the prefilter can only ADD candidates; the exact test
+// in flow_kernel removes them again.  |y~| is bounded by ymax2_bound (controller).
+__device__ __forceinline__ float prefilter_threshold(float d2_thres, const float4& a, float ymax2) {
+  const double u = 5.9604644775390625e-08;  // 2^-24
+  const double th = (double)d2_thres;
+  if (!(th > 0.0)) return -INFINITY;  // d2 < thres can never hold
+  const double nx =
+      0.25 * ((double)a.x * (double)a.x + (double)a.y * (double)a.y + (double)a.z * (double)a.z);
+  const double sN = sqrt(nx) + sqrt((double)ymax2);
+  const double margin = 16.0 * u * sN * sN + 4.0 * u * sqrt(th) * sN + 1e-6 * th;
+  float t = __double2float_ru(th - nx + margin);
+  if (isnan(a.x) || isnan(a.y) || isnan(a.z) || isnan(a.w)) t = -INFINITY;
+  return t;
+}
+
 __global__ void __launch_bounds__(256) prep_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
   float Ri[9], Ti[3];
 #pragma unroll
   for (int k = 0; k < 9; k++) Ri[k] = st->Rinv[k];
 #pragma unroll
   for (int k = 0; k < 3; k++) Ti[k] = st->Tinv[k];
-  float wmax = 0.f;
-  const int stride = gridDim.x * blockDim.x;
-  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < A.M; j += stride) {
-    const float4 y = A.tgt_xyz[j];
-    const float yv[3] = {y.x, y.y, y.z};
-    float r[3];
-    mat3f_vec(Ri, yv, r);  // (*R) * input
-    const float m0 = r[0] + Ti[0], m1 = r[1] + Ti[1], m2 = r[2] + Ti[2];
-    A.tgt_moved[j] = make_float4(m0, m1, m2, 0.f);
-    const float ux = m0 - A.cx, uy = m1 - A.cy, uz = m2 - A.cz;
-    const float w = ux * ux + uy * uy + uz * uz;
-    A.px[j] = ux;
-    A.py[j] = uy;
-    A.pz[j] = uz;
-    A.pw[j] = w;
-    wmax = fmaxf(wmax, w);
+  // ---- targets: exact moved coordinates + the centred SoA operand (padded to M_pad)
+  for (int j = gid; j < A.M_pad; j += stride) {
+    if (j < A.M) {
+      const float4 y = A.tgt_xyz[j];
+      const float yv[3] = {y.x, y.y, y.z};
+      float r[3];
+      mat3f_vec(Ri, yv, r);  // (*R) * input, CvoGPU_impl.cu:46-50
+      const float m0 = r[0] + Ti[0], m1 = r[1] + Ti[1], m2 = r[2] + Ti[2];
+      A.tgt_moved[j] = make_float4(m0, m1, m2, 0.f);
+      const float ux = m0 - A.cx, uy = m1 - A.cy, uz = m2 - A.cz;
+      A.px[j] = ux;
+      A.py[j] = uy;
+      A.pz[j] = uz;
+      A.pw[j] = ux * ux + uy * uy + uz * uz;
+    } else {
+      A.px[j] = 0.f;
+      A.py[j] = 0.f;
+      A.pz[j] = 0.f;
+      A.pw[j] = INFINITY;  // padding can never be a candidate
+    }
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
-  __shared__ float smax[8];
-  if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = wmax;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float m = smax[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); w++) m = fmaxf(m, smax[w]);
-    atomicMax(&st->ymax2_bits, __float_as_uint(m));  // non-negative floats order like uints
+  // ---- source rows: range-scaled length-scale, exact threshold, prefilter record
+  const float ell = st->ell;
+  const float ymax2 = st->ymax2_bound;
+  const int use_geometry = st->kc.use_geometry;
+  const float log_geo = st->kc.log_geo;
+  for (int r = gid; r < A.n_rows; r += stride) {
+    const float4 a = A.src_rowA[A.row_begin + r];
+    const float l = range_ell(ell, a.w);  // CvoGPU.cu:506-507
+    float d2_thres = 1.f;
+    float t;
+    if (use_geometry && A.mode == 0) {
+      d2_thres = -2.0 * l * l * log_geo;  // CvoGPU.cu:511
+      t = prefilter_threshold(d2_thres, a, ymax2);
+    } else {
+      t = INFINITY;  // no geometric cut in the reference either: every pair is a candidate
+    }
+    A.row_lt[r] = make_float2(l, d2_thres);
+    A.rowrec[2 * r] = make_float4(a.x, a.x, a.y, a.y);
+    A.rowrec[2 * r + 1] = make_float4(a.z, a.z, t, t);
   }
 }
 
 // ================================================================== pair_kernel
-// Prefilter identity: |x~ - y~|^2 = |y~|^2 - 2 x~.y~ + |x~|^2 with x~ = x - c, y~ = y' - c.
-// The kernel evaluates s = w + ax*yx + ay*yy + az*yz (a = -2 x~, w = |y~|^2) with three
-// packed FMAs per TWO pairs and tests s < t_i, t_i = thres_i - |x~_i|^2 + margin_i.
-// margin_i bounds every rounding error between s and the reference's float d2
-// (gpu_utils.cuh:73-78), so no pair that the exact test accepts is ever missed; pairs
-// that pass spuriously are rejected by the exact test in flow_kernel.
 struct __align__(16) PairSmemWarp {
-  float4 raw[kTileRows];       // TMA destination: (-2x~, -2y~, -2z~, dist_to_sensor)
-  float4 rec[2 * kTileRows];   // expanded: (ax,ax,ay,ay) (az,az,t,t)
+  float4 rec[2][2 * kTileRows];  // double-buffered TMA destination
   uint32_t cnt[kTileRows];
-  uint64_t bar;
-  uint64_t pad;
+  uint64_t bar[2];
 };
 
-__device__ __forceinline__ void expand_rows(PairSmemWarp& S, const KernConsts& kc, float ell,
-                                            float ymax2, int nrows, int mode, int lane) {
-  const double u = 5.9604644775390625e-08;  // 2^-24
-  const double yn = sqrt((double)ymax2 * (1.0 + 1e-6));
-#pragma unroll
-  for (int h = 0; h < kTileRows / 32; h++) {
-    const int r = lane + 32 * h;
-    float4 a = S.raw[r];
-    float t;
-    if (r >= nrows) {
-      a = make_float4(0.f, 0.f, 0.f, 0.f);
-      t = -INFINITY;
-    } else if (!kc.use_geometry || mode == 1) {
-      t = INFINITY;  // no geometric cut in the reference either: every pair is a candidate
-    } else {
-      const float l = range_ell(ell, a.w);
-      const float d2_thres = -2.0 * l * l * kc.log_geo;  // CvoGPU.cu:511
-      const double th = (double)d2_thres;
-      const double nx =
-          0.25 * ((double)a.x * (double)a.x + (double)a.y * (double)a.y + (double)a.z * (double)a.z);
-      const double sN = sqrt(nx) + yn;
-      const double margin = 16.0 * u * sN * sN + 4.0 * u * sqrt(fmax(th, 0.0)) * sN + 1e-6 * fabs(th);
-      t = __double2float_ru(th - nx + margin);
-      if (!(th > 0.0)) t = -INFINITY;  // d2 < thres can never hold
-      if (isnan(a.x) || isnan(a.y) || isnan(a.z) || isnan(a.w)) t = -INFINITY;
-    }
-    S.rec[2 * r] = make_float4(a.x, a.x, a.y, a.y);
-    S.rec[2 * r + 1] = make_float4(a.z, a.z, t, t);
-    S.cnt[r] = 0u;
-  }
+// candidate word: (first target index of the lane's 8-group) / 8 in the high 24 bits, the
+// 8-bit mask of candidate targets inside the group in the low bits
+__device__ __forceinline__ uint32_t make_word(int j_base, uint32_t qmask) {
+  return ((uint32_t)(j_base >> 3) << 8) | qmask;
 }
 
-__global__ void __launch_bounds__(kPairWarps * 32, 2) pair_kernel(IterArgs A) {
+__global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
   __shared__ PairSmemWarp smem[kPairWarps];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   PairSmemWarp& S = smem[warp];
-  const KernConsts kc = make_consts(A.params, A.mode);
-  const float ell = st->ell;
-  const float ymax2 = __uint_as_float(st->ymax2_bits);
   const int L = A.L;
   const unsigned lt_mask = (1u << lane) - 1u;
 
   if (lane == 0) {
-    mbar_init(&S.bar, 1);
+    mbar_init(&S.bar[0], 1);
+    mbar_init(&S.bar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t phase = 0;
+  uint32_t phase0 = 0, phase1 = 0;
 
-  while (true) {
-    int item = 0;
-    if (lane == 0) item = (int)atomicAdd(&st->work_counter, 1u);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= A.n_items) break;
+  auto fetch_item = [&]() -> int {
+    int it = 0;
+    if (lane == 0) it = (int)atomicAdd(&st->work_counter, 1u);
+    return __shfl_sync(0xffffffffu, it, 0);
+  };
+  auto issue_tile = [&](int item, int buf) {
+    if (item >= A.n_items) return;
     const int rt = item / A.nchunks;
-    const int jc = item - rt * A.nchunks;
-    const int row0 = rt * kTileRows;  // local row index inside the shard
+    const int row0 = rt * kTileRows;
     const int nrows = min(kTileRows, A.n_rows - row0);
-
-    // ---- stage the source tile: TMA bulk copy, completion on this warp's mbarrier
     if (lane == 0) {
       fence_proxy_async();
-      const uint32_t bytes = (uint32_t)nrows * (uint32_t)sizeof(float4);
-      mbar_expect_tx(&S.bar, bytes);
-      tma_bulk_g2s(S.raw, A.src_rowA + (A.row_begin + row0), bytes, &S.bar);
+      const uint32_t bytes = (uint32_t)nrows * 2u * (uint32_t)sizeof(float4);
+      mbar_expect_tx(&S.bar[buf], bytes);
+      tma_bulk_g2s(S.rec[buf], A.rowrec + 2 * (size_t)row0, bytes, &S.bar[buf]);
     }
-    mbar_wait(&S.bar, phase);
-    phase ^= 1u;
-    expand_rows(S, kc, ell, ymax2, nrows, A.mode, lane);
+  };
+
+  int item = fetch_item();
+  int buf = 0;
+  issue_tile(item, 0);
+  while (item < A.n_items) {
+    const int next = fetch_item();
+    issue_tile(next, buf ^ 1);  // prefetch the next source tile while this one is swept
+
+    const int rt = item / A.nchunks;
+    const int jc = item - rt * A.nchunks;
+    const int row0 = rt * kTileRows;
+    const int nrows = min(kTileRows, A.n_rows - row0);
+    if (buf == 0) {
+      mbar_wait(&S.bar[0], phase0);
+      phase0 ^= 1u;
+    } else {
+      mbar_wait(&S.bar[1], phase1);
+      phase1 ^= 1u;
+    }
+    float4* rec = S.rec[buf];
+#pragma unroll
+    for (int h = 0; h < kTileRows / 32; h++) {
+      const int r = lane + 32 * h;
+      S.cnt[r] = 0u;
+      if (r >= nrows) {  // rows past the end of a ragged tile: stale smem, neutralise
+        rec[2 * r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rec[2 * r + 1] = make_float4(0.f, 0.f, -INFINITY, -INFINITY);
+      }
+    }
     __syncwarp();
 
     const int j_begin = jc * A.chunk_len;
-    const int j_end = min(A.M, j_begin + A.chunk_len);
+    const int j_end = min(A.M_pad, j_begin + A.chunk_len);
     uint32_t* cell0 = A.cand + ((size_t)row0 * A.nchunks + jc) * (size_t)L;
     const size_t cell_stride = (size_t)A.nchunks * (size_t)L;
 
     for (int jb = j_begin; jb < j_end; jb += kJBlock) {
-      // ---- stream 256 targets into registers (coalesced 128-byte loads), packed in pairs
-      unsigned long long X[kJQ / 2], Y[kJQ / 2], Z[kJQ / 2], W[kJQ / 2];
-#pragma unroll
-      for (int p = 0; p < kJQ / 2; p++) {
-        const int j0 = jb + (2 * p) * 32 + lane;
-        const int j1 = j0 + 32;
-        const bool v0 = j0 < j_end, v1 = j1 < j_end;
-        const float x0 = v0 ? __ldg(A.px + j0) : 0.f, x1 = v1 ? __ldg(A.px + j1) : 0.f;
-        const float y0 = v0 ? __ldg(A.py + j0) : 0.f, y1 = v1 ? __ldg(A.py + j1) : 0.f;
-        const float z0 = v0 ? __ldg(A.pz + j0) : 0.f, z1 = v1 ? __ldg(A.pz + j1) : 0.f;
-        const float w0 = v0 ? __ldg(A.pw + j0) : INFINITY, w1 = v1 ? __ldg(A.pw + j1) : INFINITY;
-        X[p] = pack2(x0, x1);
-        Y[p] = pack2(y0, y1);
-        Z[p] = pack2(z0, z1);
-        W[p] = pack2(w0, w1);
+      // ---- stream 256 targets into registers: lane owns targets jb + 8*lane .. +7 (two float4
+      //      per coordinate, a warp reads 1 KB contiguous per array), already packed in pairs
+      const int jl = jb + 8 * lane;
+      unsigned long long X[4], Y[4], Z[4], W[4];
+      {
+        const float4 xa = __ldg(reinterpret_cast<const float4*>(A.px + jl));
+        const float4 xb = __ldg(reinterpret_cast<const float4*>(A.px + jl + 4));
+        const float4 ya = __ldg(reinterpret_cast<const float4*>(A.py + jl));
+        const float4 yb = __ldg(reinterpret_cast<const float4*>(A.py + jl + 4));
+        const float4 za = __ldg(reinterpret_cast<const float4*>(A.pz + jl));
+        const float4 zb = __ldg(reinterpret_cast<const float4*>(A.pz + jl + 4));
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(A.pw + jl));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(A.pw + jl + 4));
+        X[0] = pack2(xa.x, xa.y); X[1] = pack2(xa.z, xa.w); X[2] = pack2(xb.x, xb.y); X[3] = pack2(xb.z, xb.w);
+        Y[0] = pack2(ya.x, ya.y); Y[1] = pack2(ya.z, ya.w); Y[2] = pack2(yb.x, yb.y); Y[3] = pack2(yb.z, yb.w);
+        Z[0] = pack2(za.x, za.y); Z[1] = pack2(za.z, za.w); Z[2] = pack2(zb.x, zb.y); Z[3] = pack2(zb.z, zb.w);
+        W[0] = pack2(wa.x, wa.y); W[1] = pack2(wa.z, wa.w); W[2] = pack2(wb.x, wb.y); W[3] = pack2(wb.z, wb.w);
       }
-      // ---- sweep the staged source rows
-#pragma unroll 2
-      for (int r = 0; r < kTileRows; r++) {
-        const float4 ra = S.rec[2 * r];
-        const float4 rb = S.rec[2 * r + 1];
+      // min over the lane's 8 pair tests of one row
+      auto row_min = [&](int r, float& t) -> float {
+        const float4 ra = rec[2 * r];
+        const float4 rb = rec[2 * r + 1];
         const unsigned long long AX = pack2(ra.x, ra.y), AY = pack2(ra.z, ra.w),
                                  AZ = pack2(rb.x, rb.y);
-        const float t = rb.z;
-        float s[kJQ];
+        t = rb.z;
+        float s[8];
 #pragma unroll
-        for (int p = 0; p < kJQ / 2; p++) {
+        for (int p = 0; p < 4; p++) {
           unsigned long long v = fma2(AX, X[p], W[p]);
           v = fma2(AY, Y[p], v);
           v = fma2(AZ, Z[p], v);
           unpack2(v, s[2 * p], s[2 * p + 1]);
         }
-        float m = fminf(min3(s[0], s[1], s[2]), min3(s[3], s[4], s[5]));
-        m = min3(m, s[6], s[7]);
-        if (__any_sync(0xffffffffu, m < t)) {
-          // ---- ordered emission: target index = jb + q*32 + lane, ascending in (q, lane)
-          uint32_t c = S.cnt[r];
-          uint32_t* cell = cell0 + (size_t)r * cell_stride;
+        const float m = fminf(min3(s[0], s[1], s[2]), min3(s[3], s[4], s[5]));
+        return min3(m, s[6], s[7]);
+      };
+      // rare path: some lane of the warp holds a candidate of row r -> ordered emission
+      auto emit_row = [&](int r, unsigned lanes) {
+        const float4 ra = rec[2 * r];
+        const float4 rb = rec[2 * r + 1];
+        const unsigned long long AX = pack2(ra.x, ra.y), AY = pack2(ra.z, ra.w),
+                                 AZ = pack2(rb.x, rb.y);
+        const float t = rb.z;
+        uint32_t qmask = 0;
 #pragma unroll
-          for (int q = 0; q < kJQ; q++) {
-            const bool f = s[q] < t;
-            const unsigned mask = __ballot_sync(0xffffffffu, f);
-            if (mask) {
-              const uint32_t pos = c + __popc(mask & lt_mask);
-              if (f && pos < (uint32_t)L) cell[pos] = (uint32_t)(jb + q * 32 + lane);
-              c += __popc(mask);
-            }
+        for (int p = 0; p < 4; p++) {
+          unsigned long long v = fma2(AX, X[p], W[p]);
+          v = fma2(AY, Y[p], v);
+          v = fma2(AZ, Z[p], v);
+          float s0, s1;
+          unpack2(v, s0, s1);
+          qmask |= (s0 < t ? 1u : 0u) << (2 * p);
+          qmask |= (s1 < t ? 1u : 0u) << (2 * p + 1);
+        }
+        uint32_t c = S.cnt[r];
+        const uint32_t pos = c + __popc(lanes & lt_mask);
+        if (qmask != 0u && pos < (uint32_t)L)
+          cell0[(size_t)r * cell_stride + pos] = make_word(jl, qmask);
+        c += __popc(lanes);
+        __syncwarp();
+        if (lane == 0) {
+          S.cnt[r] = c;
+          if (c >= (uint32_t)L) {  // cell full: stop looking at this row in this chunk
+            rec[2 * r + 1].z = -INFINITY;
+            rec[2 * r + 1].w = -INFINITY;
           }
-          __syncwarp();
-          if (lane == 0) {
-            S.cnt[r] = c;
-            if (c >= (uint32_t)L) {  // cell full: stop looking at this row in this chunk
-              S.rec[2 * r + 1].z = -INFINITY;
-              S.rec[2 * r + 1].w = -INFINITY;
-            }
-          }
-          __syncwarp();
+        }
+        __syncwarp();
+      };
+      // ---- sweep the staged source rows, four rows per warp vote
+#pragma unroll 1
+      for (int r = 0; r < kTileRows; r += 4) {
+        float t0, t1, t2, t3;
+        const float m0 = row_min(r, t0);
+        const float m1 = row_min(r + 1, t1);
+        const float m2 = row_min(r + 2, t2);
+        const float m3 = row_min(r + 3, t3);
+        const bool f = (m0 < t0) | (m1 < t1) | (m2 < t2) | (m3 < t3);
+        if (__any_sync(0xffffffffu, f)) {
+          unsigned b;
+          b = __ballot_sync(0xffffffffu, m0 < t0);
+          if (b) emit_row(r, b);
+          b = __ballot_sync(0xffffffffu, m1 < t1);
+          if (b) emit_row(r + 1, b);
+          b = __ballot_sync(0xffffffffu, m2 < t2);
+          if (b) emit_row(r + 2, b);
+          b = __ballot_sync(0xffffffffu, m3 < t3);
+          if (b) emit_row(r + 3, b);
         }
       }
     }
-    // ---- publish the per-cell counts (count > L means "overflowed": flow_kernel rescans)
+    // ---- publish the per-cell word counts (count > L means "overflowed": flow_kernel rescans)
 #pragma unroll
     for (int h = 0; h < kTileRows / 32; h++) {
       const int r = lane + 32 * h;
       if (r < nrows) A.cand_cnt[(size_t)(row0 + r) * A.nchunks + jc] = S.cnt[r];
     }
     __syncwarp();
+    item = next;
+    buf ^= 1;
   }
 }
 
@@ -346,7 +373,7 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
   const float4 pb = A.tgt_moved[j];
   pb_out = pb;
   float a = 1, sk = 1, ck = 1, k = 1, geo_sim = 1;
-  if (kc.use_geo_type) {
+  if (kc.use_geo_type && A.mode == 0) {  // mode 1 switches it off, CvoGPU.cu:1948-1949
     const float2 gb = A.tgt_geo[j];
     float norm2_a = 0.f;
     norm2_a += rc.ga[0] * rc.ga[0];
@@ -416,7 +443,8 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       tmp = va.w - vb.w;
       d2_semantic += tmp * tmp;
     }
-    if (d2_semantic < kc.d2_s_thres) {
+    const float thr = (A.mode == 1) ? kc.d2_s_thres_dense : kc.d2_s_thres;
+    if (d2_semantic < thr) {
       if (A.mode == 1)
         sk = kc.s_sigma2 * exp(-d2_semantic / (2.0 * kc.s_ell_square));
       else
@@ -430,15 +458,17 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
 }
 
 // ================================================================== flow finalisation
-// thrust::reduce results -> float, joint normalisation (CvoGPU.cu:824-838).
-__device__ void finalize_flow_scalar(DevState* st, const double tot[8], unsigned int max_row) {
+// thrust::reduce results -> float, joint normalisation (CvoGPU.cu:824-838), and the omega_hat
+// powers of compute_step_size_xi (CvoGPU.cu:970-980), evaluated once per iteration, left to
+// right like the Eigen expressions ((W*W)*W)*W and (W*W)*v.
+__device__ void finalize_flow_scalar(DevState* st, const double tot[9]) {
   for (int k = 0; k < 3; k++) {
     st->omega_sum[k] = tot[k];
     st->v_sum[k] = tot[3 + k];
   }
   st->a_sum = tot[6];
   st->nnz = (unsigned long long)(tot[7] + 0.5);
-  st->max_row_nnz = max_row;
+  st->max_row_nnz = (unsigned int)(tot[8] + 0.5);
   float ov[6];
   for (int k = 0; k < 6; k++) ov[k] = (float)tot[k];
   const float z = sum3f(ov[0] * ov[0], ov[1] * ov[1], ov[2] * ov[2]) +
@@ -447,23 +477,44 @@ __device__ void finalize_flow_scalar(DevState* st, const double tot[8], unsigned
     const float nrm = sqrtf(z);
     for (int k = 0; k < 6; k++) ov[k] = ov[k] / nrm;
   }
+  float W[9], W2[9], W3[9], W4[9], t3[3];
   for (int k = 0; k < 3; k++) {
     st->omega[k] = ov[k];
     st->v[k] = ov[3 + k];
   }
+  skewf(ov, W);
+  mat3f_mul(W, W, W2);
+  mat3f_mul(W2, W, W3);
+  mat3f_mul(W3, W, W4);
+  for (int k = 0; k < 9; k++) {
+    st->W2[k] = W2[k];
+    st->W3[k] = W3[k];
+    st->W4[k] = W4[k];
+  }
+  mat3f_vec(W, ov + 3, t3);
+  for (int k = 0; k < 3; k++) st->Wv[k] = t3[k];
+  mat3f_vec(W2, ov + 3, t3);
+  for (int k = 0; k < 3; k++) st->W2v[k] = t3[k];
+  mat3f_vec(W3, ov + 3, t3);
+  for (int k = 0; k < 3; k++) st->W3v[k] = t3[k];
 }
 
-// deterministic block-wide sum of per-block partials (fixed assignment + fixed tree)
-template <int NV>
-__device__ void block_sum_partials(const double* __restrict__ part, int stride_doubles, int nparts,
-                                   double* out /* NV, valid on thread 0 */, double* sh /* 256*NV */) {
+// deterministic block-wide reduction of per-block partials: fixed thread assignment + fixed
+// tree.  The first NSUM values are summed, the rest are max-reduced.
+template <int NV, int NSUM>
+__device__ void block_reduce_partials(const double* __restrict__ part, int nparts,
+                                      double* out /* NV, valid on thread 0 */,
+                                      double* sh /* blockDim.x * NV */) {
   double acc[NV];
 #pragma unroll
   for (int k = 0; k < NV; k++) acc[k] = 0.0;
   for (int b = threadIdx.x; b < nparts; b += blockDim.x) {
-    const double* p = part + (size_t)b * stride_doubles;
+    const double* p = part + (size_t)b * NV;
 #pragma unroll
-    for (int k = 0; k < NV; k++) acc[k] += __ldcg(p + k);
+    for (int k = 0; k < NV; k++) {
+      const double x = __ldcg(p + k);
+      acc[k] = (k < NSUM) ? acc[k] + x : fmax(acc[k], x);
+    }
   }
 #pragma unroll
   for (int k = 0; k < NV; k++) sh[threadIdx.x * NV + k] = acc[k];
@@ -471,7 +522,11 @@ __device__ void block_sum_partials(const double* __restrict__ part, int stride_d
   for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) {
 #pragma unroll
-      for (int k = 0; k < NV; k++) sh[threadIdx.x * NV + k] += sh[(threadIdx.x + s) * NV + k];
+      for (int k = 0; k < NV; k++) {
+        const double x = sh[(threadIdx.x + s) * NV + k];
+        double& y = sh[threadIdx.x * NV + k];
+        y = (k < NSUM) ? y + x : fmax(y, x);
+      }
     }
     __syncthreads();
   }
@@ -482,12 +537,13 @@ __device__ void block_sum_partials(const double* __restrict__ part, int stride_d
 }
 
 // ================================================================== flow_kernel
-__global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
+constexpr int kFlowListCap = 256;  // candidates expanded from one batch of 32 words
+
+__global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
-  __shared__ double sh[kSparseThreads * 8];
-  __shared__ unsigned int sh_max[kSparseThreads / 32];
-  __shared__ unsigned long long sh_nnz[kSparseThreads / 32];
+  __shared__ double sh[kSparseThreads * 9];
+  __shared__ uint32_t s_list[kSparseThreads / 32][kFlowListCap];
   __shared__ bool is_last;
 
   const int lane = threadIdx.x & 31;
@@ -495,27 +551,25 @@ __global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
   const int warps_per_block = blockDim.x >> 5;
   const int gwarp = blockIdx.x * warps_per_block + warp_in_block;
   const int nwarps = gridDim.x * warps_per_block;
-  const KernConsts kc = make_consts(A.params, A.mode);
-  const float ell = st->ell;
+  const KernConsts kc = st->kc;
   const int cap = st->num_neighbors;
   const float c_div = A.params->c, d_div = A.params->d;  // divisors (CvoGPU.cu:785-788)
   const unsigned lt_mask = (1u << lane) - 1u;
   const int L = A.L;
+  uint32_t* list = s_list[warp_in_block];
 
-  double w_om[3] = {0, 0, 0}, w_v[3] = {0, 0, 0}, w_asum = 0.0;  // this warp's row sums (lane 0)
-  unsigned long long w_nnz = 0;
-  unsigned int w_max = 0;
+  double w_om[3] = {0, 0, 0}, w_v[3] = {0, 0, 0}, w_asum = 0.0;  // this warp's sums (lane 0)
+  double w_nnz = 0.0, w_max = 0.0;
 
   for (int row = gwarp; row < A.n_rows; row += nwarps) {
     const int ig = A.row_begin + row;
     RowCtx rc;
     {
       const float4 pa = A.src_xyz[ig];
+      const float2 lt = A.row_lt[row];
       rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
-      const float a_to_sensor = sqrtf(pa.x * pa.x + pa.y * pa.y + pa.z * pa.z);
-      rc.l = range_ell(ell, a_to_sensor);
-      rc.d2_thres = 1.f;
-      if (kc.use_geometry && A.mode == 0) rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
+      rc.l = lt.x;
+      rc.d2_thres = lt.y;
       if (kc.use_geo_type) {
         const float2 g = A.src_geo[ig];
         rc.ga[0] = g.x; rc.ga[1] = g.y;
@@ -529,7 +583,7 @@ __global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
     uint32_t* out_idx = A.ell_idx + (size_t)row * A.cap_max;
     float* out_val = A.ell_val + (size_t)row * A.cap_max;
 
-    // one candidate (valid lanes only) -> ordered, capped store + flow accumulation
+    // one candidate per valid lane -> ordered, capped store + flow accumulation
     auto consume = [&](bool valid, int j) {
       float a = 0.f;
       float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -553,13 +607,41 @@ __global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
       }
       count = min(cap, count + __popc(mask));
     };
+    // a batch of <=32 candidate words (one per lane, ascending target order): expand the bit
+    // masks into the warp's candidate list, then test the candidates 32 at a time
+    auto consume_words = [&](bool valid, uint32_t word) {
+      const uint32_t qm = valid ? (word & 0xffu) : 0u;
+      const int nb = __popc(qm);
+      int incl = nb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      int off = incl - nb;
+      const int jb8 = (int)(word >> 8) << 3;
+      uint32_t m = qm;
+      while (m) {
+        const int q = __ffs(m) - 1;
+        m &= m - 1;
+        list[off++] = (uint32_t)(jb8 + q);
+      }
+      __syncwarp();
+      for (int c0 = 0; c0 < total && count < cap; c0 += 32) {
+        const int c = c0 + lane;
+        const bool v = c < total;
+        consume(v, v ? (int)list[c] : 0);
+      }
+      __syncwarp();
+    };
 
     for (int cbase = 0; cbase < A.nchunks && count < cap; cbase += 32) {
       const int cme = cbase + lane;
       const uint32_t n_l = (cme < A.nchunks) ? A.cand_cnt[(size_t)row * A.nchunks + cme] : 0u;
       const bool any_over = __any_sync(0xffffffffu, n_l > (uint32_t)L);
       if (!any_over) {
-        // flatten the (cell, pos) sequence of up to 32 cells into batches of 32 candidates
+        // flatten the (cell, pos) sequence of up to 32 cells into batches of 32 words
         uint32_t incl = n_l;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -577,14 +659,14 @@ __global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
           for (int stp = 16; stp > 0; stp >>= 1) {
             const int probe = cidx + stp - 1;
             const uint32_t e = __shfl_sync(0xffffffffu, incl, probe & 31);
-            if (probe < 32 && e <= b) cidx += stp;
+            if (e <= b) cidx += stp;
           }
           cidx = min(cidx, 31);
           const uint32_t ex = __shfl_sync(0xffffffffu, excl, cidx);
-          int j = 0;
+          uint32_t word = 0;
           if (valid)
-            j = (int)A.cand[((size_t)row * A.nchunks + (cbase + cidx)) * (size_t)L + (b - ex)];
-          consume(valid, j);
+            word = A.cand[((size_t)row * A.nchunks + (cbase + cidx)) * (size_t)L + (b - ex)];
+          consume_words(valid, word);
         }
       } else {
         // rare: some cell overflowed its candidate list -> rescan that chunk exhaustively
@@ -596,7 +678,7 @@ __global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
             for (uint32_t b0 = 0; b0 < n && count < cap; b0 += 32) {
               const uint32_t b = b0 + lane;
               const bool valid = b < n;
-              consume(valid, valid ? (int)cell[b] : 0);
+              consume_words(valid, valid ? cell[b] : 0u);
             }
           } else {
             const int j_begin = (cbase + cc) * A.chunk_len;
@@ -627,38 +709,25 @@ __global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
         w_v[k] += (double)(vv[k] / d_div);
       }
       w_asum += asum;
-      w_nnz += (unsigned long long)count;
-      w_max = max(w_max, (unsigned int)count);
+      w_nnz += (double)count;
+      w_max = fmax(w_max, (double)count);
     }
   }
   // ---- block partial (fixed order over warps)
   if (lane == 0) {
-    double* d = sh + warp_in_block * 8;
+    double* d = sh + warp_in_block * 9;
     d[0] = w_om[0]; d[1] = w_om[1]; d[2] = w_om[2];
     d[3] = w_v[0];  d[4] = w_v[1];  d[5] = w_v[2];
-    d[6] = w_asum;  d[7] = 0.0;
-    sh_max[warp_in_block] = w_max;
-    sh_nnz[warp_in_block] = w_nnz;
+    d[6] = w_asum;  d[7] = w_nnz;   d[8] = w_max;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     FlowPartial fp;
-    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    unsigned long long nn = 0;
-    unsigned int mx = 0;
+    for (int k = 0; k < 9; k++) fp.v[k] = 0.0;
     for (int w = 0; w < warps_per_block; w++) {
-      for (int k = 0; k < 7; k++) acc[k] += sh[w * 8 + k];
-      nn += sh_nnz[w];
-      mx = max(mx, sh_max[w]);
+      for (int k = 0; k < 8; k++) fp.v[k] += sh[w * 9 + k];
+      fp.v[8] = fmax(fp.v[8], sh[w * 9 + 8]);
     }
-    for (int k = 0; k < 3; k++) {
-      fp.omega[k] = acc[k];
-      fp.v[k] = acc[3 + k];
-    }
-    fp.a_sum = acc[6];
-    fp.nnz = nn;
-    fp.max_row = mx;
-    fp.pad = 0;
     A.flow_part[blockIdx.x] = fp;
     __threadfence();
     const unsigned int prev = atomicAdd(&st->flow_blocks_done, 1u);
@@ -668,27 +737,14 @@ __global__ void __launch_bounds__(kSparseThreads) flow_kernel(IterArgs A) {
   if (!is_last) return;
   __threadfence();
   // ---- last block: reduce all block partials in a fixed order
-  double tot[8];
-  {
-    double acc7[7];
-    block_sum_partials<7>(reinterpret_cast<const double*>(A.flow_part),
-                          (int)(sizeof(FlowPartial) / sizeof(double)), (int)gridDim.x, acc7, sh);
-    if (threadIdx.x == 0) {
-      unsigned long long nn = 0;
-      unsigned int mx = 0;
-      for (int b = 0; b < (int)gridDim.x; b++) {
-        nn += __ldcg(&A.flow_part[b].nnz);
-        mx = max(mx, __ldcg(&A.flow_part[b].max_row));
-      }
-      for (int k = 0; k < 7; k++) tot[k] = acc7[k];
-      tot[7] = (double)nn;
-      st->flow_blocks_done = 0u;
-      if (A.world > 1) {
-        for (int k = 0; k < 8; k++) st->local_flow[k] = tot[k];
-        st->local_flow[8] = (double)mx;
-      } else {
-        finalize_flow_scalar(st, tot, mx);
-      }
+  double tot[9];
+  block_reduce_partials<9, 8>(reinterpret_cast<const double*>(A.flow_part), (int)gridDim.x, tot, sh);
+  if (threadIdx.x == 0) {
+    st->flow_blocks_done = 0u;
+    if (A.world > 1) {
+      for (int k = 0; k < 9; k++) st->local_flow[k] = tot[k];
+    } else {
+      finalize_flow_scalar(st, tot);
     }
   }
 }
@@ -735,8 +791,10 @@ __device__ int indicator_update(DevState* st, float indicator, const cvo_b200_pa
   return decrease;
 }
 
-__device__ void update_tf_device(DevState* st) {
-  // CvoGPU.cu:94-112: R_inv = R^T, T_inv = -R_inv * T
+// CvoGPU.cu:94-112: R_inv = R^T, T_inv = -R_inv * T; plus the bound on |y' - c| the next
+// prep_kernel needs: |Rinv (y - tc) + (Rinv tc + Tinv - c)| <= sigma_max(Rinv)*trad + |...|,
+// sigma_max^2 <= max row sum of |Rinv^T Rinv| (Gershgorin).
+__device__ void update_tf_device(const IterArgs& A, DevState* st) {
   float neg[9];
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) st->Rinv[3 * j + i] = st->R[3 * i + j];
@@ -744,6 +802,26 @@ __device__ void update_tf_device(DevState* st) {
   float tv[3];
   mat3f_vec(neg, st->T, tv);
   for (int k = 0; k < 3; k++) st->Tinv[k] = tv[k];
+  double G[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+      for (int k = 0; k < 3; k++) s += (double)st->Rinv[3 * i + k] * (double)st->Rinv[3 * j + k];
+      G[3 * i + j] = s;
+    }
+  double smax2 = 0.0;
+  for (int i = 0; i < 3; i++)
+    smax2 = fmax(smax2, fabs(G[3 * i]) + fabs(G[3 * i + 1]) + fabs(G[3 * i + 2]));
+  const double tc[3] = {(double)A.tcx, (double)A.tcy, (double)A.tcz};
+  const double cc[3] = {(double)A.cx, (double)A.cy, (double)A.cz};
+  double off2 = 0.0;
+  for (int i = 0; i < 3; i++) {
+    const double o = (double)st->Rinv[i] * tc[0] + (double)st->Rinv[3 + i] * tc[1] +
+                     (double)st->Rinv[6 + i] * tc[2] + (double)st->Tinv[i] - cc[i];
+    off2 += o * o;
+  }
+  const double ymax = (sqrt(smax2) * (double)A.trad + sqrt(off2)) * (1.0 + 1e-5) + 1e-6;
+  st->ymax2_bound = __double2float_ru(ymax * ymax);
 }
 
 // Everything align_impl does on the host after the reductions (CvoGPU.cu:1124-1158,
@@ -880,13 +958,12 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
   }
   if (tr) *tr = rec;
   // ---- set up the next iteration (or the final transform, CvoGPU.cu:1562)
-  update_tf_device(st);
+  update_tf_device(A, st);
   st->work_counter = 0u;
-  st->ymax2_bits = 0u;
   if (finished) st->done = 1;
 }
 
-__global__ void __launch_bounds__(kSparseThreads) step_kernel(IterArgs A) {
+__global__ void __launch_bounds__(kSparseThreads, 3) step_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
   __shared__ double sh[kSparseThreads * 4];
@@ -899,33 +976,36 @@ __global__ void __launch_bounds__(kSparseThreads) step_kernel(IterArgs A) {
   const float ell = st->ell;
   const int use_range_ell = A.params->is_using_range_ell;
 
-  // compute_step_size_xi prologue (CvoGPU.cu:970-980): omega_hat powers, evaluated
-  // left to right like the Eigen expressions ((W*W)*W)*W and W*W*v.
-  float omega[3], v[3];
+  // compute_step_size_xi prologue (CvoGPU.cu:970-980): precomputed by the flow finaliser
+  float omega[3], v[3], W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     omega[k] = st->omega[k];
     v[k] = st->v[k];
+    Wv[k] = st->Wv[k];
+    W2v[k] = st->W2v[k];
+    W3v[k] = st->W3v[k];
   }
-  float W[9], W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];
-  skewf(omega, W);
-  mat3f_mul(W, W, W2);
-  mat3f_mul(W2, W, W3);
-  mat3f_mul(W3, W, W4);
-  mat3f_vec(W, v, Wv);
-  mat3f_vec(W2, v, W2v);
-  mat3f_vec(W3, v, W3v);
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    W2[k] = st->W2[k];
+    W3[k] = st->W3[k];
+    W4[k] = st->W4[k];
+  }
 
   double wB = 0.0, wC = 0.0, wD = 0.0, wE = 0.0;
   for (int row = gwarp; row < A.n_rows; row += nwarps) {
+    const int n = (int)A.row_nnz[row];
+    if (n == 0) continue;
     const int ig = A.row_begin + row;
     const float4 pa = A.src_xyz[ig];
     const float px[3] = {pa.x, pa.y, pa.z};
-    const float d2_sqrt = sqrtf(dot3f(px, px));
     float temp_ell = ell;
-    if (use_range_ell) temp_ell = range_ell(ell, d2_sqrt);
+    if (use_range_ell) {
+      const float d2_sqrt = sqrtf(dot3f(px, px));
+      temp_ell = range_ell(ell, d2_sqrt);
+    }
     const float temp_coef = 1 / (2.0 * temp_ell * temp_ell);
-    const int n = (int)A.row_nnz[row];
     const uint32_t* idx = A.ell_idx + (size_t)row * A.cap_max;
     const float* val = A.ell_val + (size_t)row * A.cap_max;
     for (int e = lane; e < n; e += 32) {
@@ -1004,7 +1084,7 @@ __global__ void __launch_bounds__(kSparseThreads) step_kernel(IterArgs A) {
   if (!is_last) return;
   __threadfence();
   double tot[4];
-  block_sum_partials<4>(reinterpret_cast<const double*>(A.step_part), 4, (int)gridDim.x, tot, sh);
+  block_reduce_partials<4, 4>(reinterpret_cast<const double*>(A.step_part), (int)gridDim.x, tot, sh);
   if (threadIdx.x == 0) {
     st->step_blocks_done = 0u;
     if (A.world > 1) {
@@ -1022,15 +1102,13 @@ __global__ void finalize_flow_kernel(IterArgs A, const double* gathered, int str
   DevState* st = A.st;
   if (st->done) return;
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  unsigned int mx = 0;
+  double tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int r = 0; r < A.world; r++) {
     const double* g = gathered + (size_t)r * stride;
     for (int k = 0; k < 8; k++) tot[k] += g[k];
-    const unsigned int m = (unsigned int)(g[8] + 0.5);
-    mx = m > mx ? m : mx;
+    tot[8] = fmax(tot[8], g[8]);
   }
-  finalize_flow_scalar(st, tot, mx);
+  finalize_flow_scalar(st, tot);
 }
 __global__ void finalize_step_kernel(IterArgs A, const double* gathered, int stride) {
   DevState* st = A.st;
@@ -1043,6 +1121,12 @@ __global__ void finalize_step_kernel(IterArgs A, const double* gathered, int str
   }
   controller_step(A, st, tot);
 }
+// host-initialised state needs the same Rinv/Tinv/bound update_tf_device computes
+__global__ void init_bound_kernel(IterArgs A) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  update_tf_device(A, A.st);
+}
+
 // ================================================================== fp32 pipe microbenchmark
 // Independent FMA chains; kind 0 = scalar FFMA, 1 = packed FFMA2.  Reports lane-FMAs.
 __global__ void __launch_bounds__(256) fma_peak_kernel(int kind, int iters, float* sink) {
@@ -1081,10 +1165,6 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(int kind, int iters, floa
 }
 
 // ================================================================== host-side launchers
-struct LaunchDims {
-  int prep_blocks, pair_blocks, sparse_blocks;
-};
-
 void launch_prep(const IterArgs& A, int blocks, cudaStream_t s) {
   prep_kernel<<<blocks, 256, 0, s>>>(A);
 }
@@ -1103,6 +1183,7 @@ void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride,
 void launch_finalize_step(const IterArgs& A, const double* gathered, int stride, cudaStream_t s) {
   finalize_step_kernel<<<1, 32, 0, s>>>(A, gathered, stride);
 }
+void launch_init_bound(const IterArgs& A, cudaStream_t s) { init_bound_kernel<<<1, 32, 0, s>>>(A); }
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s) {
   fma_peak_kernel<<<blocks, 256, 0, s>>>(kind, iters, sink);
 }
@@ -1110,6 +1191,12 @@ int pair_kernel_max_blocks_per_sm() {
   int n = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, pair_kernel, kPairWarps * 32, 0);
   return n;
+}
+int sparse_kernel_max_blocks_per_sm() {
+  int a = 0, b = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel, kSparseThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, step_kernel, kSparseThreads, 0);
+  return a < b ? a : b;
 }
 
 }  // namespace cvo_b200
