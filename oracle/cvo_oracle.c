@@ -352,18 +352,20 @@ static double poly3_eval(double p2, double p1, double p0, double t) {
   return ((t + p2) * t + p1) * t + p0;
 }
 static double poly3_polish(double p2, double p1, double p0, double t) {
-  for (int it = 0; it < 60; it++) {
+  /* Newton from a closed-form start: quadratic convergence; stop on stagnation of |f| so a
+   * root that sits between two doubles cannot ping-pong until the iteration cap */
+  double fa = fabs(poly3_eval(p2, p1, p0, t));
+  for (int it = 0; it < 24; it++) {
+    if (fa == 0.0) break;
     double f = poly3_eval(p2, p1, p0, t);
     double df = (3.0 * t + 2.0 * p2) * t + p1;
     if (df == 0.0 || !isfinite(df)) break;
     double tn = t - f / df;
-    if (!isfinite(tn)) break;
-    if (tn == t) break;
-    if (fabs(tn - t) <= 4e-16 * fabs(tn)) {
-      t = tn;
-      break;
-    }
+    if (!isfinite(tn) || tn == t) break;
+    double fn = fabs(poly3_eval(p2, p1, p0, tn));
+    if (!(fn < fa)) break;
     t = tn;
+    fa = fn;
   }
   return t;
 }

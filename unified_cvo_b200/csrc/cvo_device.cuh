@@ -90,6 +90,7 @@ struct DevState {
   // multi-GPU: totals of the LOCAL row shard, written before the collective
   double local_flow[9];     // omega[3], v[3], a_sum, (double)nnz, (double)max_row_nnz
   double local_step[4];
+  unsigned long long dbg[16];  // %globaltimer stamps of the tails (tools/gpu_tails.py)
 };
 
 struct IterArgs {

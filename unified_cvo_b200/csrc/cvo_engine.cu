@@ -231,9 +231,10 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   const int warps_per_block = kSparseThreads / 32;
   int socc = sparse_kernel_max_blocks_per_sm();
   if (socc < 1) socc = 1;
-  // one warp per source row while the rows fit in one resident wave, grid-stride beyond
+  // eight lanes per source row: one block covers 32 rows; grid-stride beyond one resident wave
+  const int rows_per_block = warps_per_block * 4;
   h->sparse_blocks =
-      std::max(1, std::min(h->num_sms * socc, (n_rows + warps_per_block - 1) / warps_per_block));
+      std::max(1, std::min(h->num_sms * socc, (n_rows + rows_per_block - 1) / rows_per_block));
   CVO_CUDA(h, h->flow_part.ensure((size_t)h->sparse_blocks));
   CVO_CUDA(h, h->step_part.ensure((size_t)h->sparse_blocks));
 
@@ -287,11 +288,14 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
 int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEvent_t pair_begin,
                       cudaEvent_t pair_end) {
   cudaStream_t s = h->stream;
-  launch_prep(A, h->prep_blocks, s);
+  // CVO_B200_DEBUG_SKIP (bit mask 1 prep, 2 pair, 4 flow, 8 step): measurement aid only — the
+  // marginal cost of one kernel inside the real pipeline; results are meaningless when set
+  static const int skip = getenv("CVO_B200_DEBUG_SKIP") ? atoi(getenv("CVO_B200_DEBUG_SKIP")) : 0;
+  if (!(skip & 1)) launch_prep(A, h->prep_blocks, s);
   if (pair_begin) cudaEventRecord(pair_begin, s);
-  launch_pair(A, h->pair_blocks, s);
+  if (!(skip & 2)) launch_pair(A, h->pair_blocks, s);
   if (pair_end) cudaEventRecord(pair_end, s);
-  launch_flow(A, h->sparse_blocks, s);
+  if (!(skip & 4)) launch_flow(A, h->sparse_blocks, s);
   h->launches += 3;
   if (A.world > 1) {
     DevState* st = h->d_state;
@@ -300,7 +304,7 @@ int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEven
     launch_finalize_flow(A, h->gathered.p, 9, s);
     h->launches += 1;
   }
-  if (stage >= 3) {
+  if (stage >= 3 && !(skip & 8)) {
     launch_step(A, h->sparse_blocks, s);
     h->launches += 1;
     if (A.world > 1) {
@@ -947,6 +951,20 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   if (rc != CVO_B200_OK) return rc;
   CVO_CUDA(h, se);
   CVO_CUDA(h, cudaGetLastError());
+  if (getenv("CVO_B200_DEBUG_TAILS")) {  // %globaltimer stamps of the LAST iteration (ns)
+    unsigned long long d[16];
+    cudaMemcpy(d, (char*)h->d_state + offsetof(DevState, dbg), sizeof(d), cudaMemcpyDeviceToHost);
+    fprintf(stderr,
+            "[tails] prep_start 0 | pair_start %+lld | flow_start %+lld tail_begin %+lld reduced %+lld "
+            "finalized %+lld | step_start %+lld tail_begin %+lld reduced %+lld controller_done %+lld (ns)\n",
+            (long long)(d[9] - d[8]), (long long)(d[0] - d[8]), (long long)(d[1] - d[8]),
+            (long long)(d[2] - d[8]), (long long)(d[3] - d[8]), (long long)(d[4] - d[8]),
+            (long long)(d[5] - d[8]), (long long)(d[6] - d[8]), (long long)(d[7] - d[8]));
+    fprintf(stderr, "[tails] controller: cubic done %+lld exp+pose done %+lld se3log done %+lld end %+lld (ns after reduced)\n",
+            (long long)(d[13] - d[6]), (long long)(d[14] - d[6]), (long long)(d[15] - d[6]), (long long)(d[7] - d[6]));
+    fprintf(stderr, "[tails] flow reduce: loads done %+lld shuffles done %+lld smem done %+lld (ns after tail_begin)\n",
+            (long long)(d[10] - d[1]), (long long)(d[11] - d[1]), (long long)(d[12] - d[1]));
+  }
   if (ms_total) *ms_total = ms;
   if (ms_pair_kernel) *ms_pair_kernel = msp;
   return CVO_B200_OK;

@@ -83,6 +83,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, u
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
@@ -121,6 +126,7 @@ __global__ void __launch_bounds__(256) prep_kernel(IterArgs A) {
   if (st->done) return;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
+  if (gid == 0) st->dbg[8] = gtime();
   float Ri[9], Ti[3];
 #pragma unroll
   for (int k = 0; k < 9; k++) Ri[k] = st->Rinv[k];
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
   PairSmemWarp& S = smem[warp];
   const int L = A.L;
   const unsigned lt_mask = (1u << lane) - 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[9] = gtime();
 
   if (lane == 0) {
     mbar_init(&S.bar[0], 1);
@@ -499,98 +506,126 @@ __device__ void finalize_flow_scalar(DevState* st, const double tot[9]) {
   for (int k = 0; k < 3; k++) st->W3v[k] = t3[k];
 }
 
-// deterministic block-wide reduction of per-block partials: fixed thread assignment + fixed
-// tree.  The first NSUM values are summed, the rest are max-reduced.
+// deterministic block-wide reduction of per-block partials: fixed thread assignment, then a
+// fixed xor-shuffle tree inside each warp and a fixed order over the warps.  The first NSUM
+// values are summed, the rest are max-reduced.
 template <int NV, int NSUM>
 __device__ void block_reduce_partials(const double* __restrict__ part, int nparts,
                                       double* out /* NV, valid on thread 0 */,
-                                      double* sh /* blockDim.x * NV */) {
+                                      double* sh /* >= (blockDim.x/32 + 1) * NV */,
+                                      unsigned long long* dbg = nullptr) {
   double acc[NV];
 #pragma unroll
   for (int k = 0; k < NV; k++) acc[k] = 0.0;
+  // partials are stored value-major (part[k * nparts + b]) so these loads coalesce
   for (int b = threadIdx.x; b < nparts; b += blockDim.x) {
-    const double* p = part + (size_t)b * NV;
 #pragma unroll
     for (int k = 0; k < NV; k++) {
-      const double x = __ldcg(p + k);
+      const double x = __ldcg(part + (size_t)k * nparts + b);
       acc[k] = (k < NSUM) ? acc[k] + x : fmax(acc[k], x);
     }
   }
+  if (dbg && threadIdx.x == 0) dbg[0] = gtime() + (unsigned long long)(acc[0] == 1.2345);
 #pragma unroll
-  for (int k = 0; k < NV; k++) sh[threadIdx.x * NV + k] = acc[k];
-  __syncthreads();
-  for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) {
+  for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-      for (int k = 0; k < NV; k++) {
-        const double x = sh[(threadIdx.x + s) * NV + k];
-        double& y = sh[threadIdx.x * NV + k];
-        y = (k < NSUM) ? y + x : fmax(y, x);
-      }
+    for (int k = 0; k < NV; k++) {
+      const double x = __shfl_xor_sync(0xffffffffu, acc[k], o);
+      acc[k] = (k < NSUM) ? acc[k] + x : fmax(acc[k], x);
     }
-    __syncthreads();
   }
+  if (dbg && threadIdx.x == 0) dbg[1] = gtime() + (unsigned long long)(acc[0] == 1.2345);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // sh may still be in use by the caller's previous phase
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) sh[w * NV + k] = acc[k];
+  }
+  __syncthreads();
+  if (dbg && threadIdx.x == 0) dbg[2] = gtime();
+  if ((int)threadIdx.x < NV) {  // one thread per value: NV short chains instead of one long one
+    const int k = threadIdx.x;
+    double r = sh[k];
+    for (int i = 1; i < nw; i++) r = (k < NSUM) ? r + sh[i * NV + k] : fmax(r, sh[i * NV + k]);
+    sh[nw * NV + k] = r;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; k++) out[k] = sh[k];
+    for (int k = 0; k < NV; k++) out[k] = sh[nw * NV + k];
   }
 }
 
 // ================================================================== flow_kernel
-constexpr int kFlowListCap = 256;  // candidates expanded from one batch of 32 words
+// Eight lanes per source row (four rows per warp): candidates are ~10 per row in tracking
+// regimes, so a full warp per row would idle two thirds of its lanes and quadruple the
+// per-row bookkeeping.  Every group walks its row's candidate cells in target order, expands
+// the candidate words into a small shared-memory list and drains it eight candidates at a time.
+constexpr int kGroup = 8;                    // lanes per source row
+constexpr int kRowsPerWarp = 32 / kGroup;    // 4
+constexpr int kGroupList = 80;               // pending (<8) + one batch of 8 words (<=64)
 
 __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
   __shared__ double sh[kSparseThreads * 9];
-  __shared__ uint32_t s_list[kSparseThreads / 32][kFlowListCap];
+  __shared__ uint32_t s_list[kSparseThreads / kGroup][kGroupList];
   __shared__ bool is_last;
 
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  const int gwarp = blockIdx.x * warps_per_block + warp_in_block;
-  const int nwarps = gridDim.x * warps_per_block;
+  const int g = lane >> 3;          // group inside the warp
+  const int gl = lane & 7;          // lane inside the group
+  const int gshift = g * kGroup;
+  const unsigned lt8 = (1u << gl) - 1u;
   const KernConsts kc = st->kc;
   const int cap = st->num_neighbors;
   const float c_div = A.params->c, d_div = A.params->d;  // divisors (CvoGPU.cu:785-788)
-  const unsigned lt_mask = (1u << lane) - 1u;
   const int L = A.L;
-  uint32_t* list = s_list[warp_in_block];
+  uint32_t* list = s_list[threadIdx.x >> 3];
+  const int nch = A.nchunks;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[0] = gtime();
 
-  double w_om[3] = {0, 0, 0}, w_v[3] = {0, 0, 0}, w_asum = 0.0;  // this warp's sums (lane 0)
+  double w_om[3] = {0, 0, 0}, w_v[3] = {0, 0, 0}, w_asum = 0.0;  // group sums (leader lane)
   double w_nnz = 0.0, w_max = 0.0;
 
-  for (int row = gwarp; row < A.n_rows; row += nwarps) {
-    const int ig = A.row_begin + row;
+  const int slot0 = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp + g;
+  const int slot_stride = gridDim.x * warps_per_block * kRowsPerWarp;
+  for (int row = slot0;; row += slot_stride) {
+    const bool rvalid = row < A.n_rows;
+    if (!__any_sync(0xffffffffu, rvalid)) break;
+    const int ig = A.row_begin + (rvalid ? row : 0);
     RowCtx rc;
     {
       const float4 pa = A.src_xyz[ig];
-      const float2 lt = A.row_lt[row];
+      const float2 lt = A.row_lt[rvalid ? row : 0];
       rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
       rc.l = lt.x;
       rc.d2_thres = lt.y;
+      rc.ga[0] = rc.ga[1] = 0.f;
       if (kc.use_geo_type) {
-        const float2 g = A.src_geo[ig];
-        rc.ga[0] = g.x; rc.ga[1] = g.y;
-      } else {
-        rc.ga[0] = rc.ga[1] = 0.f;
+        const float2 gg = A.src_geo[ig];
+        rc.ga[0] = gg.x; rc.ga[1] = gg.y;
       }
     }
     float om[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
     double asum = 0.0;
-    int count = 0;  // survivors stored so far (warp-uniform)
-    uint32_t* out_idx = A.ell_idx + (size_t)row * A.cap_max;
-    float* out_val = A.ell_val + (size_t)row * A.cap_max;
+    int count = 0;   // survivors stored so far (group-uniform)
+    int nlist = 0;   // pending candidates in the group's list (group-uniform)
+    uint32_t* out_idx = A.ell_idx + (size_t)(rvalid ? row : 0) * A.cap_max;
+    float* out_val = A.ell_val + (size_t)(rvalid ? row : 0) * A.cap_max;
+    const uint32_t* cnt_row = A.cand_cnt + (size_t)(rvalid ? row : 0) * nch;
+    const uint32_t* cell_row = A.cand + (size_t)(rvalid ? row : 0) * nch * (size_t)L;
 
-    // one candidate per valid lane -> ordered, capped store + flow accumulation
-    auto consume = [&](bool valid, int j) {
+    // <=8 candidates per group -> exact test, ordered capped store, flow accumulation
+    auto consume8 = [&](bool valid, int j) {
       float a = 0.f;
       float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
       bool surv = false;
       if (valid) surv = eval_pair(A, kc, rc, ig, j, a, pb);
-      const unsigned mask = __ballot_sync(0xffffffffu, surv);
-      const int pos = count + __popc(mask & lt_mask);
+      const unsigned bits = (__ballot_sync(0xffffffffu, surv) >> gshift) & 0xffu;
+      const int pos = count + __popc(bits & lt8);
       if (surv && pos < cap) {
         out_idx[pos] = (uint32_t)j;
         out_val[pos] = a;
@@ -605,21 +640,39 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
         }
         asum += (double)a;
       }
-      count = min(cap, count + __popc(mask));
+      count = min(cap, count + __popc(bits));
     };
-    // a batch of <=32 candidate words (one per lane, ascending target order): expand the bit
-    // masks into the warp's candidate list, then test the candidates 32 at a time
-    auto consume_words = [&](bool valid, uint32_t word) {
+    // drain the list while some group holds at least `need` pending candidates
+    auto drain = [&](int need) {
+      int head = 0;
+      while (true) {
+        const bool go = (nlist - head) >= need && (nlist - head) > 0 && count < cap;
+        if (!__any_sync(0xffffffffu, go)) break;
+        const bool v = go && (head + gl) < nlist;
+        consume8(v, v ? (int)list[head + gl] : 0);
+        if (go) head += kGroup;
+      }
+      // compact what is left to the front (at most 7 entries, group-uniform branch)
+      const int rest = max(0, nlist - head);
+      uint32_t keep = 0;
+      if (gl < rest) keep = list[head + gl];
+      __syncwarp();
+      if (gl < rest) list[gl] = keep;
+      nlist = (count < cap) ? rest : 0;
+      __syncwarp();
+    };
+    // append the candidates of one word per lane (ascending target order) to the list
+    auto append_words = [&](bool valid, uint32_t word) {
       const uint32_t qm = valid ? (word & 0xffu) : 0u;
       const int nb = __popc(qm);
       int incl = nb;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
+      for (int o = 1; o < kGroup; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o, kGroup);
+        if (gl >= o) incl += t;
       }
-      const int total = __shfl_sync(0xffffffffu, incl, 31);
-      int off = incl - nb;
+      const int total = __shfl_sync(0xffffffffu, incl, kGroup - 1, kGroup);
+      int off = nlist + incl - nb;
       const int jb8 = (int)(word >> 8) << 3;
       uint32_t m = qm;
       while (m) {
@@ -627,81 +680,97 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
         m &= m - 1;
         list[off++] = (uint32_t)(jb8 + q);
       }
-      __syncwarp();
-      for (int c0 = 0; c0 < total && count < cap; c0 += 32) {
-        const int c = c0 + lane;
-        const bool v = c < total;
-        consume(v, v ? (int)list[c] : 0);
-      }
+      nlist += total;
       __syncwarp();
     };
 
-    for (int cbase = 0; cbase < A.nchunks && count < cap; cbase += 32) {
-      const int cme = cbase + lane;
-      const uint32_t n_l = (cme < A.nchunks) ? A.cand_cnt[(size_t)row * A.nchunks + cme] : 0u;
-      const bool any_over = __any_sync(0xffffffffu, n_l > (uint32_t)L);
-      if (!any_over) {
-        // flatten the (cell, pos) sequence of up to 32 cells into batches of 32 words
-        uint32_t incl = n_l;
+    for (int cbase = 0;; cbase += 4 * kGroup) {
+      const bool wact = rvalid && cbase < nch && count < cap;
+      if (!__any_sync(0xffffffffu, wact)) break;
+      // ---- four cell counts per lane: a window of 32 cells per group
+      uint32_t c4[4];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
+      for (int k = 0; k < 4; k++) {
+        const int c = cbase + 4 * gl + k;
+        c4[k] = (wact && c < nch) ? cnt_row[c] : 0u;
+      }
+      const bool over = (c4[0] > (uint32_t)L) | (c4[1] > (uint32_t)L) | (c4[2] > (uint32_t)L) |
+                        (c4[3] > (uint32_t)L);
+      if (!__any_sync(0xffffffffu, over)) {
+        // ---- flatten the window's words: prefix over (lane, k)
+        const uint32_t p1 = c4[0], p2 = p1 + c4[1], p3 = p2 + c4[2], s4 = p3 + c4[3];
+        uint32_t incl = s4;
+#pragma unroll
+        for (int o = 1; o < kGroup; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o, kGroup);
+          if (gl >= o) incl += t;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        const uint32_t excl = incl - n_l;
-        for (uint32_t b0 = 0; b0 < total && count < cap; b0 += 32) {
-          const uint32_t b = b0 + lane;
-          const bool valid = b < total;
-          // cell = number of cells whose inclusive count is <= b  (binary search by shuffles)
-          int cidx = 0;
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, kGroup - 1, kGroup);
+        const uint32_t excl = incl - s4;
+        for (uint32_t wb = 0;; wb += kGroup) {
+          const bool bact = wb < total && count < cap;
+          if (!__any_sync(0xffffffffu, bact)) break;
+          const uint32_t b = wb + gl;
+          const bool valid = bact && b < total;
+          // owner lane = number of lanes whose inclusive count is <= b
+          int o = 0;
 #pragma unroll
-          for (int stp = 16; stp > 0; stp >>= 1) {
-            const int probe = cidx + stp - 1;
-            const uint32_t e = __shfl_sync(0xffffffffu, incl, probe & 31);
-            if (e <= b) cidx += stp;
+          for (int stp = 4; stp > 0; stp >>= 1) {
+            const uint32_t e = __shfl_sync(0xffffffffu, incl, (o + stp - 1) & 7, kGroup);
+            if (e <= b) o += stp;
           }
-          cidx = min(cidx, 31);
-          const uint32_t ex = __shfl_sync(0xffffffffu, excl, cidx);
+          o = min(o, kGroup - 1);
+          const uint32_t oex = __shfl_sync(0xffffffffu, excl, o, kGroup);
+          const uint32_t q1 = __shfl_sync(0xffffffffu, p1, o, kGroup);
+          const uint32_t q2 = __shfl_sync(0xffffffffu, p2, o, kGroup);
+          const uint32_t q3 = __shfl_sync(0xffffffffu, p3, o, kGroup);
+          const uint32_t rr = b - oex;
+          const int k = (rr >= q1) + (rr >= q2) + (rr >= q3);
+          const uint32_t kbase = k == 0 ? 0u : (k == 1 ? q1 : (k == 2 ? q2 : q3));
           uint32_t word = 0;
-          if (valid)
-            word = A.cand[((size_t)row * A.nchunks + (cbase + cidx)) * (size_t)L + (b - ex)];
-          consume_words(valid, word);
+          if (valid) word = cell_row[(size_t)(cbase + 4 * o + k) * (size_t)L + (rr - kbase)];
+          append_words(valid, word);
+          drain(kGroup);
         }
       } else {
-        // rare: some cell overflowed its candidate list -> rescan that chunk exhaustively
-        const int ncell = min(32, A.nchunks - cbase);
-        for (int cc = 0; cc < ncell && count < cap; cc++) {
-          const uint32_t n = __shfl_sync(0xffffffffu, n_l, cc);
-          if (n <= (uint32_t)L) {
-            const uint32_t* cell = A.cand + ((size_t)row * A.nchunks + (cbase + cc)) * (size_t)L;
-            for (uint32_t b0 = 0; b0 < n && count < cap; b0 += 32) {
-              const uint32_t b = b0 + lane;
-              const bool valid = b < n;
-              consume_words(valid, valid ? cell[b] : 0u);
+        // ---- rare: a cell overflowed its word list -> walk the window cell by cell and
+        //      rescan the overflowed chunks exhaustively (still in ascending target order)
+        for (int cc = 0; cc < 4 * kGroup; cc++) {
+          const uint32_t n = __shfl_sync(0xffffffffu, c4[cc & 3], cc >> 2, kGroup);
+          const bool cact = wact && (cbase + cc) < nch && count < cap;
+          if (!__any_sync(0xffffffffu, cact && n > 0u)) continue;
+          const bool is_over = cact && n > (uint32_t)L;
+          if (__any_sync(0xffffffffu, is_over)) drain(1);  // flush: order before the rescan
+          const int j_begin = (cbase + cc) * A.chunk_len;
+          const int j_end = min(A.M, j_begin + A.chunk_len);
+          const uint32_t* cell = cell_row + (size_t)(cbase + cc) * (size_t)L;
+          for (uint32_t s = 0;; s += kGroup) {
+            const bool list_go = cact && !is_over && s < n && count < cap;
+            const bool scan_go = is_over && (j_begin + (int)s) < j_end && count < cap;
+            if (!__any_sync(0xffffffffu, list_go | scan_go)) break;
+            if (__any_sync(0xffffffffu, scan_go)) {
+              const int j = j_begin + (int)s + gl;
+              consume8(scan_go && j < j_end, j);
             }
-          } else {
-            const int j_begin = (cbase + cc) * A.chunk_len;
-            const int j_end = min(A.M, j_begin + A.chunk_len);
-            for (int jb = j_begin; jb < j_end && count < cap; jb += 32) {
-              const int j = jb + lane;
-              consume(j < j_end, j);
-            }
+            const bool v = list_go && (s + gl) < n;
+            append_words(v, v ? cell[s + gl] : 0u);
+            drain(kGroup);
           }
         }
       }
     }
+    drain(1);  // whatever is still pending
     // ---- row epilogue: omega_i / c, v_i / d in float, then double (CvoGPU.cu:785-788)
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = kGroup / 2; o > 0; o >>= 1) {
 #pragma unroll
       for (int k = 0; k < 3; k++) {
-        om[k] += __shfl_xor_sync(0xffffffffu, om[k], o);
-        vv[k] += __shfl_xor_sync(0xffffffffu, vv[k], o);
+        om[k] += __shfl_xor_sync(0xffffffffu, om[k], o, kGroup);
+        vv[k] += __shfl_xor_sync(0xffffffffu, vv[k], o, kGroup);
       }
-      asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      asum += __shfl_xor_sync(0xffffffffu, asum, o, kGroup);
     }
-    if (lane == 0) {
+    if (gl == 0 && rvalid) {
       A.row_nnz[row] = (uint32_t)count;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -713,39 +782,49 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       w_max = fmax(w_max, (double)count);
     }
   }
-  // ---- block partial (fixed order over warps)
+  // ---- block partial: fixed xor tree over the four group leaders of a warp, then over warps
+  double bp[9] = {w_om[0], w_om[1], w_om[2], w_v[0], w_v[1], w_v[2], w_asum, w_nnz, w_max};
+#pragma unroll
+  for (int o = 8; o <= 16; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const double x = __shfl_xor_sync(0xffffffffu, bp[k], o);
+      bp[k] = (k < 8) ? bp[k] + x : fmax(bp[k], x);
+    }
+  }
   if (lane == 0) {
-    double* d = sh + warp_in_block * 9;
-    d[0] = w_om[0]; d[1] = w_om[1]; d[2] = w_om[2];
-    d[3] = w_v[0];  d[4] = w_v[1];  d[5] = w_v[2];
-    d[6] = w_asum;  d[7] = w_nnz;   d[8] = w_max;
+#pragma unroll
+    for (int k = 0; k < 9; k++) sh[warp_in_block * 9 + k] = bp[k];
+  }
+  __syncthreads();
+  if (threadIdx.x < 9) {
+    const int k = threadIdx.x;
+    double r = sh[k];
+    for (int w = 1; w < warps_per_block; w++) r = (k < 8) ? r + sh[w * 9 + k] : fmax(r, sh[w * 9 + k]);
+    reinterpret_cast<double*>(A.flow_part)[(size_t)k * gridDim.x + blockIdx.x] = r;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    FlowPartial fp;
-    for (int k = 0; k < 9; k++) fp.v[k] = 0.0;
-    for (int w = 0; w < warps_per_block; w++) {
-      for (int k = 0; k < 8; k++) fp.v[k] += sh[w * 9 + k];
-      fp.v[8] = fmax(fp.v[8], sh[w * 9 + 8]);
-    }
-    A.flow_part[blockIdx.x] = fp;
-    __threadfence();
+    __threadfence();  // release: this block's partial (written before the barrier above)
     const unsigned int prev = atomicAdd(&st->flow_blocks_done, 1u);
     is_last = (prev == gridDim.x - 1);
+    if (is_last) __threadfence();  // acquire for the whole block (readers use ld.cg after the barrier)
   }
   __syncthreads();
   if (!is_last) return;
-  __threadfence();
   // ---- last block: reduce all block partials in a fixed order
+  if (threadIdx.x == 0) st->dbg[1] = gtime();
   double tot[9];
-  block_reduce_partials<9, 8>(reinterpret_cast<const double*>(A.flow_part), (int)gridDim.x, tot, sh);
+  block_reduce_partials<9, 8>(reinterpret_cast<const double*>(A.flow_part), (int)gridDim.x, tot, sh, &st->dbg[10]);
   if (threadIdx.x == 0) {
+    st->dbg[2] = gtime();
     st->flow_blocks_done = 0u;
     if (A.world > 1) {
       for (int k = 0; k < 9; k++) st->local_flow[k] = tot[k];
     } else {
       finalize_flow_scalar(st, tot);
     }
+    st->dbg[3] = gtime();
   }
 }
 
@@ -837,6 +916,7 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
     for (int i = 0; i < 3; i++)
       if (re[i] > 0 && re[i] < temp_step && fabs(im[i]) < 1e-5) temp_step = re[i];
   }
+  st->dbg[13] = gtime();
   float step;
   if (temp_step > params->max_step)
     step = params->max_step;
@@ -874,7 +954,7 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
   const double on = sqrt(sum3d((double)omega[0] * omega[0], (double)omega[1] * omega[1],
                                (double)omega[2] * omega[2]));
   const double vn = sqrt(sum3d((double)v[0] * v[0], (double)v[1] * v[1], (double)v[2] * v[2]));
-  if (on < params->eps && vn < params->eps) {
+  if (on < params->eps && vn < params->eps && st->controller_on != 2) {  // mode 2: timing loop
     const float onf = sqrtf(dot3f(omega, omega)), vnf = sqrtf(dot3f(v, v));
     int reason = CVO_B200_STOP_GRAD_SMALL;
     if (onf < 1e-8 && vnf < 1e-8) {
@@ -907,7 +987,9 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
       for (int i = 0; i < 3; i++)
         st->R[3 * j + i] = (float)sum3d(Rd[i] * dR[3 * j], Rd[3 + i] * dR[3 * j + 1],
                                         Rd[6 + i] * dR[3 * j + 2]);
+    st->dbg[14] = gtime();
     const double dist_this_iter = se3_log_norm(dR, dT);
+    st->dbg[15] = gtime();
     st->dist = dist_this_iter;
     rec.dist = dist_this_iter;
     for (int q = 0; q < 9; q++) rec.R[q] = st->R[q];
@@ -971,10 +1053,10 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel(IterArgs A) {
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  const int gwarp = blockIdx.x * warps_per_block + warp_in_block;
-  const int nwarps = gridDim.x * warps_per_block;
+  const int g = lane >> 3, gl = lane & 7;
   const float ell = st->ell;
   const int use_range_ell = A.params->is_using_range_ell;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[4] = gtime();
 
   // compute_step_size_xi prologue (CvoGPU.cu:970-980): precomputed by the flow finaliser
   float omega[3], v[3], W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];
@@ -994,7 +1076,10 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel(IterArgs A) {
   }
 
   double wB = 0.0, wC = 0.0, wD = 0.0, wE = 0.0;
-  for (int row = gwarp; row < A.n_rows; row += nwarps) {
+  // eight lanes per source row, four rows per warp (rows hold ~10 entries in tracking regimes)
+  const int slot0 = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp + g;
+  const int slot_stride = gridDim.x * warps_per_block * kRowsPerWarp;
+  for (int row = slot0; row < A.n_rows; row += slot_stride) {
     const int n = (int)A.row_nnz[row];
     if (n == 0) continue;
     const int ig = A.row_begin + row;
@@ -1008,7 +1093,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel(IterArgs A) {
     const float temp_coef = 1 / (2.0 * temp_ell * temp_ell);
     const uint32_t* idx = A.ell_idx + (size_t)row * A.cap_max;
     const float* val = A.ell_val + (size_t)row * A.cap_max;
-    for (int e = lane; e < n; e += 32) {
+    for (int e = gl; e < n; e += kGroup) {
       const int j = (int)idx[e];
       const float A_ij = val[e];
       const float4 yb = A.tgt_moved[j];
@@ -1067,31 +1152,32 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel(IterArgs A) {
     sh[warp_in_block * 4 + 3] = wE;
   }
   __syncthreads();
+  if (threadIdx.x < 4) {
+    double r = sh[threadIdx.x];
+    for (int w = 1; w < warps_per_block; w++) r += sh[w * 4 + threadIdx.x];
+    reinterpret_cast<double*>(A.step_part)[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = r;
+  }
+  __syncthreads();
   if (threadIdx.x == 0) {
-    StepPartial sp = {0, 0, 0, 0};
-    for (int w = 0; w < warps_per_block; w++) {
-      sp.b += sh[w * 4 + 0];
-      sp.c += sh[w * 4 + 1];
-      sp.d += sh[w * 4 + 2];
-      sp.e += sh[w * 4 + 3];
-    }
-    A.step_part[blockIdx.x] = sp;
     __threadfence();
     const unsigned int prev = atomicAdd(&st->step_blocks_done, 1u);
     is_last = (prev == gridDim.x - 1);
+    if (is_last) __threadfence();
   }
   __syncthreads();
   if (!is_last) return;
-  __threadfence();
+  if (threadIdx.x == 0) st->dbg[5] = gtime();
   double tot[4];
   block_reduce_partials<4, 4>(reinterpret_cast<const double*>(A.step_part), (int)gridDim.x, tot, sh);
   if (threadIdx.x == 0) {
+    st->dbg[6] = gtime();
     st->step_blocks_done = 0u;
     if (A.world > 1) {
       for (int k = 0; k < 4; k++) st->local_step[k] = tot[k];
     } else {
       controller_step(A, st, tot);
     }
+    st->dbg[7] = gtime();
   }
 }
 

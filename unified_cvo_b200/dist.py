@@ -1,0 +1,30 @@
+"""Host-side plumbing of the multi-GPU path: one process per GPU, source rows sharded,
+target replicated, NCCL unique id exchanged over whatever control plane the host has
+(torch.distributed here).  The data path itself (two tiny all-gathers per iteration) lives
+in libcvo_b200.so."""
+from __future__ import annotations
+
+
+def shard_rows(n_rows: int, world: int, rank: int) -> tuple[int, int]:
+    """Contiguous block partition of the source rows: [begin, end) of `rank`."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    per = (n_rows + world - 1) // world
+    begin = min(n_rows, rank * per)
+    return begin, min(n_rows, begin + per)
+
+
+def attach(gpu, n_rows: int, rank: int, world: int, dist_module=None) -> tuple[int, int]:
+    """Create the NCCL communicator of `gpu` (a CvoGPU) and set its row shard.
+
+    dist_module: an initialised torch.distributed (any backend) used only to broadcast the
+    128-byte NCCL unique id from rank 0."""
+    from .cvo import CvoGPU
+
+    if world > 1:
+        uid = [CvoGPU.comm_unique_id() if rank == 0 else None]
+        dist_module.broadcast_object_list(uid, src=0)
+        gpu.comm_init(rank, world, uid[0])
+    b, e = shard_rows(n_rows, world, rank)
+    gpu.set_row_range(b, e)
+    return b, e
