@@ -2,6 +2,12 @@
 //
 // Data layout in HBM (all SoA; the reference's 192-byte AoS CvoPoint,
 // utils/PointSegmentedDistribution.hpp:147-229, is NOT used on the device):
+//   Both clouds are stored in MORTON (Z-curve) order of their own coordinates.  Source rows are
+//   always used in that order (row order never matters: every accumulated quantity is a sum or
+//   max over rows).  The target has two views: view 0 = Morton order (spatially compact 256-target
+//   blocks that whole source tiles can skip), view 1 = the caller's original order, needed
+//   whenever a row reaches its cap, because the reference keeps the FIRST num_neighbors survivors
+//   in ORIGINAL target order (CvoGPU.cu:524-526).
 //   source cloud (the rows of the kernel matrix, N points)
 //     src_xyz   float4[N]      exact coordinates (x,y,z,0)
 //     src_rowA  float4[N]      prefilter record (-2(x-c), dist_to_sensor); c = source centroid
@@ -80,6 +86,11 @@ struct DevState {
   unsigned int flow_blocks_done;
   unsigned int step_blocks_done;
   float ymax2_bound;        // upper bound of max_j |y'_j - c|^2 for the CURRENT Rinv/Tinv
+  float smax;               // upper bound of sigma_max(Rinv) (scales block radii)
+  int prune_on;             // this run may use the Morton view
+  int view;                 // target view of the CURRENT iteration: 0 Morton (pruned), 1 original
+  unsigned int n_sat;       // view 0: rows that reached their cap (redone exactly by the flow tail)
+  unsigned int n_capped;    // view 1: rows that reached their cap (keeps the run on view 1)
   // constants and per-iteration matrices shared by all threads
   KernConsts kc;
   float W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];  // omega_hat powers (CvoGPU.cu:970-980)
@@ -91,6 +102,13 @@ struct DevState {
   double local_flow[9];     // omega[3], v[3], a_sum, (double)nnz, (double)max_row_nnz
   double local_step[4];
   unsigned long long dbg[16];  // %globaltimer stamps of the tails (tools/gpu_tails.py)
+};
+
+struct TargetView {
+  const float4* xyz;
+  const float* feat;
+  const float* lab;
+  const float2* geo;
 };
 
 struct IterArgs {
@@ -105,13 +123,16 @@ struct IterArgs {
   int row_begin;   // first global source row of this shard
   int n_rows;      // rows in this shard
   int n_src_total; // N (all shards) — the indicator uses N*M
-  // target
-  const float4* tgt_xyz;
+  // target: view 0 = Morton order (prunable), view 1 = original order (exact row cap)
+  TargetView tv[2];
+  int prune;       // view 0 may skip (source tile, target block) pairs by bounding spheres
+  const int* tgt_inv;         // original target index -> Morton position
+  uint32_t* sat_list;         // [n_rows] rows of the Morton view that reached their cap
+  const float4* blk_sphere;   // [M_pad/256] view-0 target blocks: centre xyz, radius (own frame)
+  const float4* tile_sphere;  // [ceil(N/64)] source tiles: centre xyz, radius
+  const float* tile_maxdist;  // [ceil(N/64)] max distance-to-sensor inside the tile
   float4* tgt_moved;
   float* px; float* py; float* pz; float* pw;
-  const float* tgt_feat;
-  const float* tgt_lab;
-  const float2* tgt_geo;
   int M;
   int Fp, Cp;      // padded feature / class dims (same for both clouds)
   float cx, cy, cz;        // prefilter centre (source centroid)

@@ -102,11 +102,23 @@ struct DevBuf {
 struct CloudDev {
   int n = 0, F = 0, C = 0;
   bool has_geo = false;
+  // Morton-ordered arrays (source role, and target view 0)
   DevBuf<float4> xyz;
   DevBuf<float4> rowA;  // prefilter records (any cloud can play the source role)
   DevBuf<float> feat;   // n * Fp
   DevBuf<float> lab;    // n * Cp
   DevBuf<float2> geo;
+  // original-order arrays (target view 1)
+  DevBuf<float4> xyz_o;
+  DevBuf<float> feat_o;
+  DevBuf<float> lab_o;
+  DevBuf<float2> geo_o;
+  // pruning data over the Morton order
+  DevBuf<float4> blk_sphere;   // per 256 points (target role)
+  DevBuf<float4> tile_sphere;  // per 64 points (source role)
+  DevBuf<float> tile_maxdist;
+  DevBuf<int> inv;             // original index -> Morton position (device)
+  std::vector<int> perm;       // Morton position -> original index (host, for exports)
   int Fp = 0, Cp = 0;   // strides the buffers were packed with
   float cx = 0, cy = 0, cz = 0;  // centroid (float)
   float radius = 0;              // max_i |x_i - centroid| (rounded up)
@@ -127,6 +139,7 @@ struct cvo_b200_handle {
   DevBuf<float> px, py, pz, pw;
   DevBuf<float4> rowrec;
   DevBuf<float2> row_lt;
+  DevBuf<uint32_t> sat_list;
   DevBuf<uint32_t> cand, cand_cnt, ell_idx, row_nnz;
   DevBuf<float> ell_val;
   DevBuf<FlowPartial> flow_part;
@@ -208,6 +221,7 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   CVO_CUDA(h, h->pw.ensure((size_t)M_pad));
   CVO_CUDA(h, h->rowrec.ensure((size_t)std::max(n_rows, 1) * 2));
   CVO_CUDA(h, h->row_lt.ensure((size_t)std::max(n_rows, 1)));
+  CVO_CUDA(h, h->sat_list.ensure((size_t)std::max(n_rows, 1)));
   CVO_CUDA(h, h->cand.ensure((size_t)std::max(n_rows, 1) * nchunks * L));
   CVO_CUDA(h, h->cand_cnt.ensure((size_t)std::max(n_rows, 1) * nchunks));
   CVO_CUDA(h, h->ell_idx.ensure((size_t)std::max(n_rows, 1) * cap_max));
@@ -249,12 +263,24 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.row_begin = rb;
   A.n_rows = n_rows;
   A.n_src_total = N;
-  A.tgt_xyz = ct.xyz.p;
+  A.tv[0].xyz = ct.xyz.p;
+  A.tv[0].feat = ct.Fp ? ct.feat.p : h->zeros_f.p;
+  A.tv[0].lab = ct.Cp ? ct.lab.p : h->zeros_f.p;
+  A.tv[0].geo = ct.has_geo ? ct.geo.p : h->zeros_g.p;
+  A.tv[1].xyz = ct.xyz_o.p;
+  A.tv[1].feat = ct.Fp ? ct.feat_o.p : h->zeros_f.p;
+  A.tv[1].lab = ct.Cp ? ct.lab_o.p : h->zeros_f.p;
+  A.tv[1].geo = ct.has_geo ? ct.geo_o.p : h->zeros_g.p;
+  // the Morton view needs tile spheres aligned with this shard and a geometric cut-off to prune on
+  static const bool no_prune = getenv("CVO_B200_NO_PRUNE") && getenv("CVO_B200_NO_PRUNE")[0] == '1';
+  A.prune = (!no_prune && mode == 0 && h->params.is_using_geometry && (rb % kTileRows) == 0) ? 1 : 0;
+  A.tgt_inv = ct.inv.p;
+  A.sat_list = h->sat_list.p;
+  A.blk_sphere = ct.blk_sphere.p;
+  A.tile_sphere = cs.tile_sphere.p;
+  A.tile_maxdist = cs.tile_maxdist.p;
   A.tgt_moved = h->tgt_moved.p;
   A.px = h->px.p; A.py = h->py.p; A.pz = h->pz.p; A.pw = h->pw.p;
-  A.tgt_feat = ct.Fp ? ct.feat.p : h->zeros_f.p;
-  A.tgt_lab = ct.Cp ? ct.lab.p : h->zeros_f.p;
-  A.tgt_geo = ct.has_geo ? ct.geo.p : h->zeros_g.p;
   A.M = M;
   A.Fp = Fp;
   A.Cp = Cp;
@@ -369,7 +395,7 @@ KernConsts make_consts(const cvo_b200_params& p) {
 
 int init_state(cvo_b200_handle* h, const IterArgs& A, const float R[9], const float T[3], float ell,
                int cap, int controller_on, int max_iter, cvo_b200_iter_trace* d_trace,
-               int trace_cap) {
+               int trace_cap, bool allow_morton = true) {
   static thread_local DevState hs;  // ~8.5 KB; keep it off the stack of small callers
   std::memset(&hs, 0, sizeof(hs));
   std::memcpy(hs.R, R, sizeof(hs.R));
@@ -382,6 +408,8 @@ int init_state(cvo_b200_handle* h, const IterArgs& A, const float R[9], const fl
   hs.trace = d_trace;
   hs.trace_cap = trace_cap;
   hs.kc = make_consts(h->params);
+  hs.prune_on = (allow_morton && A.prune) ? 1 : 0;
+  hs.view = hs.prune_on ? 0 : 1;
   CVO_CUDA(h, cudaMemcpyAsync(h->d_state, &hs, sizeof(hs), cudaMemcpyHostToDevice, h->stream));
   // the source of an async copy from pageable memory is staged before the call returns
   launch_init_bound(A, h->stream);  // Rinv/Tinv + the |y'-c| bound, same code as the controller
@@ -433,6 +461,28 @@ int ensure_graph(cvo_b200_handle* h, const IterArgs& A, int batch) {
 
 int launches_per_iteration(const cvo_b200_handle* h) { return h->world > 1 ? 6 : 4; }
 
+// 63-bit Morton key of a point inside the cloud's bounding box (21 bits per axis)
+inline uint64_t spread21(uint64_t v) {
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+template <typename T>
+int upload_vec(cvo_b200_handle* h, DevBuf<T>& dst, const std::vector<T>& src) {
+  CVO_CUDA(h, dst.ensure(src.size()));
+  if (!src.empty())
+    CVO_CUDA(h, cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  CVO_CUDA(h, cudaStreamSynchronize(h->stream));  // src is a temporary of the caller
+  return CVO_B200_OK;
+}
+
+// Replaces CvoPointCloud_to_gpu (CvoGPU_impl.cu:206-285): SoA pack + upload, in two orders:
+// Morton order (source role and prunable target view) and the caller's order (exact view).
 int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F,
                  const float* features, int C, const float* labels, const float* geotype) {
   if (n < 0 || F < 0 || C < 0 || (n > 0 && !xyz)) return fail(h, CVO_B200_ERR_INVALID, "bad cloud arguments");
@@ -443,65 +493,146 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
   c.Cp = round_up(c.C, 4);
   c.has_geo = geotype != nullptr;
   c.set = true;
+  c.perm.resize((size_t)n);
   if (n == 0) return CVO_B200_OK;
-  std::vector<float4> buf((size_t)n);
+
+  // ---- bounding box, centroid (finite points only)
   double mx = 0, my = 0, mz = 0;
   size_t n_finite = 0;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   for (int i = 0; i < n; i++) {
-    const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-    buf[i] = make_float4(x, y, z, 0.f);
-    if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) {
-      mx += x; my += y; mz += z;
+    const float* p = xyz + 3 * (size_t)i;
+    if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
+      mx += p[0]; my += p[1]; mz += p[2];
       n_finite++;
+      for (int k = 0; k < 3; k++) {
+        lo[k] = std::min(lo[k], p[k]);
+        hi[k] = std::max(hi[k], p[k]);
+      }
     }
   }
-  CVO_CUDA(h, c.xyz.ensure((size_t)n));
-  CVO_CUDA(h, cudaMemcpyAsync(c.xyz.p, buf.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-  CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+  c.cx = n_finite ? (float)(mx / (double)n_finite) : 0.f;
+  c.cy = n_finite ? (float)(my / (double)n_finite) : 0.f;
+  c.cz = n_finite ? (float)(mz / (double)n_finite) : 0.f;
+  // ---- Morton order (non-finite points last, in their original order)
   {
-    // prefilter records: a = -2 (x - c) and the reference's a_to_sensor (CvoGPU.cu:506)
-    c.cx = n_finite ? (float)(mx / (double)n_finite) : 0.f;
-    c.cy = n_finite ? (float)(my / (double)n_finite) : 0.f;
-    c.cz = n_finite ? (float)(mz / (double)n_finite) : 0.f;
-    double r2max = 0.0;
+    const double ext = std::max({(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2], 1e-30});
+    const double scale = 2097151.0 / ext;  // one isotropic grid: cells are cubes
+    std::vector<std::pair<uint64_t, int>> keys((size_t)n);
     for (int i = 0; i < n; i++) {
-      const double dx = (double)xyz[3 * (size_t)i] - c.cx, dy = (double)xyz[3 * (size_t)i + 1] - c.cy,
-                   dz = (double)xyz[3 * (size_t)i + 2] - c.cz;
-      const double r2 = dx * dx + dy * dy + dz * dz;
-      if (r2 > r2max) r2max = r2;  // NaN compares false; +inf propagates (every pair a candidate)
+      const float* p = xyz + 3 * (size_t)i;
+      uint64_t key = ~0ull;
+      if (n_finite && std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
+        const uint64_t qx = (uint64_t)(((double)p[0] - lo[0]) * scale);
+        const uint64_t qy = (uint64_t)(((double)p[1] - lo[1]) * scale);
+        const uint64_t qz = (uint64_t)(((double)p[2] - lo[2]) * scale);
+        key = spread21(qx) | (spread21(qy) << 1) | (spread21(qz) << 2);
+      }
+      keys[i] = {key, i};
     }
-    c.radius = (float)(std::sqrt(r2max) * (1.0 + 1e-6)) + 1e-6f;
-    for (int i = 0; i < n; i++) {
-      const float x = xyz[3 * (size_t)i], y = xyz[3 * (size_t)i + 1], z = xyz[3 * (size_t)i + 2];
-      volatile float xx = x * x, yy = y * y, zz = z * z;
-      volatile float sxy = xx + yy;
-      const float dist = sqrtf(sxy + zz);
-      buf[i] = make_float4(-2.f * (x - c.cx), -2.f * (y - c.cy), -2.f * (z - c.cz), dist);
-    }
-    CVO_CUDA(h, c.rowA.ensure((size_t)n));
-    CVO_CUDA(h, cudaMemcpyAsync(c.rowA.p, buf.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
-    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::sort(keys.begin(), keys.end());
+    for (int i = 0; i < n; i++) c.perm[i] = keys[i].second;
   }
+  const std::vector<int>& perm = c.perm;
+  {
+    std::vector<int> inv((size_t)n);
+    for (int s2 = 0; s2 < n; s2++) inv[perm[s2]] = s2;
+    int rc0 = upload_vec(h, c.inv, inv);
+    if (rc0 != CVO_B200_OK) return rc0;
+  }
+
+  // ---- coordinates in both orders, prefilter records, extent
+  std::vector<float4> buf((size_t)n), buf_o((size_t)n), recA((size_t)n);
+  double r2max = 0.0;
+  for (int i = 0; i < n; i++) {
+    const float* p = xyz + 3 * (size_t)i;
+    buf_o[i] = make_float4(p[0], p[1], p[2], 0.f);
+    const double dx = (double)p[0] - c.cx, dy = (double)p[1] - c.cy, dz = (double)p[2] - c.cz;
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 > r2max) r2max = r2;  // NaN compares false; +inf propagates (every pair a candidate)
+  }
+  c.radius = (float)(std::sqrt(r2max) * (1.0 + 1e-6)) + 1e-6f;
+  for (int s = 0; s < n; s++) {
+    const float* p = xyz + 3 * (size_t)perm[s];
+    const float x = p[0], y = p[1], z = p[2];
+    buf[s] = make_float4(x, y, z, 0.f);
+    // prefilter record: a = -2 (x - c) and the reference's a_to_sensor (CvoGPU.cu:506)
+    volatile float xx = x * x, yy = y * y, zz = z * z;
+    volatile float sxy = xx + yy;
+    const float dist = sqrtf(sxy + zz);
+    recA[s] = make_float4(-2.f * (x - c.cx), -2.f * (y - c.cy), -2.f * (z - c.cz), dist);
+  }
+  int rc;
+  if ((rc = upload_vec(h, c.xyz, buf)) != CVO_B200_OK) return rc;
+  if ((rc = upload_vec(h, c.xyz_o, buf_o)) != CVO_B200_OK) return rc;
+  if ((rc = upload_vec(h, c.rowA, recA)) != CVO_B200_OK) return rc;
+
+  // ---- bounding spheres over the Morton order: 256-point blocks (target role, padded to a
+  //      whole block) and 64-point tiles (source role).  Non-finite points make the sphere
+  //      infinite, i.e. never skipped.
+  auto spheres = [&](int group, std::vector<float4>& out, std::vector<float>* maxdist) {
+    const int ng = (n + group - 1) / group;
+    out.assign((size_t)std::max(ng, 1), make_float4(0.f, 0.f, 0.f, INFINITY));
+    if (maxdist) maxdist->assign((size_t)std::max(ng, 1), INFINITY);
+    for (int g = 0; g < ng; g++) {
+      const int b = g * group, e = std::min(n, b + group);
+      double l3[3] = {1e300, 1e300, 1e300}, h3[3] = {-1e300, -1e300, -1e300};
+      bool finite = true;
+      float md = 0.f;
+      for (int s = b; s < e; s++) {
+        const float4 q = buf[s];
+        if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) { finite = false; break; }
+        l3[0] = std::min(l3[0], (double)q.x); h3[0] = std::max(h3[0], (double)q.x);
+        l3[1] = std::min(l3[1], (double)q.y); h3[1] = std::max(h3[1], (double)q.y);
+        l3[2] = std::min(l3[2], (double)q.z); h3[2] = std::max(h3[2], (double)q.z);
+        md = std::max(md, recA[s].w);
+      }
+      if (!finite) continue;
+      const double cx = 0.5 * (l3[0] + h3[0]), cy = 0.5 * (l3[1] + h3[1]), cz = 0.5 * (l3[2] + h3[2]);
+      double r2 = 0.0;
+      for (int s = b; s < e; s++) {
+        const double dx = buf[s].x - cx, dy = buf[s].y - cy, dz = buf[s].z - cz;
+        r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
+      }
+      out[g] = make_float4((float)cx, (float)cy, (float)cz,
+                           (float)(std::sqrt(r2) * (1.0 + 1e-5)) + 1e-5f * (float)(std::fabs(cx) + std::fabs(cy) + std::fabs(cz)) + 1e-6f);
+      if (maxdist) (*maxdist)[g] = md;
+    }
+  };
+  std::vector<float4> sph;
+  std::vector<float> md;
+  spheres(kJBlock, sph, nullptr);
+  if ((rc = upload_vec(h, c.blk_sphere, sph)) != CVO_B200_OK) return rc;
+  spheres(kTileRows, sph, &md);
+  if ((rc = upload_vec(h, c.tile_sphere, sph)) != CVO_B200_OK) return rc;
+  if ((rc = upload_vec(h, c.tile_maxdist, md)) != CVO_B200_OK) return rc;
+
   if (c.F > 0) {
-    std::vector<float> fb((size_t)n * c.Fp, 0.f);
-    for (int i = 0; i < n; i++)
-      std::memcpy(&fb[(size_t)i * c.Fp], features + (size_t)i * c.F, sizeof(float) * c.F);
-    CVO_CUDA(h, c.feat.ensure(fb.size()));
-    CVO_CUDA(h, cudaMemcpyAsync(c.feat.p, fb.data(), fb.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::vector<float> fb((size_t)n * c.Fp, 0.f), fo((size_t)n * c.Fp, 0.f);
+    for (int s = 0; s < n; s++) {
+      std::memcpy(&fb[(size_t)s * c.Fp], features + (size_t)perm[s] * c.F, sizeof(float) * c.F);
+      std::memcpy(&fo[(size_t)s * c.Fp], features + (size_t)s * c.F, sizeof(float) * c.F);
+    }
+    if ((rc = upload_vec(h, c.feat, fb)) != CVO_B200_OK) return rc;
+    if ((rc = upload_vec(h, c.feat_o, fo)) != CVO_B200_OK) return rc;
   }
   if (c.C > 0) {
-    std::vector<float> lb((size_t)n * c.Cp, 0.f);
-    for (int i = 0; i < n; i++)
-      std::memcpy(&lb[(size_t)i * c.Cp], labels + (size_t)i * c.C, sizeof(float) * c.C);
-    CVO_CUDA(h, c.lab.ensure(lb.size()));
-    CVO_CUDA(h, cudaMemcpyAsync(c.lab.p, lb.data(), lb.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::vector<float> lb((size_t)n * c.Cp, 0.f), lo2((size_t)n * c.Cp, 0.f);
+    for (int s = 0; s < n; s++) {
+      std::memcpy(&lb[(size_t)s * c.Cp], labels + (size_t)perm[s] * c.C, sizeof(float) * c.C);
+      std::memcpy(&lo2[(size_t)s * c.Cp], labels + (size_t)s * c.C, sizeof(float) * c.C);
+    }
+    if ((rc = upload_vec(h, c.lab, lb)) != CVO_B200_OK) return rc;
+    if ((rc = upload_vec(h, c.lab_o, lo2)) != CVO_B200_OK) return rc;
   }
   if (geotype) {
-    CVO_CUDA(h, c.geo.ensure((size_t)n));
-    CVO_CUDA(h, cudaMemcpyAsync(c.geo.p, geotype, (size_t)n * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
-    CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::vector<float2> gs((size_t)n), go((size_t)n);
+    for (int s = 0; s < n; s++) {
+      gs[s] = make_float2(geotype[2 * (size_t)perm[s]], geotype[2 * (size_t)perm[s] + 1]);
+      go[s] = make_float2(geotype[2 * (size_t)s], geotype[2 * (size_t)s + 1]);
+    }
+    if ((rc = upload_vec(h, c.geo, gs)) != CVO_B200_OK) return rc;
+    if ((rc = upload_vec(h, c.geo_o, go)) != CVO_B200_OK) return rc;
   }
   return CVO_B200_OK;
 }
@@ -608,9 +739,11 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (CloudDev* c : {&h->src, &h->tgt}) {
     c->xyz.release(); c->rowA.release(); c->feat.release(); c->lab.release(); c->geo.release();
+    c->xyz_o.release(); c->feat_o.release(); c->lab_o.release(); c->geo_o.release();
+    c->blk_sphere.release(); c->tile_sphere.release(); c->tile_maxdist.release(); c->inv.release();
   }
   h->tgt_moved.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
-  h->rowrec.release(); h->row_lt.release();
+  h->rowrec.release(); h->row_lt.release(); h->sat_list.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
   h->zeros_g.release(); h->d_trace.release(); h->gathered.release();
@@ -818,7 +951,7 @@ static int inner_product_common(cvo_b200_handle* h, const float T16[16], float e
   float R[9], T[3];
   split_pose(T16, R, T);
   // inner_product_impl uses num_neighbors = nearest_neighbors_max (CvoGPU.cu:1752-1754)
-  rc = init_state(h, A, R, T, ell, A.cap_max, 0, 1, nullptr, 0);
+  rc = init_state(h, A, R, T, ell, A.cap_max, 0, 1, nullptr, 0, false);
   if (rc != CVO_B200_OK) return rc;
   rc = enqueue_iteration(h, A, 2, nullptr, nullptr);
   if (rc != CVO_B200_OK) return rc;
@@ -888,13 +1021,17 @@ int cvo_b200_association(cvo_b200_handle* h, const float T[16], float ell, const
   IterArgs A;
   int rc = inner_product_common(h, T, ell, kernel3x3, &s, &A);
   if (rc != CVO_B200_OK) return rc;
+  // device rows are in the source cloud's Morton order: un-permute to the caller's row order
   const int n_rows = A.n_rows;
   std::vector<uint32_t> cnt((size_t)n_rows);
   CVO_CUDA(h, cudaMemcpy(cnt.data(), A.row_nnz, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost));
+  const std::vector<int>& perm = h->src.perm;  // Morton position -> original row
+  std::vector<int> inv((size_t)n_rows);
+  for (int s = 0; s < n_rows; s++) inv[perm[s]] = s;
   int64_t total = 0;
   if (row_ptr) row_ptr[0] = 0;
   for (int i = 0; i < n_rows; i++) {
-    total += cnt[i];
+    total += cnt[inv[i]];
     if (row_ptr) row_ptr[i + 1] = (int32_t)total;
   }
   *nnz = total;
@@ -904,11 +1041,13 @@ int cvo_b200_association(cvo_b200_handle* h, const float T[16], float ell, const
   CVO_CUDA(h, cudaMemcpy(idx.data(), A.ell_idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
   CVO_CUDA(h, cudaMemcpy(val.data(), A.ell_val, val.size() * sizeof(float), cudaMemcpyDeviceToHost));
   int64_t o = 0;
-  for (int i = 0; i < n_rows; i++)
-    for (uint32_t k = 0; k < cnt[i]; k++, o++) {
-      cols[o] = (int32_t)idx[(size_t)i * A.cap_max + k];
-      vals[o] = val[(size_t)i * A.cap_max + k];
+  for (int i = 0; i < n_rows; i++) {
+    const int s = inv[i];
+    for (uint32_t k = 0; k < cnt[s]; k++, o++) {
+      cols[o] = (int32_t)idx[(size_t)s * A.cap_max + k];  // exact view: original target indices
+      vals[o] = val[(size_t)s * A.cap_max + k];
     }
+  }
   return CVO_B200_OK;
 }
 

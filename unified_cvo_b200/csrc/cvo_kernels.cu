@@ -124,6 +124,7 @@ __device__ __forceinline__ float prefilter_threshold(float d2_thres, const float
 __global__ void __launch_bounds__(256) prep_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
+  const int view = st->view;
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int stride = gridDim.x * blockDim.x;
   if (gid == 0) st->dbg[8] = gtime();
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(256) prep_kernel(IterArgs A) {
   // ---- targets: exact moved coordinates + the centred SoA operand (padded to M_pad)
   for (int j = gid; j < A.M_pad; j += stride) {
     if (j < A.M) {
-      const float4 y = A.tgt_xyz[j];
+      const float4 y = A.tv[view].xyz[j];
       const float yv[3] = {y.x, y.y, y.z};
       float r[3];
       mat3f_vec(Ri, yv, r);  // (*R) * input, CvoGPU_impl.cu:46-50
@@ -191,6 +192,7 @@ __device__ __forceinline__ uint32_t make_word(int j_base, uint32_t qmask) {
 __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
+  const int view = st->view;
   __shared__ PairSmemWarp smem[kPairWarps];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -207,10 +209,15 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
   __syncwarp();
   uint32_t phase0 = 0, phase1 = 0;
 
+  // static round-robin over (tile, chunk) items: a single global work counter costs ~10^4
+  // same-address L2 atomics per launch, more than the sweep itself on 10k x 10k clouds
+  const int gwarp = blockIdx.x * kPairWarps + warp;
+  const int nwarps = gridDim.x * kPairWarps;
+  int next_item = gwarp;
   auto fetch_item = [&]() -> int {
-    int it = 0;
-    if (lane == 0) it = (int)atomicAdd(&st->work_counter, 1u);
-    return __shfl_sync(0xffffffffu, it, 0);
+    const int it = next_item;
+    next_item += nwarps;
+    return it;
   };
   auto issue_tile = [&](int item, int buf) {
     if (item >= A.n_items) return;
@@ -259,8 +266,31 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
     const int j_end = min(A.M_pad, j_begin + A.chunk_len);
     uint32_t* cell0 = A.cand + ((size_t)row0 * A.nchunks + jc) * (size_t)L;
     const size_t cell_stride = (size_t)A.nchunks * (size_t)L;
+    // ---- pruning data of this source tile: bounding sphere and the largest cut-off radius of
+    //      its rows, sqrt(max_i d2_thres_i) with l_i = ell (1 + dist_i/500)  (CvoGPU.cu:506-511)
+    float4 tsph = make_float4(0.f, 0.f, 0.f, 0.f);
+    float reach = INFINITY;
+    const bool prune = A.prune && view == 0;
+    if (prune) {
+      const int gt = (A.row_begin + row0) / kTileRows;
+      tsph = A.tile_sphere[gt];
+      const double lmax = ((double)A.tile_maxdist[gt] / 500.0 + 1.0) * (double)st->ell;
+      const double th = -2.0 * lmax * lmax * (double)st->kc.log_geo * (1.0 + 1e-5);
+      reach = (float)(sqrt(fmax(th, 0.0)) * (1.0 + 1e-5)) + tsph.w + 1e-4f;
+    }
 
     for (int jb = j_begin; jb < j_end; jb += kJBlock) {
+      if (prune) {
+        // conservative skip: no pair of this (tile, block) can pass d2 < thres when the moved
+        // block sphere and the tile sphere are farther apart than the largest cut-off
+        const float4 b = A.blk_sphere[jb / kJBlock];
+        const float bx = st->Rinv[0] * b.x + st->Rinv[3] * b.y + st->Rinv[6] * b.z + st->Tinv[0];
+        const float by = st->Rinv[1] * b.x + st->Rinv[4] * b.y + st->Rinv[7] * b.z + st->Tinv[1];
+        const float bz = st->Rinv[2] * b.x + st->Rinv[5] * b.y + st->Rinv[8] * b.z + st->Tinv[2];
+        const float dx = bx - tsph.x, dy = by - tsph.y, dz = bz - tsph.z;
+        const float lim = reach + b.w * st->smax * 1.0001f + 1e-4f * (fabsf(bx) + fabsf(by) + fabsf(bz));
+        if (dx * dx + dy * dy + dz * dz > lim * lim) continue;
+      }
       // ---- stream 256 targets into registers: lane owns targets jb + 8*lane .. +7 (two float4
       //      per coordinate, a warp reads 1 KB contiguous per array), already packed in pairs
       const int jl = jb + 8 * lane;
@@ -374,14 +404,13 @@ struct RowCtx {
 
 // The body of the j-loop of fill_in_A_mat_gpu (CvoGPU.cu:534-589) / of the dense-kernel
 // variant (:279-321) for one (i, j).  Returns true if the pair is stored; a = A_ij.
+// pb = the moved target point y'_j; j indexes the target arrays of `view`.
 __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& kc,
-                                          const RowCtx& rc, int i_global, int j, float& a_out,
-                                          float4& pb_out) {
-  const float4 pb = A.tgt_moved[j];
-  pb_out = pb;
+                                          const RowCtx& rc, int i_global, int view, int j,
+                                          const float4& pb, float& a_out) {
   float a = 1, sk = 1, ck = 1, k = 1, geo_sim = 1;
   if (kc.use_geo_type && A.mode == 0) {  // mode 1 switches it off, CvoGPU.cu:1948-1949
-    const float2 gb = A.tgt_geo[j];
+    const float2 gb = A.tv[view].geo[j];
     float norm2_a = 0.f;
     norm2_a += rc.ga[0] * rc.ga[0];
     norm2_a += rc.ga[1] * rc.ga[1];
@@ -416,7 +445,7 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
   if (kc.use_intensity) {
     float d2_color = 0.f;
     const float* fa = A.src_feat + (size_t)i_global * A.Fp;
-    const float* fb = A.tgt_feat + (size_t)j * A.Fp;
+    const float* fb = A.tv[view].feat + (size_t)j * A.Fp;
     for (int f = 0; f < A.Fp; f += 4) {
       const float4 va = *reinterpret_cast<const float4*>(fa + f);
       const float4 vb = *reinterpret_cast<const float4*>(fb + f);
@@ -437,7 +466,7 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
   if (kc.use_semantics) {
     float d2_semantic = 0.f;
     const float* la = A.src_lab + (size_t)i_global * A.Cp;
-    const float* lb = A.tgt_lab + (size_t)j * A.Cp;
+    const float* lb = A.tv[view].lab + (size_t)j * A.Cp;
     for (int c = 0; c < A.Cp; c += 4) {
       const float4 va = *reinterpret_cast<const float4*>(la + c);
       const float4 vb = *reinterpret_cast<const float4*>(lb + c);
@@ -568,6 +597,7 @@ constexpr int kGroupList = 80;               // pending (<8) + one batch of 8 wo
 __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
   DevState* st = A.st;
   if (st->done) return;
+  const int view = st->view;
   __shared__ double sh[kSparseThreads * 9];
   __shared__ uint32_t s_list[kSparseThreads / kGroup][kGroupList];
   __shared__ bool is_last;
@@ -623,7 +653,10 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       float a = 0.f;
       float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
       bool surv = false;
-      if (valid) surv = eval_pair(A, kc, rc, ig, j, a, pb);
+      if (valid) {
+        pb = A.tgt_moved[j];
+        surv = eval_pair(A, kc, rc, ig, view, j, pb, a);
+      }
       const unsigned bits = (__ballot_sync(0xffffffffu, surv) >> gshift) & 0xffu;
       const int pos = count + __popc(bits & lt8);
       if (surv && pos < cap) {
@@ -770,7 +803,17 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       }
       asum += __shfl_xor_sync(0xffffffffu, asum, o, kGroup);
     }
-    if (gl == 0 && rvalid) {
+    // A row that reached its cap: in the Morton view it may hold the wrong survivors (the
+    // reference keeps the first ones in ORIGINAL target order), so it is queued for the exact
+    // redo in this kernel's tail and contributes nothing here.
+    const bool capped = rvalid && count >= cap;
+    if (capped && gl == 0) {
+      if (view == 0)
+        A.sat_list[atomicAdd(&st->n_sat, 1u)] = (uint32_t)row;
+      else
+        atomicAdd(&st->n_capped, 1u);
+    }
+    if (gl == 0 && rvalid && !(capped && view == 0)) {
       A.row_nnz[row] = (uint32_t)count;
 #pragma unroll
       for (int k = 0; k < 3; k++) {
@@ -816,6 +859,107 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
   if (threadIdx.x == 0) st->dbg[1] = gtime();
   double tot[9];
   block_reduce_partials<9, 8>(reinterpret_cast<const double*>(A.flow_part), (int)gridDim.x, tot, sh, &st->dbg[10]);
+  // ---- exact redo of the rows that reached their cap in the Morton view: one warp per row scans
+  //      ALL targets in the caller's original order with the reference's arithmetic (the literal
+  //      loop of CvoGPU.cu:524-591).  Rare in tracking regimes; when it is not, the controller
+  //      moves the run to the original-order view.
+  const unsigned int n_sat = (view == 0) ? *(volatile unsigned int*)&st->n_sat : 0u;
+  if (n_sat > 0u) {
+    double f_om[3] = {0, 0, 0}, f_v[3] = {0, 0, 0}, f_asum = 0.0, f_nnz = 0.0, f_max = 0.0;
+    float Ri[9], Ti[3];
+#pragma unroll
+    for (int q = 0; q < 9; q++) Ri[q] = st->Rinv[q];
+#pragma unroll
+    for (int q = 0; q < 3; q++) Ti[q] = st->Tinv[q];
+    const unsigned lt32 = (1u << lane) - 1u;
+    for (unsigned int si = warp_in_block; si < n_sat; si += warps_per_block) {
+      const int row = (int)__ldcg(&A.sat_list[si]);
+      const int ig = A.row_begin + row;
+      RowCtx rc;
+      {
+        const float4 pa = A.src_xyz[ig];
+        const float2 lt = A.row_lt[row];
+        rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
+        rc.l = lt.x;
+        rc.d2_thres = lt.y;
+        rc.ga[0] = rc.ga[1] = 0.f;
+        if (kc.use_geo_type) {
+          const float2 gg = A.src_geo[ig];
+          rc.ga[0] = gg.x; rc.ga[1] = gg.y;
+        }
+      }
+      float om[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
+      double asum = 0.0;
+      int count = 0;
+      uint32_t* out_idx = A.ell_idx + (size_t)row * A.cap_max;
+      float* out_val = A.ell_val + (size_t)row * A.cap_max;
+      for (int jb = 0; jb < A.M && count < cap; jb += 32) {
+        const int j = jb + lane;
+        float a = 0.f;
+        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+        bool surv = false;
+        if (j < A.M) {
+          const float4 y = A.tv[1].xyz[j];
+          const float yv[3] = {y.x, y.y, y.z};
+          float r[3];
+          mat3f_vec(Ri, yv, r);  // same arithmetic as prep_kernel
+          pb = make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], 0.f);
+          surv = eval_pair(A, kc, rc, ig, 1, j, pb, a);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, surv);
+        const int pos = count + __popc(mask & lt32);
+        if (surv && pos < cap) {
+          out_idx[pos] = (uint32_t)A.tgt_inv[j];  // tgt_moved of this iteration is in Morton order
+          out_val[pos] = a;
+          const float py[3] = {pb.x, pb.y, pb.z};
+          float cr[3];
+          cross3f(rc.px, py, cr);
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            om[q] = om[q] + cr[q] * a;
+            vv[q] = vv[q] + (py[q] - rc.px[q]) * a;
+          }
+          asum += (double)a;
+        }
+        count = min(cap, count + __popc(mask));
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          om[q] += __shfl_xor_sync(0xffffffffu, om[q], o);
+          vv[q] += __shfl_xor_sync(0xffffffffu, vv[q], o);
+        }
+        asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      }
+      if (lane == 0) {
+        A.row_nnz[row] = (uint32_t)count;
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          f_om[q] += (double)(om[q] / c_div);
+          f_v[q] += (double)(vv[q] / d_div);
+        }
+        f_asum += asum;
+        f_nnz += (double)count;
+        f_max = fmax(f_max, (double)count);
+      }
+    }
+    // fold the redone rows into the totals (fixed order over the warps of this block)
+    __syncthreads();
+    if (lane == 0) {
+      double* d = sh + warp_in_block * 9;
+      d[0] = f_om[0]; d[1] = f_om[1]; d[2] = f_om[2];
+      d[3] = f_v[0];  d[4] = f_v[1];  d[5] = f_v[2];
+      d[6] = f_asum;  d[7] = f_nnz;   d[8] = f_max;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 0; w < warps_per_block; w++) {
+        for (int q = 0; q < 8; q++) tot[q] += sh[w * 9 + q];
+        tot[8] = fmax(tot[8], sh[w * 9 + 8]);
+      }
+    }
+  }
   if (threadIdx.x == 0) {
     st->dbg[2] = gtime();
     st->flow_blocks_done = 0u;
@@ -901,6 +1045,14 @@ __device__ void update_tf_device(const IterArgs& A, DevState* st) {
   }
   const double ymax = (sqrt(smax2) * (double)A.trad + sqrt(off2)) * (1.0 + 1e-5) + 1e-6;
   st->ymax2_bound = __double2float_ru(ymax * ymax);
+  st->smax = __double2float_ru(sqrt(smax2) * (1.0 + 1e-6));
+  // target view of the next iteration: leave the Morton view when many rows reach their cap
+  // (each costs an O(M) exact redo), come back once no row does
+  int next_view = 1;
+  if (st->prune_on) next_view = (st->view == 0) ? (st->n_sat > 16u ? 1 : 0) : (st->n_capped == 0u ? 0 : 1);
+  st->view = next_view;
+  st->n_sat = 0u;
+  st->n_capped = 0u;
 }
 
 // Everything align_impl does on the host after the reductions (CvoGPU.cu:1124-1158,
