@@ -37,11 +37,14 @@ WORKLOADS = {
            dict(is_using_intensity=0, is_using_geometric_type=0, ell_init=0.95),
            "synthetic N=M=10000 geometric kernel (BASELINE configs[1]); cvo_outdoor_params.yaml "
            "with intensity/geometric-type off, ell_init=0.95; one step = one full align()"),
-    "KITTI05": ("KITTI05", "cvo_intensity_params_img_gpu0.yaml", dict(),
-                "synthetic KITTI-05-sized N=M=16384, geometry+5-dim colour; one step = one align()"),
-    "C4": ("C4", "cvo_intensity_params_img_gpu0.yaml", dict(MAX_ITER=50),
-           "synthetic N=M=200000 geometry+5-dim colour (BASELINE configs[3]), MAX_ITER=50; "
-           "one step = one align() of 50 iterations"),
+    # FIRST_FRAME = what main_cvo_gpu_align_raw_image.cpp:43-45 does before the first pair of a
+    # sequence: ell_init / ell_decay_rate / ell_decay_start <- their *_first_frame values
+    "KITTI05": ("KITTI05", "cvo_intensity_params_img_gpu0.yaml", dict(FIRST_FRAME=1),
+                "synthetic KITTI-05-sized N=M=16384, geometry+5-dim colour, first-frame parameters "
+                "(ell_init=1.5); one step = one align()"),
+    "C4": ("C4", "cvo_intensity_params_img_gpu0.yaml", dict(FIRST_FRAME=1, MAX_ITER=50),
+           "synthetic N=M=200000 geometry+5-dim colour (BASELINE configs[3]), first-frame "
+           "parameters (ell_init=1.5), MAX_ITER=50; one step = one align() of 50 iterations"),
 }
 
 
@@ -53,7 +56,12 @@ def load_workload(name):
     d = synthetic.make_config(cfg)
     p = u.read_params_yaml(os.path.join(DATA, yaml))
     for k, v in over.items():
-        setattr(p, k, v)
+        if k == "FIRST_FRAME":
+            p.ell_init = p.ell_init_first_frame
+            p.ell_decay_rate = p.ell_decay_rate_first_frame
+            p.ell_decay_start = p.ell_decay_start_first_frame
+        else:
+            setattr(p, k, v)
 
     def cloud(c):
         return u.CvoPointCloud(c["xyz"], c["features"], c["labels"], c["geotype"])
@@ -174,8 +182,8 @@ def run_ours(args, rank, world, local_rank):
         uid = [u.CvoGPU.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         g.comm_init(rank, world, uid[0])
-        per = (N + world - 1) // world
-        g.set_row_range(rank * per, min(N, (rank + 1) * per))
+        from unified_cvo_b200.dist import shard_rows
+        g.set_row_range(*shard_rows(N, world, rank))
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,7 +252,12 @@ def run_ours(args, rank, world, local_rank):
     roof, fp32 = None, None
     peaks, peak_src = measured_peaks()
     ms_tot, ms_pair = g.time_iterations(np.eye(3), np.zeros(3), p.ell_init, p.nearest_neighbors_max, 40)
-    rows_local = N if world == 1 else (min(N, (rank + 1) * ((N + world - 1) // world)) - rank * ((N + world - 1) // world))
+    if world == 1:
+        rows_local = N
+    else:
+        from unified_cvo_b200.dist import shard_rows
+        rb, re_ = shard_rows(N, world, rank)
+        rows_local = re_ - rb
     t_pair = ms_pair / 40 * 1e-3
     alg_bytes = algorithmic_bytes_per_iteration(rows_local, M, F, C)
     achieved = alg_bytes / t_pair / 1e9

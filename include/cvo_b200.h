@@ -237,6 +237,17 @@ int cvo_b200_association(cvo_b200_handle* h, const float T[16], float ell,
                          const float* kernel3x3, int64_t* nnz, int32_t* row_ptr,
                          int32_t* cols, float* vals);
 
+/* The kernel matrix of the LAST iteration of the most recent cvo_b200_align on this handle
+ * (replaces the export at the end of align_impl, CvoGPU.cu:1552-1556 ->
+ * gpu_association_to_cpu, CvoGPU_impl.cu:366-427, done when is_exporting_association).
+ * Same two-call CSR protocol as cvo_b200_association; row_ptr has n_src+1 entries; rows outside
+ * this handle's row range are empty.  CVO_B200_ERR_STATE if another call has overwritten the
+ * matrix since.  (The reference reads its matrix back with the row stride of the NEXT
+ * iteration's cap when the loop ends on MAX_ITER — CvoGPU.cu:1518-1529 then :1553 — which
+ * scrambles it; this call always returns the matrix as computed.)                          */
+int cvo_b200_align_association(cvo_b200_handle* h, int64_t* nnz, int32_t* row_ptr,
+                               int32_t* cols, float* vals);
+
 /* ---- measurement helpers --------------------------------------------------
  * Runs `iters` iterations back to back at a FIXED state (pose, ell, cap),
  * timed with CUDA events on the handle's stream.  ms_total = whole iteration

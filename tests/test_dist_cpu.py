@@ -61,16 +61,20 @@ WORKER = textwrap.dedent("""
     dist.broadcast_object_list(uid, src=0)
     assert uid[0] == bytes(range(128))
     dist.barrier()
-    print("rank", rank, "ok")
+    os.write(1, ("rank %d ok" % rank + os.linesep).encode())   # one write: the ranks share a pipe
 """)
 
 
 def test_two_rank_sharded_reduction_equals_unsharded(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER.format(root=ROOT))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29577", OMP_NUM_THREADS="2")
+    import socket
+    with socket.socket() as sk:  # a free port: a fixed one can linger in TIME_WAIT between runs
+        sk.bind(("127.0.0.1", 0))
+        port = str(sk.getsockname()[1])
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port, OMP_NUM_THREADS="2")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout

@@ -166,6 +166,10 @@ SYMBOLS = {
         C.c_int,
         [C.c_void_p, _f32p, C.c_float, _f32p, C.POINTER(C.c_int64), _i32p, _i32p, _f32p],
     ),
+    "cvo_b200_align_association": (
+        C.c_int,
+        [C.c_void_p, C.POINTER(C.c_int64), _i32p, _i32p, _f32p],
+    ),
     "cvo_b200_time_iterations": (
         C.c_int,
         [C.c_void_p, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p],

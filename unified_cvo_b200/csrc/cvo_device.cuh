@@ -89,6 +89,7 @@ struct DevState {
   float smax;               // upper bound of sigma_max(Rinv) (scales block radii)
   int prune_on;             // this run may use the Morton view
   int view;                 // target view of the CURRENT iteration: 0 Morton (pruned), 1 original
+  int last_view;            // view the LAST executed iteration used (its ELL matrix is in that index space)
   unsigned int n_sat;       // view 0: rows that reached their cap (redone exactly by the flow tail)
   unsigned int n_capped;    // view 1: rows that reached their cap (keeps the run on view 1)
   // constants and per-iteration matrices shared by all threads

@@ -163,6 +163,10 @@ struct cvo_b200_handle {
   int rank = 0, world = 1;
   std::string err;
   uint64_t launches = 0;
+  // the kernel matrix left behind by the last align() (cvo_b200_align_association)
+  bool last_valid = false;
+  int last_view = 1;
+  IterArgs last_args;
 };
 
 namespace {
@@ -186,6 +190,7 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const CloudDev* S = nullptr,
             const CloudDev* Tg = nullptr, bool sharded = true) {
   if (!h->src.set || !h->tgt.set) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
+  h->last_valid = false;  // every caller of prepare() overwrites the ELL matrix
   const CloudDev& cs = S ? *S : h->src;
   const CloudDev& ct = Tg ? *Tg : h->tgt;
   const int N = cs.n, M = ct.n;
@@ -879,6 +884,9 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
     info->registration_seconds = (double)ms / 1000.0;
     info->pairs_tested = (uint64_t)h->src.n * (uint64_t)h->tgt.n * (uint64_t)executed;
   }
+  h->last_valid = true;
+  h->last_view = hs.last_view;
+  h->last_args = A;
   if (trace_cap > 0) {
     const int nrec = std::min(trace_cap, executed);
     CVO_CUDA(h, cudaMemcpy(trace, h->d_trace.p, sizeof(cvo_b200_iter_trace) * (size_t)nrec, cudaMemcpyDeviceToHost));
@@ -1046,6 +1054,53 @@ int cvo_b200_association(cvo_b200_handle* h, const float T[16], float ell, const
     for (uint32_t k = 0; k < cnt[s]; k++, o++) {
       cols[o] = (int32_t)idx[(size_t)s * A.cap_max + k];  // exact view: original target indices
       vals[o] = val[(size_t)s * A.cap_max + k];
+    }
+  }
+  return CVO_B200_OK;
+}
+
+int cvo_b200_align_association(cvo_b200_handle* h, int64_t* nnz, int32_t* row_ptr, int32_t* cols,
+                               float* vals) {
+  if (!h || !nnz) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  *nnz = 0;
+  if (!h->last_valid) return fail(h, CVO_B200_ERR_STATE, "no align() result is resident");
+  const IterArgs& A = h->last_args;
+  const int N = A.n_src_total, n_rows = A.n_rows, rb = A.row_begin;
+  std::vector<uint32_t> cnt((size_t)std::max(n_rows, 1));
+  CVO_CUDA(h, cudaMemcpy(cnt.data(), A.row_nnz, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost));
+  // device rows are Morton positions of the source cloud; this shard holds [rb, rb + n_rows)
+  const std::vector<int>& sperm = h->src.perm;  // Morton position -> original row
+  std::vector<int> srow((size_t)N, -1);         // original row -> local device row
+  for (int s = 0; s < n_rows; s++) srow[sperm[rb + s]] = s;
+  int64_t total = 0;
+  if (row_ptr) row_ptr[0] = 0;
+  for (int i = 0; i < N; i++) {
+    if (srow[i] >= 0) total += cnt[srow[i]];
+    if (row_ptr) row_ptr[i + 1] = (int32_t)total;
+  }
+  *nnz = total;
+  if (!cols || !vals || total == 0) return CVO_B200_OK;
+  std::vector<uint32_t> idx((size_t)n_rows * A.cap_max);
+  std::vector<float> val((size_t)n_rows * A.cap_max);
+  CVO_CUDA(h, cudaMemcpy(idx.data(), A.ell_idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  CVO_CUDA(h, cudaMemcpy(val.data(), A.ell_val, val.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  const std::vector<int>& tperm = h->tgt.perm;  // Morton position -> original target index
+  std::vector<std::pair<int32_t, float>> row;
+  int64_t o = 0;
+  for (int i = 0; i < N; i++) {
+    const int s = srow[i];
+    if (s < 0) continue;
+    row.clear();
+    for (uint32_t k = 0; k < cnt[s]; k++) {
+      const uint32_t j = idx[(size_t)s * A.cap_max + k];
+      row.emplace_back(h->last_view == 0 ? (int32_t)tperm[j] : (int32_t)j, val[(size_t)s * A.cap_max + k]);
+    }
+    std::sort(row.begin(), row.end());  // ascending target index, the reference's insertion order
+    for (const auto& e : row) {
+      cols[o] = e.first;
+      vals[o] = e.second;
+      o++;
     }
   }
   return CVO_B200_OK;

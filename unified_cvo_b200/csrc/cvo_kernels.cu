@@ -1048,6 +1048,7 @@ __device__ void update_tf_device(const IterArgs& A, DevState* st) {
   st->smax = __double2float_ru(sqrt(smax2) * (1.0 + 1e-6));
   // target view of the next iteration: leave the Morton view when many rows reach their cap
   // (each costs an O(M) exact redo), come back once no row does
+  st->last_view = st->view;
   int next_view = 1;
   if (st->prune_on) next_view = (st->view == 0) ? (st->n_sat > 16u ? 1 : 0) : (st->n_capped == 0u ? 0 : 1);
   st->view = next_view;

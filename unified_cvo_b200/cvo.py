@@ -264,10 +264,9 @@ class CvoGPU:
         self._check(self._lib.cvo_b200_align(self._h, _ptr(Ti), _ptr(To), C.byref(info), trace, trace_cap))
         Tm = To.reshape(4, 4).T.copy()
         if association is not None and self.params.is_exporting_association:
-            # align_impl exports the LAST iteration's matrix (CvoGPU.cu:1552-1556); equivalent
-            # here to one association pass at the final pose / ell / cap.
-            raise CvoError("is_exporting_association inside align is not wired yet; "
-                           "call compute_association_gpu with the returned transform")
+            # align_impl exports the LAST iteration's matrix (CvoGPU.cu:1552-1556)
+            self._fill_association(association, source.num_points(), target.num_points(),
+                                   lambda *a: self._lib.cvo_b200_align_association(self._h, *a))
         if trace_cap:
             executed = info.iterations + (0 if info.stop_reason == _abi.STOP_MAX_ITER else 1)
             n = min(trace_cap, executed)
@@ -329,19 +328,24 @@ class CvoGPU:
             ell, K = float(ell_or_kernel), None
         else:
             ell, K = 0.0, np.ascontiguousarray(np.asarray(ell_or_kernel, np.float32).reshape(3, 3).T).reshape(9)
+        self._fill_association(assoc, source.num_points(), target.num_points(),
+                               lambda *a: self._lib.cvo_b200_association(
+                                   self._h, _ptr(T16), C.c_float(ell), _ptr(K), *a))
+        return assoc
+
+    def _fill_association(self, assoc: Association, n: int, m: int, call):
+        """Two-call CSR protocol of cvo_b200_association / cvo_b200_align_association, filled
+        like gpu_association_to_cpu (CvoGPU_impl.cu:366-427)."""
         nnz = C.c_int64(0)
-        n = source.num_points()
         row_ptr = np.zeros(n + 1, np.int32)
-        self._check(self._lib.cvo_b200_association(
-            self._h, _ptr(T16), C.c_float(ell), _ptr(K), C.byref(nnz),
-            row_ptr.ctypes.data_as(C.POINTER(C.c_int32)), None, None))
+        i32p = C.POINTER(C.c_int32)
+        self._check(call(C.byref(nnz), row_ptr.ctypes.data_as(i32p), None, None))
         cols = np.zeros(max(nnz.value, 1), np.int32)
         vals = np.zeros(max(nnz.value, 1), np.float32)
         if nnz.value > 0:
-            self._check(self._lib.cvo_b200_association(
-                self._h, _ptr(T16), C.c_float(ell), _ptr(K), C.byref(nnz),
-                row_ptr.ctypes.data_as(C.POINTER(C.c_int32)),
-                cols.ctypes.data_as(C.POINTER(C.c_int32)), _ptr(vals)))
+            self._check(call(C.byref(nnz), row_ptr.ctypes.data_as(i32p),
+                             cols.ctypes.data_as(i32p), _ptr(vals)))
+        assoc.shape = (n, m)
         assoc.row_ptr = row_ptr.astype(np.int64)
         assoc.cols = cols[: nnz.value]
         assoc.vals = vals[: nnz.value]

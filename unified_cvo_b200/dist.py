@@ -4,12 +4,17 @@ target replicated, NCCL unique id exchanged over whatever control plane the host
 in libcvo_b200.so."""
 from __future__ import annotations
 
+ROW_TILE = 64  # kTileRows of csrc/cvo_device.cuh
+
 
 def shard_rows(n_rows: int, world: int, rank: int) -> tuple[int, int]:
-    """Contiguous block partition of the source rows: [begin, end) of `rank`."""
+    """Contiguous block partition of the source rows: [begin, end) of `rank`.  Shards start on
+    a multiple of 64 rows (the source tile of the pair kernel) so that every rank can use the
+    per-tile bounding spheres of the Morton-ordered cloud."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError("bad rank/world")
     per = (n_rows + world - 1) // world
+    per = (per + ROW_TILE - 1) // ROW_TILE * ROW_TILE
     begin = min(n_rows, rank * per)
     return begin, min(n_rows, begin + per)
 
