@@ -73,7 +73,8 @@ def compare_traces(got, ref, twist_tol=1e-4, scalar_tol=1e-6):
         e = rel_err(list(getattr(got, name)), list(getattr(ref, name)))
         scale = np.linalg.norm(list(ref.omega_sum) + list(ref.v_sum))
         ea = np.linalg.norm(np.array(list(getattr(got, name))) - np.array(list(getattr(ref, name))))
-        if not ea <= 1e-5 * max(scale, 1e-30):
+        # float row sums in a different order (8 lanes per row, Morton-ordered candidates)
+        if not ea <= 3e-5 * max(scale, 1e-30):
             bad.append(f"{name} abs err {ea:.3e} (scale {scale:.3e})")
     bcde_g = np.array([got.B, got.C, got.D, got.E])
     bcde_r = np.array([ref.B, ref.C, ref.D, ref.E])

@@ -59,8 +59,22 @@ def _teacher_forced(gpu, p, src, tgt, ks, max_iter=None):
     return failures
 
 
+@pytest.fixture(scope="module", params=["dense", "grid", "auto"], autouse=True)
+def candidate_mode(request):
+    """Every test runs with the dense N x M scan (pair_kernel), with cell queries
+    (flow_kernel_t<true>) and with the automatic per-batch choice: the candidate generator must
+    never change a result.  Read by cvo_b200_create."""
+    old = os.environ.get("CVO_B200_MODE")
+    os.environ["CVO_B200_MODE"] = request.param
+    yield request.param
+    if old is None:
+        os.environ.pop("CVO_B200_MODE", None)
+    else:
+        os.environ["CVO_B200_MODE"] = old
+
+
 @pytest.fixture(scope="module")
-def gpu_geo():
+def gpu_geo(candidate_mode):
     g = u.CvoGPU(geometric_params())
     yield g
     g.close()

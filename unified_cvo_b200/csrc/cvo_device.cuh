@@ -22,6 +22,7 @@
 //   kernel matrix    ELL: ell_idx uint32[N*cap_max], ell_val float[N*cap_max], row_nnz[N]
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 #include "../../include/cvo_b200.h"
@@ -47,6 +48,8 @@ struct KernConsts {
   float log_geo;      // logf(sp_thres / sigma2)
   float d2_c_thres, d2_s_thres, d2_s_thres_dense;
   int use_geo_type, use_geometry, use_intensity, use_semantics;
+  int use_range_ell;   // CvoParams::is_using_range_ell (step kernel)
+  float c_div, d_div;  // CvoParams::c, d: divisors of the per-row flow (CvoGPU.cu:785-788)
 };
 struct StepPartial {
   double b, c, d, e;
@@ -54,7 +57,11 @@ struct StepPartial {
 
 // Device-resident controller state: everything align_impl keeps in host
 // variables (CvoGPU.cu:1363-1386) lives here so the loop needs no host round trip.
+// Layout: the first kHot1Bytes are what every block of every kernel reads at its start (one
+// cooperative load into shared memory = one L2 round trip instead of a chain of dependent
+// loads); the next block is the step kernel's input.  The host polls iter..stop_reason.
 struct DevState {
+  // ---- hot block 1: pose, schedule, constants
   float R[9], T[3];         // current T_target_to_source blocks (column-major R)
   float Rinv[9], Tinv[3];   // update_tf output; Rinv/Tinv are also the final transform
   float ell;
@@ -66,12 +73,23 @@ struct DevState {
   int max_iter;
   int controller_on;        // 1: align loop; 0: single iterate() call (queues/ell/cap untouched);
                             // 2: fixed-state timing loop (pose restored, runs to max_iter)
-  // flow
+  float ymax2_bound;        // upper bound of max_j |y'_j - c|^2 for the CURRENT Rinv/Tinv
+  float smax;               // upper bound of sigma_max(Rinv) (scales block radii)
+  float grid_slack;         // absolute slack [m] of a cell query in the target's own frame
+  int prune_on;             // this run may use the Morton view
+  int view;                 // target view of the CURRENT iteration: 0 Morton (pruned), 1 original
+  int pad_hot;
+  KernConsts kc;
+  // ---- hot block 2: flow result = step kernel input
   float omega[3], v[3];
+  float W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];  // omega_hat powers (CvoGPU.cu:970-980)
+  // ---- the rest
   double omega_sum[3], v_sum[3];
   double a_sum;
   unsigned long long nnz;
   unsigned int max_row_nnz;
+  int last_grid;            // the LAST executed iteration used cell queries (Morton index space)
+  int last_view;            // view the LAST executed iteration used (its ELL matrix is in that index space)
   // step
   double B, C, D, E;
   float step;
@@ -85,16 +103,9 @@ struct DevState {
   unsigned int work_counter;
   unsigned int flow_blocks_done;
   unsigned int step_blocks_done;
-  float ymax2_bound;        // upper bound of max_j |y'_j - c|^2 for the CURRENT Rinv/Tinv
-  float smax;               // upper bound of sigma_max(Rinv) (scales block radii)
-  int prune_on;             // this run may use the Morton view
-  int view;                 // target view of the CURRENT iteration: 0 Morton (pruned), 1 original
-  int last_view;            // view the LAST executed iteration used (its ELL matrix is in that index space)
   unsigned int n_sat;       // view 0: rows that reached their cap (redone exactly by the flow tail)
   unsigned int n_capped;    // view 1: rows that reached their cap (keeps the run on view 1)
-  // constants and per-iteration matrices shared by all threads
-  KernConsts kc;
-  float W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];  // omega_hat powers (CvoGPU.cu:970-980)
+  unsigned int sat_total;   // running sum of n_sat + n_capped over the iterations (host policy)
   // trace
   cvo_b200_iter_trace* trace;
   int trace_cap;
@@ -103,6 +114,22 @@ struct DevState {
   double local_flow[9];     // omega[3], v[3], a_sum, (double)nnz, (double)max_row_nnz
   double local_step[4];
   unsigned long long dbg[16];  // %globaltimer stamps of the tails (tools/gpu_tails.py)
+};
+constexpr int kHot1Words = (int)(offsetof(DevState, omega) / 4);
+constexpr int kHot2Words = (int)((offsetof(DevState, omega_sum) - offsetof(DevState, omega)) / 4);
+
+
+// Cell index of the target cloud in its OWN frame (built once per upload; a rigid motion of the
+// target does not invalidate it: source rows are mapped INTO that frame to query it).
+// The Morton-ordered target (view 0) is a linear octree: every cube cell of every level is a
+// contiguous range of the sorted 63-bit keys.
+struct GridView {
+  const unsigned long long* keys;  // [M] sorted Morton keys (non-finite points: ~0, at the end)
+  const uint32_t* coarse;          // [2^(3*cbits) + 1] lower bound of each coarse cell's keys
+  int cbits;                       // bits per axis of the coarse table
+  int n_finite;                    // points with a finite key
+  float lo[3];                     // origin of the key lattice
+  float scale;                     // lattice units per metre ((2^21 - 1) / extent)
 };
 
 struct TargetView {
@@ -157,6 +184,9 @@ struct IterArgs {
   // kernel variant
   int mode;        // 0 isotropic (fill_in_A_mat_gpu), 1 Mahalanobis (.._dense_mat_kernel)
   float kinv[9];   // column-major inverse kernel for mode 1
+  unsigned long long* stamps;  // debug (CVO_B200_STAMPS=1): [blocks][8] %globaltimer of block phases
+  int grid;        // 1: candidates come from cell queries (flow_kernel<true>; no prep/pair launch)
+  GridView gv;
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective
   int n_items;     // pair-kernel work items = row_tiles * nchunks
 };

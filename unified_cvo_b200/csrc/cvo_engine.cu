@@ -30,6 +30,7 @@ void launch_init_bound(const IterArgs& A, cudaStream_t s);
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s);
 int pair_kernel_max_blocks_per_sm();
 int sparse_kernel_max_blocks_per_sm();
+int grid_kernel_max_blocks_per_sm();
 }  // namespace cvo_b200
 
 using namespace cvo_b200;
@@ -119,6 +120,15 @@ struct CloudDev {
   DevBuf<float> tile_maxdist;
   DevBuf<int> inv;             // original index -> Morton position (device)
   std::vector<int> perm;       // Morton position -> original index (host, for exports)
+  // cell index over the Morton order (target role, grid mode): see GridView
+  DevBuf<unsigned long long> keys;
+  DevBuf<uint32_t> coarse;
+  int cbits = 0, n_finite = 0;
+  float lo[3] = {0, 0, 0};
+  float key_scale = 0;         // lattice units per metre
+  double extent = 0;           // edge of the key lattice's cube [m]
+  double occupied_volume = 0;  // volume of the occupied coarse cells [m^3] (density estimate)
+  float max_dist = 0;          // max_i |x_i| (largest range-scaled length-scale, source role)
   int Fp = 0, Cp = 0;   // strides the buffers were packed with
   float cx = 0, cy = 0, cz = 0;  // centroid (float)
   float radius = 0;              // max_i |x_i - centroid| (rounded up)
@@ -148,14 +158,18 @@ struct cvo_b200_handle {
   DevBuf<float2> zeros_g;   // stand-in for absent geometric types
   DevBuf<cvo_b200_iter_trace> d_trace;
   DevBuf<double> gathered;  // multi-GPU all-gather receive buffer
+  DevBuf<unsigned long long> stamps;  // debug: per-block phase stamps (CVO_B200_STAMPS=1)
   int row_begin = 0, row_end = -1;
   // launch geometry
   int prep_blocks = 1, pair_blocks = 1, sparse_blocks = 1;
-  // graph cache for the align loop
-  cudaGraphExec_t graph_exec = nullptr;
-  IterArgs graph_args;
-  int graph_batch = 0;
+  // graph cache for the align loop: [0] dense scan (prep, pair, flow, step), [1] cell queries
+  // (flow, step)
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  IterArgs graph_args[2];
+  int graph_batch[2] = {0, 0};
   bool use_graph = true;
+  int grid_blocks = 1;
+  int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries
   // host poll buffer (pinned)
   int* h_poll = nullptr;
   // comm
@@ -254,8 +268,12 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   const int rows_per_block = warps_per_block * 4;
   h->sparse_blocks =
       std::max(1, std::min(h->num_sms * socc, (n_rows + rows_per_block - 1) / rows_per_block));
-  CVO_CUDA(h, h->flow_part.ensure((size_t)h->sparse_blocks));
-  CVO_CUDA(h, h->step_part.ensure((size_t)h->sparse_blocks));
+  int gocc = grid_kernel_max_blocks_per_sm();
+  if (gocc < 1) gocc = 1;
+  h->grid_blocks =
+      std::max(1, std::min(h->num_sms * gocc, (n_rows + rows_per_block - 1) / rows_per_block));
+  CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, h->grid_blocks)));
+  CVO_CUDA(h, h->step_part.ensure((size_t)std::max(h->sparse_blocks, h->grid_blocks)));
 
   std::memset(&A, 0, sizeof(A));
   A.params = h->d_params;
@@ -311,6 +329,18 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
     for (int k = 0; k < 9; k++) A.kinv[k] = kinv[k];
   A.world = sharded ? h->world : 1;
   A.n_items = n_items;
+  A.stamps = nullptr;
+  if (getenv("CVO_B200_STAMPS")) {
+    CVO_CUDA(h, h->stamps.ensure((size_t)8 * 4096));
+    A.stamps = h->stamps.p;
+  }
+  A.grid = 0;
+  A.gv.keys = ct.keys.p;
+  A.gv.coarse = ct.coarse.p;
+  A.gv.cbits = ct.cbits;
+  A.gv.n_finite = ct.n_finite;
+  A.gv.lo[0] = ct.lo[0]; A.gv.lo[1] = ct.lo[1]; A.gv.lo[2] = ct.lo[2];
+  A.gv.scale = ct.key_scale;
   if (h->world > 1) CVO_CUDA(h, h->gathered.ensure((size_t)h->world * 16));
   return CVO_B200_OK;
 }
@@ -322,12 +352,20 @@ int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEven
   // CVO_B200_DEBUG_SKIP (bit mask 1 prep, 2 pair, 4 flow, 8 step): measurement aid only — the
   // marginal cost of one kernel inside the real pipeline; results are meaningless when set
   static const int skip = getenv("CVO_B200_DEBUG_SKIP") ? atoi(getenv("CVO_B200_DEBUG_SKIP")) : 0;
-  if (!(skip & 1)) launch_prep(A, h->prep_blocks, s);
-  if (pair_begin) cudaEventRecord(pair_begin, s);
-  if (!(skip & 2)) launch_pair(A, h->pair_blocks, s);
-  if (pair_end) cudaEventRecord(pair_end, s);
-  if (!(skip & 4)) launch_flow(A, h->sparse_blocks, s);
-  h->launches += 3;
+  const int sparse_blocks = A.grid ? h->grid_blocks : h->sparse_blocks;
+  if (A.grid) {  // cell queries: no O(M) prep, no O(N*M) scan
+    if (pair_begin) cudaEventRecord(pair_begin, s);
+    if (!(skip & 4)) launch_flow(A, sparse_blocks, s);
+    if (pair_end) cudaEventRecord(pair_end, s);
+    h->launches += 1;
+  } else {
+    if (!(skip & 1)) launch_prep(A, h->prep_blocks, s);
+    if (pair_begin) cudaEventRecord(pair_begin, s);
+    if (!(skip & 2)) launch_pair(A, h->pair_blocks, s);
+    if (pair_end) cudaEventRecord(pair_end, s);
+    if (!(skip & 4)) launch_flow(A, h->sparse_blocks, s);
+    h->launches += 3;
+  }
   if (A.world > 1) {
     DevState* st = h->d_state;
     int rc = g_nccl.AllGather(&st->local_flow[0], h->gathered.p, 9, kNcclFloat64, h->comm, s);
@@ -336,7 +374,7 @@ int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEven
     h->launches += 1;
   }
   if (stage >= 3 && !(skip & 8)) {
-    launch_step(A, h->sparse_blocks, s);
+    launch_step(A, sparse_blocks, s);
     h->launches += 1;
     if (A.world > 1) {
       DevState* st = h->d_state;
@@ -380,6 +418,9 @@ KernConsts make_consts(const cvo_b200_params& p) {
   k.use_geometry = p.is_using_geometry;
   k.use_intensity = p.is_using_intensity;
   k.use_semantics = p.is_using_semantics;
+  k.use_range_ell = p.is_using_range_ell;
+  k.c_div = p.c;
+  k.d_div = p.d;
   volatile float q_geo = p.sp_thres / sigma2;
   k.log_geo = logf(q_geo);
   k.d2_c_thres = 1.f;
@@ -429,18 +470,23 @@ void split_pose(const float T16[16], float R[9], float T[3]) {
 }
 
 void destroy_graph(cvo_b200_handle* h) {
-  if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
-  h->graph_exec = nullptr;
-  h->graph_batch = 0;
+  for (int m = 0; m < 2; m++) {
+    if (h->graph_exec[m]) cudaGraphExecDestroy(h->graph_exec[m]);
+    h->graph_exec[m] = nullptr;
+    h->graph_batch[m] = 0;
+  }
 }
 
 // Capture `batch` iterations into one graph.  All per-iteration values (pose, ell, cap,
 // flags) live in DevState, so the graph is parameter-free and is rebuilt only when the
 // buffers or the decomposition change.
 int ensure_graph(cvo_b200_handle* h, const IterArgs& A, int batch) {
-  if (h->graph_exec && h->graph_batch == batch && std::memcmp(&h->graph_args, &A, sizeof(A)) == 0)
+  const int m = A.grid ? 1 : 0;
+  if (h->graph_exec[m] && h->graph_batch[m] == batch && std::memcmp(&h->graph_args[m], &A, sizeof(A)) == 0)
     return CVO_B200_OK;
-  destroy_graph(h);
+  if (h->graph_exec[m]) cudaGraphExecDestroy(h->graph_exec[m]);
+  h->graph_exec[m] = nullptr;
+  h->graph_batch[m] = 0;
   cudaGraph_t graph = nullptr;
   CVO_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   const uint64_t before = h->launches;
@@ -453,18 +499,42 @@ int ensure_graph(cvo_b200_handle* h, const IterArgs& A, int batch) {
     return rc;
   }
   if (e != cudaSuccess) return fail(h, CVO_B200_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
-  e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+  e = cudaGraphInstantiate(&h->graph_exec[m], graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) {
-    h->graph_exec = nullptr;
+    h->graph_exec[m] = nullptr;
     return fail(h, CVO_B200_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
   }
-  h->graph_args = A;
-  h->graph_batch = batch;
+  h->graph_args[m] = A;
+  h->graph_batch[m] = batch;
   return CVO_B200_OK;
 }
 
-int launches_per_iteration(const cvo_b200_handle* h) { return h->world > 1 ? 6 : 4; }
+int launches_per_iteration(const cvo_b200_handle* h, const IterArgs& A) {
+  return (A.grid ? 2 : 4) + (h->world > 1 ? 2 : 0);
+}
+
+// Candidate-generator policy.  A cell query tests, per source row, the points of <= 27 cube cells
+// of edge h in [r, 2r) (r = largest cut-off radius of the cloud, CvoGPU.cu:506-511); the dense
+// scan tests M points per row at ~1/6 of the per-test cost.  Cell queries win while the expected
+// tests per row stay below ~M/8.  The density comes from the occupied coarse cells, so
+// slab- or surface-like clouds are not mistaken for sparse ones.
+bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDev& ct, float ell) {
+  const cvo_b200_params& p = h->params;
+  if (!p.is_using_geometry) return false;  // no geometric cut-off: every pair is a candidate
+  if (h->force_mode >= 0) return h->force_mode == 1;
+  if (ct.n_finite == 0 || !(ct.occupied_volume > 0.0)) return false;
+  const double lmax = ((double)cs.max_dist / 500.0 + 1.0) * (double)ell;
+  const double q = (double)p.sp_thres / ((double)p.sigma * (double)p.sigma);
+  if (!(q > 0.0) || !(q < 1.0)) return !(q > 0.0) ? false : true;  // q >= 1: nothing survives
+  const double r = lmax * std::sqrt(-2.0 * std::log(q));
+  if (!(r > 0.0) || !std::isfinite(r)) return false;
+  double hcell = ct.extent;
+  while (hcell * 0.5 >= r && hcell > ct.extent / 2097152.0) hcell *= 0.5;  // finest level with h >= r
+  const double density = (double)ct.n_finite / ct.occupied_volume;
+  const double tests = std::min((double)ct.n, 27.0 * hcell * hcell * hcell * density);
+  return tests < 0.125 * (double)ct.n;
+}
 
 // 63-bit Morton key of a point inside the cloud's bounding box (21 bits per axis)
 inline uint64_t spread21(uint64_t v) {
@@ -499,6 +569,8 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
   c.has_geo = geotype != nullptr;
   c.set = true;
   c.perm.resize((size_t)n);
+  c.max_dist = 0.f;
+  c.n_finite = 0;
   if (n == 0) return CVO_B200_OK;
 
   // ---- bounding box, centroid (finite points only)
@@ -537,6 +609,33 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
     }
     std::sort(keys.begin(), keys.end());
     for (int i = 0; i < n; i++) c.perm[i] = keys[i].second;
+    // ---- cell index: sorted keys + lower bounds of a coarse level (~1 point per cell on
+    //      a slab-like cloud, 4..7 bits per axis: <= 8 MB) so the search inside a coarse
+    //      cell is 0..2 steps
+    std::vector<unsigned long long> skeys((size_t)n);
+    for (int i = 0; i < n; i++) skeys[i] = keys[i].first;
+    c.n_finite = (int)n_finite;
+    int cb = 4;
+    while (cb < 7 && ((size_t)1 << (3 * cb)) < (size_t)16 * (size_t)n) cb++;
+    c.cbits = cb;
+    const int csh = 3 * (21 - cb);
+    const size_t ncell = (size_t)1 << (3 * cb);
+    std::vector<uint32_t> coarse(ncell + 1);
+    size_t pos = 0, occupied = 0;
+    for (size_t cell = 0; cell < ncell; cell++) {
+      while (pos < n_finite && (skeys[pos] >> csh) < cell) pos++;
+      coarse[cell] = (uint32_t)pos;
+      if (pos < n_finite && (skeys[pos] >> csh) == cell) occupied++;
+    }
+    coarse[ncell] = (uint32_t)n_finite;
+    c.lo[0] = lo[0]; c.lo[1] = lo[1]; c.lo[2] = lo[2];
+    c.key_scale = (float)scale;
+    c.extent = ext;
+    const double hc = ext / (double)(1 << cb);
+    c.occupied_volume = (double)occupied * hc * hc * hc;
+    int rck = upload_vec(h, c.keys, skeys);
+    if (rck == CVO_B200_OK) rck = upload_vec(h, c.coarse, coarse);
+    if (rck != CVO_B200_OK) return rck;
   }
   const std::vector<int>& perm = c.perm;
   {
@@ -565,6 +664,7 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
     volatile float xx = x * x, yy = y * y, zz = z * z;
     volatile float sxy = xx + yy;
     const float dist = sqrtf(sxy + zz);
+    if (dist > c.max_dist) c.max_dist = dist;
     recA[s] = make_float4(-2.f * (x - c.cx), -2.f * (y - c.cy), -2.f * (z - c.cz), dist);
   }
   int rc;
@@ -643,18 +743,24 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
 }
 
 // Runs the device-resident loop to completion.  Returns when DevState.done is set.
-int run_loop(cvo_b200_handle* h, const IterArgs& A, int max_iter) {
+// The candidate generator (dense scan / cell queries) is chosen per batch of iterations from the
+// polled device state; it never changes a result, only the cost of an iteration.
+int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0) {
   const int batch = 32;
   int rc;
-  if (h->use_graph) {
-    rc = ensure_graph(h, A, batch);
-    if (rc != CVO_B200_OK) return rc;
-  }
   int launched_iters = 0;
+  float ell = ell0;
+  unsigned int sat_seen = 0;
+  bool sat_recent = false;
   while (true) {
+    // rows that reach their cap are redone exhaustively (O(M) each) by one block in the
+    // Morton-ordered modes: leave cell queries while that happens a lot
+    A.grid = (grid_profitable(h, h->src, h->tgt, ell) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
     if (h->use_graph) {
-      CVO_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
-      h->launches += (uint64_t)batch * launches_per_iteration(h);
+      rc = ensure_graph(h, A, batch);
+      if (rc != CVO_B200_OK) return rc;
+      CVO_CUDA(h, cudaGraphLaunch(h->graph_exec[A.grid ? 1 : 0], h->stream));
+      h->launches += (uint64_t)batch * launches_per_iteration(h, A);
     } else {
       for (int b = 0; b < batch; b++) {
         rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
@@ -662,9 +768,17 @@ int run_loop(cvo_b200_handle* h, const IterArgs& A, int max_iter) {
       }
     }
     launched_iters += batch;
+    // iter, done, ret, stop_reason | ell | sat_total
     CVO_CUDA(h, cudaMemcpyAsync(h->h_poll, &h->d_state->iter, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CVO_CUDA(h, cudaMemcpyAsync(h->h_poll + 4, &h->d_state->ell, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CVO_CUDA(h, cudaMemcpyAsync(h->h_poll + 5, &h->d_state->sat_total, sizeof(unsigned int), cudaMemcpyDeviceToHost, h->stream));
     CVO_CUDA(h, cudaStreamSynchronize(h->stream));
     if (h->h_poll[1] /*done*/) break;
+    std::memcpy(&ell, h->h_poll + 4, sizeof(float));
+    unsigned int sat_now;
+    std::memcpy(&sat_now, h->h_poll + 5, sizeof(unsigned int));
+    sat_recent = (sat_now - sat_seen) > 16u * (unsigned)batch;
+    sat_seen = sat_now;
     if (launched_iters > max_iter + batch) return fail(h, CVO_B200_ERR_STATE, "align loop did not terminate");
   }
   return CVO_B200_OK;
@@ -732,6 +846,9 @@ int cvo_b200_create(const cvo_b200_params* p, int device, cvo_b200_handle** out)
   cudaMemset(h->d_state, 0, sizeof(DevState));
   const char* ng = getenv("CVO_B200_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
+  const char* fm = getenv("CVO_B200_MODE");  // dense | grid (anything else: automatic)
+  if (fm && std::strcmp(fm, "dense") == 0) h->force_mode = 0;
+  if (fm && std::strcmp(fm, "grid") == 0) h->force_mode = 1;
   *out = h;
   return CVO_B200_OK;
 }
@@ -746,12 +863,13 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
     c->xyz.release(); c->rowA.release(); c->feat.release(); c->lab.release(); c->geo.release();
     c->xyz_o.release(); c->feat_o.release(); c->lab_o.release(); c->geo_o.release();
     c->blk_sphere.release(); c->tile_sphere.release(); c->tile_maxdist.release(); c->inv.release();
+    c->keys.release(); c->coarse.release();
   }
   h->tgt_moved.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
   h->rowrec.release(); h->row_lt.release(); h->sat_list.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
-  h->zeros_g.release(); h->d_trace.release(); h->gathered.release();
+  h->zeros_g.release(); h->d_trace.release(); h->gathered.release(); h->stamps.release();
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_state) cudaFree(h->d_state);
   if (h->h_poll) cudaFreeHost(h->h_poll);
@@ -802,6 +920,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) return fail(h, CVO_B200_ERR_INVALID, "num_neighbors exceeds nearest_neighbors_max");
   CVO_CUDA(h, h->d_trace.ensure(1));
+  A.grid = grid_profitable(h, h->src, h->tgt, ell) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
   rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
@@ -849,12 +968,14 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   cudaEvent_t ev0, ev1;
   CVO_CUDA(h, cudaEventCreate(&ev0));
   CVO_CUDA(h, cudaEventCreate(&ev1));
-  if (h->use_graph) {
-    rc = ensure_graph(h, A, 32);
+  if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
+    IterArgs Ag = A;
+    Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init) ? 1 : 0;
+    rc = ensure_graph(h, Ag, 32);
     if (rc != CVO_B200_OK) return rc;
   }
   cudaEventRecord(ev0, h->stream);
-  rc = run_loop(h, A, max_iter);
+  rc = run_loop(h, A, max_iter, h->params.ell_init);
   cudaEventRecord(ev1, h->stream);
   if (rc != CVO_B200_OK) {
     cudaEventDestroy(ev0);
@@ -885,7 +1006,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
     info->pairs_tested = (uint64_t)h->src.n * (uint64_t)h->tgt.n * (uint64_t)executed;
   }
   h->last_valid = true;
-  h->last_view = hs.last_view;
+  h->last_view = hs.last_grid ? 0 : hs.last_view;
   h->last_args = A;
   if (trace_cap > 0) {
     const int nrec = std::min(trace_cap, executed);
@@ -1115,6 +1236,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   if (rc != CVO_B200_OK) return rc;
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) num_neighbors = A.cap_max;
+  A.grid = grid_profitable(h, h->src, h->tgt, ell) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
   const int n_ev = ms_pair_kernel ? iters : 0;
@@ -1158,6 +1280,21 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
             (long long)(d[13] - d[6]), (long long)(d[14] - d[6]), (long long)(d[15] - d[6]), (long long)(d[7] - d[6]));
     fprintf(stderr, "[tails] flow reduce: loads done %+lld shuffles done %+lld smem done %+lld (ns after tail_begin)\n",
             (long long)(d[10] - d[1]), (long long)(d[11] - d[1]), (long long)(d[12] - d[1]));
+  }
+  if (A.stamps) {  // per-block phase stamps of the LAST flow launch (ns, relative to the first block)
+    const int nb = A.grid ? h->grid_blocks : h->sparse_blocks;
+    std::vector<unsigned long long> st8((size_t)8 * nb);
+    cudaMemcpy(st8.data(), A.stamps, st8.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int b = 0; b < nb; b++) t0 = std::min(t0, st8[8 * (size_t)b]);
+    const char* names[6] = {"entry", "hot loaded", "rows done", "partial written", "fence done", "atomic done"};
+    for (int k = 0; k < 6; k++) {
+      std::vector<long long> v;
+      for (int b = 0; b < nb; b++) v.push_back((long long)(st8[8 * (size_t)b + k] - t0));
+      std::sort(v.begin(), v.end());
+      fprintf(stderr, "[stamps] %-16s min %6lld  p50 %6lld  p90 %6lld  max %6lld ns\n", names[k], v[0],
+              v[v.size() / 2], v[v.size() * 9 / 10], v.back());
+    }
   }
   if (ms_total) *ms_total = ms;
   if (ms_pair_kernel) *ms_pair_kernel = msp;

@@ -395,6 +395,11 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
 }
 
 // ================================================================== exact pair arithmetic
+// The reference's device exp(double) (CvoGPU.cu:552,567,580).  One out-of-line copy: the
+// sparse kernels inline eval_pair at several call sites and each holds three exps; inlined,
+// the kernels grow past 200 KB of SASS and stall on instruction fetch.
+__device__ __noinline__ double exp_ref(double x) { return exp(x); }
+
 struct RowCtx {
   float px[3];
   float l;          // range-scaled length-scale of this row
@@ -428,7 +433,7 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       const float dx = pb.x - rc.px[0], dy = pb.y - rc.px[1], dz = pb.z - rc.px[2];
       const float d2 = dx * dx + dy * dy + dz * dz;
       if (d2 < rc.d2_thres)
-        k = kc.sigma2 * exp(-d2 / (2.0 * rc.l * rc.l));
+        k = kc.sigma2 * exp_ref(-d2 / (2.0 * rc.l * rc.l));
       else
         return false;
     } else {
@@ -439,7 +444,7 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
         row[c] = sum3f(dist[0] * A.kinv[3 * c], dist[1] * A.kinv[3 * c + 1],
                        dist[2] * A.kinv[3 * c + 2]);
       const float d2 = dot3f(row, dist);
-      k = kc.sigma2 * exp(-d2 / 2.0);
+      k = kc.sigma2 * exp_ref(-d2 / 2.0);
     }
   }
   if (kc.use_intensity) {
@@ -459,7 +464,7 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       d2_color += tmp * tmp;
     }
     if (d2_color < kc.d2_c_thres)
-      ck = kc.c_sigma2 * exp(-d2_color / (2.0 * kc.c2));
+      ck = kc.c_sigma2 * exp_ref(-d2_color / (2.0 * kc.c2));
     else
       return false;
   }
@@ -482,9 +487,9 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
     const float thr = (A.mode == 1) ? kc.d2_s_thres_dense : kc.d2_s_thres;
     if (d2_semantic < thr) {
       if (A.mode == 1)
-        sk = kc.s_sigma2 * exp(-d2_semantic / (2.0 * kc.s_ell_square));
+        sk = kc.s_sigma2 * exp_ref(-d2_semantic / (2.0 * kc.s_ell_square));
       else
-        sk = kc.s_sigma2 * exp(-d2_semantic / (2.0 * kc.s_ell * kc.s_ell));
+        sk = kc.s_sigma2 * exp_ref(-d2_semantic / (2.0 * kc.s_ell * kc.s_ell));
     } else
       return false;
   }
@@ -585,7 +590,78 @@ __device__ void block_reduce_partials(const double* __restrict__ part, int npart
   }
 }
 
+// ================================================================== cell queries (grid mode)
+// y' = Rinv*y + Tinv with the arithmetic of prep_kernel (CvoGPU_impl.cu:46-50): grid mode has no
+// prep launch, every consumer of a moved target point recomputes it from the static cloud.
+__device__ __forceinline__ float4 move_point(const float* Ri, const float* Ti, const float4 y) {
+  const float yv[3] = {y.x, y.y, y.z};
+  float r[3];
+  mat3f_vec(Ri, yv, r);
+  return make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], 0.f);
+}
+// 21 bits -> every third bit (the host's spread21, cvo_engine.cu)
+__device__ __forceinline__ unsigned long long spread21_dev(unsigned int a) {
+  unsigned long long v = a & 0x1fffffull;
+  v = (v | (v << 32)) & 0x1f00000000ffffull;
+  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+// Ranges [start, start+len) of the Morton-ordered target covered by two cube cells of edge
+// 2^lvl lattice units with first keys k0, k1 (v0/v1: the lane has such a cell).  A cell's keys
+// are [k, k + 8^lvl).  Each of the four bounds is one coarse-table lookup plus a binary search
+// inside that coarse cell (a handful of points); the four searches advance together so that
+// their loads overlap: the dependent-load chain, not the arithmetic, is what a query costs.
+__device__ __forceinline__ void cell_ranges2(const GridView& G, int lvl3, bool v0,
+                                             unsigned long long k0, bool v1, unsigned long long k1,
+                                             uint32_t& s0, uint32_t& l0, uint32_t& s1, uint32_t& l1) {
+  const int csh = 3 * (21 - G.cbits);
+  const unsigned long long ncoarse = 1ull << (3 * G.cbits);
+  unsigned long long key[4] = {k0, k0 + (1ull << lvl3), k1, k1 + (1ull << lvl3)};
+  uint32_t lo[4], hi[4];
+#pragma unroll
+  for (int t = 0; t < 4; t++) {
+    const bool v = (t < 2) ? v0 : v1;
+    const unsigned long long c = key[t] >> csh;
+    lo[t] = hi[t] = 0u;
+    if (v) {
+      if (c >= ncoarse) {
+        lo[t] = hi[t] = (uint32_t)G.n_finite;  // past the last cell (key 2^63)
+      } else {
+        lo[t] = __ldg(G.coarse + c);
+        hi[t] = ((c << csh) == key[t]) ? lo[t] : __ldg(G.coarse + c + 1);  // first key of a coarse cell
+      }
+    }
+  }
+  while ((lo[0] < hi[0]) | (lo[1] < hi[1]) | (lo[2] < hi[2]) | (lo[3] < hi[3])) {
+    uint32_t mid[4];
+    unsigned long long km[4];
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      mid[t] = (lo[t] + hi[t]) >> 1;
+      km[t] = (lo[t] < hi[t]) ? __ldg(G.keys + mid[t]) : 0ull;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      if (lo[t] < hi[t]) {
+        if (km[t] < key[t]) lo[t] = mid[t] + 1; else hi[t] = mid[t];
+      }
+    }
+  }
+  s0 = lo[0]; l0 = lo[1] - lo[0];
+  s1 = lo[2]; l1 = lo[3] - lo[2];
+}
+
 // ================================================================== flow_kernel
+// Two candidate generators feed the same exact per-pair arithmetic:
+//   kGrid = false  the ordered candidate cells written by pair_kernel (dense scan);
+//   kGrid = true   cell queries: the source row is mapped into the target's own frame
+//                  (q = R x + T), the cube cells of the target's linear octree that the ball
+//                  |y - q| <= r_i touches (<= 3 per axis, level chosen per row) are looked up as
+//                  contiguous ranges of the Morton-ordered target, and every point of those
+//                  ranges gets the exact test.  Nothing of the iteration is O(N*M) then.
 // Eight lanes per source row (four rows per warp): candidates are ~10 per row in tracking
 // regimes, so a full warp per row would idle two thirds of its lanes and quadruple the
 // per-row bookkeeping.  Every group walks its row's candidate cells in target order, expands
@@ -594,13 +670,25 @@ constexpr int kGroup = 8;                    // lanes per source row
 constexpr int kRowsPerWarp = 32 / kGroup;    // 4
 constexpr int kGroupList = 80;               // pending (<8) + one batch of 8 words (<=64)
 
-__global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
+template <bool kGrid>
+__global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
   DevState* st = A.st;
-  if (st->done) return;
-  const int view = st->view;
   __shared__ double sh[kSparseThreads * 9];
+  __shared__ uint32_t s_hot[kHot1Words];  // pose, schedule, constants: one cooperative load
   __shared__ uint32_t s_list[kSparseThreads / kGroup][kGroupList];
   __shared__ bool is_last;
+  unsigned long long* stamp = (A.stamps && threadIdx.x == 0) ? A.stamps + 8 * (size_t)blockIdx.x : nullptr;
+  if (stamp) stamp[0] = gtime();
+  for (int i = threadIdx.x; i < kHot1Words; i += blockDim.x)
+    s_hot[i] = __ldcg(reinterpret_cast<const uint32_t*>(st) + i);
+  __syncthreads();
+  const DevState* hs = reinterpret_cast<const DevState*>(s_hot);
+  if (hs->done) return;
+  if (stamp) stamp[1] = gtime();
+  const int view = kGrid ? 0 : hs->view;  // cell queries index the Morton-ordered target
+  const float* s_pose = hs->Rinv;          // Rinv[9], Tinv[3] are contiguous
+  const float ell_now = hs->ell;
+  const float g_smax = hs->smax, g_slack = hs->grid_slack;
 
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -609,9 +697,14 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
   const int gl = lane & 7;          // lane inside the group
   const int gshift = g * kGroup;
   const unsigned lt8 = (1u << gl) - 1u;
-  const KernConsts kc = st->kc;
-  const int cap = st->num_neighbors;
-  const float c_div = A.params->c, d_div = A.params->d;  // divisors (CvoGPU.cu:785-788)
+  const KernConsts& kc = hs->kc;
+  const int cap = hs->num_neighbors;
+  // Cell queries visit a row's candidates in Morton order, so a row that was cut at its cap
+  // holds the wrong survivors and is redone in original target order by the tail.  Counting one
+  // survivor PAST the cap tells a complete row with exactly `cap` survivors (nothing to redo;
+  // common when the cap has adapted down to 1.2 * max row count = a handful) from a cut one.
+  const int cap_stop = kGrid ? cap + 1 : cap;
+  const float c_div = kc.c_div, d_div = kc.d_div;  // divisors (CvoGPU.cu:785-788)
   const int L = A.L;
   uint32_t* list = s_list[threadIdx.x >> 3];
   const int nch = A.nchunks;
@@ -629,10 +722,15 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
     RowCtx rc;
     {
       const float4 pa = A.src_xyz[ig];
-      const float2 lt = A.row_lt[rvalid ? row : 0];
       rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
-      rc.l = lt.x;
-      rc.d2_thres = lt.y;
+      if (kGrid) {  // what prep_kernel writes to row_lt (CvoGPU.cu:506-511)
+        rc.l = range_ell(ell_now, A.src_rowA[ig].w);
+        rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
+      } else {
+        const float2 lt = A.row_lt[rvalid ? row : 0];
+        rc.l = lt.x;
+        rc.d2_thres = lt.y;
+      }
       rc.ga[0] = rc.ga[1] = 0.f;
       if (kc.use_geo_type) {
         const float2 gg = A.src_geo[ig];
@@ -654,7 +752,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
       bool surv = false;
       if (valid) {
-        pb = A.tgt_moved[j];
+        pb = kGrid ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
         surv = eval_pair(A, kc, rc, ig, view, j, pb, a);
       }
       const unsigned bits = (__ballot_sync(0xffffffffu, surv) >> gshift) & 0xffu;
@@ -673,13 +771,13 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
         }
         asum += (double)a;
       }
-      count = min(cap, count + __popc(bits));
+      count = min(cap_stop, count + __popc(bits));
     };
     // drain the list while some group holds at least `need` pending candidates
     auto drain = [&](int need) {
       int head = 0;
       while (true) {
-        const bool go = (nlist - head) >= need && (nlist - head) > 0 && count < cap;
+        const bool go = (nlist - head) >= need && (nlist - head) > 0 && count < cap_stop;
         if (!__any_sync(0xffffffffu, go)) break;
         const bool v = go && (head + gl) < nlist;
         consume8(v, v ? (int)list[head + gl] : 0);
@@ -691,7 +789,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       if (gl < rest) keep = list[head + gl];
       __syncwarp();
       if (gl < rest) list[gl] = keep;
-      nlist = (count < cap) ? rest : 0;
+      nlist = (count < cap_stop) ? rest : 0;
       __syncwarp();
     };
     // append the candidates of one word per lane (ascending target order) to the list
@@ -717,6 +815,124 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       __syncwarp();
     };
 
+    if constexpr (kGrid) {
+      // ---- the cube cells of the target's octree that the ball around q = R x + T touches
+      const GridView& G = A.gv;
+      int nx = 0, ny = 0, ncell = 0, lvl = 0;
+      unsigned long long kx0 = 0, ky0 = 0, kz0 = 0;  // dilated coordinates of the first cell
+      const unsigned long long mx = 0x1249249249249249ull;
+      if (rvalid && rc.d2_thres > 0.f && cap > 0) {
+        const float* Rf = hs->R;
+        const float* Tf = hs->T;
+        float q[3];
+        mat3f_vec(Rf, rc.px, q);
+        q[0] += Tf[0]; q[1] += Tf[1]; q[2] += Tf[2];
+        // |y - q| <= smax |y' - x| + slack (see update_tf_device); d2 < thres in float
+        const float rq = sqrtf(rc.d2_thres) * g_smax * 1.00001f + g_slack +
+                         2e-6f * (fabsf(rc.px[0]) + fabsf(rc.px[1]) + fabsf(rc.px[2]) + fabsf(q[0]) +
+                                  fabsf(q[1]) + fabsf(q[2]));
+        const float top = 2097151.f;
+        const float fx0 = (q[0] - rq - G.lo[0]) * G.scale, fx1 = (q[0] + rq - G.lo[0]) * G.scale;
+        const float fy0 = (q[1] - rq - G.lo[1]) * G.scale, fy1 = (q[1] + rq - G.lo[1]) * G.scale;
+        const float fz0 = (q[2] - rq - G.lo[2]) * G.scale, fz1 = (q[2] + rq - G.lo[2]) * G.scale;
+        // a NaN anywhere makes every comparison false: no candidates, like d2 < thres
+        const bool hit = fx1 >= -2.f && fy1 >= -2.f && fz1 >= -2.f && fx0 <= top + 2.f &&
+                         fy0 <= top + 2.f && fz0 <= top + 2.f;
+        if (hit) {
+          // one lattice unit of padding on both sides covers the float rounding of f*0/f*1
+          const int ix0 = (int)fminf(fmaxf(floorf(fx0) - 1.f, 0.f), top);
+          const int iy0 = (int)fminf(fmaxf(floorf(fy0) - 1.f, 0.f), top);
+          const int iz0 = (int)fminf(fmaxf(floorf(fz0) - 1.f, 0.f), top);
+          const int ix1 = (int)fminf(fmaxf(floorf(fx1) + 1.f, 0.f), top);
+          const int iy1 = (int)fminf(fmaxf(floorf(fy1) + 1.f, 0.f), top);
+          const int iz1 = (int)fminf(fmaxf(floorf(fz1) + 1.f, 0.f), top);
+          const int span = max(ix1 - ix0, max(iy1 - iy0, iz1 - iz0));
+          lvl = span <= 2 ? 0 : (31 - __clz(span)) - 1;
+          while (((ix1 >> lvl) - (ix0 >> lvl)) > 2 || ((iy1 >> lvl) - (iy0 >> lvl)) > 2 ||
+                 ((iz1 >> lvl) - (iz0 >> lvl)) > 2)
+            lvl++;
+          nx = (ix1 >> lvl) - (ix0 >> lvl) + 1;
+          ny = (iy1 >> lvl) - (iy0 >> lvl) + 1;
+          ncell = nx * ny * ((iz1 >> lvl) - (iz0 >> lvl) + 1);
+          kx0 = spread21_dev((unsigned)(ix0 >> lvl));
+          ky0 = spread21_dev((unsigned)(iy0 >> lvl));
+          kz0 = spread21_dev((unsigned)(iz0 >> lvl));
+        }
+      }
+      // first key of cell number `cell` (= cxi + nx (cyi + ny czi)) of the row's cell block
+      auto cell_key = [&](int cell) -> unsigned long long {
+        // nx, ny in {1,2,3}, cell < 27: divisions by table
+        const int t2 = nx == 1 ? cell : (nx == 2 ? (cell >> 1) : ((cell * 22) >> 6));
+        const int cxi = cell - t2 * nx;
+        const int czi = ny == 1 ? t2 : (ny == 2 ? (t2 >> 1) : ((t2 * 22) >> 6));
+        const int cyi = t2 - czi * ny;
+        // dilated increments ((k | ~mask) + 1) & mask instead of a bit spread per cell
+        unsigned long long sx = kx0, sy = ky0, sz = kz0;
+        if (cxi >= 1) sx = ((sx | ~mx) + 1ull) & mx;
+        if (cxi >= 2) sx = ((sx | ~mx) + 1ull) & mx;
+        if (cyi >= 1) sy = ((sy | ~mx) + 1ull) & mx;
+        if (cyi >= 2) sy = ((sy | ~mx) + 1ull) & mx;
+        if (czi >= 1) sz = ((sz | ~mx) + 1ull) & mx;
+        if (czi >= 2) sz = ((sz | ~mx) + 1ull) & mx;
+        return (sx | (sy << 1) | (sz << 2)) << (3 * lvl);
+      };
+      for (int cbase = 0;; cbase += 2 * kGroup) {
+        const bool wact = cbase < ncell && count < cap_stop;
+        if (!__any_sync(0xffffffffu, wact)) break;
+        // ---- two cells per lane: their ranges of the Morton-ordered target.  The order in
+        //      which a row's candidates are visited is free (a cut row is redone anyway).
+        uint32_t start0 = 0, len0 = 0, start1 = 0, len1 = 0;
+        {
+          const int c0 = cbase + gl, c1 = cbase + kGroup + gl;
+          const bool v0 = wact && c0 < ncell, v1 = wact && c1 < ncell;
+          cell_ranges2(G, 3 * lvl, v0, v0 ? cell_key(c0) : 0ull, v1, v1 ? cell_key(c1) : 0ull,
+                       start0, len0, start1, len1);
+        }
+        const uint32_t len = len0 + len1;
+        uint32_t incl = len;
+#pragma unroll
+        for (int o = 1; o < kGroup; o <<= 1) {
+          const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o, kGroup);
+          if (gl >= o) incl += t;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, kGroup - 1, kGroup);
+        const uint32_t excl = incl - len;
+        // ---- stage 1: the geometric cut alone on every point of the ranges (cheap); the
+        //      survivors are queued so that the full kernel (double exp, colour, semantics)
+        //      runs on packed lanes (stage 2 = drain -> consume8)
+        for (uint32_t wb = 0;; wb += kGroup) {
+          const bool bact = wb < total && count < cap_stop;
+          if (!__any_sync(0xffffffffu, bact)) break;
+          const uint32_t b = wb + gl;
+          const bool valid = bact && b < total;
+          int o = 0;  // owner lane = number of lanes whose inclusive count is <= b
+#pragma unroll
+          for (int stp = 4; stp > 0; stp >>= 1) {
+            const uint32_t e = __shfl_sync(0xffffffffu, incl, (o + stp - 1) & 7, kGroup);
+            if (e <= b) o += stp;
+          }
+          o = min(o, kGroup - 1);
+          const uint32_t oex = __shfl_sync(0xffffffffu, excl, o, kGroup);
+          const uint32_t ol0 = __shfl_sync(0xffffffffu, len0, o, kGroup);
+          const uint32_t os0 = __shfl_sync(0xffffffffu, start0, o, kGroup);
+          const uint32_t os1 = __shfl_sync(0xffffffffu, start1, o, kGroup);
+          const uint32_t rr = b - oex;
+          const int j = (int)(rr < ol0 ? os0 + rr : os1 + (rr - ol0));
+          bool pass = false;
+          if (valid) {
+            const float4 pb = move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]);
+            const float dx = pb.x - rc.px[0], dy = pb.y - rc.px[1], dz = pb.z - rc.px[2];
+            const float d2 = dx * dx + dy * dy + dz * dz;  // as eval_pair (gpu_utils.cuh:73-78)
+            pass = d2 < rc.d2_thres;
+          }
+          const unsigned bits = (__ballot_sync(0xffffffffu, pass) >> gshift) & 0xffu;
+          if (pass) list[nlist + __popc(bits & lt8)] = (uint32_t)j;
+          nlist += __popc(bits);
+          __syncwarp();
+          drain(kGroup);
+        }
+      }
+    } else {
     for (int cbase = 0;; cbase += 4 * kGroup) {
       const bool wact = rvalid && cbase < nch && count < cap;
       if (!__any_sync(0xffffffffu, wact)) break;
@@ -792,6 +1008,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
         }
       }
     }
+    }
     drain(1);  // whatever is still pending
     // ---- row epilogue: omega_i / c, v_i / d in float, then double (CvoGPU.cu:785-788)
 #pragma unroll
@@ -806,7 +1023,8 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
     // A row that reached its cap: in the Morton view it may hold the wrong survivors (the
     // reference keeps the first ones in ORIGINAL target order), so it is queued for the exact
     // redo in this kernel's tail and contributes nothing here.
-    const bool capped = rvalid && count >= cap;
+    const bool capped = rvalid && count >= cap_stop && !(kGrid && cap == 0);
+    count = min(count, cap);
     if (capped && gl == 0) {
       if (view == 0)
         A.sat_list[atomicAdd(&st->n_sat, 1u)] = (uint32_t)row;
@@ -825,6 +1043,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       w_max = fmax(w_max, (double)count);
     }
   }
+  if (stamp) stamp[2] = gtime();
   // ---- block partial: fixed xor tree over the four group leaders of a warp, then over warps
   double bp[9] = {w_om[0], w_om[1], w_om[2], w_v[0], w_v[1], w_v[2], w_asum, w_nnz, w_max};
 #pragma unroll
@@ -847,11 +1066,14 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
     reinterpret_cast<double*>(A.flow_part)[(size_t)k * gridDim.x + blockIdx.x] = r;
   }
   __syncthreads();
+  if (stamp) stamp[3] = gtime();
   if (threadIdx.x == 0) {
     __threadfence();  // release: this block's partial (written before the barrier above)
+    if (stamp) stamp[4] = gtime();
     const unsigned int prev = atomicAdd(&st->flow_blocks_done, 1u);
     is_last = (prev == gridDim.x - 1);
     if (is_last) __threadfence();  // acquire for the whole block (readers use ld.cg after the barrier)
+    if (stamp) stamp[5] = gtime();
   }
   __syncthreads();
   if (!is_last) return;
@@ -878,10 +1100,15 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel(IterArgs A) {
       RowCtx rc;
       {
         const float4 pa = A.src_xyz[ig];
-        const float2 lt = A.row_lt[row];
         rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
-        rc.l = lt.x;
-        rc.d2_thres = lt.y;
+        if (kGrid) {
+          rc.l = range_ell(ell_now, A.src_rowA[ig].w);
+          rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
+        } else {
+          const float2 lt = A.row_lt[row];
+          rc.l = lt.x;
+          rc.d2_thres = lt.y;
+        }
         rc.ga[0] = rc.ga[1] = 0.f;
         if (kc.use_geo_type) {
           const float2 gg = A.src_geo[ig];
@@ -1046,12 +1273,33 @@ __device__ void update_tf_device(const IterArgs& A, DevState* st) {
   const double ymax = (sqrt(smax2) * (double)A.trad + sqrt(off2)) * (1.0 + 1e-5) + 1e-6;
   st->ymax2_bound = __double2float_ru(ymax * ymax);
   st->smax = __double2float_ru(sqrt(smax2) * (1.0 + 1e-6));
+  // Slack of a cell query (flow_kernel_t<true>).  With y' = fl(R^T y + Tinv), Tinv = fl(-R^T T),
+  // q = fl(R x + T), E = R R^T - I and u = 2^-24:
+  //   |y - q| <= smax |y' - x| + |E| (|y| + |T|) + 8u smax^2 (|y| + |T|) + 4u (smax |x| + |T|)
+  // (the |x| term is added per row).  |y| <= |tc| + trad.  2x safety + 1 um.
+  {
+    double e2 = 0.0;
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) {
+        const double d = G[3 * i + j] - (i == j ? 1.0 : 0.0);  // Rinv Rinv^T = R^T R; same norm class
+        e2 += d * d;
+      }
+    // R R^T and R^T R have the same eigenvalues; |E|_2 <= |E|_F of either
+    const double tn = sqrt((double)st->T[0] * st->T[0] + (double)st->T[1] * st->T[1] + (double)st->T[2] * st->T[2]);
+    const double yn = sqrt(tc[0] * tc[0] + tc[1] * tc[1] + tc[2] * tc[2]) + (double)A.trad;
+    const double u = 5.9604644775390625e-08;
+    const double sm = sqrt(smax2);
+    const double slack = 2.0 * (sqrt(e2) * (yn + tn) + 8.0 * u * sm * sm * (yn + tn) + 4.0 * u * tn) + 1e-6;
+    st->grid_slack = __double2float_ru(slack);
+  }
   // target view of the next iteration: leave the Morton view when many rows reach their cap
   // (each costs an O(M) exact redo), come back once no row does
   st->last_view = st->view;
+  st->last_grid = A.grid;
   int next_view = 1;
   if (st->prune_on) next_view = (st->view == 0) ? (st->n_sat > 16u ? 1 : 0) : (st->n_capped == 0u ? 0 : 1);
   st->view = next_view;
+  st->sat_total += st->n_sat + st->n_capped;
   st->n_sat = 0u;
   st->n_capped = 0u;
 }
@@ -1198,35 +1446,35 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
   if (finished) st->done = 1;
 }
 
-__global__ void __launch_bounds__(kSparseThreads, 3) step_kernel(IterArgs A) {
+template <bool kGrid>
+__global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
   DevState* st = A.st;
-  if (st->done) return;
   __shared__ double sh[kSparseThreads * 4];
+  __shared__ uint32_t s_hot[kHot1Words + kHot2Words];  // pose + constants, flow result
   __shared__ bool is_last;
+  for (int i = threadIdx.x; i < kHot1Words + kHot2Words; i += blockDim.x)
+    s_hot[i] = __ldcg(reinterpret_cast<const uint32_t*>(st) + i);
+  __syncthreads();
+  const DevState* hs = reinterpret_cast<const DevState*>(s_hot);
+  if (hs->done) return;
+  const float* s_pose = hs->Rinv;  // Rinv[9], Tinv[3] are contiguous
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
   const int g = lane >> 3, gl = lane & 7;
-  const float ell = st->ell;
-  const int use_range_ell = A.params->is_using_range_ell;
+  const float ell = hs->ell;
+  const int use_range_ell = hs->kc.use_range_ell;
   if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[4] = gtime();
 
   // compute_step_size_xi prologue (CvoGPU.cu:970-980): precomputed by the flow finaliser
-  float omega[3], v[3], W2[9], W3[9], W4[9], Wv[3], W2v[3], W3v[3];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    omega[k] = st->omega[k];
-    v[k] = st->v[k];
-    Wv[k] = st->Wv[k];
-    W2v[k] = st->W2v[k];
-    W3v[k] = st->W3v[k];
-  }
-#pragma unroll
-  for (int k = 0; k < 9; k++) {
-    W2[k] = st->W2[k];
-    W3[k] = st->W3[k];
-    W4[k] = st->W4[k];
-  }
+  const float* omega = hs->omega;
+  const float* v = hs->v;
+  const float* W2 = hs->W2;
+  const float* W3 = hs->W3;
+  const float* W4 = hs->W4;
+  const float* Wv = hs->Wv;
+  const float* W2v = hs->W2v;
+  const float* W3v = hs->W3v;
 
   double wB = 0.0, wC = 0.0, wD = 0.0, wE = 0.0;
   // eight lanes per source row, four rows per warp (rows hold ~10 entries in tracking regimes)
@@ -1249,7 +1497,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel(IterArgs A) {
     for (int e = gl; e < n; e += kGroup) {
       const int j = (int)idx[e];
       const float A_ij = val[e];
-      const float4 yb = A.tgt_moved[j];
+      const float4 yb = kGrid ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
       const float y[3] = {yb.x, yb.y, yb.z};
       // compute_step_size_xi, CvoGPU.cu:974-983
       float z1[3], z2[3], z3[3], z4[3], t[3];
@@ -1411,10 +1659,16 @@ void launch_pair(const IterArgs& A, int blocks, cudaStream_t s) {
   pair_kernel<<<blocks, kPairWarps * 32, 0, s>>>(A);
 }
 void launch_flow(const IterArgs& A, int blocks, cudaStream_t s) {
-  flow_kernel<<<blocks, kSparseThreads, 0, s>>>(A);
+  if (A.grid)
+    flow_kernel_t<true><<<blocks, kSparseThreads, 0, s>>>(A);
+  else
+    flow_kernel_t<false><<<blocks, kSparseThreads, 0, s>>>(A);
 }
 void launch_step(const IterArgs& A, int blocks, cudaStream_t s) {
-  step_kernel<<<blocks, kSparseThreads, 0, s>>>(A);
+  if (A.grid)
+    step_kernel_t<true><<<blocks, kSparseThreads, 0, s>>>(A);
+  else
+    step_kernel_t<false><<<blocks, kSparseThreads, 0, s>>>(A);
 }
 void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride, cudaStream_t s) {
   finalize_flow_kernel<<<1, 32, 0, s>>>(A, gathered, stride);
@@ -1433,8 +1687,14 @@ int pair_kernel_max_blocks_per_sm() {
 }
 int sparse_kernel_max_blocks_per_sm() {
   int a = 0, b = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel, kSparseThreads, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, step_kernel, kSparseThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel_t<false>, kSparseThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, step_kernel_t<false>, kSparseThreads, 0);
+  return a < b ? a : b;
+}
+int grid_kernel_max_blocks_per_sm() {
+  int a = 0, b = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel_t<true>, kSparseThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, step_kernel_t<true>, kSparseThreads, 0);
   return a < b ? a : b;
 }
 
