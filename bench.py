@@ -117,6 +117,16 @@ def measured_peaks():
         return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def load_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+    captures (profiles/traffic.json, written by tools/ncu_traffic.py): {"workload:kernel": bytes}."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
 def algorithmic_bytes_per_iteration(N, M, F, C):
     """compulsory traffic of one iteration = (N+M)(16+4F+4C) + 256 bytes."""
     return (N + M) * (16 + 4 * F + 4 * C) + 256
@@ -208,7 +218,7 @@ def run_ours(args, rank, world, local_rank):
     sampler.start()
     barrier()
     launches0 = g.launch_count()
-    dev_s, pairs, iters = 0.0, 0, 0
+    dev_s, pairs, iters, grid_frac = 0.0, 0, 0, 0.0
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         flush.fill_(1)
@@ -217,6 +227,7 @@ def run_ours(args, rank, world, local_rank):
         dev_s += info.registration_seconds
         pairs += info.pairs_tested
         iters += info.iterations + (0 if info.stop_reason == 8 else 1)
+        grid_frac += info.cell_query_fraction / args.steps
     barrier()
     wall = time.perf_counter() - wall0
     launches = g.launch_count() - launches0
@@ -248,27 +259,46 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, e2e_s = float(t[0]), float(t[1])
 
-    # ---- roofline of the dominant kernel (pair_kernel), measured live with CUDA events
-    roof, fp32 = None, None
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the handle's stream
     peaks, peak_src = measured_peaks()
-    ms_tot, ms_pair = g.time_iterations(np.eye(3), np.zeros(3), p.ell_init, p.nearest_neighbors_max, 40)
     if world == 1:
         rows_local = N
     else:
         from unified_cvo_b200.dist import shard_rows
         rb, re_ = shard_rows(N, world, rank)
         rows_local = re_ - rb
-    t_pair = ms_pair / 40 * 1e-3
-    alg_bytes = algorithmic_bytes_per_iteration(rows_local, M, F, C)
-    achieved = alg_bytes / t_pair / 1e9
+    alg_bytes_iter = algorithmic_bytes_per_iteration(rows_local, M, F, C)
+    traffic = load_traffic()
+    if grid_frac >= 0.5 and world == 1:
+        # cell-query mode on one GPU: the whole loop is ONE launch of align_grid_kernel, so the
+        # kernel's duration is the timed region itself (registration_seconds = CUDA events around
+        # that launch) and one launch processes `iterations` iterations
+        kernel = "align_grid_kernel"
+        t_kernel = dev_s / args.steps
+        launch_units = iters / args.steps
+        share = 1.0
+    else:
+        # one launch per phase: time the dominant kernel of an iteration at the initial state
+        kernel = "pair_kernel" if grid_frac < 0.5 else "flow_kernel_t<true>"
+        ms_tot, ms_k = g.time_iterations(np.eye(3), np.zeros(3), p.ell_init, p.nearest_neighbors_max, 40)
+        t_kernel = ms_k / 40 * 1e-3
+        launch_units = 1.0
+        share = ms_k / ms_tot
+    achieved = launch_units * alg_bytes_iter / t_kernel / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
-            "kernel": "pair_kernel", "kernel_us": t_pair * 1e6, "kernel_share_of_iteration": ms_pair / ms_tot,
-            "note": "the path is fp32-pipe bound, not HBM bound (SURVEY.md §8d): see fp32"}
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic.get(f"{name}:{kernel}"),
+            "peak_source": peak_src, "kernel": kernel, "kernel_us": t_kernel * 1e6,
+            "iterations_per_launch": launch_units, "algorithmic_bytes_per_iteration": alg_bytes_iter,
+            "kernel_share_of_step": share,
+            "note": "algorithmic bytes = (N+M)(16+4F+4C)+256 per iteration (SURVEY.md 8d): the clouds "
+                    "are L2-resident and the path is latency/fp32 bound, not HBM bound; see fp32"}
     fma = g.fma_peak(1, 8192)
-    pair_rate = rows_local * M / t_pair
+    pair_rate = rows_local * M * launch_units / t_kernel
     fp32 = {"pair_tests_per_s": pair_rate, "fma_peak_per_s": fma, "fma_per_pair": 3,
-            "peak_pair_tests_per_s": fma / 3.0, "frac": pair_rate / (fma / 3.0)}
+            "peak_pair_tests_per_s": fma / 3.0, "frac": pair_rate / (fma / 3.0),
+            "note": "N*M pairs per iteration / kernel time against a dense scan at the measured "
+                    "packed-FMA peak (3 FMA per pair); cell queries skip most pairs, so this "
+                    "dense-equivalent fraction can exceed 1"}
 
     if rank != 0:
         return
@@ -281,6 +311,7 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic",
         "config": {"workload": f"{name}: {desc}", "N": N, "M": M, "F": F, "C": C,
                    "iterations_per_step": iters / args.steps, "l2_flush_between_steps": True,
+                   "cell_query_fraction": grid_frac,
                    "parallelism": "single GPU" if world == 1 else f"source rows sharded x{world}, NCCL all-gather",
                    "timing": "CUDA events on the launching stream inside cvo_b200_align, summed over steps"},
         "e2e": {"value": e2e_pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,

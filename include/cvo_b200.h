@@ -144,7 +144,7 @@ typedef struct cvo_b200_align_info {
   int32_t stop_reason;       /* CVO_B200_STOP_*                                     */
   int32_t final_num_neighbors;
   float final_ell;
-  float reserved0;
+  float cell_query_fraction; /* share of the loop run with cell queries instead of the dense scan */
   double registration_seconds; /* CUDA-event time of the loop only (CvoGPU.cu:1534-1560) */
   double upload_seconds;       /* host->device of the clouds, when align is given host clouds */
   uint64_t pairs_tested;       /* N*M*iterations: the unit of the headline metric   */

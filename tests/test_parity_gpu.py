@@ -59,18 +59,21 @@ def _teacher_forced(gpu, p, src, tgt, ks, max_iter=None):
     return failures
 
 
-@pytest.fixture(scope="module", params=["dense", "grid", "auto"], autouse=True)
+@pytest.fixture(scope="module", params=["dense", "grid", "grid-launches", "auto"], autouse=True)
 def candidate_mode(request):
-    """Every test runs with the dense N x M scan (pair_kernel), with cell queries
-    (flow_kernel_t<true>) and with the automatic per-batch choice: the candidate generator must
-    never change a result.  Read by cvo_b200_create."""
-    old = os.environ.get("CVO_B200_MODE")
-    os.environ["CVO_B200_MODE"] = request.param
+    """Every test runs with the dense N x M scan (pair_kernel), with cell queries in the
+    persistent cooperative kernel (align_grid_kernel), with cell queries as one launch per phase
+    (flow_kernel_t<true> / step_kernel_t<true>) and with the automatic choice: the candidate
+    generator and the launch structure must never change a result.  Read by cvo_b200_create."""
+    old = {k: os.environ.get(k) for k in ("CVO_B200_MODE", "CVO_B200_PERSIST")}
+    os.environ["CVO_B200_MODE"] = request.param.split("-")[0]
+    os.environ["CVO_B200_PERSIST"] = "0" if request.param.endswith("-launches") else "1"
     yield request.param
-    if old is None:
-        os.environ.pop("CVO_B200_MODE", None)
-    else:
-        os.environ["CVO_B200_MODE"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 @pytest.fixture(scope="module")

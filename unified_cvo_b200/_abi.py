@@ -119,7 +119,7 @@ class AlignInfo(C.Structure):
         ("stop_reason", C.c_int32),
         ("final_num_neighbors", C.c_int32),
         ("final_ell", C.c_float),
-        ("reserved0", C.c_float),
+        ("cell_query_fraction", C.c_float),
         ("registration_seconds", C.c_double),
         ("upload_seconds", C.c_double),
         ("pairs_tested", C.c_uint64),

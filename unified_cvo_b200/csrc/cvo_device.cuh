@@ -106,6 +106,8 @@ struct DevState {
   unsigned int n_sat;       // view 0: rows that reached their cap (redone exactly by the flow tail)
   unsigned int n_capped;    // view 1: rows that reached their cap (keeps the run on view 1)
   unsigned int sat_total;   // running sum of n_sat + n_capped over the iterations (host policy)
+  unsigned int bar_count;   // grid barrier of the persistent kernel (monotone arrival counter)
+  unsigned int pad1;
   // trace
   cvo_b200_iter_trace* trace;
   int trace_cap;
@@ -124,8 +126,8 @@ constexpr int kHot2Words = (int)((offsetof(DevState, omega_sum) - offsetof(DevSt
 // The Morton-ordered target (view 0) is a linear octree: every cube cell of every level is a
 // contiguous range of the sorted 63-bit keys.
 struct GridView {
-  const unsigned long long* keys;  // [M] sorted Morton keys (non-finite points: ~0, at the end)
-  const uint32_t* coarse;          // [2^(3*cbits) + 1] lower bound of each coarse cell's keys
+  const uint32_t* coarse;          // [2^(3*cbits) + 1] first Morton position of each coarse cell
+                                   // (non-finite points sort last and belong to no cell)
   int cbits;                       // bits per axis of the coarse table
   int n_finite;                    // points with a finite key
   float lo[3];                     // origin of the key lattice
@@ -180,6 +182,7 @@ struct IterArgs {
   int cap_max;
   // partial sums
   FlowPartial* flow_part;
+  FlowPartial* flow_part2;  // persistent kernel: partials of the exact redo of cut rows
   StepPartial* step_part;
   // kernel variant
   int mode;        // 0 isotropic (fill_in_A_mat_gpu), 1 Mahalanobis (.._dense_mat_kernel)

@@ -31,6 +31,8 @@ void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t 
 int pair_kernel_max_blocks_per_sm();
 int sparse_kernel_max_blocks_per_sm();
 int grid_kernel_max_blocks_per_sm();
+cudaError_t launch_align_grid(const IterArgs& A, int blocks, cudaStream_t s);
+int align_grid_max_blocks_per_sm();
 }  // namespace cvo_b200
 
 using namespace cvo_b200;
@@ -121,7 +123,6 @@ struct CloudDev {
   DevBuf<int> inv;             // original index -> Morton position (device)
   std::vector<int> perm;       // Morton position -> original index (host, for exports)
   // cell index over the Morton order (target role, grid mode): see GridView
-  DevBuf<unsigned long long> keys;
   DevBuf<uint32_t> coarse;
   int cbits = 0, n_finite = 0;
   float lo[3] = {0, 0, 0};
@@ -152,7 +153,7 @@ struct cvo_b200_handle {
   DevBuf<uint32_t> sat_list;
   DevBuf<uint32_t> cand, cand_cnt, ell_idx, row_nnz;
   DevBuf<float> ell_val;
-  DevBuf<FlowPartial> flow_part;
+  DevBuf<FlowPartial> flow_part, flow_part2;
   DevBuf<StepPartial> step_part;
   DevBuf<float> zeros_f;    // stand-in for absent features / labels
   DevBuf<float2> zeros_g;   // stand-in for absent geometric types
@@ -169,6 +170,8 @@ struct cvo_b200_handle {
   int graph_batch[2] = {0, 0};
   bool use_graph = true;
   int grid_blocks = 1;
+  int persist_blocks = 1;   // cooperative grid of align_grid_kernel (all blocks co-resident)
+  bool use_persist = true;  // CVO_B200_PERSIST=0: one launch per phase even in cell-query mode
   int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries
   // host poll buffer (pinned)
   int* h_poll = nullptr;
@@ -272,8 +275,13 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   if (gocc < 1) gocc = 1;
   h->grid_blocks =
       std::max(1, std::min(h->num_sms * gocc, (n_rows + rows_per_block - 1) / rows_per_block));
-  CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, h->grid_blocks)));
-  CVO_CUDA(h, h->step_part.ensure((size_t)std::max(h->sparse_blocks, h->grid_blocks)));
+  int pocc = align_grid_max_blocks_per_sm();
+  if (pocc < 1) pocc = 1;
+  h->persist_blocks =
+      std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_block - 1) / rows_per_block));
+  CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
+  CVO_CUDA(h, h->flow_part2.ensure((size_t)h->persist_blocks));
+  CVO_CUDA(h, h->step_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
 
   std::memset(&A, 0, sizeof(A));
   A.params = h->d_params;
@@ -323,6 +331,7 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.row_nnz = h->row_nnz.p;
   A.cap_max = cap_max;
   A.flow_part = h->flow_part.p;
+  A.flow_part2 = h->flow_part2.p;
   A.step_part = h->step_part.p;
   A.mode = mode;
   if (kinv)
@@ -335,7 +344,6 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
     A.stamps = h->stamps.p;
   }
   A.grid = 0;
-  A.gv.keys = ct.keys.p;
   A.gv.coarse = ct.coarse.p;
   A.gv.cbits = ct.cbits;
   A.gv.n_finite = ct.n_finite;
@@ -530,7 +538,8 @@ bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDe
   const double r = lmax * std::sqrt(-2.0 * std::log(q));
   if (!(r > 0.0) || !std::isfinite(r)) return false;
   double hcell = ct.extent;
-  while (hcell * 0.5 >= r && hcell > ct.extent / 2097152.0) hcell *= 0.5;  // finest level with h >= r
+  const double hmin = ct.extent / (double)(1 << ct.cbits);  // query cells are never finer than the coarse table
+  while (hcell * 0.5 >= r && hcell * 0.5 >= hmin) hcell *= 0.5;  // finest usable level with h >= r
   const double density = (double)ct.n_finite / ct.occupied_volume;
   const double tests = std::min((double)ct.n, 27.0 * hcell * hcell * hcell * density);
   return tests < 0.125 * (double)ct.n;
@@ -633,8 +642,7 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
     c.extent = ext;
     const double hc = ext / (double)(1 << cb);
     c.occupied_volume = (double)occupied * hc * hc * hc;
-    int rck = upload_vec(h, c.keys, skeys);
-    if (rck == CVO_B200_OK) rck = upload_vec(h, c.coarse, coarse);
+    int rck = upload_vec(h, c.coarse, coarse);
     if (rck != CVO_B200_OK) return rck;
   }
   const std::vector<int>& perm = c.perm;
@@ -745,8 +753,10 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
 // Runs the device-resident loop to completion.  Returns when DevState.done is set.
 // The candidate generator (dense scan / cell queries) is chosen per batch of iterations from the
 // polled device state; it never changes a result, only the cost of an iteration.
-int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0) {
+int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* grid_fraction) {
   const int batch = 32;
+  int batches = 0, grid_batches = 0;
+  if (grid_fraction) *grid_fraction = 0.f;
   int rc;
   int launched_iters = 0;
   float ell = ell0;
@@ -756,6 +766,19 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0) {
     // rows that reach their cap are redone exhaustively (O(M) each) by one block in the
     // Morton-ordered modes: leave cell queries while that happens a lot
     A.grid = (grid_profitable(h, h->src, h->tgt, ell) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
+    if (A.grid && h->use_persist && A.world == 1) {
+      // the whole loop in one cooperative launch (align_grid_kernel); it returns when done
+      CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->stream));
+      h->launches += 1;
+      CVO_CUDA(h, cudaMemcpyAsync(h->h_poll, &h->d_state->iter, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      CVO_CUDA(h, cudaStreamSynchronize(h->stream));
+      batches++;
+      grid_batches++;
+      if (h->h_poll[1] /*done*/) break;
+      return fail(h, CVO_B200_ERR_STATE, "persistent align kernel returned without finishing");
+    }
+    batches++;
+    grid_batches += A.grid ? 1 : 0;
     if (h->use_graph) {
       rc = ensure_graph(h, A, batch);
       if (rc != CVO_B200_OK) return rc;
@@ -781,6 +804,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0) {
     sat_seen = sat_now;
     if (launched_iters > max_iter + batch) return fail(h, CVO_B200_ERR_STATE, "align loop did not terminate");
   }
+  if (grid_fraction && batches > 0) *grid_fraction = (float)grid_batches / (float)batches;
   return CVO_B200_OK;
 }
 
@@ -849,6 +873,8 @@ int cvo_b200_create(const cvo_b200_params* p, int device, cvo_b200_handle** out)
   const char* fm = getenv("CVO_B200_MODE");  // dense | grid (anything else: automatic)
   if (fm && std::strcmp(fm, "dense") == 0) h->force_mode = 0;
   if (fm && std::strcmp(fm, "grid") == 0) h->force_mode = 1;
+  const char* pe = getenv("CVO_B200_PERSIST");
+  h->use_persist = !(pe && pe[0] == '0');
   *out = h;
   return CVO_B200_OK;
 }
@@ -863,10 +889,10 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
     c->xyz.release(); c->rowA.release(); c->feat.release(); c->lab.release(); c->geo.release();
     c->xyz_o.release(); c->feat_o.release(); c->lab_o.release(); c->geo_o.release();
     c->blk_sphere.release(); c->tile_sphere.release(); c->tile_maxdist.release(); c->inv.release();
-    c->keys.release(); c->coarse.release();
+    c->coarse.release();
   }
   h->tgt_moved.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
-  h->rowrec.release(); h->row_lt.release(); h->sat_list.release();
+  h->rowrec.release(); h->row_lt.release(); h->sat_list.release(); h->flow_part2.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
   h->zeros_g.release(); h->d_trace.release(); h->gathered.release(); h->stamps.release();
@@ -923,8 +949,13 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   A.grid = grid_profitable(h, h->src, h->tgt, ell) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
-  rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
-  if (rc != CVO_B200_OK) return rc;
+  if (A.grid && h->use_persist && A.world == 1) {
+    CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->stream));
+    h->launches += 1;
+  } else {
+    rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
+    if (rc != CVO_B200_OK) return rc;
+  }
   CVO_CUDA(h, cudaMemcpyAsync(trace, h->d_trace.p, sizeof(*trace), cudaMemcpyDeviceToHost, h->stream));
   CVO_CUDA(h, cudaStreamSynchronize(h->stream));
   CVO_CUDA(h, cudaGetLastError());
@@ -971,11 +1002,14 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
     IterArgs Ag = A;
     Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init) ? 1 : 0;
-    rc = ensure_graph(h, Ag, 32);
-    if (rc != CVO_B200_OK) return rc;
+    if (!(Ag.grid && h->use_persist && A.world == 1)) {
+      rc = ensure_graph(h, Ag, 32);
+      if (rc != CVO_B200_OK) return rc;
+    }
   }
   cudaEventRecord(ev0, h->stream);
-  rc = run_loop(h, A, max_iter, h->params.ell_init);
+  float grid_fraction = 0.f;
+  rc = run_loop(h, A, max_iter, h->params.ell_init, &grid_fraction);
   cudaEventRecord(ev1, h->stream);
   if (rc != CVO_B200_OK) {
     cudaEventDestroy(ev0);
@@ -1002,6 +1036,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
     info->stop_reason = hs.stop_reason;
     info->final_num_neighbors = hs.num_neighbors;
     info->final_ell = hs.ell;
+    info->cell_query_fraction = grid_fraction;
     info->registration_seconds = (double)ms / 1000.0;
     info->pairs_tested = (uint64_t)h->src.n * (uint64_t)h->tgt.n * (uint64_t)executed;
   }
@@ -1239,7 +1274,9 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   A.grid = grid_profitable(h, h->src, h->tgt, ell) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
-  const int n_ev = ms_pair_kernel ? iters : 0;
+  const bool persist = A.grid && h->use_persist && A.world == 1;
+  // per-kernel events only exist when every phase is its own launch
+  const int n_ev = (ms_pair_kernel && !persist) ? iters : 0;
   std::vector<cudaEvent_t> ea((size_t)n_ev), eb((size_t)n_ev);
   for (int i = 0; i < n_ev; i++) {
     cudaEventCreate(&ea[i]);
@@ -1249,8 +1286,14 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   CVO_CUDA(h, cudaEventCreate(&e0));
   CVO_CUDA(h, cudaEventCreate(&e1));
   cudaEventRecord(e0, h->stream);
-  for (int i = 0; i < iters && rc == CVO_B200_OK; i++)
-    rc = enqueue_iteration(h, A, 3, n_ev ? ea[i] : nullptr, n_ev ? eb[i] : nullptr);
+  if (persist) {  // one launch runs all `iters` iterations; no per-kernel events
+    cudaError_t le = launch_align_grid(A, h->persist_blocks, h->stream);
+    if (le != cudaSuccess) rc = fail(h, CVO_B200_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(le));
+    h->launches += 1;
+  } else {
+    for (int i = 0; i < iters && rc == CVO_B200_OK; i++)
+      rc = enqueue_iteration(h, A, 3, n_ev ? ea[i] : nullptr, n_ev ? eb[i] : nullptr);
+  }
   cudaEventRecord(e1, h->stream);
   cudaError_t se = cudaStreamSynchronize(h->stream);
   float ms = 0.f, msp = 0.f;
@@ -1281,7 +1324,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
     fprintf(stderr, "[tails] flow reduce: loads done %+lld shuffles done %+lld smem done %+lld (ns after tail_begin)\n",
             (long long)(d[10] - d[1]), (long long)(d[11] - d[1]), (long long)(d[12] - d[1]));
   }
-  if (A.stamps) {  // per-block phase stamps of the LAST flow launch (ns, relative to the first block)
+  if (A.stamps && !persist) {  // per-block phase stamps of the LAST flow launch (ns, relative to the first block)
     const int nb = A.grid ? h->grid_blocks : h->sparse_blocks;
     std::vector<unsigned long long> st8((size_t)8 * nb);
     cudaMemcpy(st8.data(), A.stamps, st8.size() * 8, cudaMemcpyDeviceToHost);

@@ -611,47 +611,23 @@ __device__ __forceinline__ unsigned long long spread21_dev(unsigned int a) {
 }
 // Ranges [start, start+len) of the Morton-ordered target covered by two cube cells of edge
 // 2^lvl lattice units with first keys k0, k1 (v0/v1: the lane has such a cell).  A cell's keys
-// are [k, k + 8^lvl).  Each of the four bounds is one coarse-table lookup plus a binary search
-// inside that coarse cell (a handful of points); the four searches advance together so that
-// their loads overlap: the dependent-load chain, not the arithmetic, is what a query costs.
+// are [k, k + 8^lvl).  Query cells are never finer than the cells of the coarse table
+// (lvl >= 21 - cbits), so both bounds of a range are table entries: four independent loads,
+// no search.  The table is sized for <1 point per coarse cell, so late iterations (cut-off
+// radius far below the coarse cell) still test only a handful of points per row.
 __device__ __forceinline__ void cell_ranges2(const GridView& G, int lvl3, bool v0,
                                              unsigned long long k0, bool v1, unsigned long long k1,
                                              uint32_t& s0, uint32_t& l0, uint32_t& s1, uint32_t& l1) {
   const int csh = 3 * (21 - G.cbits);
-  const unsigned long long ncoarse = 1ull << (3 * G.cbits);
-  unsigned long long key[4] = {k0, k0 + (1ull << lvl3), k1, k1 + (1ull << lvl3)};
-  uint32_t lo[4], hi[4];
-#pragma unroll
-  for (int t = 0; t < 4; t++) {
-    const bool v = (t < 2) ? v0 : v1;
-    const unsigned long long c = key[t] >> csh;
-    lo[t] = hi[t] = 0u;
-    if (v) {
-      if (c >= ncoarse) {
-        lo[t] = hi[t] = (uint32_t)G.n_finite;  // past the last cell (key 2^63)
-      } else {
-        lo[t] = __ldg(G.coarse + c);
-        hi[t] = ((c << csh) == key[t]) ? lo[t] : __ldg(G.coarse + c + 1);  // first key of a coarse cell
-      }
-    }
+  s0 = l0 = s1 = l1 = 0u;
+  if (v0) {
+    s0 = __ldg(G.coarse + (k0 >> csh));
+    l0 = __ldg(G.coarse + ((k0 + (1ull << lvl3)) >> csh)) - s0;
   }
-  while ((lo[0] < hi[0]) | (lo[1] < hi[1]) | (lo[2] < hi[2]) | (lo[3] < hi[3])) {
-    uint32_t mid[4];
-    unsigned long long km[4];
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      mid[t] = (lo[t] + hi[t]) >> 1;
-      km[t] = (lo[t] < hi[t]) ? __ldg(G.keys + mid[t]) : 0ull;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-      if (lo[t] < hi[t]) {
-        if (km[t] < key[t]) lo[t] = mid[t] + 1; else hi[t] = mid[t];
-      }
-    }
+  if (v1) {
+    s1 = __ldg(G.coarse + (k1 >> csh));
+    l1 = __ldg(G.coarse + ((k1 + (1ull << lvl3)) >> csh)) - s1;
   }
-  s0 = lo[0]; l0 = lo[1] - lo[0];
-  s1 = lo[2]; l1 = lo[3] - lo[2];
 }
 
 // ================================================================== flow_kernel
@@ -670,21 +646,100 @@ constexpr int kGroup = 8;                    // lanes per source row
 constexpr int kRowsPerWarp = 32 / kGroup;    // 4
 constexpr int kGroupList = 80;               // pending (<8) + one batch of 8 words (<=64)
 
+// Exact redo of ONE source row by one warp: all targets in the caller's original order with the
+// reference's arithmetic (the literal loop of CvoGPU.cu:524-591), for rows that were cut at their
+// cap in a Morton-ordered candidate walk.  Adds the row's contribution to f (lane 0):
+// omega[3], v[3], a_sum, nnz, max.  ELL indices are Morton positions (tgt_inv), like the rest of
+// the matrix in these modes.
 template <bool kGrid>
-__global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
-  DevState* st = A.st;
-  __shared__ double sh[kSparseThreads * 9];
-  __shared__ uint32_t s_hot[kHot1Words];  // pose, schedule, constants: one cooperative load
-  __shared__ uint32_t s_list[kSparseThreads / kGroup][kGroupList];
-  __shared__ bool is_last;
-  unsigned long long* stamp = (A.stamps && threadIdx.x == 0) ? A.stamps + 8 * (size_t)blockIdx.x : nullptr;
-  if (stamp) stamp[0] = gtime();
-  for (int i = threadIdx.x; i < kHot1Words; i += blockDim.x)
-    s_hot[i] = __ldcg(reinterpret_cast<const uint32_t*>(st) + i);
-  __syncthreads();
-  const DevState* hs = reinterpret_cast<const DevState*>(s_hot);
-  if (hs->done) return;
-  if (stamp) stamp[1] = gtime();
+__device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc, const float* Ri,
+                                         const float* Ti, float ell_now, int cap, int row, int lane,
+                                         double (&f)[9]) {
+  const float c_div = kc.c_div, d_div = kc.d_div;
+  const unsigned lt32 = (1u << lane) - 1u;
+    const int ig = A.row_begin + row;
+    RowCtx rc;
+    {
+      const float4 pa = A.src_xyz[ig];
+      rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
+      if (kGrid) {
+        rc.l = range_ell(ell_now, A.src_rowA[ig].w);
+        rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
+      } else {
+        const float2 lt = A.row_lt[row];
+        rc.l = lt.x;
+        rc.d2_thres = lt.y;
+      }
+      rc.ga[0] = rc.ga[1] = 0.f;
+      if (kc.use_geo_type) {
+        const float2 gg = A.src_geo[ig];
+        rc.ga[0] = gg.x; rc.ga[1] = gg.y;
+      }
+    }
+    float om[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
+    double asum = 0.0;
+    int count = 0;
+    uint32_t* out_idx = A.ell_idx + (size_t)row * A.cap_max;
+    float* out_val = A.ell_val + (size_t)row * A.cap_max;
+    for (int jb = 0; jb < A.M && count < cap; jb += 32) {
+      const int j = jb + lane;
+      float a = 0.f;
+      float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool surv = false;
+      if (j < A.M) {
+        const float4 y = A.tv[1].xyz[j];
+        const float yv[3] = {y.x, y.y, y.z};
+        float r[3];
+        mat3f_vec(Ri, yv, r);  // same arithmetic as prep_kernel
+        pb = make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], 0.f);
+        surv = eval_pair(A, kc, rc, ig, 1, j, pb, a);
+      }
+      const unsigned mask = __ballot_sync(0xffffffffu, surv);
+      const int pos = count + __popc(mask & lt32);
+      if (surv && pos < cap) {
+        out_idx[pos] = (uint32_t)A.tgt_inv[j];  // tgt_moved of this iteration is in Morton order
+        out_val[pos] = a;
+        const float py[3] = {pb.x, pb.y, pb.z};
+        float cr[3];
+        cross3f(rc.px, py, cr);
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          om[q] = om[q] + cr[q] * a;
+          vv[q] = vv[q] + (py[q] - rc.px[q]) * a;
+        }
+        asum += (double)a;
+      }
+      count = min(cap, count + __popc(mask));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        om[q] += __shfl_xor_sync(0xffffffffu, om[q], o);
+        vv[q] += __shfl_xor_sync(0xffffffffu, vv[q], o);
+      }
+      asum += __shfl_xor_sync(0xffffffffu, asum, o);
+    }
+    if (lane == 0) {
+      A.row_nnz[row] = (uint32_t)count;
+#pragma unroll
+      for (int q = 0; q < 3; q++) {
+        f[q] += (double)(om[q] / c_div);
+        f[3 + q] += (double)(vv[q] / d_div);
+      }
+      f[6] += asum;
+      f[7] += (double)count;
+      f[8] = fmax(f[8], (double)count);
+    }
+}
+
+// The source rows of this block (grid-stride over 8-lane row groups): candidates -> exact pair
+// arithmetic -> ELL rows + per-row flow; returns the warp's partial sums in bp (valid on lane 0):
+// omega[3], v[3], a_sum, nnz, max row count.  hs = this block's shared-memory copy of the hot
+// state; st = the global state (saturation counters only).
+template <bool kGrid>
+__device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const DevState* hs,
+                                          uint32_t* list, double (&bp)[9]) {
   const int view = kGrid ? 0 : hs->view;  // cell queries index the Morton-ordered target
   const float* s_pose = hs->Rinv;          // Rinv[9], Tinv[3] are contiguous
   const float ell_now = hs->ell;
@@ -706,7 +761,6 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
   const int cap_stop = kGrid ? cap + 1 : cap;
   const float c_div = kc.c_div, d_div = kc.d_div;  // divisors (CvoGPU.cu:785-788)
   const int L = A.L;
-  uint32_t* list = s_list[threadIdx.x >> 3];
   const int nch = A.nchunks;
   if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[0] = gtime();
 
@@ -848,6 +902,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
           const int iz1 = (int)fminf(fmaxf(floorf(fz1) + 1.f, 0.f), top);
           const int span = max(ix1 - ix0, max(iy1 - iy0, iz1 - iz0));
           lvl = span <= 2 ? 0 : (31 - __clz(span)) - 1;
+          lvl = max(lvl, 21 - G.cbits);  // never finer than the coarse table (cell_ranges2)
           while (((ix1 >> lvl) - (ix0 >> lvl)) > 2 || ((iy1 >> lvl) - (iy0 >> lvl)) > 2 ||
                  ((iz1 >> lvl) - (iz0 >> lvl)) > 2)
             lvl++;
@@ -1043,9 +1098,9 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
       w_max = fmax(w_max, (double)count);
     }
   }
-  if (stamp) stamp[2] = gtime();
   // ---- block partial: fixed xor tree over the four group leaders of a warp, then over warps
-  double bp[9] = {w_om[0], w_om[1], w_om[2], w_v[0], w_v[1], w_v[2], w_asum, w_nnz, w_max};
+  bp[0] = w_om[0]; bp[1] = w_om[1]; bp[2] = w_om[2]; bp[3] = w_v[0]; bp[4] = w_v[1]; bp[5] = w_v[2];
+  bp[6] = w_asum; bp[7] = w_nnz; bp[8] = w_max;
 #pragma unroll
   for (int o = 8; o <= 16; o <<= 1) {
 #pragma unroll
@@ -1054,6 +1109,34 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
       bp[k] = (k < 8) ? bp[k] + x : fmax(bp[k], x);
     }
   }
+}
+
+template <bool kGrid>
+__global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
+  DevState* st = A.st;
+  __shared__ double sh[kSparseThreads * 9];
+  __shared__ uint32_t s_hot[kHot1Words];  // pose, schedule, constants: one cooperative load
+  __shared__ uint32_t s_list[kSparseThreads / kGroup][kGroupList];
+  __shared__ bool is_last;
+  unsigned long long* stamp = (A.stamps && threadIdx.x == 0) ? A.stamps + 8 * (size_t)blockIdx.x : nullptr;
+  if (stamp) stamp[0] = gtime();
+  for (int i = threadIdx.x; i < kHot1Words; i += blockDim.x)
+    s_hot[i] = __ldcg(reinterpret_cast<const uint32_t*>(st) + i);
+  __syncthreads();
+  const DevState* hs = reinterpret_cast<const DevState*>(s_hot);
+  if (hs->done) return;
+  if (stamp) stamp[1] = gtime();
+  double bp[9];
+  flow_rows<kGrid>(A, st, hs, s_list[threadIdx.x >> 3], bp);
+  const int view = kGrid ? 0 : hs->view;
+  const float ell_now = hs->ell;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  const KernConsts& kc = hs->kc;
+  const int cap = hs->num_neighbors;
+  const float c_div = kc.c_div, d_div = kc.d_div;
+  if (stamp) stamp[2] = gtime();
   if (lane == 0) {
 #pragma unroll
     for (int k = 0; k < 9; k++) sh[warp_in_block * 9 + k] = bp[k];
@@ -1087,97 +1170,20 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
   //      moves the run to the original-order view.
   const unsigned int n_sat = (view == 0) ? *(volatile unsigned int*)&st->n_sat : 0u;
   if (n_sat > 0u) {
-    double f_om[3] = {0, 0, 0}, f_v[3] = {0, 0, 0}, f_asum = 0.0, f_nnz = 0.0, f_max = 0.0;
+    double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     float Ri[9], Ti[3];
 #pragma unroll
     for (int q = 0; q < 9; q++) Ri[q] = st->Rinv[q];
 #pragma unroll
     for (int q = 0; q < 3; q++) Ti[q] = st->Tinv[q];
-    const unsigned lt32 = (1u << lane) - 1u;
-    for (unsigned int si = warp_in_block; si < n_sat; si += warps_per_block) {
-      const int row = (int)__ldcg(&A.sat_list[si]);
-      const int ig = A.row_begin + row;
-      RowCtx rc;
-      {
-        const float4 pa = A.src_xyz[ig];
-        rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
-        if (kGrid) {
-          rc.l = range_ell(ell_now, A.src_rowA[ig].w);
-          rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
-        } else {
-          const float2 lt = A.row_lt[row];
-          rc.l = lt.x;
-          rc.d2_thres = lt.y;
-        }
-        rc.ga[0] = rc.ga[1] = 0.f;
-        if (kc.use_geo_type) {
-          const float2 gg = A.src_geo[ig];
-          rc.ga[0] = gg.x; rc.ga[1] = gg.y;
-        }
-      }
-      float om[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
-      double asum = 0.0;
-      int count = 0;
-      uint32_t* out_idx = A.ell_idx + (size_t)row * A.cap_max;
-      float* out_val = A.ell_val + (size_t)row * A.cap_max;
-      for (int jb = 0; jb < A.M && count < cap; jb += 32) {
-        const int j = jb + lane;
-        float a = 0.f;
-        float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool surv = false;
-        if (j < A.M) {
-          const float4 y = A.tv[1].xyz[j];
-          const float yv[3] = {y.x, y.y, y.z};
-          float r[3];
-          mat3f_vec(Ri, yv, r);  // same arithmetic as prep_kernel
-          pb = make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], 0.f);
-          surv = eval_pair(A, kc, rc, ig, 1, j, pb, a);
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, surv);
-        const int pos = count + __popc(mask & lt32);
-        if (surv && pos < cap) {
-          out_idx[pos] = (uint32_t)A.tgt_inv[j];  // tgt_moved of this iteration is in Morton order
-          out_val[pos] = a;
-          const float py[3] = {pb.x, pb.y, pb.z};
-          float cr[3];
-          cross3f(rc.px, py, cr);
-#pragma unroll
-          for (int q = 0; q < 3; q++) {
-            om[q] = om[q] + cr[q] * a;
-            vv[q] = vv[q] + (py[q] - rc.px[q]) * a;
-          }
-          asum += (double)a;
-        }
-        count = min(cap, count + __popc(mask));
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          om[q] += __shfl_xor_sync(0xffffffffu, om[q], o);
-          vv[q] += __shfl_xor_sync(0xffffffffu, vv[q], o);
-        }
-        asum += __shfl_xor_sync(0xffffffffu, asum, o);
-      }
-      if (lane == 0) {
-        A.row_nnz[row] = (uint32_t)count;
-#pragma unroll
-        for (int q = 0; q < 3; q++) {
-          f_om[q] += (double)(om[q] / c_div);
-          f_v[q] += (double)(vv[q] / d_div);
-        }
-        f_asum += asum;
-        f_nnz += (double)count;
-        f_max = fmax(f_max, (double)count);
-      }
-    }
+    for (unsigned int si = warp_in_block; si < n_sat; si += warps_per_block)
+      redo_row<kGrid>(A, kc, Ri, Ti, ell_now, cap, (int)__ldcg(&A.sat_list[si]), lane, f);
     // fold the redone rows into the totals (fixed order over the warps of this block)
     __syncthreads();
     if (lane == 0) {
       double* d = sh + warp_in_block * 9;
-      d[0] = f_om[0]; d[1] = f_om[1]; d[2] = f_om[2];
-      d[3] = f_v[0];  d[4] = f_v[1];  d[5] = f_v[2];
-      d[6] = f_asum;  d[7] = f_nnz;   d[8] = f_max;
+#pragma unroll
+      for (int q = 0; q < 9; q++) d[q] = f[q];
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1305,158 +1311,192 @@ __device__ void update_tf_device(const IterArgs& A, DevState* st) {
 }
 
 // Everything align_impl does on the host after the reductions (CvoGPU.cu:1124-1158,
-// 1452-1531), run by ONE thread.  bcde = global sums.
-__device__ void controller_step(const IterArgs& A, DevState* st, const double bcde[4]) {
+// 1452-1531).  It is a chain of dependent double-precision scalar work (cubic, Exp, log), i.e.
+// pure latency, and it sits on the critical path of every iteration, so it is split over TWO
+// warps of the calling block (threads 0 and 32 run on different schedulers):
+//   phase 1   A: cubic -> clamped step            B: gradient test, indicator queues
+//   phase 2   A: Exp_SEK3, pose update, update_tf B: Exp_SEK3 (same arithmetic), se(3) log norm,
+//                                                    eps_2 test, ell decay, row-cap update
+//   phase 3   A: iteration counter, stop flags, trace record
+// Every thread of the block must call it (it contains block barriers); bcde (the global sums
+// B, C, D, E) needs to be valid on thread 0 only.  `st` may live in shared or global memory.
+struct CtrlScratch {
+  int grad_small, need_decay, finished, flags;
+  float ell_used;
+  int cap_used;
+  double dist;
+};
+
+__device__ void controller_step(const IterArgs& A, DevState* st, const double bcde[4], CtrlScratch* sc) {
   const cvo_b200_params* params = A.params;
-  st->B = bcde[0]; st->C = bcde[1]; st->D = bcde[2]; st->E = bcde[3];
-  // ---- step size (CvoGPU.cu:1124-1158)
-  const double coef[4] = {4.0 * bcde[3], 3.0 * bcde[2], 2.0 * bcde[1], bcde[0]};
-  double re[3], im[3];
-  double temp_step = 1.7976931348623157e308;  // numeric_limits<double>::max()
-  if (cubic_roots(coef, re, im)) {
-    for (int i = 0; i < 3; i++)
-      if (re[i] > 0 && re[i] < temp_step && fabs(im[i]) < 1e-5) temp_step = re[i];
-  }
-  st->dbg[13] = gtime();
-  float step;
-  if (temp_step > params->max_step)
-    step = params->max_step;
-  else if (temp_step < params->min_step)
-    step = params->min_step;
-  else
-    step = (float)temp_step;
-  st->step = step;
-
-  const int k = st->iter;
-  cvo_b200_iter_trace* tr = (st->trace && k < st->trace_cap) ? &st->trace[k] : nullptr;
-  cvo_b200_iter_trace rec;
-  rec.iter = k;
-  rec.num_neighbors = st->num_neighbors;
-  rec.ell = st->ell;
-  rec.max_row_nnz = st->max_row_nnz;
-  rec.nnz = st->nnz;
-  for (int q = 0; q < 3; q++) {
-    rec.omega_sum[q] = st->omega_sum[q];
-    rec.v_sum[q] = st->v_sum[q];
-    rec.omega[q] = st->omega[q];
-    rec.v[q] = st->v[q];
-  }
-  rec.B = bcde[0]; rec.C = bcde[1]; rec.D = bcde[2]; rec.E = bcde[3];
-  rec.step = step;
-  rec.flags = 0;
-  rec.dist = 0.0;
-  rec.a_sum = st->a_sum;
-  for (int q = 0; q < 6; q++) rec.reserved[q] = 0;
-
-  const float* omega = st->omega;
-  const float* v = st->v;
-  bool finished = false;
-  // ---- gradient test (CvoGPU.cu:1454-1458)
-  const double on = sqrt(sum3d((double)omega[0] * omega[0], (double)omega[1] * omega[1],
-                               (double)omega[2] * omega[2]));
-  const double vn = sqrt(sum3d((double)v[0] * v[0], (double)v[1] * v[1], (double)v[2] * v[2]));
-  if (on < params->eps && vn < params->eps && st->controller_on != 2) {  // mode 2: timing loop
-    const float onf = sqrtf(dot3f(omega, omega)), vnf = sqrtf(dot3f(v, v));
-    int reason = CVO_B200_STOP_GRAD_SMALL;
-    if (onf < 1e-8 && vnf < 1e-8) {
-      st->ret = -1;
-      reason |= CVO_B200_STOP_GRAD_ZERO;
-    }
-    st->stop_reason = reason;
-    rec.flags = reason;
-    finished = true;
-  } else {
-    // ---- pose update (CvoGPU.cu:1460-1476)
-    const float vec_joined[6] = {omega[0], omega[1], omega[2], v[0], v[1], v[2]};
-    float dtrans[12];
-    exp_sek3(vec_joined, step, dtrans);
-    double dR[9], dT[3], Rd[9], Td[3];
-    for (int q = 0; q < 9; q++) {
-      dR[q] = (double)dtrans[q];
-      Rd[q] = (double)st->R[q];
-    }
-    for (int q = 0; q < 3; q++) {
-      dT[q] = (double)dtrans[9 + q];
-      Td[q] = (double)st->T[q];
-    }
-    float R_keep[9], T_keep[3];
-    for (int q = 0; q < 9; q++) R_keep[q] = st->R[q];
-    for (int q = 0; q < 3; q++) T_keep[q] = st->T[q];
-    for (int i = 0; i < 3; i++)
-      st->T[i] = (float)(sum3d(Rd[i] * dT[0], Rd[3 + i] * dT[1], Rd[6 + i] * dT[2]) + Td[i]);
-    for (int j = 0; j < 3; j++)
+  const int tid = threadIdx.x;
+  // ---------------------------------------------------------------- phase 1
+  if (tid == 0) {
+    st->B = bcde[0]; st->C = bcde[1]; st->D = bcde[2]; st->E = bcde[3];
+    // step size (CvoGPU.cu:1124-1158)
+    const double coef[4] = {4.0 * bcde[3], 3.0 * bcde[2], 2.0 * bcde[1], bcde[0]};
+    double re[3], im[3];
+    double temp_step = 1.7976931348623157e308;  // numeric_limits<double>::max()
+    if (cubic_roots(coef, re, im)) {
       for (int i = 0; i < 3; i++)
-        st->R[3 * j + i] = (float)sum3d(Rd[i] * dR[3 * j], Rd[3 + i] * dR[3 * j + 1],
-                                        Rd[6 + i] * dR[3 * j + 2]);
-    st->dbg[14] = gtime();
-    const double dist_this_iter = se3_log_norm(dR, dT);
-    st->dbg[15] = gtime();
-    st->dist = dist_this_iter;
-    rec.dist = dist_this_iter;
-    for (int q = 0; q < 9; q++) rec.R[q] = st->R[q];
-    for (int q = 0; q < 3; q++) rec.T[q] = st->T[q];
-    if (st->controller_on == 2) {  // fixed-state timing loop: keep the pose where it was
-      for (int q = 0; q < 9; q++) st->R[q] = R_keep[q];
-      for (int q = 0; q < 3; q++) st->T[q] = T_keep[q];
+        if (re[i] > 0 && re[i] < temp_step && fabs(im[i]) < 1e-5) temp_step = re[i];
     }
-    if (st->controller_on == 1) {
-      // ---- indicator (CvoGPU.cu:1486-1493)
+    st->dbg[13] = gtime();
+    float step;
+    if (temp_step > params->max_step)
+      step = params->max_step;
+    else if (temp_step < params->min_step)
+      step = params->min_step;
+    else
+      step = (float)temp_step;
+    st->step = step;
+  } else if (tid == 32) {
+    sc->ell_used = st->ell;
+    sc->cap_used = st->num_neighbors;
+    sc->flags = 0;
+    sc->finished = 0;
+    sc->need_decay = 0;
+    sc->dist = 0.0;
+    const float* omega = st->omega;
+    const float* v = st->v;
+    // gradient test (CvoGPU.cu:1454-1458)
+    const double on = sqrt(sum3d((double)omega[0] * omega[0], (double)omega[1] * omega[1],
+                                 (double)omega[2] * omega[2]));
+    const double vn = sqrt(sum3d((double)v[0] * v[0], (double)v[1] * v[1], (double)v[2] * v[2]));
+    int gs = 0;
+    if (on < params->eps && vn < params->eps && st->controller_on != 2) {  // mode 2: timing loop
+      const float onf = sqrtf(dot3f(omega, omega)), vnf = sqrtf(dot3f(v, v));
+      int reason = CVO_B200_STOP_GRAD_SMALL;
+      if (onf < 1e-8 && vnf < 1e-8) {
+        st->ret = -1;
+        reason |= CVO_B200_STOP_GRAD_ZERO;
+      }
+      st->stop_reason = reason;
+      sc->flags = reason;
+      sc->finished = 1;
+      gs = 1;
+    } else if (st->controller_on == 1) {
+      // indicator (CvoGPU.cu:1486-1493): does not depend on the step
       const float ip_curr =
           (float)((double)st->nnz / sqrt((double)A.n_src_total * (double)A.M));
-      const int need_decay_ell = indicator_update(st, ip_curr, params);
-      if (dist_this_iter < params->eps_2) {  // :1505-1508
-        st->stop_reason = CVO_B200_STOP_DIST_SMALL;
-        rec.flags = CVO_B200_STOP_DIST_SMALL;
-        finished = true;
-      } else {
-        if (k > params->ell_decay_start && need_decay_ell) {  // :1509-1513
-          st->ell = st->ell * params->ell_decay_rate;
-          if (st->ell < params->ell_min) st->ell = params->ell_min;
-          rec.flags |= CVO_B200_ELL_DECAYED;
+      sc->need_decay = indicator_update(st, ip_curr, params);
+    }
+    sc->grad_small = gs;
+  }
+  __syncthreads();
+  // ---------------------------------------------------------------- phase 2
+  const bool moving = !sc->grad_small;
+  if ((tid == 0 || tid == 32) && moving) {
+    // pose update (CvoGPU.cu:1460-1476); both threads evaluate the same Exp_SEK3
+    const float vec_joined[6] = {st->omega[0], st->omega[1], st->omega[2], st->v[0], st->v[1], st->v[2]};
+    float dtrans[12];
+    exp_sek3(vec_joined, st->step, dtrans);
+    double dR[9], dT[3];
+    for (int q = 0; q < 9; q++) dR[q] = (double)dtrans[q];
+    for (int q = 0; q < 3; q++) dT[q] = (double)dtrans[9 + q];
+    if (tid == 0) {
+      double Rd[9], Td[3];
+      for (int q = 0; q < 9; q++) Rd[q] = (double)st->R[q];
+      for (int q = 0; q < 3; q++) Td[q] = (double)st->T[q];
+      float Rn[9], Tn[3];
+      for (int i = 0; i < 3; i++)
+        Tn[i] = (float)(sum3d(Rd[i] * dT[0], Rd[3 + i] * dT[1], Rd[6 + i] * dT[2]) + Td[i]);
+      for (int j = 0; j < 3; j++)
+        for (int i = 0; i < 3; i++)
+          Rn[3 * j + i] = (float)sum3d(Rd[i] * dR[3 * j], Rd[3 + i] * dR[3 * j + 1],
+                                       Rd[6 + i] * dR[3 * j + 2]);
+      // the trace reports the pose AFTER the update; the fixed-state timing loop (mode 2) then
+      // keeps the pose where it was
+      cvo_b200_iter_trace* tr = (st->trace && st->iter < st->trace_cap) ? &st->trace[st->iter] : nullptr;
+      if (tr) {
+        for (int q = 0; q < 9; q++) tr->R[q] = Rn[q];
+        for (int q = 0; q < 3; q++) tr->T[q] = Tn[q];
+      }
+      if (st->controller_on != 2) {
+        for (int q = 0; q < 9; q++) st->R[q] = Rn[q];
+        for (int q = 0; q < 3; q++) st->T[q] = Tn[q];
+      }
+      st->dbg[14] = gtime();
+      update_tf_device(A, st);  // next iteration's Rinv/Tinv and bounds (or the final transform)
+    } else {
+      const double dist_this_iter = se3_log_norm(dR, dT);
+      st->dbg[15] = gtime();
+      st->dist = dist_this_iter;
+      sc->dist = dist_this_iter;
+      if (st->controller_on == 1) {
+        if (dist_this_iter < params->eps_2) {  // :1505-1508
+          st->stop_reason = CVO_B200_STOP_DIST_SMALL;
+          sc->flags = CVO_B200_STOP_DIST_SMALL;
+          sc->finished = 1;
+        } else {
+          if (st->iter > params->ell_decay_start && sc->need_decay) {  // :1509-1513
+            st->ell = st->ell * params->ell_decay_rate;
+            if (st->ell < params->ell_min) st->ell = params->ell_min;
+            sc->flags |= CVO_B200_ELL_DECAYED;
+          }
+          // :1518-1529
+          const int cand = (int)(st->max_row_nnz * 1.2);
+          st->num_neighbors = params->nearest_neighbors_max < cand ? params->nearest_neighbors_max : cand;
         }
-        // :1518-1529
-        const int cand = (int)(st->max_row_nnz * 1.2);
-        st->num_neighbors = params->nearest_neighbors_max < cand ? params->nearest_neighbors_max : cand;
       }
     }
   }
-  if (finished && rec.dist == 0.0) {  // gradient-vanished exit: pose untouched
-    for (int q = 0; q < 9; q++) rec.R[q] = st->R[q];
-    for (int q = 0; q < 3; q++) rec.T[q] = st->T[q];
-  }
-  rec.ell_next = st->ell;
-  rec.num_neighbors_next = st->num_neighbors;
-  if (st->controller_on == 0) {
-    const int cand = (int)(st->max_row_nnz * 1.2);
-    rec.num_neighbors_next =
-        params->nearest_neighbors_max < cand ? params->nearest_neighbors_max : cand;
-    finished = true;
-  }
-  if (!finished) {
-    st->iter = k + 1;
-    if (st->iter >= st->max_iter) {
-      st->stop_reason = CVO_B200_STOP_MAX_ITER;
+  __syncthreads();
+  // ---------------------------------------------------------------- phase 3
+  if (tid == 0) {
+    const int k = st->iter;
+    cvo_b200_iter_trace* tr = (st->trace && k < st->trace_cap) ? &st->trace[k] : nullptr;
+    bool finished = sc->finished != 0;
+    if (!moving) update_tf_device(A, st);  // gradient vanished: pose untouched, final transform
+    int cap_next = st->num_neighbors;
+    if (st->controller_on == 0) {
+      const int cand = (int)(st->max_row_nnz * 1.2);
+      cap_next = params->nearest_neighbors_max < cand ? params->nearest_neighbors_max : cand;
       finished = true;
     }
+    if (tr) {
+      tr->iter = k;
+      tr->num_neighbors = sc->cap_used;
+      tr->ell = sc->ell_used;
+      tr->max_row_nnz = st->max_row_nnz;
+      tr->nnz = st->nnz;
+      for (int q = 0; q < 3; q++) {
+        tr->omega_sum[q] = st->omega_sum[q];
+        tr->v_sum[q] = st->v_sum[q];
+        tr->omega[q] = st->omega[q];
+        tr->v[q] = st->v[q];
+      }
+      tr->B = st->B; tr->C = st->C; tr->D = st->D; tr->E = st->E;
+      tr->step = st->step;
+      tr->flags = sc->flags;
+      tr->dist = sc->dist;
+      tr->a_sum = st->a_sum;
+      for (int q = 0; q < 6; q++) tr->reserved[q] = 0;
+      if (!moving) {  // pose untouched
+        for (int q = 0; q < 9; q++) tr->R[q] = st->R[q];
+        for (int q = 0; q < 3; q++) tr->T[q] = st->T[q];
+      }
+      tr->ell_next = st->ell;
+      tr->num_neighbors_next = cap_next;
+    }
+    if (!finished) {
+      st->iter = k + 1;
+      if (st->iter >= st->max_iter) {
+        st->stop_reason = CVO_B200_STOP_MAX_ITER;
+        finished = true;
+      }
+    }
+    st->work_counter = 0u;
+    if (finished) st->done = 1;
   }
-  if (tr) *tr = rec;
-  // ---- set up the next iteration (or the final transform, CvoGPU.cu:1562)
-  update_tf_device(A, st);
-  st->work_counter = 0u;
-  if (finished) st->done = 1;
 }
 
+// compute_step_size_xi + compute_step_size_poly_coeff (CvoGPU.cu:953-1082) over the ELL rows of
+// this block; returns the warp's B, C, D, E sums (all lanes).  Row data written by other blocks
+// (exact redo) is read past L1.
 template <bool kGrid>
-__global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
-  DevState* st = A.st;
-  __shared__ double sh[kSparseThreads * 4];
-  __shared__ uint32_t s_hot[kHot1Words + kHot2Words];  // pose + constants, flow result
-  __shared__ bool is_last;
-  for (int i = threadIdx.x; i < kHot1Words + kHot2Words; i += blockDim.x)
-    s_hot[i] = __ldcg(reinterpret_cast<const uint32_t*>(st) + i);
-  __syncthreads();
-  const DevState* hs = reinterpret_cast<const DevState*>(s_hot);
-  if (hs->done) return;
+__device__ __forceinline__ void step_rows(const IterArgs& A, const DevState* hs, double& wB,
+                                          double& wC, double& wD, double& wE) {
   const float* s_pose = hs->Rinv;  // Rinv[9], Tinv[3] are contiguous
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -1464,7 +1504,6 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
   const int g = lane >> 3, gl = lane & 7;
   const float ell = hs->ell;
   const int use_range_ell = hs->kc.use_range_ell;
-  if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[4] = gtime();
 
   // compute_step_size_xi prologue (CvoGPU.cu:970-980): precomputed by the flow finaliser
   const float* omega = hs->omega;
@@ -1476,12 +1515,12 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
   const float* W2v = hs->W2v;
   const float* W3v = hs->W3v;
 
-  double wB = 0.0, wC = 0.0, wD = 0.0, wE = 0.0;
+  wB = wC = wD = wE = 0.0;
   // eight lanes per source row, four rows per warp (rows hold ~10 entries in tracking regimes)
   const int slot0 = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp + g;
   const int slot_stride = gridDim.x * warps_per_block * kRowsPerWarp;
   for (int row = slot0; row < A.n_rows; row += slot_stride) {
-    const int n = (int)A.row_nnz[row];
+    const int n = (int)__ldcg(A.row_nnz + row);
     if (n == 0) continue;
     const int ig = A.row_begin + row;
     const float4 pa = A.src_xyz[ig];
@@ -1495,8 +1534,8 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
     const uint32_t* idx = A.ell_idx + (size_t)row * A.cap_max;
     const float* val = A.ell_val + (size_t)row * A.cap_max;
     for (int e = gl; e < n; e += kGroup) {
-      const int j = (int)idx[e];
-      const float A_ij = val[e];
+      const int j = (int)__ldcg(idx + e);
+      const float A_ij = __ldcg(val + e);
       const float4 yb = kGrid ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
       const float y[3] = {yb.x, yb.y, yb.z};
       // compute_step_size_xi, CvoGPU.cu:974-983
@@ -1546,6 +1585,25 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
     wD += __shfl_xor_sync(0xffffffffu, wD, o);
     wE += __shfl_xor_sync(0xffffffffu, wE, o);
   }
+}
+
+template <bool kGrid>
+__global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
+  DevState* st = A.st;
+  __shared__ double sh[kSparseThreads * 4];
+  __shared__ uint32_t s_hot[kHot1Words + kHot2Words];  // pose + constants, flow result
+  __shared__ bool is_last;
+  for (int i = threadIdx.x; i < kHot1Words + kHot2Words; i += blockDim.x)
+    s_hot[i] = __ldcg(reinterpret_cast<const uint32_t*>(st) + i);
+  __syncthreads();
+  const DevState* hs = reinterpret_cast<const DevState*>(s_hot);
+  if (hs->done) return;
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[4] = gtime();
+  double wB, wC, wD, wE;
+  step_rows<kGrid>(A, hs, wB, wC, wD, wE);
   if (lane == 0) {
     sh[warp_in_block * 4 + 0] = wB;
     sh[warp_in_block * 4 + 1] = wC;
@@ -1575,10 +1633,137 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
     st->step_blocks_done = 0u;
     if (A.world > 1) {
       for (int k = 0; k < 4; k++) st->local_step[k] = tot[k];
-    } else {
-      controller_step(A, st, tot);
     }
-    st->dbg[7] = gtime();
+  }
+  if (A.world <= 1) {  // block-uniform: the controller runs on two warps of this (last) block
+    __shared__ CtrlScratch s_ctrl;
+    __syncthreads();
+    controller_step(A, st, tot, &s_ctrl);
+    if (threadIdx.x == 0) st->dbg[7] = gtime();
+  }
+}
+
+// ================================================================== persistent align kernel
+// One cooperative launch runs the whole registration loop in cell-query mode: every block keeps
+// its own copy of the controller state in shared memory, the two cross-row reductions of an
+// iteration are grid barriers after which EVERY block reduces the block partials in the same
+// fixed order and runs the (deterministic) controller itself, so all copies stay bit-identical
+// and nothing is broadcast.  Compared with one launch per phase this removes, per iteration,
+// two kernel boundaries, two last-block hand-offs and the reloads of the state, and keeps the
+// static clouds in L1 across iterations.  Block 0 records the trace and writes the state back.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// all blocks are co-resident (cooperative launch); counter is monotone: barrier #e completes when
+// it reaches e * gridDim.x
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int& epoch) {
+  __syncthreads();
+  epoch += 1u;
+  if (threadIdx.x == 0) {
+    __threadfence();  // release this block's writes (cumulative over the barrier above)
+    atomicAdd(counter, 1u);
+    const unsigned int target = epoch * gridDim.x;
+    while (ld_acquire_u32(counter) < target) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+// block partial (NV values per warp in v, valid on lane 0) -> part[k * gridDim.x + blockIdx.x]
+template <int NV, int NSUM>
+__device__ __forceinline__ void publish_block_partial(const double (&v)[NV], double* sh, double* part) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();  // sh may still be read by the previous phase
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) sh[w * NV + k] = v[k];
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < NV) {
+    const int k = threadIdx.x;
+    double r = sh[k];
+    for (int i = 1; i < nw; i++) r = (k < NSUM) ? r + sh[i * NV + k] : fmax(r, sh[i * NV + k]);
+    part[(size_t)k * gridDim.x + blockIdx.x] = r;
+  }
+}
+
+__global__ void __launch_bounds__(kSparseThreads, 3) align_grid_kernel(IterArgs A) {
+  __shared__ double sh[kSparseThreads * 9];
+  __shared__ uint32_t s_list[kSparseThreads / kGroup][kGroupList];
+  __shared__ __align__(16) DevState s_st;
+  __shared__ unsigned int s_nsat;
+  __shared__ CtrlScratch s_ctrl;
+  DevState* gst = A.st;
+  for (int i = threadIdx.x; i < (int)(sizeof(DevState) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&s_st)[i] = __ldcg(reinterpret_cast<const uint32_t*>(gst) + i);
+  __syncthreads();
+  if (threadIdx.x == 0 && blockIdx.x != 0) s_st.trace = nullptr;  // block 0 records the trace
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp_in_block = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  unsigned int epoch = 0;
+  double* flow_part = reinterpret_cast<double*>(A.flow_part);
+  double* flow_part2 = reinterpret_cast<double*>(A.flow_part2);
+  double* step_part = reinterpret_cast<double*>(A.step_part);
+
+  while (!s_st.done) {  // the same value in every block
+    // ---- flow phase (fill_in_A_mat_gpu + compute_flow_gpu_no_eigen on this block's rows)
+    {
+      double bp[9];
+      flow_rows<true>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp);
+      publish_block_partial<9, 8>(bp, sh, flow_part);
+    }
+    grid_barrier(&gst->bar_count, epoch);
+    // ---- rows cut at their cap: exact redo, one warp per row over the whole grid
+    if (threadIdx.x == 0) s_nsat = __ldcg(&gst->n_sat);
+    __syncthreads();
+    const unsigned int n_sat = s_nsat;
+    if (n_sat > 0u) {
+      double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (unsigned int si = blockIdx.x * warps_per_block + warp_in_block; si < n_sat;
+           si += gridDim.x * warps_per_block)
+        redo_row<true>(A, s_st.kc, s_st.Rinv, s_st.Tinv, s_st.ell, s_st.num_neighbors,
+                       (int)__ldcg(&A.sat_list[si]), lane, f);
+      publish_block_partial<9, 8>(f, sh, flow_part2);
+      grid_barrier(&gst->bar_count, epoch);
+    }
+    // ---- every block: totals in a fixed order, normalisation, omega_hat powers
+    {
+      double tot[9], tot2[9];
+      block_reduce_partials<9, 8>(flow_part, (int)gridDim.x, tot, sh);
+      if (n_sat > 0u) block_reduce_partials<9, 8>(flow_part2, (int)gridDim.x, tot2, sh);
+      if (threadIdx.x == 0) {
+        if (n_sat > 0u) {
+          for (int q = 0; q < 8; q++) tot[q] += tot2[q];
+          tot[8] = fmax(tot[8], tot2[8]);
+          if (blockIdx.x == 0) gst->n_sat = 0u;  // every block has read it (barrier above)
+        }
+        s_st.n_sat = n_sat;  // update_tf_device's bookkeeping
+        finalize_flow_scalar(&s_st, tot);
+      }
+    }
+    __syncthreads();
+    // ---- step phase (compute_step_size_xi + _poly_coeff on this block's ELL rows)
+    {
+      double w4[4];
+      step_rows<true>(A, &s_st, w4[0], w4[1], w4[2], w4[3]);
+      publish_block_partial<4, 4>(w4, sh, step_part);
+    }
+    grid_barrier(&gst->bar_count, epoch);
+    {
+      double tot[4];
+      block_reduce_partials<4, 4>(step_part, (int)gridDim.x, tot, sh);
+      controller_step(A, &s_st, tot, &s_ctrl);
+    }
+    __syncthreads();
+  }
+  // ---- block 0 hands the final state (pose, flags, counters) back
+  if (blockIdx.x == 0) {
+    for (int i = threadIdx.x; i < (int)(sizeof(DevState) / 4); i += blockDim.x)
+      reinterpret_cast<uint32_t*>(gst)[i] = reinterpret_cast<const uint32_t*>(&s_st)[i];
   }
 }
 
@@ -1599,14 +1784,16 @@ __global__ void finalize_flow_kernel(IterArgs A, const double* gathered, int str
 }
 __global__ void finalize_step_kernel(IterArgs A, const double* gathered, int stride) {
   DevState* st = A.st;
-  if (st->done) return;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  __shared__ CtrlScratch s_ctrl;
+  if (st->done) return;  // uniform: one block
   double tot[4] = {0, 0, 0, 0};
-  for (int r = 0; r < A.world; r++) {
-    const double* g = gathered + (size_t)r * stride;
-    for (int k = 0; k < 4; k++) tot[k] += g[k];
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < A.world; r++) {
+      const double* g = gathered + (size_t)r * stride;
+      for (int k = 0; k < 4; k++) tot[k] += g[k];
+    }
   }
-  controller_step(A, st, tot);
+  controller_step(A, st, tot, &s_ctrl);
 }
 // host-initialised state needs the same Rinv/Tinv/bound update_tf_device computes
 __global__ void init_bound_kernel(IterArgs A) {
@@ -1674,11 +1861,22 @@ void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride,
   finalize_flow_kernel<<<1, 32, 0, s>>>(A, gathered, stride);
 }
 void launch_finalize_step(const IterArgs& A, const double* gathered, int stride, cudaStream_t s) {
-  finalize_step_kernel<<<1, 32, 0, s>>>(A, gathered, stride);
+  finalize_step_kernel<<<1, 64, 0, s>>>(A, gathered, stride);
 }
 void launch_init_bound(const IterArgs& A, cudaStream_t s) { init_bound_kernel<<<1, 32, 0, s>>>(A); }
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s) {
   fma_peak_kernel<<<blocks, 256, 0, s>>>(kind, iters, sink);
+}
+cudaError_t launch_align_grid(const IterArgs& A, int blocks, cudaStream_t s) {
+  IterArgs a = A;
+  void* args[] = {&a};
+  return cudaLaunchCooperativeKernel((const void*)align_grid_kernel, dim3(blocks), dim3(kSparseThreads),
+                                     args, 0, s);
+}
+int align_grid_max_blocks_per_sm() {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_kernel, kSparseThreads, 0);
+  return n;
 }
 int pair_kernel_max_blocks_per_sm() {
   int n = 0;
