@@ -42,10 +42,28 @@ WORKLOADS = {
     "KITTI05": ("KITTI05", "cvo_intensity_params_img_gpu0.yaml", dict(FIRST_FRAME=1),
                 "synthetic KITTI-05-sized N=M=16384, geometry+5-dim colour, first-frame parameters "
                 "(ell_init=1.5); one step = one align()"),
+    # a frame of a running sequence: the yaml's regular parameters (ell_init = 0.15) and the
+    # constant-velocity initial guess
+    "KITTI05_TRACK": ("KITTI05", "cvo_intensity_params_img_gpu0.yaml", dict(TRACK=1),
+                      "synthetic KITTI-05-sized N=M=16384, geometry+5-dim colour, regular (tracking) "
+                      "parameters, constant-velocity initial guess with 5 % error; one step = one align()"),
     "C4": ("C4", "cvo_intensity_params_img_gpu0.yaml", dict(FIRST_FRAME=1, MAX_ITER=50),
            "synthetic N=M=200000 geometry+5-dim colour (BASELINE configs[3]), first-frame "
            "parameters (ell_init=1.5), MAX_ITER=50; one step = one align() of 50 iterations"),
 }
+
+
+def tracking_init():
+    """Initial guess of a tracking frame: the constant-velocity prediction the sequence drivers
+    feed to align (main_cvo_gpu_align_raw_image.cpp:158-160), modelled as the true inter-frame
+    motion with a 5 % error.  Returned as T_target_to_source (= inverse of the predicted result)."""
+    a = np.deg2rad(2.0 * 0.95)
+    R = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]])
+    Tr = np.eye(4)
+    Tr[:3, 3] = np.array([0.05, 0.02, 0.50]) * 0.95
+    Rm = np.eye(4)
+    Rm[:3, :3] = R
+    return np.linalg.inv(Rm @ Tr).astype(np.float32)
 
 
 def load_workload(name):
@@ -56,6 +74,8 @@ def load_workload(name):
     d = synthetic.make_config(cfg)
     p = u.read_params_yaml(os.path.join(DATA, yaml))
     for k, v in over.items():
+        if k == "TRACK":
+            continue
         if k == "FIRST_FRAME":
             p.ell_init = p.ell_init_first_frame
             p.ell_decay_rate = p.ell_decay_rate_first_frame
@@ -175,12 +195,39 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def frame_pairs_leg(u, name, steps=5):
+    """frame-pairs/s = 1 / (device time of one full align) on a KITTI-05-sized synthetic pair."""
+    src, tgt, p, desc = load_workload(name)
+    T_init = tracking_init() if WORKLOADS[name][2].get("TRACK") else None
+    g = u.CvoGPU(p)
+    g.set_cloud(0, src)
+    g.set_cloud(1, tgt)
+    for _ in range(2):
+        g.align(src, tgt, T_init, resident=True)
+    dev, iters, wall0 = 0.0, 0, time.perf_counter()
+    for _ in range(steps):
+        ret, T, info = g.align(src, tgt, T_init, resident=True)
+        dev += info.registration_seconds
+        iters += info.iterations + (0 if info.stop_reason == 8 else 1)
+    wall = time.perf_counter() - wall0
+    t0 = time.perf_counter()
+    g.align_host(src, tgt, T_init)
+    e2e = time.perf_counter() - t0
+    from unified_cvo_b200 import synthetic
+    err = float(np.abs(T - synthetic.gt_transform()).max())
+    g.close()
+    return {"workload": f"{name}: {desc}", "frame_pairs_per_s": steps / dev, "ms_per_frame_pair": 1e3 * dev / steps,
+            "iterations_per_frame_pair": iters / steps, "e2e_frame_pairs_per_s": 1.0 / e2e,
+            "wall_ms_per_frame_pair": 1e3 * wall / steps, "max_abs_pose_error_vs_truth": err, "ret": int(ret)}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import unified_cvo_b200 as u
 
     name = args.workload or ("C2" if world == 1 else "C4")
     src, tgt, p, desc = load_workload(name)
+    T_init = tracking_init() if WORKLOADS[name][2].get("TRACK") else None
     N, M, F, C = src.num_points(), tgt.num_points(), src.feature_dimensions(), src.num_classes()
     torch.cuda.set_device(local_rank)
     g = u.CvoGPU(p, device=local_rank)
@@ -208,7 +255,7 @@ def run_ours(args, rank, world, local_rank):
     t_warm = time.perf_counter()
     w = 0
     while w < args.warmup or time.perf_counter() - t_warm < 0.5:
-        g.align(src, tgt, resident=True)
+        g.align(src, tgt, T_init, resident=True)
         w += 1
         if w > args.warmup + 50:
             break
@@ -223,7 +270,7 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        _, _, info = g.align(src, tgt, resident=True)
+        _, _, info = g.align(src, tgt, T_init, resident=True)
         dev_s += info.registration_seconds
         pairs += info.pairs_tested
         iters += info.iterations + (0 if info.stop_reason == 8 else 1)
@@ -238,7 +285,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1:
         for _ in range(max(1, min(args.steps, 5))):
             t0 = time.perf_counter()
-            _, _, info = g.align_host(src, tgt)
+            _, _, info = g.align_host(src, tgt, T_init)
             e2e_s += time.perf_counter() - t0
             e2e_pairs += info.pairs_tested
         e2e_steps = max(1, min(args.steps, 5))
@@ -249,7 +296,7 @@ def run_ours(args, rank, world, local_rank):
             t0 = time.perf_counter()
             g.set_cloud(0, src)
             g.set_cloud(1, tgt)
-            _, _, info = g.align(src, tgt, resident=True)
+            _, _, info = g.align(src, tgt, T_init, resident=True)
             e2e_s += time.perf_counter() - t0
             e2e_pairs += info.pairs_tested
 
@@ -324,6 +371,9 @@ def run_ours(args, rank, world, local_rank):
         "wall_ms_per_step": 1e3 * wall / args.steps,
         "frame_pairs_per_s": args.steps / dev_s,
     }
+    # frame-pairs/s on KITTI-05-sized clouds (north_star): a tracking frame and a first frame
+    if world == 1 and args.workload is None and not args.no_frames:
+        line["frame_pairs"] = [frame_pairs_leg(u, wl) for wl in ("KITTI05_TRACK", "KITTI05")]
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same registration
     if world == 1 and not args.no_cpu_baseline:
         import oracle
@@ -350,6 +400,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frames", action="store_true", help="skip the KITTI-05-sized frame-pairs/s legs")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

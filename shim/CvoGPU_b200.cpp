@@ -12,13 +12,18 @@
 //
 // The class layout is fixed by the reference header (CvoParams* params_gpu; CvoParams params;),
 // so the device handle lives in a side table keyed by `this`.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
 
+#ifndef CVO_SHIM_SYNTAX_CHECK
 #include "cvo/CvoGPU.hpp"
+#endif
 #include "cvo_b200.h"
 
 namespace cvo {

@@ -1,0 +1,135 @@
+// reference_api_stub.hpp — TEST-ONLY stand-ins for the third-party and reference types that
+// shim/CvoGPU_b200.cpp touches (Eigen, PCL, cvo::CvoPointCloud/CvoParams/Association/CvoGPU).
+// The build container has neither Eigen nor PCL, so tests/test_shim_syntax.py compiles the shim
+// against these declarations (-DCVO_SHIM_SYNTAX_CHECK -include this file) to keep it
+// syntactically and type-wise honest.  Nothing here is shipped or linked; in a real build the
+// shim includes the reference's own headers instead.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <list>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "cvo_b200.h"
+
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+#ifndef NUM_CLASSES
+#define NUM_CLASSES 19
+#endif
+#ifndef FEATURE_DIMENSIONS
+#define FEATURE_DIMENSIONS 5
+#endif
+
+namespace Eigen {
+constexpr int Dynamic = -1;
+constexpr int RowMajor = 1;
+template <class T, int R, int C>
+struct Matrix {
+  std::vector<T> d;
+  int r = R > 0 ? R : 0, c = C > 0 ? C : 0;
+  Matrix() : d((size_t)(R > 0 ? R : 0) * (C > 0 ? C : 0)) {}
+  long rows() const { return r; }
+  long cols() const { return c; }
+  T* data() { return d.data(); }
+  const T* data() const { return d.data(); }
+  T& operator()(int i, int j) { return d[(size_t)j * r + i]; }
+  const T& operator()(int i, int j) const { return d[(size_t)j * r + i]; }
+  T& operator()(int i) { return d[i]; }
+  const T& operator()(int i) const { return d[i]; }
+  static Matrix Identity() { return Matrix(); }
+};
+using Matrix4f = Matrix<float, 4, 4>;
+using Matrix3f = Matrix<float, 3, 3>;
+using Vector3f = Matrix<float, 3, 1>;
+using MatrixXf = Matrix<float, Dynamic, Dynamic>;
+template <class M>
+struct Ref {
+  M* m;
+  Ref(M& x) : m(&x) {}
+  Ref& operator=(const M& x) { *m = x; return *this; }
+};
+template <class T>
+struct aligned_allocator : std::allocator<T> {
+  template <class U> struct rebind { using other = aligned_allocator<U>; };
+};
+template <class T>
+struct Triplet {
+  Triplet(int, int, T) {}
+};
+template <class T, int Opt>
+struct SparseMatrix {
+  void resize(int, int) {}
+  template <class It> void setFromTriplets(It, It) {}
+  void makeCompressed() {}
+};
+}  // namespace Eigen
+
+namespace pcl {
+template <class P>
+struct PointCloud {
+  std::vector<P> points;
+  size_t size() const { return points.size(); }
+  const P& operator[](size_t i) const { return points[i]; }
+};
+}  // namespace pcl
+
+namespace cvo {
+struct CvoPoint {
+  float x, y, z;
+  float features[FEATURE_DIMENSIONS];
+  float label_distribution[NUM_CLASSES];
+  float geometric_type[2];
+};
+struct CvoParams : cvo_b200_params {};
+struct Association {
+  std::vector<int> source_inliers, target_inliers;
+  Eigen::SparseMatrix<float, Eigen::RowMajor> pairs;
+};
+class CvoPointCloud {
+ public:
+  int num_points() const { return 0; }
+  int num_classes() const { return 0; }
+  const std::vector<Eigen::Vector3f, Eigen::aligned_allocator<Eigen::Vector3f>>& positions() const { return p_; }
+  const Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic>& labels() const { return l_; }
+  const Eigen::MatrixXf& features() const { return f_; }
+  const std::vector<float>& geometric_types() const { return g_; }
+
+ private:
+  std::vector<Eigen::Vector3f, Eigen::aligned_allocator<Eigen::Vector3f>> p_;
+  Eigen::MatrixXf f_, l_;
+  std::vector<float> g_;
+};
+class CvoFrame;
+class BinaryState;
+// the members of cvo::CvoGPU that the shim defines (signatures as in the reference header)
+class CvoGPU {
+ private:
+  CvoParams* params_gpu;
+  CvoParams params;
+
+ public:
+  CvoGPU(const std::string& f);
+  ~CvoGPU();
+  CvoParams& get_params() { return params; }
+  const CvoParams* get_params_gpu() { return params_gpu; }
+  void write_params(const CvoParams* p_cpu);
+  int align(const CvoPointCloud&, const CvoPointCloud&, const Eigen::Matrix4f&, Eigen::Ref<Eigen::Matrix4f>,
+            Association* = nullptr, double* = nullptr) const;
+  int align(const pcl::PointCloud<CvoPoint>&, const pcl::PointCloud<CvoPoint>&, const Eigen::Matrix4f&,
+            Eigen::Ref<Eigen::Matrix4f>, Association* = nullptr, double* = nullptr) const;
+  float function_angle(const CvoPointCloud&, const CvoPointCloud&, const Eigen::Matrix4f&, float,
+                       bool is_approximate = true, bool is_gpu = true) const;
+  float function_angle(const pcl::PointCloud<CvoPoint>&, const pcl::PointCloud<CvoPoint>&,
+                       const Eigen::Matrix4f&, float, bool is_approximate = true) const;
+  void compute_association_gpu(const CvoPointCloud&, const CvoPointCloud&, const Eigen::Matrix4f&, float,
+                               Association&) const;
+  void compute_association_gpu(const CvoPointCloud&, const CvoPointCloud&, const Eigen::Matrix4f&,
+                               const Eigen::Matrix3f&, Association&) const;
+  float inner_product_gpu(const CvoPointCloud&, const CvoPointCloud&, const Eigen::Matrix4f&, float) const;
+  float inner_product_gpu(const pcl::PointCloud<CvoPoint>&, const pcl::PointCloud<CvoPoint>&,
+                          const Eigen::Matrix4f&, float) const;
+  float inner_product_cpu(const CvoPointCloud&, const CvoPointCloud&, const Eigen::Matrix4f&, float) const;
+};
+}  // namespace cvo

@@ -1,0 +1,40 @@
+"""The reference-side binding (shim/CvoGPU_b200.cpp: cvo::CvoGPU forwarded to the C-ABI) cannot be
+built against the real Eigen/PCL headers in this image, so it is compiled against the stand-in
+declarations of shim/stubs/ and LINKED against libcvo_b200.so with --no-undefined: every C-ABI
+symbol the shim calls must exist with a compatible signature."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+from helpers import ROOT
+
+GXX = shutil.which("g++") or "/usr/bin/g++"
+
+
+def test_shim_compiles_and_links_against_the_c_abi(tmp_path):
+    lib = os.path.join(ROOT, "unified_cvo_b200", "csrc", "libcvo_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("libcvo_b200.so not built")
+    stub = os.path.join(ROOT, "shim", "stubs", "reference_api_stub.hpp")
+    common = [GXX, "-std=c++17", "-fPIC", "-Wall", "-Werror=return-type", "-DCVO_SHIM_SYNTAX_CHECK",
+              "-I" + os.path.join(ROOT, "include"), "-include", stub]
+    obj = tmp_path / "shim.o"
+    out = subprocess.run(common + ["-c", os.path.join(ROOT, "shim", "CvoGPU_b200.cpp"), "-o", str(obj)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    # the one member the shim leaves to the reference's own CvoGPU.cpp
+    rest = tmp_path / "rest.cpp"
+    rest.write_text("namespace cvo { float CvoGPU::inner_product_cpu(const CvoPointCloud&, const CvoPointCloud&,"
+                    " const Eigen::Matrix4f&, float) const { return 0.f; } }\n")
+    so = tmp_path / "libshim_check.so"
+    out = subprocess.run(common + ["-shared", str(obj), str(rest), "-o", str(so), "-Wl,--no-undefined",
+                                   "-L" + os.path.dirname(lib), "-lcvo_b200",
+                                   "-Wl,-rpath," + os.path.dirname(lib)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    syms = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True).stdout
+    for member in ("CvoGPU5align", "CvoGPU14function_angle", "CvoGPU23compute_association_gpu",
+                   "CvoGPU17inner_product_gpu", "CvoGPU12write_params"):
+        assert member in syms, member

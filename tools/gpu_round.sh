@@ -1,14 +1,19 @@
 #!/bin/bash
-# One GPU-box session: breakdown, large workloads, ncu launch list + full capture.
-# usage: gpurun --timeout 1500 -- 'bash tools/gpu_round.sh TAG'
+# One GPU-box session: tests, benches, ncu launch list + full captures.
+# usage: gpurun --timeout 1800 -- 'bash tools/gpu_round.sh TAG'
 TAG=${1:-x}
 O=gpurun_out
 mkdir -p $O
 export PYTHONUNBUFFERED=1
-( timeout 200 python tools/gpu_breakdown.py C2 0.95; timeout 200 python tools/gpu_breakdown.py C2 0.3; timeout 200 python tools/gpu_breakdown.py KITTI05 0.3 ) > $O/${TAG}_breakdown.log 2>&1
-timeout 300 python bench.py --workload KITTI05 --steps 5 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_kitti05.log 2>&1
+timeout 600 python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; tail -2 $O/${TAG}_pytest.log
+timeout 500 python bench.py > $O/${TAG}_bench.log 2>&1
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/${TAG}_bench_ref.log 2>&1
 timeout 300 python bench.py --workload C4 --steps 2 --warmup 3 --no-cpu-baseline > $O/${TAG}_bench_c4.log 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/${TAG}_ncu_launch.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pair_kernel|flow_kernel|step_kernel|prep_kernel' -c 12 -o $O/${TAG}_full_c2 -f python tools/gpu_profile.py C2 3 0.95 > $O/${TAG}_ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pair_kernel|flow_kernel|step_kernel|prep_kernel' -c 8 -o $O/${TAG}_full_c4 -f python tools/gpu_profile.py C4 2 0.3 > $O/${TAG}_ncu_full_c4.log 2>&1
-tail -3 $O/${TAG}_breakdown.log; tail -c 600 $O/${TAG}_bench_c4.log
+# launch list of the default bench command (cold-cache, serialised: shares, not absolutes)
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-frames > $O/${TAG}_ncu_launch.log 2>&1
+# full capture of the persistent kernel on C2 (one launch = one whole registration)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'align_grid_kernel' -s 3 -c 1 -o $O/${TAG}_full_c2_persist -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-frames > $O/${TAG}_ncu_full.log 2>&1
+# full capture of the per-phase kernels in both modes (fixed state, C2)
+CVO_B200_PERSIST=0 CVO_B200_MODE=grid timeout 600 ncu --set full --clock-control none --import-source on -k regex:'flow_kernel|step_kernel' -c 4 -o $O/${TAG}_full_c2_grid -f python tools/gpu_profile.py C2 2 0.95 >> $O/${TAG}_ncu_full.log 2>&1
+CVO_B200_MODE=dense timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pair_kernel|flow_kernel|step_kernel|prep_kernel' -c 8 -o $O/${TAG}_full_c2_dense -f python tools/gpu_profile.py C2 2 0.95 >> $O/${TAG}_ncu_full.log 2>&1
+tail -c 600 $O/${TAG}_bench.log

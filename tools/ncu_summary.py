@@ -1,0 +1,45 @@
+"""Summarise an ncu --set full report: one block of key metrics per profiled launch, and (with
+--traffic KEY_PREFIX) the dram bytes per launch merged into profiles/traffic.json.
+usage: ncu_summary.py report.ncu-rep [--traffic WORKLOAD] > profiles/<name>_summary.txt"""
+import csv, io, json, os, subprocess, sys
+
+rep = sys.argv[1]
+wl = sys.argv[sys.argv.index("--traffic") + 1] if "--traffic" in sys.argv else None
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hdr, units = rows[0], rows[1]
+want = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.sum", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__cycles_active.avg", "sm__cycles_elapsed.max", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct",
+        "l1tex__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio"]
+stall = [h for h in hdr if "pcsamp_warps_issue_stalled" in h and not h.endswith("_not_issued")]
+traffic = {}
+K = hdr.index("Kernel Name")
+for r in rows[2:]:
+    name = r[K].split("(")[0].replace("void ", "")
+    print(f"== {r[K]}")
+    for w in want:
+        if w in hdr:
+            i = hdr.index(w)
+            print(f"   {w:70s} {r[i]:>16s} {units[i]}")
+    tot = sum(float(r[hdr.index(h)] or 0) for h in stall) or 1.0
+    top = sorted(((float(r[hdr.index(h)] or 0), h) for h in stall), reverse=True)[:6]
+    print("   stall samples: " + ", ".join(f"{h.replace('smsp__pcsamp_warps_issue_stalled_', '')} {100 * v / tot:.0f}%" for v, h in top))
+    def to_bytes(col):
+        i = hdr.index(col)
+        v = float(r[i].replace(",", "") or 0)
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[i], 1)
+    traffic[name] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+if wl:
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    try:
+        cur = json.load(open(path))
+    except Exception:
+        cur = {}
+    for k, v in traffic.items():
+        cur[f"{wl}:{k}"] = v
+    json.dump(cur, open(path, "w"), indent=1, sort_keys=True)

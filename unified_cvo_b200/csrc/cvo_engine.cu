@@ -525,7 +525,7 @@ int launches_per_iteration(const cvo_b200_handle* h, const IterArgs& A) {
 // Candidate-generator policy.  A cell query tests, per source row, the points of <= 27 cube cells
 // of edge h in [r, 2r) (r = largest cut-off radius of the cloud, CvoGPU.cu:506-511); the dense
 // scan tests M points per row at ~1/6 of the per-test cost.  Cell queries win while the expected
-// tests per row stay below ~M/8.  The density comes from the occupied coarse cells, so
+// tests per row stay below ~M/16 (measured break-even on KITTI-sized clouds with ell = 1.5).  The density comes from the occupied coarse cells, so
 // slab- or surface-like clouds are not mistaken for sparse ones.
 bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDev& ct, float ell) {
   const cvo_b200_params& p = h->params;
@@ -542,7 +542,7 @@ bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDe
   while (hcell * 0.5 >= r && hcell * 0.5 >= hmin) hcell *= 0.5;  // finest usable level with h >= r
   const double density = (double)ct.n_finite / ct.occupied_volume;
   const double tests = std::min((double)ct.n, 27.0 * hcell * hcell * hcell * density);
-  return tests < 0.125 * (double)ct.n;
+  return tests < 0.06 * (double)ct.n;
 }
 
 // 63-bit Morton key of a point inside the cloud's bounding box (21 bits per axis)
@@ -630,18 +630,30 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
     const int csh = 3 * (21 - cb);
     const size_t ncell = (size_t)1 << (3 * cb);
     std::vector<uint32_t> coarse(ncell + 1);
-    size_t pos = 0, occupied = 0;
+    size_t pos = 0;
     for (size_t cell = 0; cell < ncell; cell++) {
       while (pos < n_finite && (skeys[pos] >> csh) < cell) pos++;
       coarse[cell] = (uint32_t)pos;
-      if (pos < n_finite && (skeys[pos] >> csh) == cell) occupied++;
     }
     coarse[ncell] = (uint32_t)n_finite;
     c.lo[0] = lo[0]; c.lo[1] = lo[1]; c.lo[2] = lo[2];
     c.key_scale = (float)scale;
     c.extent = ext;
-    const double hc = ext / (double)(1 << cb);
-    c.occupied_volume = (double)occupied * hc * hc * hc;
+    // density estimate for the mode policy: volume of the occupied cells two levels above the
+    // table (64x its cell volume, tens of points per cell: insensitive to sampling noise, still
+    // follows slab- and surface-like clouds)
+    {
+      const int db = std::max(1, cb - 2);
+      const int dsh = 3 * (21 - db);
+      size_t occ = 0;
+      unsigned long long prev = ~0ull;
+      for (size_t i2 = 0; i2 < n_finite; i2++) {
+        const unsigned long long cell = skeys[i2] >> dsh;
+        if (cell != prev) { occ++; prev = cell; }
+      }
+      const double hd = ext / (double)(1 << db);
+      c.occupied_volume = (double)occ * hd * hd * hd;
+    }
     int rck = upload_vec(h, c.coarse, coarse);
     if (rck != CVO_B200_OK) return rck;
   }
