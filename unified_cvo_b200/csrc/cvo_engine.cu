@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "cvo_device.cuh"
+#include "cvo_upload.cuh"
 
 namespace cvo_b200 {
 void launch_prep(const IterArgs& A, int blocks, cudaStream_t s);
@@ -121,7 +122,10 @@ struct CloudDev {
   DevBuf<float4> tile_sphere;  // per 64 points (source role)
   DevBuf<float> tile_maxdist;
   DevBuf<int> inv;             // original index -> Morton position (device)
-  std::vector<int> perm;       // Morton position -> original index (host, for exports)
+  std::vector<int> perm;       // Morton position -> original index (host copy, fetched lazily for exports)
+  bool perm_on_host = false;
+  DevBuf<int> perm_d;          // the same on the device
+  DevBuf<unsigned long long> keys_d;  // sorted Morton keys (build only)
   // cell index over the Morton order (target role, grid mode): see GridView
   DevBuf<uint32_t> coarse;
   int cbits = 0, n_finite = 0;
@@ -160,6 +164,13 @@ struct cvo_b200_handle {
   DevBuf<cvo_b200_iter_trace> d_trace;
   DevBuf<double> gathered;  // multi-GPU all-gather receive buffer
   DevBuf<unsigned long long> stamps;  // debug: per-block phase stamps (CVO_B200_STAMPS=1)
+  // cloud build scratch (cvo_upload.cu)
+  DevBuf<float> raw_xyz, raw_feat, raw_lab, raw_geo;
+  DevBuf<unsigned long long> keys_in;
+  DevBuf<int> idx_in;
+  DevBuf<unsigned char> sort_temp;
+  DevBuf<CloudStats> d_stats;
+  CloudStats* h_stats = nullptr;  // pinned
   int row_begin = 0, row_end = -1;
   // launch geometry
   int prep_blocks = 1, pair_blocks = 1, sparse_blocks = 1;
@@ -545,28 +556,9 @@ bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDe
   return tests < 0.06 * (double)ct.n;
 }
 
-// 63-bit Morton key of a point inside the cloud's bounding box (21 bits per axis)
-inline uint64_t spread21(uint64_t v) {
-  v &= 0x1fffffull;
-  v = (v | (v << 32)) & 0x1f00000000ffffull;
-  v = (v | (v << 16)) & 0x1f0000ff0000ffull;
-  v = (v | (v << 8)) & 0x100f00f00f00f00full;
-  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
-  v = (v | (v << 2)) & 0x1249249249249249ull;
-  return v;
-}
-
-template <typename T>
-int upload_vec(cvo_b200_handle* h, DevBuf<T>& dst, const std::vector<T>& src) {
-  CVO_CUDA(h, dst.ensure(src.size()));
-  if (!src.empty())
-    CVO_CUDA(h, cudaMemcpyAsync(dst.p, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-  CVO_CUDA(h, cudaStreamSynchronize(h->stream));  // src is a temporary of the caller
-  return CVO_B200_OK;
-}
-
-// Replaces CvoPointCloud_to_gpu (CvoGPU_impl.cu:206-285): SoA pack + upload, in two orders:
-// Morton order (source role and prunable target view) and the caller's order (exact view).
+// Replaces CvoPointCloud_to_gpu (CvoGPU_impl.cu:206-285).  The caller's arrays go to the device
+// as they are (four copies); Morton order, SoA packing, the cell table and the bounding spheres
+// are built there (cvo_upload.cu); one small read-back returns the scalars the host needs.
 int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F,
                  const float* features, int C, const float* labels, const float* geotype) {
   if (n < 0 || F < 0 || C < 0 || (n > 0 && !xyz)) return fail(h, CVO_B200_ERR_INVALID, "bad cloud arguments");
@@ -577,188 +569,99 @@ int upload_cloud(cvo_b200_handle* h, CloudDev& c, int n, const float* xyz, int F
   c.Cp = round_up(c.C, 4);
   c.has_geo = geotype != nullptr;
   c.set = true;
-  c.perm.resize((size_t)n);
+  c.perm.clear();
+  c.perm_on_host = false;
   c.max_dist = 0.f;
   c.n_finite = 0;
+  h->last_valid = false;
   if (n == 0) return CVO_B200_OK;
-
-  // ---- bounding box, centroid (finite points only)
-  double mx = 0, my = 0, mz = 0;
-  size_t n_finite = 0;
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  for (int i = 0; i < n; i++) {
-    const float* p = xyz + 3 * (size_t)i;
-    if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
-      mx += p[0]; my += p[1]; mz += p[2];
-      n_finite++;
-      for (int k = 0; k < 3; k++) {
-        lo[k] = std::min(lo[k], p[k]);
-        hi[k] = std::max(hi[k], p[k]);
-      }
-    }
+  cudaStream_t s = h->stream;
+  const size_t nn = (size_t)n;
+  // ---- raw input -> device
+  CVO_CUDA(h, h->raw_xyz.ensure(nn * 3));
+  CVO_CUDA(h, cudaMemcpyAsync(h->raw_xyz.p, xyz, nn * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (c.F) {
+    CVO_CUDA(h, h->raw_feat.ensure(nn * c.F));
+    CVO_CUDA(h, cudaMemcpyAsync(h->raw_feat.p, features, nn * c.F * sizeof(float), cudaMemcpyHostToDevice, s));
   }
-  c.cx = n_finite ? (float)(mx / (double)n_finite) : 0.f;
-  c.cy = n_finite ? (float)(my / (double)n_finite) : 0.f;
-  c.cz = n_finite ? (float)(mz / (double)n_finite) : 0.f;
-  // ---- Morton order (non-finite points last, in their original order)
-  {
-    const double ext = std::max({(double)hi[0] - lo[0], (double)hi[1] - lo[1], (double)hi[2] - lo[2], 1e-30});
-    const double scale = 2097151.0 / ext;  // one isotropic grid: cells are cubes
-    std::vector<std::pair<uint64_t, int>> keys((size_t)n);
-    for (int i = 0; i < n; i++) {
-      const float* p = xyz + 3 * (size_t)i;
-      uint64_t key = ~0ull;
-      if (n_finite && std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2])) {
-        const uint64_t qx = (uint64_t)(((double)p[0] - lo[0]) * scale);
-        const uint64_t qy = (uint64_t)(((double)p[1] - lo[1]) * scale);
-        const uint64_t qz = (uint64_t)(((double)p[2] - lo[2]) * scale);
-        key = spread21(qx) | (spread21(qy) << 1) | (spread21(qz) << 2);
-      }
-      keys[i] = {key, i};
-    }
-    std::sort(keys.begin(), keys.end());
-    for (int i = 0; i < n; i++) c.perm[i] = keys[i].second;
-    // ---- cell index: sorted keys + lower bounds of a coarse level (~1 point per cell on
-    //      a slab-like cloud, 4..7 bits per axis: <= 8 MB) so the search inside a coarse
-    //      cell is 0..2 steps
-    std::vector<unsigned long long> skeys((size_t)n);
-    for (int i = 0; i < n; i++) skeys[i] = keys[i].first;
-    c.n_finite = (int)n_finite;
-    int cb = 4;
-    while (cb < 7 && ((size_t)1 << (3 * cb)) < (size_t)16 * (size_t)n) cb++;
-    c.cbits = cb;
-    const int csh = 3 * (21 - cb);
-    const size_t ncell = (size_t)1 << (3 * cb);
-    std::vector<uint32_t> coarse(ncell + 1);
-    size_t pos = 0;
-    for (size_t cell = 0; cell < ncell; cell++) {
-      while (pos < n_finite && (skeys[pos] >> csh) < cell) pos++;
-      coarse[cell] = (uint32_t)pos;
-    }
-    coarse[ncell] = (uint32_t)n_finite;
-    c.lo[0] = lo[0]; c.lo[1] = lo[1]; c.lo[2] = lo[2];
-    c.key_scale = (float)scale;
-    c.extent = ext;
-    // density estimate for the mode policy: volume of the occupied cells two levels above the
-    // table (64x its cell volume, tens of points per cell: insensitive to sampling noise, still
-    // follows slab- and surface-like clouds)
-    {
-      const int db = std::max(1, cb - 2);
-      const int dsh = 3 * (21 - db);
-      size_t occ = 0;
-      unsigned long long prev = ~0ull;
-      for (size_t i2 = 0; i2 < n_finite; i2++) {
-        const unsigned long long cell = skeys[i2] >> dsh;
-        if (cell != prev) { occ++; prev = cell; }
-      }
-      const double hd = ext / (double)(1 << db);
-      c.occupied_volume = (double)occ * hd * hd * hd;
-    }
-    int rck = upload_vec(h, c.coarse, coarse);
-    if (rck != CVO_B200_OK) return rck;
-  }
-  const std::vector<int>& perm = c.perm;
-  {
-    std::vector<int> inv((size_t)n);
-    for (int s2 = 0; s2 < n; s2++) inv[perm[s2]] = s2;
-    int rc0 = upload_vec(h, c.inv, inv);
-    if (rc0 != CVO_B200_OK) return rc0;
-  }
-
-  // ---- coordinates in both orders, prefilter records, extent
-  std::vector<float4> buf((size_t)n), buf_o((size_t)n), recA((size_t)n);
-  double r2max = 0.0;
-  for (int i = 0; i < n; i++) {
-    const float* p = xyz + 3 * (size_t)i;
-    buf_o[i] = make_float4(p[0], p[1], p[2], 0.f);
-    const double dx = (double)p[0] - c.cx, dy = (double)p[1] - c.cy, dz = (double)p[2] - c.cz;
-    const double r2 = dx * dx + dy * dy + dz * dz;
-    if (r2 > r2max) r2max = r2;  // NaN compares false; +inf propagates (every pair a candidate)
-  }
-  c.radius = (float)(std::sqrt(r2max) * (1.0 + 1e-6)) + 1e-6f;
-  for (int s = 0; s < n; s++) {
-    const float* p = xyz + 3 * (size_t)perm[s];
-    const float x = p[0], y = p[1], z = p[2];
-    buf[s] = make_float4(x, y, z, 0.f);
-    // prefilter record: a = -2 (x - c) and the reference's a_to_sensor (CvoGPU.cu:506)
-    volatile float xx = x * x, yy = y * y, zz = z * z;
-    volatile float sxy = xx + yy;
-    const float dist = sqrtf(sxy + zz);
-    if (dist > c.max_dist) c.max_dist = dist;
-    recA[s] = make_float4(-2.f * (x - c.cx), -2.f * (y - c.cy), -2.f * (z - c.cz), dist);
-  }
-  int rc;
-  if ((rc = upload_vec(h, c.xyz, buf)) != CVO_B200_OK) return rc;
-  if ((rc = upload_vec(h, c.xyz_o, buf_o)) != CVO_B200_OK) return rc;
-  if ((rc = upload_vec(h, c.rowA, recA)) != CVO_B200_OK) return rc;
-
-  // ---- bounding spheres over the Morton order: 256-point blocks (target role, padded to a
-  //      whole block) and 64-point tiles (source role).  Non-finite points make the sphere
-  //      infinite, i.e. never skipped.
-  auto spheres = [&](int group, std::vector<float4>& out, std::vector<float>* maxdist) {
-    const int ng = (n + group - 1) / group;
-    out.assign((size_t)std::max(ng, 1), make_float4(0.f, 0.f, 0.f, INFINITY));
-    if (maxdist) maxdist->assign((size_t)std::max(ng, 1), INFINITY);
-    for (int g = 0; g < ng; g++) {
-      const int b = g * group, e = std::min(n, b + group);
-      double l3[3] = {1e300, 1e300, 1e300}, h3[3] = {-1e300, -1e300, -1e300};
-      bool finite = true;
-      float md = 0.f;
-      for (int s = b; s < e; s++) {
-        const float4 q = buf[s];
-        if (!(std::isfinite(q.x) && std::isfinite(q.y) && std::isfinite(q.z))) { finite = false; break; }
-        l3[0] = std::min(l3[0], (double)q.x); h3[0] = std::max(h3[0], (double)q.x);
-        l3[1] = std::min(l3[1], (double)q.y); h3[1] = std::max(h3[1], (double)q.y);
-        l3[2] = std::min(l3[2], (double)q.z); h3[2] = std::max(h3[2], (double)q.z);
-        md = std::max(md, recA[s].w);
-      }
-      if (!finite) continue;
-      const double cx = 0.5 * (l3[0] + h3[0]), cy = 0.5 * (l3[1] + h3[1]), cz = 0.5 * (l3[2] + h3[2]);
-      double r2 = 0.0;
-      for (int s = b; s < e; s++) {
-        const double dx = buf[s].x - cx, dy = buf[s].y - cy, dz = buf[s].z - cz;
-        r2 = std::max(r2, dx * dx + dy * dy + dz * dz);
-      }
-      out[g] = make_float4((float)cx, (float)cy, (float)cz,
-                           (float)(std::sqrt(r2) * (1.0 + 1e-5)) + 1e-5f * (float)(std::fabs(cx) + std::fabs(cy) + std::fabs(cz)) + 1e-6f);
-      if (maxdist) (*maxdist)[g] = md;
-    }
-  };
-  std::vector<float4> sph;
-  std::vector<float> md;
-  spheres(kJBlock, sph, nullptr);
-  if ((rc = upload_vec(h, c.blk_sphere, sph)) != CVO_B200_OK) return rc;
-  spheres(kTileRows, sph, &md);
-  if ((rc = upload_vec(h, c.tile_sphere, sph)) != CVO_B200_OK) return rc;
-  if ((rc = upload_vec(h, c.tile_maxdist, md)) != CVO_B200_OK) return rc;
-
-  if (c.F > 0) {
-    std::vector<float> fb((size_t)n * c.Fp, 0.f), fo((size_t)n * c.Fp, 0.f);
-    for (int s = 0; s < n; s++) {
-      std::memcpy(&fb[(size_t)s * c.Fp], features + (size_t)perm[s] * c.F, sizeof(float) * c.F);
-      std::memcpy(&fo[(size_t)s * c.Fp], features + (size_t)s * c.F, sizeof(float) * c.F);
-    }
-    if ((rc = upload_vec(h, c.feat, fb)) != CVO_B200_OK) return rc;
-    if ((rc = upload_vec(h, c.feat_o, fo)) != CVO_B200_OK) return rc;
-  }
-  if (c.C > 0) {
-    std::vector<float> lb((size_t)n * c.Cp, 0.f), lo2((size_t)n * c.Cp, 0.f);
-    for (int s = 0; s < n; s++) {
-      std::memcpy(&lb[(size_t)s * c.Cp], labels + (size_t)perm[s] * c.C, sizeof(float) * c.C);
-      std::memcpy(&lo2[(size_t)s * c.Cp], labels + (size_t)s * c.C, sizeof(float) * c.C);
-    }
-    if ((rc = upload_vec(h, c.lab, lb)) != CVO_B200_OK) return rc;
-    if ((rc = upload_vec(h, c.lab_o, lo2)) != CVO_B200_OK) return rc;
+  if (c.C) {
+    CVO_CUDA(h, h->raw_lab.ensure(nn * c.C));
+    CVO_CUDA(h, cudaMemcpyAsync(h->raw_lab.p, labels, nn * c.C * sizeof(float), cudaMemcpyHostToDevice, s));
   }
   if (geotype) {
-    std::vector<float2> gs((size_t)n), go((size_t)n);
-    for (int s = 0; s < n; s++) {
-      gs[s] = make_float2(geotype[2 * (size_t)perm[s]], geotype[2 * (size_t)perm[s] + 1]);
-      go[s] = make_float2(geotype[2 * (size_t)s], geotype[2 * (size_t)s + 1]);
-    }
-    if ((rc = upload_vec(h, c.geo, gs)) != CVO_B200_OK) return rc;
-    if ((rc = upload_vec(h, c.geo_o, go)) != CVO_B200_OK) return rc;
+    CVO_CUDA(h, h->raw_geo.ensure(nn * 2));
+    CVO_CUDA(h, cudaMemcpyAsync(h->raw_geo.p, geotype, nn * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
   }
+  // ---- cell table resolution: ~1 point per 16 cells on a slab-like cloud, 4..7 bits per axis
+  //      (<= 8 MB), so late iterations (cut-off radius far below the cell) test a handful of points
+  int cb = 4;
+  while (cb < 7 && ((size_t)1 << (3 * cb)) < (size_t)16 * nn) cb++;
+  c.cbits = cb;
+  const int db = std::max(1, cb - 2);  // density estimate: cells with tens of points
+  const size_t ncell = ((size_t)1 << (3 * cb)) + 1;
+  const int nblk = (n + kJBlock - 1) / kJBlock, ntile = (n + kTileRows - 1) / kTileRows;
+  const size_t temp_bytes = cloud_sort_temp_bytes(n);
+  CVO_CUDA(h, h->keys_in.ensure(nn));
+  CVO_CUDA(h, h->idx_in.ensure(nn));
+  CVO_CUDA(h, h->sort_temp.ensure(temp_bytes));
+  CVO_CUDA(h, h->d_stats.ensure(1));
+  CVO_CUDA(h, c.keys_d.ensure(nn));
+  CVO_CUDA(h, c.perm_d.ensure(nn));
+  CVO_CUDA(h, c.inv.ensure(nn));
+  CVO_CUDA(h, c.xyz.ensure(nn));
+  CVO_CUDA(h, c.xyz_o.ensure(nn));
+  CVO_CUDA(h, c.rowA.ensure(nn));
+  if (c.Fp) { CVO_CUDA(h, c.feat.ensure(nn * c.Fp)); CVO_CUDA(h, c.feat_o.ensure(nn * c.Fp)); }
+  if (c.Cp) { CVO_CUDA(h, c.lab.ensure(nn * c.Cp)); CVO_CUDA(h, c.lab_o.ensure(nn * c.Cp)); }
+  if (geotype) { CVO_CUDA(h, c.geo.ensure(nn)); CVO_CUDA(h, c.geo_o.ensure(nn)); }
+  CVO_CUDA(h, c.coarse.ensure(ncell));
+  CVO_CUDA(h, c.blk_sphere.ensure((size_t)std::max(nblk, 1)));
+  CVO_CUDA(h, c.tile_sphere.ensure((size_t)std::max(ntile, 1)));
+  CVO_CUDA(h, c.tile_maxdist.ensure((size_t)std::max(ntile, 1)));
+  CloudBuild B;
+  std::memset(&B, 0, sizeof(B));
+  B.n = n; B.F = c.F; B.C = c.C; B.Fp = c.Fp; B.Cp = c.Cp; B.cbits = cb; B.dbits = db;
+  B.xyz3 = h->raw_xyz.p;
+  B.feat_in = c.F ? h->raw_feat.p : nullptr;
+  B.lab_in = c.C ? h->raw_lab.p : nullptr;
+  B.geo_in = geotype ? h->raw_geo.p : nullptr;
+  B.keys_in = h->keys_in.p; B.idx_in = h->idx_in.p;
+  B.sort_temp = h->sort_temp.p; B.sort_temp_bytes = temp_bytes;
+  B.stats = h->d_stats.p;
+  B.keys = c.keys_d.p; B.perm = c.perm_d.p; B.inv = c.inv.p;
+  B.xyz = c.xyz.p; B.xyz_o = c.xyz_o.p; B.rowA = c.rowA.p;
+  B.feat = c.feat.p; B.feat_o = c.feat_o.p; B.lab = c.lab.p; B.lab_o = c.lab_o.p;
+  B.geo = c.geo.p; B.geo_o = c.geo_o.p;
+  B.coarse = c.coarse.p;
+  B.blk_sphere = c.blk_sphere.p; B.tile_sphere = c.tile_sphere.p; B.tile_maxdist = c.tile_maxdist.p;
+  CVO_CUDA(h, build_cloud_device(B, s));
+  h->launches += 8;
+  CVO_CUDA(h, cudaMemcpyAsync(h->h_stats, h->d_stats.p, sizeof(CloudStats), cudaMemcpyDeviceToHost, s));
+  CVO_CUDA(h, cudaStreamSynchronize(s));  // the caller's arrays may be released after this call
+  const CloudStats& st = *h->h_stats;
+  c.n_finite = st.n_finite;
+  c.cx = st.centroid[0]; c.cy = st.centroid[1]; c.cz = st.centroid[2];
+  c.lo[0] = st.lo[0]; c.lo[1] = st.lo[1]; c.lo[2] = st.lo[2];
+  c.key_scale = (float)st.scale;
+  c.extent = st.extent;
+  c.max_dist = st.max_dist;
+  {
+    float r2;
+    std::memcpy(&r2, &st.radius2_bits, sizeof(float));
+    c.radius = (float)(std::sqrt((double)r2) * (1.0 + 1e-6)) + 1e-6f;  // +inf stays +inf
+  }
+  const double hd = st.extent / (double)(1 << db);
+  c.occupied_volume = (double)st.occupied_cells * hd * hd * hd;
+  return CVO_B200_OK;
+}
+
+// Morton position -> original index, fetched from the device on first use (exports only)
+int fetch_perm(cvo_b200_handle* h, CloudDev& c) {
+  if (c.perm_on_host) return CVO_B200_OK;
+  c.perm.resize((size_t)c.n);
+  if (c.n > 0)
+    CVO_CUDA(h, cudaMemcpy(c.perm.data(), c.perm_d.p, sizeof(int) * (size_t)c.n, cudaMemcpyDeviceToHost));
+  c.perm_on_host = true;
   return CVO_B200_OK;
 }
 
@@ -873,7 +776,8 @@ int cvo_b200_create(const cvo_b200_params* p, int device, cvo_b200_handle** out)
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc((void**)&h->d_params, sizeof(cvo_b200_params)) != cudaSuccess ||
       cudaMalloc((void**)&h->d_state, sizeof(DevState)) != cudaSuccess ||
-      cudaMallocHost((void**)&h->h_poll, 16 * sizeof(int)) != cudaSuccess) {
+      cudaMallocHost((void**)&h->h_poll, 16 * sizeof(int)) != cudaSuccess ||
+      cudaMallocHost((void**)&h->h_stats, sizeof(CloudStats)) != cudaSuccess) {
     std::string msg = std::string("handle allocation: ") + cudaGetErrorString(cudaGetLastError());
     cvo_b200_destroy(h);
     return fail(nullptr, CVO_B200_ERR_CUDA, msg);
@@ -901,16 +805,19 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
     c->xyz.release(); c->rowA.release(); c->feat.release(); c->lab.release(); c->geo.release();
     c->xyz_o.release(); c->feat_o.release(); c->lab_o.release(); c->geo_o.release();
     c->blk_sphere.release(); c->tile_sphere.release(); c->tile_maxdist.release(); c->inv.release();
-    c->coarse.release();
+    c->coarse.release(); c->perm_d.release(); c->keys_d.release();
   }
   h->tgt_moved.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
   h->rowrec.release(); h->row_lt.release(); h->sat_list.release(); h->flow_part2.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
   h->zeros_g.release(); h->d_trace.release(); h->gathered.release(); h->stamps.release();
+  h->raw_xyz.release(); h->raw_feat.release(); h->raw_lab.release(); h->raw_geo.release();
+  h->keys_in.release(); h->idx_in.release(); h->sort_temp.release(); h->d_stats.release();
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_state) cudaFree(h->d_state);
   if (h->h_poll) cudaFreeHost(h->h_poll);
+  if (h->h_stats) cudaFreeHost(h->h_stats);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1201,6 +1108,8 @@ int cvo_b200_association(cvo_b200_handle* h, const float T[16], float ell, const
   const int n_rows = A.n_rows;
   std::vector<uint32_t> cnt((size_t)n_rows);
   CVO_CUDA(h, cudaMemcpy(cnt.data(), A.row_nnz, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost));
+  rc = fetch_perm(h, h->src);
+  if (rc != CVO_B200_OK) return rc;
   const std::vector<int>& perm = h->src.perm;  // Morton position -> original row
   std::vector<int> inv((size_t)n_rows);
   for (int s = 0; s < n_rows; s++) inv[perm[s]] = s;
@@ -1238,6 +1147,9 @@ int cvo_b200_align_association(cvo_b200_handle* h, int64_t* nnz, int32_t* row_pt
   std::vector<uint32_t> cnt((size_t)std::max(n_rows, 1));
   CVO_CUDA(h, cudaMemcpy(cnt.data(), A.row_nnz, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost));
   // device rows are Morton positions of the source cloud; this shard holds [rb, rb + n_rows)
+  int rcp = fetch_perm(h, h->src);
+  if (rcp == CVO_B200_OK) rcp = fetch_perm(h, h->tgt);
+  if (rcp != CVO_B200_OK) return rcp;
   const std::vector<int>& sperm = h->src.perm;  // Morton position -> original row
   std::vector<int> srow((size_t)N, -1);         // original row -> local device row
   for (int s = 0; s < n_rows; s++) srow[sperm[rb + s]] = s;
