@@ -34,6 +34,8 @@ constexpr int kJQ = 8;                 // targets held per lane
 constexpr int kJBlock = 32 * kJQ;      // targets per warp sweep
 constexpr int kPairWarps = 8;          // warps per CTA of the pair kernel
 constexpr int kSparseThreads = 256;    // CTA size of the sparse kernels
+constexpr int kPersistThreads = 768;   // CTA size of the persistent kernel: ONE block per SM (24 warps),
+                                       // so the all-to-all reduction after a grid barrier reads 148 partials
 constexpr int kQueueCap = 1024;        // max indicator_window_size supported
 
 // per-block partial sums of the flow pass: omega[3], v[3], a_sum, nnz, max_row (all as doubles:

@@ -288,8 +288,9 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
       std::max(1, std::min(h->num_sms * gocc, (n_rows + rows_per_block - 1) / rows_per_block));
   int pocc = align_grid_max_blocks_per_sm();
   if (pocc < 1) pocc = 1;
+  const int rows_per_pblock = (kPersistThreads / 32) * 4;
   h->persist_blocks =
-      std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_block - 1) / rows_per_block));
+      std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_pblock - 1) / rows_per_pblock));
   CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
   CVO_CUDA(h, h->flow_part2.ensure((size_t)h->persist_blocks));
   CVO_CUDA(h, h->step_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
@@ -1247,6 +1248,14 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
             (long long)(d[13] - d[6]), (long long)(d[14] - d[6]), (long long)(d[15] - d[6]), (long long)(d[7] - d[6]));
     fprintf(stderr, "[tails] flow reduce: loads done %+lld shuffles done %+lld smem done %+lld (ns after tail_begin)\n",
             (long long)(d[10] - d[1]), (long long)(d[11] - d[1]), (long long)(d[12] - d[1]));
+  }
+  if (A.stamps && persist) {  // per-phase time of block 0 / thread 0, averaged over the iterations
+    unsigned long long acc[10];
+    cudaMemcpy(acc, A.stamps, sizeof(acc), cudaMemcpyDeviceToHost);
+    const char* names[10] = {"flow rows", "publish", "barrier 1", "reduce", "finalize", "step rows",
+                             "publish", "barrier 2", "reduce", "controller"};
+    for (int k = 0; k < 10; k++)
+      fprintf(stderr, "[phases] %-10s %7.2f us/iter\n", names[k], (double)acc[k] / 1e3 / (double)iters);
   }
   if (A.stamps && !persist) {  // per-block phase stamps of the LAST flow launch (ns, relative to the first block)
     const int nb = A.grid ? h->grid_blocks : h->sparse_blocks;

@@ -413,7 +413,13 @@ struct RowCtx {
 __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& kc,
                                           const RowCtx& rc, int i_global, int view, int j,
                                           const float4& pb, float& a_out) {
+  // The reference interleaves tests and kernel values (geometry test -> k = exp -> colour test ->
+  // ck = exp -> ...).  Every test only rejects the pair (no side effect), so all the cheap float
+  // tests run first and the double-precision exps only for pairs that pass them all: the same
+  // pairs are stored with the same values, and a pair that fails the colour test (most
+  // geometric survivors do) never pays for an exp.
   float a = 1, sk = 1, ck = 1, k = 1, geo_sim = 1;
+  float d2 = 0.f, d2_color = 0.f, d2_semantic = 0.f;
   if (kc.use_geo_type && A.mode == 0) {  // mode 1 switches it off, CvoGPU.cu:1948-1949
     const float2 gb = A.tv[view].geo[j];
     float norm2_a = 0.f;
@@ -431,11 +437,8 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
   if (kc.use_geometry) {
     if (A.mode == 0) {
       const float dx = pb.x - rc.px[0], dy = pb.y - rc.px[1], dz = pb.z - rc.px[2];
-      const float d2 = dx * dx + dy * dy + dz * dz;
-      if (d2 < rc.d2_thres)
-        k = kc.sigma2 * exp_ref(-d2 / (2.0 * rc.l * rc.l));
-      else
-        return false;
+      d2 = dx * dx + dy * dy + dz * dz;
+      if (!(d2 < rc.d2_thres)) return false;
     } else {
       const float dist[3] = {rc.px[0] - pb.x, rc.px[1] - pb.y, rc.px[2] - pb.z};
       float row[3];
@@ -443,12 +446,10 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       for (int c = 0; c < 3; c++)
         row[c] = sum3f(dist[0] * A.kinv[3 * c], dist[1] * A.kinv[3 * c + 1],
                        dist[2] * A.kinv[3 * c + 2]);
-      const float d2 = dot3f(row, dist);
-      k = kc.sigma2 * exp_ref(-d2 / 2.0);
+      d2 = dot3f(row, dist);
     }
   }
   if (kc.use_intensity) {
-    float d2_color = 0.f;
     const float* fa = A.src_feat + (size_t)i_global * A.Fp;
     const float* fb = A.tv[view].feat + (size_t)j * A.Fp;
     for (int f = 0; f < A.Fp; f += 4) {
@@ -463,13 +464,9 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       tmp = va.w - vb.w;
       d2_color += tmp * tmp;
     }
-    if (d2_color < kc.d2_c_thres)
-      ck = kc.c_sigma2 * exp_ref(-d2_color / (2.0 * kc.c2));
-    else
-      return false;
+    if (!(d2_color < kc.d2_c_thres)) return false;
   }
   if (kc.use_semantics) {
-    float d2_semantic = 0.f;
     const float* la = A.src_lab + (size_t)i_global * A.Cp;
     const float* lb = A.tv[view].lab + (size_t)j * A.Cp;
     for (int c = 0; c < A.Cp; c += 4) {
@@ -485,13 +482,17 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       d2_semantic += tmp * tmp;
     }
     const float thr = (A.mode == 1) ? kc.d2_s_thres_dense : kc.d2_s_thres;
-    if (d2_semantic < thr) {
-      if (A.mode == 1)
-        sk = kc.s_sigma2 * exp_ref(-d2_semantic / (2.0 * kc.s_ell_square));
-      else
-        sk = kc.s_sigma2 * exp_ref(-d2_semantic / (2.0 * kc.s_ell * kc.s_ell));
-    } else
-      return false;
+    if (!(d2_semantic < thr)) return false;
+  }
+  // ---- kernel values (CvoGPU.cu:552,567,580 and :297,311,318 for the dense-kernel variant)
+  if (kc.use_geometry)
+    k = (A.mode == 0) ? kc.sigma2 * exp_ref(-d2 / (2.0 * rc.l * rc.l)) : kc.sigma2 * exp_ref(-d2 / 2.0);
+  if (kc.use_intensity) ck = kc.c_sigma2 * exp_ref(-d2_color / (2.0 * kc.c2));
+  if (kc.use_semantics) {
+    if (A.mode == 1)
+      sk = kc.s_sigma2 * exp_ref(-d2_semantic / (2.0 * kc.s_ell_square));
+    else
+      sk = kc.s_sigma2 * exp_ref(-d2_semantic / (2.0 * kc.s_ell * kc.s_ell));
   }
   a = ck * k * sk * geo_sim;
   a_out = a;
@@ -540,53 +541,36 @@ __device__ void finalize_flow_scalar(DevState* st, const double tot[9]) {
   for (int k = 0; k < 3; k++) st->W3v[k] = t3[k];
 }
 
-// deterministic block-wide reduction of per-block partials: fixed thread assignment, then a
-// fixed xor-shuffle tree inside each warp and a fixed order over the warps.  The first NSUM
-// values are summed, the rest are max-reduced.
+// deterministic block-wide reduction of per-block partials (value-major: part[k * nparts + b]).
+// One WARP per value: its lanes stride over the partials in a fixed order, then a fixed
+// xor-shuffle tree.  The first NSUM values are summed, the rest are max-reduced.  All NV values
+// are reduced concurrently when the block has >= NV warps, so the latency is one load round
+// plus one shuffle tree regardless of NV.  out[] is valid on thread 0.
 template <int NV, int NSUM>
 __device__ void block_reduce_partials(const double* __restrict__ part, int nparts,
                                       double* out /* NV, valid on thread 0 */,
-                                      double* sh /* >= (blockDim.x/32 + 1) * NV */,
+                                      double* sh /* >= NV */,
                                       unsigned long long* dbg = nullptr) {
-  double acc[NV];
-#pragma unroll
-  for (int k = 0; k < NV; k++) acc[k] = 0.0;
-  // partials are stored value-major (part[k * nparts + b]) so these loads coalesce
-  for (int b = threadIdx.x; b < nparts; b += blockDim.x) {
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-      const double x = __ldcg(part + (size_t)k * nparts + b);
-      acc[k] = (k < NSUM) ? acc[k] + x : fmax(acc[k], x);
-    }
-  }
-  if (dbg && threadIdx.x == 0) dbg[0] = gtime() + (unsigned long long)(acc[0] == 1.2345);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-    for (int k = 0; k < NV; k++) {
-      const double x = __shfl_xor_sync(0xffffffffu, acc[k], o);
-      acc[k] = (k < NSUM) ? acc[k] + x : fmax(acc[k], x);
-    }
-  }
-  if (dbg && threadIdx.x == 0) dbg[1] = gtime() + (unsigned long long)(acc[0] == 1.2345);
-  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncthreads();  // sh may still be in use by the caller's previous phase
-  if ((threadIdx.x & 31) == 0) {
+  for (int k = w; k < NV; k += nw) {  // one pass when the block has >= NV warps
+    double acc = 0.0;
+    for (int b = lane; b < nparts; b += 32) {
+      const double x = __ldcg(part + (size_t)k * nparts + b);
+      acc = (k < NSUM) ? acc + x : fmax(acc, x);
+    }
 #pragma unroll
-    for (int k = 0; k < NV; k++) sh[w * NV + k] = acc[k];
+    for (int o = 16; o > 0; o >>= 1) {
+      const double x = __shfl_xor_sync(0xffffffffu, acc, o);
+      acc = (k < NSUM) ? acc + x : fmax(acc, x);
+    }
+    if (lane == 0) sh[k] = acc;
   }
-  __syncthreads();
-  if (dbg && threadIdx.x == 0) dbg[2] = gtime();
-  if ((int)threadIdx.x < NV) {  // one thread per value: NV short chains instead of one long one
-    const int k = threadIdx.x;
-    double r = sh[k];
-    for (int i = 1; i < nw; i++) r = (k < NSUM) ? r + sh[i * NV + k] : fmax(r, sh[i * NV + k]);
-    sh[nw * NV + k] = r;
-  }
+  if (dbg && threadIdx.x == 0) dbg[0] = dbg[1] = dbg[2] = gtime();
   __syncthreads();
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int k = 0; k < NV; k++) out[k] = sh[nw * NV + k];
+    for (int k = 0; k < NV; k++) out[k] = sh[k];
   }
 }
 
@@ -873,6 +857,8 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       // ---- the cube cells of the target's octree that the ball around q = R x + T touches
       const GridView& G = A.gv;
       int nx = 0, ny = 0, ncell = 0, lvl = 0;
+      int icx0 = 0, icy0 = 0, icz0 = 0;              // first cell of the block (cell units)
+      float fq0 = 0.f, fq1 = 0.f, fq2 = 0.f, frq2 = 0.f;  // ball centre / radius^2 in lattice units
       unsigned long long kx0 = 0, ky0 = 0, kz0 = 0;  // dilated coordinates of the first cell
       const unsigned long long mx = 0x1249249249249249ull;
       if (rvalid && rc.d2_thres > 0.f && cap > 0) {
@@ -909,13 +895,19 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
           nx = (ix1 >> lvl) - (ix0 >> lvl) + 1;
           ny = (iy1 >> lvl) - (iy0 >> lvl) + 1;
           ncell = nx * ny * ((iz1 >> lvl) - (iz0 >> lvl) + 1);
-          kx0 = spread21_dev((unsigned)(ix0 >> lvl));
-          ky0 = spread21_dev((unsigned)(iy0 >> lvl));
-          kz0 = spread21_dev((unsigned)(iz0 >> lvl));
+          icx0 = ix0 >> lvl; icy0 = iy0 >> lvl; icz0 = iz0 >> lvl;
+          kx0 = spread21_dev((unsigned)icx0);
+          ky0 = spread21_dev((unsigned)icy0);
+          kz0 = spread21_dev((unsigned)icz0);
+          fq0 = (q[0] - G.lo[0]) * G.scale;
+          fq1 = (q[1] - G.lo[1]) * G.scale;
+          fq2 = (q[2] - G.lo[2]) * G.scale;
+          const float frq = rq * G.scale + 3.f;  // + the padding of the box above
+          frq2 = frq * frq * 1.00001f;
         }
       }
       // first key of cell number `cell` (= cxi + nx (cyi + ny czi)) of the row's cell block
-      auto cell_key = [&](int cell) -> unsigned long long {
+      auto cell_key = [&](int cell, bool& touches) -> unsigned long long {
         // nx, ny in {1,2,3}, cell < 27: divisions by table
         const int t2 = nx == 1 ? cell : (nx == 2 ? (cell >> 1) : ((cell * 22) >> 6));
         const int cxi = cell - t2 * nx;
@@ -929,6 +921,14 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
         if (cyi >= 2) sy = ((sy | ~mx) + 1ull) & mx;
         if (czi >= 1) sz = ((sz | ~mx) + 1ull) & mx;
         if (czi >= 2) sz = ((sz | ~mx) + 1ull) & mx;
+        // cells of the block that the ball does not reach (its corners, mostly) are skipped
+        const float ch = (float)(1 << lvl);
+        const float bx = (float)((icx0 + cxi) << lvl), by = (float)((icy0 + cyi) << lvl),
+                    bz = (float)((icz0 + czi) << lvl);
+        const float ex = fmaxf(0.f, fmaxf(bx - fq0, fq0 - (bx + ch)));
+        const float ey = fmaxf(0.f, fmaxf(by - fq1, fq1 - (by + ch)));
+        const float ez = fmaxf(0.f, fmaxf(bz - fq2, fq2 - (bz + ch)));
+        touches = (ex * ex + ey * ey + ez * ez) <= frq2;
         return (sx | (sy << 1) | (sz << 2)) << (3 * lvl);
       };
       for (int cbase = 0;; cbase += 2 * kGroup) {
@@ -939,21 +939,28 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
         uint32_t start0 = 0, len0 = 0, start1 = 0, len1 = 0;
         {
           const int c0 = cbase + gl, c1 = cbase + kGroup + gl;
-          const bool v0 = wact && c0 < ncell, v1 = wact && c1 < ncell;
-          cell_ranges2(G, 3 * lvl, v0, v0 ? cell_key(c0) : 0ull, v1, v1 ? cell_key(c1) : 0ull,
-                       start0, len0, start1, len1);
+          bool v0 = wact && c0 < ncell, v1 = wact && c1 < ncell;
+          bool t0 = false, t1 = false;
+          const unsigned long long k0 = v0 ? cell_key(c0, t0) : 0ull;
+          const unsigned long long k1 = v1 ? cell_key(c1, t1) : 0ull;
+          v0 = v0 && t0;
+          v1 = v1 && t1;
+          cell_ranges2(G, 3 * lvl, v0, k0, v1, k1, start0, len0, start1, len1);
         }
-        const uint32_t len = len0 + len1;
-        uint32_t incl = len;
+        // ---- flatten in units of QUADS (4 consecutive targets of one range): a lane tests four
+        //      points per pass, so the owner search is amortised and the four loads overlap
+        const uint32_t nq0 = (len0 + 3u) >> 2, nq1 = (len1 + 3u) >> 2;
+        const uint32_t nq = nq0 + nq1;
+        uint32_t incl = nq;
 #pragma unroll
         for (int o = 1; o < kGroup; o <<= 1) {
           const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o, kGroup);
           if (gl >= o) incl += t;
         }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, kGroup - 1, kGroup);
-        const uint32_t excl = incl - len;
+        const uint32_t excl = incl - nq;
         // ---- stage 1: the geometric cut alone on every point of the ranges (cheap); the
-        //      survivors are queued so that the full kernel (double exp, colour, semantics)
+        //      survivors are queued so that the full kernel (colour, semantics, double exp)
         //      runs on packed lanes (stage 2 = drain -> consume8)
         for (uint32_t wb = 0;; wb += kGroup) {
           const bool bact = wb < total && count < cap_stop;
@@ -968,21 +975,39 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
           }
           o = min(o, kGroup - 1);
           const uint32_t oex = __shfl_sync(0xffffffffu, excl, o, kGroup);
+          const uint32_t oq0 = __shfl_sync(0xffffffffu, nq0, o, kGroup);
           const uint32_t ol0 = __shfl_sync(0xffffffffu, len0, o, kGroup);
           const uint32_t os0 = __shfl_sync(0xffffffffu, start0, o, kGroup);
+          const uint32_t ol1 = __shfl_sync(0xffffffffu, len1, o, kGroup);
           const uint32_t os1 = __shfl_sync(0xffffffffu, start1, o, kGroup);
           const uint32_t rr = b - oex;
-          const int j = (int)(rr < ol0 ? os0 + rr : os1 + (rr - ol0));
-          bool pass = false;
-          if (valid) {
+          const bool first = rr < oq0;
+          const uint32_t jb = first ? os0 + 4u * rr : os1 + 4u * (rr - oq0);
+          const uint32_t je = first ? os0 + ol0 : os1 + ol1;
+          auto test_slot = [&](uint32_t j, bool vt) -> bool {
+            if (!vt) return false;
             const float4 pb = move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]);
             const float dx = pb.x - rc.px[0], dy = pb.y - rc.px[1], dz = pb.z - rc.px[2];
             const float d2 = dx * dx + dy * dy + dz * dz;  // as eval_pair (gpu_utils.cuh:73-78)
-            pass = d2 < rc.d2_thres;
+            return d2 < rc.d2_thres;
+          };
+          auto queue_slot = [&](uint32_t j, bool pass) {
+            const unsigned bits = (__ballot_sync(0xffffffffu, pass) >> gshift) & 0xffu;
+            if (pass) list[nlist + __popc(bits & lt8)] = j;
+            nlist += __popc(bits);
+          };
+          // how many slots of its quad the busiest lane of the warp needs: short ranges (the
+          // sparse regimes) take the one-slot path, long ranges four independent loads + tests
+          const int need = valid ? (int)min(4u, je - jb) : 0;
+          if (__reduce_max_sync(0xffffffffu, need) <= 1) {
+            queue_slot(jb, test_slot(jb, need >= 1));
+          } else {
+            bool pass[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) pass[t] = test_slot(jb + (uint32_t)t, t < need);
+#pragma unroll
+            for (int t = 0; t < 4; t++) queue_slot(jb + (uint32_t)t, pass[t]);
           }
-          const unsigned bits = (__ballot_sync(0xffffffffu, pass) >> gshift) & 0xffu;
-          if (pass) list[nlist + __popc(bits & lt8)] = (uint32_t)j;
-          nlist += __popc(bits);
           __syncwarp();
           drain(kGroup);
         }
@@ -1258,45 +1283,47 @@ __device__ void update_tf_device(const IterArgs& A, DevState* st) {
   float tv[3];
   mat3f_vec(neg, st->T, tv);
   for (int k = 0; k < 3; k++) st->Tinv[k] = tv[k];
-  double G[9];
+  // ---- conservative bounds for the candidate generators.  They sit on the critical path of every
+  //      iteration, so they are evaluated in float (a quarter of the latency of the double
+  //      chain); every float rounding (relative 2^-24 per operation, a handful of operations)
+  //      is covered by the explicit inflation factors below.
+  float G[9];  // Rinv^T Rinv = R R^T
   for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      double s = 0.0;
-      for (int k = 0; k < 3; k++) s += (double)st->Rinv[3 * i + k] * (double)st->Rinv[3 * j + k];
-      G[3 * i + j] = s;
-    }
-  double smax2 = 0.0;
+    for (int j = 0; j < 3; j++)
+      G[3 * i + j] = st->Rinv[3 * i] * st->Rinv[3 * j] + st->Rinv[3 * i + 1] * st->Rinv[3 * j + 1] +
+                     st->Rinv[3 * i + 2] * st->Rinv[3 * j + 2];
+  float smax2 = 0.f;  // sigma_max^2 <= max row sum (Gershgorin)
   for (int i = 0; i < 3; i++)
-    smax2 = fmax(smax2, fabs(G[3 * i]) + fabs(G[3 * i + 1]) + fabs(G[3 * i + 2]));
-  const double tc[3] = {(double)A.tcx, (double)A.tcy, (double)A.tcz};
-  const double cc[3] = {(double)A.cx, (double)A.cy, (double)A.cz};
-  double off2 = 0.0;
+    smax2 = fmaxf(smax2, fabsf(G[3 * i]) + fabsf(G[3 * i + 1]) + fabsf(G[3 * i + 2]));
+  const float sm = sqrtf(smax2) * 1.00001f;
+  // |y' - c| = |Rinv (y - tc) + (Rinv tc + Tinv - c)| <= sm * trad + |Rinv tc + Tinv - c|
+  float off2 = 0.f;
   for (int i = 0; i < 3; i++) {
-    const double o = (double)st->Rinv[i] * tc[0] + (double)st->Rinv[3 + i] * tc[1] +
-                     (double)st->Rinv[6 + i] * tc[2] + (double)st->Tinv[i] - cc[i];
-    off2 += o * o;
+    const float o = st->Rinv[i] * A.tcx + st->Rinv[3 + i] * A.tcy + st->Rinv[6 + i] * A.tcz + st->Tinv[i];
+    const float oc = fabsf(o - (i == 0 ? A.cx : (i == 1 ? A.cy : A.cz))) +
+                     4e-7f * (fabsf(o) + fabsf(st->Tinv[i]) + sm * (fabsf(A.tcx) + fabsf(A.tcy) + fabsf(A.tcz)));
+    off2 += oc * oc;
   }
-  const double ymax = (sqrt(smax2) * (double)A.trad + sqrt(off2)) * (1.0 + 1e-5) + 1e-6;
-  st->ymax2_bound = __double2float_ru(ymax * ymax);
-  st->smax = __double2float_ru(sqrt(smax2) * (1.0 + 1e-6));
-  // Slack of a cell query (flow_kernel_t<true>).  With y' = fl(R^T y + Tinv), Tinv = fl(-R^T T),
+  const float ymax = (sm * A.trad + sqrtf(off2)) * 1.00002f + 1e-6f;
+  st->ymax2_bound = ymax * ymax * 1.000001f;
+  st->smax = sm;
+  // Slack of a cell query (flow_rows<true>).  With y' = fl(R^T y + Tinv), Tinv = fl(-R^T T),
   // q = fl(R x + T), E = R R^T - I and u = 2^-24:
   //   |y - q| <= smax |y' - x| + |E| (|y| + |T|) + 8u smax^2 (|y| + |T|) + 4u (smax |x| + |T|)
-  // (the |x| term is added per row).  |y| <= |tc| + trad.  2x safety + 1 um.
+  // (the |x| term is added per row).  |y| <= |tc| + trad; |E|_2 <= |E|_F, each entry of G known
+  // to 4u in float.  2x safety + 1 um.
   {
-    double e2 = 0.0;
+    float e2 = 0.f;
     for (int i = 0; i < 3; i++)
       for (int j = 0; j < 3; j++) {
-        const double d = G[3 * i + j] - (i == j ? 1.0 : 0.0);  // Rinv Rinv^T = R^T R; same norm class
+        const float d = fabsf(G[3 * i + j] - (i == j ? 1.f : 0.f)) + 3e-7f * smax2;
         e2 += d * d;
       }
-    // R R^T and R^T R have the same eigenvalues; |E|_2 <= |E|_F of either
-    const double tn = sqrt((double)st->T[0] * st->T[0] + (double)st->T[1] * st->T[1] + (double)st->T[2] * st->T[2]);
-    const double yn = sqrt(tc[0] * tc[0] + tc[1] * tc[1] + tc[2] * tc[2]) + (double)A.trad;
-    const double u = 5.9604644775390625e-08;
-    const double sm = sqrt(smax2);
-    const double slack = 2.0 * (sqrt(e2) * (yn + tn) + 8.0 * u * sm * sm * (yn + tn) + 4.0 * u * tn) + 1e-6;
-    st->grid_slack = __double2float_ru(slack);
+    const float tn = sqrtf(st->T[0] * st->T[0] + st->T[1] * st->T[1] + st->T[2] * st->T[2]) * 1.000001f;
+    const float yn = (sqrtf(A.tcx * A.tcx + A.tcy * A.tcy + A.tcz * A.tcz) + A.trad) * 1.000001f;
+    const float u = 5.9604644775390625e-08f;
+    st->grid_slack =
+        (2.f * (sqrtf(e2) * (yn + tn) + 8.f * u * sm * sm * (yn + tn) + 4.f * u * tn) + 1e-6f) * 1.00001f;
   }
   // target view of the next iteration: leave the Morton view when many rows reach their cap
   // (each costs an O(M) exact redo), come back once no row does
@@ -1681,20 +1708,38 @@ __device__ __forceinline__ void publish_block_partial(const double (&v)[NV], dou
     for (int k = 0; k < NV; k++) sh[w * NV + k] = v[k];
   }
   __syncthreads();
-  if ((int)threadIdx.x < NV) {
-    const int k = threadIdx.x;
-    double r = sh[k];
-    for (int i = 1; i < nw; i++) r = (k < NSUM) ? r + sh[i * NV + k] : fmax(r, sh[i * NV + k]);
-    part[(size_t)k * gridDim.x + blockIdx.x] = r;
+  // one warp per value: lanes = the block's warps (<= 32), fixed xor tree
+  for (int k = w; k < NV; k += nw) {
+    double r = (lane < nw) ? sh[lane * NV + k] : 0.0;  // 0 is neutral for the sums and the max (>= 0)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double x = __shfl_xor_sync(0xffffffffu, r, o);
+      r = (k < NSUM) ? r + x : fmax(r, x);
+    }
+    if (lane == 0) part[(size_t)k * gridDim.x + blockIdx.x] = r;
   }
 }
 
-__global__ void __launch_bounds__(kSparseThreads, 3) align_grid_kernel(IterArgs A) {
-  __shared__ double sh[kSparseThreads * 9];
-  __shared__ uint32_t s_list[kSparseThreads / kGroup][kGroupList];
+__global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs A) {
+  __shared__ double sh[(kPersistThreads / 32 + 2) * 9];
+  __shared__ uint32_t s_list[kPersistThreads / kGroup][kGroupList];
   __shared__ __align__(16) DevState s_st;
   __shared__ unsigned int s_nsat;
   __shared__ CtrlScratch s_ctrl;
+  // debug (CVO_B200_STAMPS=1): time spent per phase by thread 0 of block 0, summed over the loop
+  __shared__ unsigned long long s_acc[12];
+  unsigned long long t_prev = 0ull;
+  const bool stamping = A.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  if (stamping) {
+    for (int q = 0; q < 12; q++) s_acc[q] = 0ull;
+    t_prev = gtime();
+  }
+#define CVO_PHASE(q)                    \
+  if (stamping) {                       \
+    const unsigned long long t = gtime(); \
+    s_acc[q] += t - t_prev;             \
+    t_prev = t;                         \
+  }
   DevState* gst = A.st;
   for (int i = threadIdx.x; i < (int)(sizeof(DevState) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&s_st)[i] = __ldcg(reinterpret_cast<const uint32_t*>(gst) + i);
@@ -1714,52 +1759,64 @@ __global__ void __launch_bounds__(kSparseThreads, 3) align_grid_kernel(IterArgs 
     {
       double bp[9];
       flow_rows<true>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp);
+      CVO_PHASE(0)
       publish_block_partial<9, 8>(bp, sh, flow_part);
+      CVO_PHASE(1)
     }
     grid_barrier(&gst->bar_count, epoch);
-    // ---- rows cut at their cap: exact redo, one warp per row over the whole grid
-    if (threadIdx.x == 0) s_nsat = __ldcg(&gst->n_sat);
-    __syncthreads();
+    CVO_PHASE(2)
+    // ---- every block: totals in a fixed order.  The number of rows cut at their cap is fetched
+    //      by an otherwise idle warp while the partials are being reduced.
+    double tot[9];
+    if (threadIdx.x == 32 * 12) s_nsat = __ldcg(&gst->n_sat);
+    block_reduce_partials<9, 8>(flow_part, (int)gridDim.x, tot, sh);  // ends with a block barrier
     const unsigned int n_sat = s_nsat;
     if (n_sat > 0u) {
-      double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      // exact redo of the cut rows, one warp per row over the whole grid, behind one more barrier
+      double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tot2[9];
       for (unsigned int si = blockIdx.x * warps_per_block + warp_in_block; si < n_sat;
            si += gridDim.x * warps_per_block)
         redo_row<true>(A, s_st.kc, s_st.Rinv, s_st.Tinv, s_st.ell, s_st.num_neighbors,
                        (int)__ldcg(&A.sat_list[si]), lane, f);
       publish_block_partial<9, 8>(f, sh, flow_part2);
       grid_barrier(&gst->bar_count, epoch);
-    }
-    // ---- every block: totals in a fixed order, normalisation, omega_hat powers
-    {
-      double tot[9], tot2[9];
-      block_reduce_partials<9, 8>(flow_part, (int)gridDim.x, tot, sh);
-      if (n_sat > 0u) block_reduce_partials<9, 8>(flow_part2, (int)gridDim.x, tot2, sh);
+      block_reduce_partials<9, 8>(flow_part2, (int)gridDim.x, tot2, sh);
       if (threadIdx.x == 0) {
-        if (n_sat > 0u) {
-          for (int q = 0; q < 8; q++) tot[q] += tot2[q];
-          tot[8] = fmax(tot[8], tot2[8]);
-          if (blockIdx.x == 0) gst->n_sat = 0u;  // every block has read it (barrier above)
-        }
-        s_st.n_sat = n_sat;  // update_tf_device's bookkeeping
-        finalize_flow_scalar(&s_st, tot);
+        for (int q = 0; q < 8; q++) tot[q] += tot2[q];
+        tot[8] = fmax(tot[8], tot2[8]);
+        if (blockIdx.x == 0) gst->n_sat = 0u;  // every block has read it (barrier above)
       }
     }
+    CVO_PHASE(3)
+    // ---- normalisation, omega_hat powers
+    if (threadIdx.x == 0) {
+      s_st.n_sat = n_sat;  // update_tf_device's bookkeeping
+      finalize_flow_scalar(&s_st, tot);
+    }
     __syncthreads();
+    CVO_PHASE(4)
     // ---- step phase (compute_step_size_xi + _poly_coeff on this block's ELL rows)
     {
       double w4[4];
       step_rows<true>(A, &s_st, w4[0], w4[1], w4[2], w4[3]);
+      CVO_PHASE(5)
       publish_block_partial<4, 4>(w4, sh, step_part);
+      CVO_PHASE(6)
     }
     grid_barrier(&gst->bar_count, epoch);
+    CVO_PHASE(7)
     {
       double tot[4];
       block_reduce_partials<4, 4>(step_part, (int)gridDim.x, tot, sh);
+      CVO_PHASE(8)
       controller_step(A, &s_st, tot, &s_ctrl);
     }
     __syncthreads();
+    CVO_PHASE(9)
   }
+  if (stamping)
+    for (int q = 0; q < 10; q++) A.stamps[q] = s_acc[q];
+#undef CVO_PHASE
   // ---- block 0 hands the final state (pose, flags, counters) back
   if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < (int)(sizeof(DevState) / 4); i += blockDim.x)
@@ -1870,12 +1927,12 @@ void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t 
 cudaError_t launch_align_grid(const IterArgs& A, int blocks, cudaStream_t s) {
   IterArgs a = A;
   void* args[] = {&a};
-  return cudaLaunchCooperativeKernel((const void*)align_grid_kernel, dim3(blocks), dim3(kSparseThreads),
+  return cudaLaunchCooperativeKernel((const void*)align_grid_kernel, dim3(blocks), dim3(kPersistThreads),
                                      args, 0, s);
 }
 int align_grid_max_blocks_per_sm() {
   int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_kernel, kSparseThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_kernel, kPersistThreads, 0);
   return n;
 }
 int pair_kernel_max_blocks_per_sm() {
