@@ -3,16 +3,26 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Metric (BASELINE.json): point-pairs/s per CVO iteration = N_src * M_tgt * iterations / time.
-A "step" is one full registration (CvoGPU::align) of one synthetic frame pair:
-  N=1  -> workload C2  (BASELINE configs[1]: N=M=10 000, geometric kernel; SURVEY.md §8d)
-  N>1  -> workload C4  (BASELINE configs[3]: N=M=200 000, geometry + 5-dim colour, MAX_ITER
-          capped at 50), SOURCE rows sharded across ranks, two 72/32-byte NCCL all-gathers per
-          iteration (strong scaling: the job is fixed, per-GPU work shrinks).
-`value` times the loop with the clouds already resident in HBM (CUDA events on the launching
-stream, inside libcvo_b200); `e2e` times the reference-facing call with HOST buffers (upload,
-loop, pose read-back) by wall clock.  `--impl reference` times the CPU restatement of the
-reference's algorithm (oracle/, OpenMP on all host cores) on a bounded number of iterations.
+Metric (BASELINE.json): point-pairs/s per CVO iteration = N_src * M_tgt * iterations / time (all
+pairs counted, tested or skipped).  A "step" is one full registration
+(CvoGPU::align) of one synthetic frame pair:
+  N=1  -> workload C2  (BASELINE configs[1]: N=M=10 000, geometric kernel; SURVEY.md 8d)
+  N>1  -> workload C4  (BASELINE configs[3]: N=M=200 000, geometry + 5-dim colour, first-frame
+          parameters, MAX_ITER capped at 50), SOURCE rows sharded across ranks, two 72/32-byte
+          NCCL all-gathers per iteration (strong scaling: the job is fixed, per-GPU work shrinks).
+`value`  times the loop with the clouds already resident in HBM (CUDA events on the launching
+         stream, inside libcvo_b200), L2 flushed between steps.
+`e2e`    times the reference-facing call with HOST buffers (cvo_b200_align_host: upload + device-side
+         build of the cloud, loop, pose read-back) by wall clock.
+`roofline`  the dominant kernel, timed live: in cell-query mode on one GPU the whole loop is ONE
+         launch of align_grid_kernel (its duration = the timed region, one launch = all the
+         iterations); otherwise the dominant per-phase kernel (pair_kernel) at the initial state.
+         `traffic` = dram bytes per launch from the committed ncu capture (profiles/traffic.json).
+`fp32`   pair tests/s against the measured packed-FMA peak (the meaningful bound of a dense scan).
+`frame_pairs`  frame-pairs/s on KITTI-05-sized clouds: a tracking frame (regular parameters,
+         constant-velocity initial guess) and a first frame (ell_init = 1.5).
+`cpu_baseline` / `--impl reference`  the CPU restatement of the reference's algorithm (oracle/,
+         OpenMP on all host cores) on a bounded number of leading iterations of the same job.
 """
 import argparse
 import json

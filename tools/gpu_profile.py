@@ -13,5 +13,5 @@ src, tgt, _ = synthetic_pair(P, N, M, seed, F=F, C=C)
 p = geometric_params() if F == 0 else u.read_params_yaml(os.path.join(DATA, "cvo_intensity_params_img_gpu0.yaml"))
 g = u.CvoGPU(p)
 g.set_cloud(0, src); g.set_cloud(1, tgt)
-ms, msp = g.time_iterations(np.eye(3), np.zeros(3), ell, 64, iters, pair_kernel=False)
+ms, msp = g.time_iterations(np.eye(3), np.zeros(3), ell, 256, iters, pair_kernel=False)
 print(name, "iters", iters, "ms/iter", ms / iters)

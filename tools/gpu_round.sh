@@ -16,4 +16,6 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'ali
 # full capture of the per-phase kernels in both modes (fixed state, C2)
 CVO_B200_PERSIST=0 CVO_B200_MODE=grid timeout 600 ncu --set full --clock-control none --import-source on -k regex:'flow_kernel|step_kernel' -c 4 -o $O/${TAG}_full_c2_grid -f python tools/gpu_profile.py C2 2 0.95 >> $O/${TAG}_ncu_full.log 2>&1
 CVO_B200_MODE=dense timeout 600 ncu --set full --clock-control none --import-source on -k regex:'pair_kernel|flow_kernel|step_kernel|prep_kernel' -c 8 -o $O/${TAG}_full_c2_dense -f python tools/gpu_profile.py C2 2 0.95 >> $O/${TAG}_ncu_full.log 2>&1
+# the 200k workload in the mode its policy picks (dense scan at ell = 1.5): the dominant kernel of the multi-GPU runs
+CVO_B200_MODE=dense timeout 900 ncu --set full --clock-control none --import-source on -k regex:'pair_kernel|flow_kernel|step_kernel|prep_kernel' -c 4 -o $O/${TAG}_full_c4_dense -f python tools/gpu_profile.py C4 1 1.5 >> $O/${TAG}_ncu_full.log 2>&1
 tail -c 600 $O/${TAG}_bench.log

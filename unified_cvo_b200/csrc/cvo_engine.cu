@@ -534,12 +534,19 @@ int launches_per_iteration(const cvo_b200_handle* h, const IterArgs& A) {
   return (A.grid ? 2 : 4) + (h->world > 1 ? 2 : 0);
 }
 
-// Candidate-generator policy.  A cell query tests, per source row, the points of <= 27 cube cells
-// of edge h in [r, 2r) (r = largest cut-off radius of the cloud, CvoGPU.cu:506-511); the dense
-// scan tests M points per row at ~1/6 of the per-test cost.  Cell queries win while the expected
-// tests per row stay below ~M/16 (measured break-even on KITTI-sized clouds with ell = 1.5).  The density comes from the occupied coarse cells, so
-// slab- or surface-like clouds are not mistaken for sparse ones.
-bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDev& ct, float ell) {
+// Candidate-generator policy: a cost model calibrated on B200 (r01: C2, KITTI-sized and 200k
+// clouds at ell = 0.1 .. 1.5).  Per source row and iteration
+//   cell queries  test the points of <= 27 cube cells of edge h in [r, 2r) (r = largest cut-off
+//                 radius, CvoGPU.cu:506-511): tests_g = 27 h^3 rho_t, ~2.4 ps each (one lane, one
+//                 test) inside the persistent kernel;
+//   dense scan    tests every target of the 256-point Morton blocks whose bounding sphere is
+//                 within r of the row's 64-row tile: tests_d = rho_t 4/3 pi (r + r_tile + r_blk)^3,
+//                 ~0.62 ps each (packed FMA prefilter), plus ~45 us per iteration for four
+//                 launches with last-block tails instead of one persistent kernel.
+// Densities come from the occupied coarse cells, so slab- or surface-like clouds are not
+// mistaken for sparse ones.  The choice never changes a result.
+bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDev& ct, float ell,
+                     int n_rows = -1) {
   const cvo_b200_params& p = h->params;
   if (!p.is_using_geometry) return false;  // no geometric cut-off: every pair is a candidate
   if (h->force_mode >= 0) return h->force_mode == 1;
@@ -553,8 +560,16 @@ bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDe
   const double hmin = ct.extent / (double)(1 << ct.cbits);  // query cells are never finer than the coarse table
   while (hcell * 0.5 >= r && hcell * 0.5 >= hmin) hcell *= 0.5;  // finest usable level with h >= r
   const double density = (double)ct.n_finite / ct.occupied_volume;
-  const double tests = std::min((double)ct.n, 27.0 * hcell * hcell * hcell * density);
-  return tests < 0.06 * (double)ct.n;
+  const double tests_g = std::min((double)ct.n, 27.0 * hcell * hcell * hcell * density);
+  const double rho_s = (cs.n_finite > 0 && cs.occupied_volume > 0.0) ? (double)cs.n_finite / cs.occupied_volume : density;
+  const double r_tile = 0.85 * std::cbrt((double)kTileRows / rho_s);
+  const double r_blk = 0.85 * std::cbrt((double)kJBlock / density);
+  const double reach = r + r_tile + r_blk;
+  const double tests_d = std::min((double)ct.n, density * 4.18879 * reach * reach * reach);
+  const double rows = (double)(n_rows >= 0 ? n_rows : cs.n);
+  const double us_grid = rows * tests_g * 2.4e-6;
+  const double us_dense = rows * tests_d * 0.62e-6 + 45.0;
+  return us_grid < us_dense;
 }
 
 // Replaces CvoPointCloud_to_gpu (CvoGPU_impl.cu:206-285).  The caller's arrays go to the device
@@ -681,7 +696,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
   while (true) {
     // rows that reach their cap are redone exhaustively (O(M) each) by one block in the
     // Morton-ordered modes: leave cell queries while that happens a lot
-    A.grid = (grid_profitable(h, h->src, h->tgt, ell) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
+    A.grid = (grid_profitable(h, h->src, h->tgt, ell, A.n_rows) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
     if (A.grid && h->use_persist && A.world == 1) {
       // the whole loop in one cooperative launch (align_grid_kernel); it returns when done
       CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->stream));
@@ -866,7 +881,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) return fail(h, CVO_B200_ERR_INVALID, "num_neighbors exceeds nearest_neighbors_max");
   CVO_CUDA(h, h->d_trace.ensure(1));
-  A.grid = grid_profitable(h, h->src, h->tgt, ell) ? 1 : 0;
+  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.n_rows) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
   if (A.grid && h->use_persist && A.world == 1) {
@@ -921,7 +936,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   CVO_CUDA(h, cudaEventCreate(&ev1));
   if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
     IterArgs Ag = A;
-    Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init) ? 1 : 0;
+    Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init, A.n_rows) ? 1 : 0;
     if (!(Ag.grid && h->use_persist && A.world == 1)) {
       rc = ensure_graph(h, Ag, 32);
       if (rc != CVO_B200_OK) return rc;
@@ -1196,7 +1211,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   if (rc != CVO_B200_OK) return rc;
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) num_neighbors = A.cap_max;
-  A.grid = grid_profitable(h, h->src, h->tgt, ell) ? 1 : 0;
+  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.n_rows) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
   const bool persist = A.grid && h->use_persist && A.world == 1;

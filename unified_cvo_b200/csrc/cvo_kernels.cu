@@ -742,7 +742,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
   // holds the wrong survivors and is redone in original target order by the tail.  Counting one
   // survivor PAST the cap tells a complete row with exactly `cap` survivors (nothing to redo;
   // common when the cap has adapted down to 1.2 * max row count = a handful) from a cut one.
-  const int cap_stop = kGrid ? cap + 1 : cap;
+  const int cap_stop = (kGrid || view == 0) ? cap + 1 : cap;  // both Morton-ordered walks
   const float c_div = kc.c_div, d_div = kc.d_div;  // divisors (CvoGPU.cu:785-788)
   const int L = A.L;
   const int nch = A.nchunks;
@@ -751,9 +751,24 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
   double w_om[3] = {0, 0, 0}, w_v[3] = {0, 0, 0}, w_asum = 0.0;  // group sums (leader lane)
   double w_nnz = 0.0, w_max = 0.0;
 
-  const int slot0 = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp + g;
-  const int slot_stride = gridDim.x * warps_per_block * kRowsPerWarp;
-  for (int row = slot0;; row += slot_stride) {
+  // Row groups: the first pass is static (warp w of block b takes rows 4(b*W+w)..+3); when there
+  // are more rows than resident row slots, cell-query mode hands out the rest dynamically, four
+  // rows per warp from a global counter: rows differ a lot in cost in the dense regimes (a cloud's
+  // boundary rows see half the neighbours) and a static split left 20 % of C4's flow phase idle.
+  const int total_slots = gridDim.x * warps_per_block * kRowsPerWarp;
+  const bool dynamic_rows = kGrid && A.n_rows > total_slots;
+  int row_base = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp;
+  for (bool first_pass = true;; first_pass = false) {
+    if (!first_pass) {
+      if (dynamic_rows) {
+        int nb = 0;
+        if (lane == 0) nb = total_slots + (int)atomicAdd(&st->work_counter, (unsigned)kRowsPerWarp);
+        row_base = __shfl_sync(0xffffffffu, nb, 0);
+      } else {
+        row_base += total_slots;
+      }
+    }
+    const int row = row_base + g;
     const bool rvalid = row < A.n_rows;
     if (!__any_sync(0xffffffffu, rvalid)) break;
     const int ig = A.row_begin + (rvalid ? row : 0);
@@ -858,6 +873,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       const GridView& G = A.gv;
       int nx = 0, ny = 0, ncell = 0, lvl = 0;
       int icx0 = 0, icy0 = 0, icz0 = 0;              // first cell of the block (cell units)
+      float qx = 0.f, qy = 0.f, qz = 0.f, rq2 = -1.f;  // the row in the target's frame, query radius^2
       float fq0 = 0.f, fq1 = 0.f, fq2 = 0.f, frq2 = 0.f;  // ball centre / radius^2 in lattice units
       unsigned long long kx0 = 0, ky0 = 0, kz0 = 0;  // dilated coordinates of the first cell
       const unsigned long long mx = 0x1249249249249249ull;
@@ -902,6 +918,8 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
           fq0 = (q[0] - G.lo[0]) * G.scale;
           fq1 = (q[1] - G.lo[1]) * G.scale;
           fq2 = (q[2] - G.lo[2]) * G.scale;
+          qx = q[0]; qy = q[1]; qz = q[2];
+          rq2 = rq * rq * 1.000001f;
           const float frq = rq * G.scale + 3.f;  // + the padding of the box above
           frq2 = frq * frq * 1.00001f;
         }
@@ -984,12 +1002,15 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
           const bool first = rr < oq0;
           const uint32_t jb = first ? os0 + 4u * rr : os1 + 4u * (rr - oq0);
           const uint32_t je = first ? os0 + ol0 : os1 + ol1;
+          // stage-1 test in the target's OWN frame: |y - q|^2 <= rq^2 with q = R x + T and the
+          // conservative query radius rq (every pair with the reference's d2 < d2_thres is inside,
+          // see update_tf_device) - one load, three subtractions, three FMAs; the exact test of
+          // the reference's arithmetic follows in stage 2
           auto test_slot = [&](uint32_t j, bool vt) -> bool {
             if (!vt) return false;
-            const float4 pb = move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]);
-            const float dx = pb.x - rc.px[0], dy = pb.y - rc.px[1], dz = pb.z - rc.px[2];
-            const float d2 = dx * dx + dy * dy + dz * dz;  // as eval_pair (gpu_utils.cuh:73-78)
-            return d2 < rc.d2_thres;
+            const float4 y = A.tv[0].xyz[j];
+            const float dx = y.x - qx, dy = y.y - qy, dz = y.z - qz;
+            return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) <= rq2;
           };
           auto queue_slot = [&](uint32_t j, bool pass) {
             const unsigned bits = (__ballot_sync(0xffffffffu, pass) >> gshift) & 0xffu;
@@ -1014,7 +1035,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       }
     } else {
     for (int cbase = 0;; cbase += 4 * kGroup) {
-      const bool wact = rvalid && cbase < nch && count < cap;
+      const bool wact = rvalid && cbase < nch && count < cap_stop;
       if (!__any_sync(0xffffffffu, wact)) break;
       // ---- four cell counts per lane: a window of 32 cells per group
       uint32_t c4[4];
@@ -1037,7 +1058,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
         const uint32_t total = __shfl_sync(0xffffffffu, incl, kGroup - 1, kGroup);
         const uint32_t excl = incl - s4;
         for (uint32_t wb = 0;; wb += kGroup) {
-          const bool bact = wb < total && count < cap;
+          const bool bact = wb < total && count < cap_stop;
           if (!__any_sync(0xffffffffu, bact)) break;
           const uint32_t b = wb + gl;
           const bool valid = bact && b < total;
@@ -1066,7 +1087,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
         //      rescan the overflowed chunks exhaustively (still in ascending target order)
         for (int cc = 0; cc < 4 * kGroup; cc++) {
           const uint32_t n = __shfl_sync(0xffffffffu, c4[cc & 3], cc >> 2, kGroup);
-          const bool cact = wact && (cbase + cc) < nch && count < cap;
+          const bool cact = wact && (cbase + cc) < nch && count < cap_stop;
           if (!__any_sync(0xffffffffu, cact && n > 0u)) continue;
           const bool is_over = cact && n > (uint32_t)L;
           if (__any_sync(0xffffffffu, is_over)) drain(1);  // flush: order before the rescan
@@ -1074,8 +1095,8 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
           const int j_end = min(A.M, j_begin + A.chunk_len);
           const uint32_t* cell = cell_row + (size_t)(cbase + cc) * (size_t)L;
           for (uint32_t s = 0;; s += kGroup) {
-            const bool list_go = cact && !is_over && s < n && count < cap;
-            const bool scan_go = is_over && (j_begin + (int)s) < j_end && count < cap;
+            const bool list_go = cact && !is_over && s < n && count < cap_stop;
+            const bool scan_go = is_over && (j_begin + (int)s) < j_end && count < cap_stop;
             if (!__any_sync(0xffffffffu, list_go | scan_go)) break;
             if (__any_sync(0xffffffffu, scan_go)) {
               const int j = j_begin + (int)s + gl;
@@ -1103,7 +1124,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
     // A row that reached its cap: in the Morton view it may hold the wrong survivors (the
     // reference keeps the first ones in ORIGINAL target order), so it is queued for the exact
     // redo in this kernel's tail and contributes nothing here.
-    const bool capped = rvalid && count >= cap_stop && !(kGrid && cap == 0);
+    const bool capped = rvalid && count >= cap_stop && !((kGrid || view == 0) && cap == 0);
     count = min(count, cap);
     if (capped && gl == 0) {
       if (view == 0)
@@ -1764,6 +1785,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs
       CVO_PHASE(1)
     }
     grid_barrier(&gst->bar_count, epoch);
+    if (blockIdx.x == 0 && threadIdx.x == 0) gst->work_counter = 0u;  // next iteration's dynamic rows
     CVO_PHASE(2)
     // ---- every block: totals in a fixed order.  The number of rows cut at their cap is fetched
     //      by an otherwise idle warp while the partials are being reduced.
