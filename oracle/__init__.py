@@ -230,5 +230,10 @@ def se3_log_norm(dR, dT):
                                        t.ctypes.data_as(C.POINTER(C.c_double))))
 
 
+def set_accel(on: bool) -> None:
+    """Accelerated candidate enumeration on (default) / off (the literal dense loop)."""
+    lib().oracle_set_accel(1 if on else 0)
+
+
 def num_threads() -> int:
     return int(lib().oracle_num_threads())

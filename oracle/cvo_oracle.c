@@ -14,6 +14,11 @@
  *     the 6-term norm of the stacked twist as (c0+(c1+c2)) + (c3+(c4+c5)).
  *   - no FMA contraction anywhere.
  *   - thrust::reduce order = ascending row order, double.
+ *
+ * The dense N x M row loop of fill_in_A_mat_gpu is the normative statement; by default the rows
+ * enumerate their candidates through a uniform grid (same targets that can pass, same ascending
+ * order => bit-identical outputs, tests/test_oracle.py), which is what makes this file usable as
+ * a CPU baseline.  ORACLE_DENSE=1 or oracle_set_accel(0) runs the literal loop.
  */
 #include "cvo_oracle.h"
 
@@ -160,6 +165,123 @@ static inline float range_ell(float curr_ell, float dist_to_sensor) {
 
 static const float kZero2[2] = {0.f, 0.f};
 
+/* ---------- accelerated candidate enumeration (same outputs as the dense loop) ---------------
+ * The reference's row loop visits every target j in ascending order and `continue`s on
+ * d2 >= d2_thres (CvoGPU.cu:549-554).  With the isotropic geometric kernel on, a target farther
+ * than h = max_i sqrt(d2_thres_i) from the row can therefore never change anything, so the row
+ * may visit only the targets of the 27 cells of a uniform grid of edge h around it - in
+ * ASCENDING j, so that the first-num_neighbors truncation (:526) and the order of every float
+ * sum are those of the dense loop.  Outputs are bit-identical (tests/test_oracle.py checks it);
+ * the dense loop stays the normative statement and is what ORACLE_DENSE=1 / oracle_set_accel(0)
+ * run.  This is what makes the oracle a fair CPU baseline: the reference's own CPU path
+ * (cvo::cvo::align, Cvo.cpp:349-456) also searches neighbours (nanoflann kd-tree) instead of
+ * scanning N x M. */
+static int g_accel = -1;
+void oracle_set_accel(int on) { g_accel = on ? 1 : 0; }
+static int accel_enabled(void) {
+  if (g_accel < 0) {
+    const char* e = getenv("ORACLE_DENSE");
+    g_accel = (e && e[0] == '1') ? 0 : 1;
+  }
+  return g_accel;
+}
+typedef struct {
+  int nx, ny, nz;
+  float lo[3], inv_h;
+  int* cell_start; /* ncell + 1 */
+  int* items;      /* target indices, ascending inside a cell */
+} cand_grid;
+static int cmp_int(const void* a, const void* b) {
+  const int x = *(const int*)a, y = *(const int*)b;
+  return (x > y) - (x < y);
+}
+static int grid_cell_coord(float v, float lo, float inv_h, int n) {
+  int c = (int)floorf((v - lo) * inv_h);
+  if (c < 0) c = 0;
+  if (c >= n) c = n - 1;
+  return c;
+}
+/* returns 0 when the grid is not applicable (caller falls back to the dense loop) */
+static int grid_build(cand_grid* g, const float* y, int m, float h) {
+  memset(g, 0, sizeof(*g));
+  if (!(h > 0.f) || !isfinite(h) || m <= 0) return 0;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int nfin = 0;
+  for (int j = 0; j < m; j++) {
+    const float* q = y + 3 * (size_t)j;
+    if (!(isfinite(q[0]) && isfinite(q[1]) && isfinite(q[2]))) continue;
+    for (int k = 0; k < 3; k++) {
+      if (q[k] < lo[k]) lo[k] = q[k];
+      if (q[k] > hi[k]) hi[k] = q[k];
+    }
+    nfin++;
+  }
+  if (nfin == 0) return 0;
+  double dims[3];
+  for (int k = 0; k < 3; k++) dims[k] = floor(((double)hi[k] - (double)lo[k]) / (double)h) + 1.0;
+  if (dims[0] * dims[1] * dims[2] > 4.0e6) return 0;
+  g->nx = (int)dims[0]; g->ny = (int)dims[1]; g->nz = (int)dims[2];
+  for (int k = 0; k < 3; k++) g->lo[k] = lo[k];
+  g->inv_h = 1.0f / h;
+  const int ncell = g->nx * g->ny * g->nz;
+  g->cell_start = (int*)calloc((size_t)ncell + 1, sizeof(int));
+  g->items = (int*)malloc(sizeof(int) * (size_t)(nfin > 0 ? nfin : 1));
+  int* cell_of = (int*)malloc(sizeof(int) * (size_t)m);
+  for (int j = 0; j < m; j++) {
+    const float* q = y + 3 * (size_t)j;
+    if (!(isfinite(q[0]) && isfinite(q[1]) && isfinite(q[2]))) {
+      cell_of[j] = -1; /* a non-finite target never passes d2 < thres */
+      continue;
+    }
+    const int cx = grid_cell_coord(q[0], lo[0], g->inv_h, g->nx);
+    const int cy = grid_cell_coord(q[1], lo[1], g->inv_h, g->ny);
+    const int cz = grid_cell_coord(q[2], lo[2], g->inv_h, g->nz);
+    cell_of[j] = (cz * g->ny + cy) * g->nx + cx;
+    g->cell_start[cell_of[j] + 1]++;
+  }
+  for (int c = 0; c < ncell; c++) g->cell_start[c + 1] += g->cell_start[c];
+  int* fill = (int*)malloc(sizeof(int) * (size_t)ncell);
+  memcpy(fill, g->cell_start, sizeof(int) * (size_t)ncell);
+  for (int j = 0; j < m; j++) /* ascending j inside every cell */
+    if (cell_of[j] >= 0) g->items[fill[cell_of[j]]++] = j;
+  free(fill);
+  free(cell_of);
+  return 1;
+}
+static void grid_free(cand_grid* g) {
+  free(g->cell_start);
+  free(g->items);
+}
+/* targets of the 27 cells around point p, ascending; returns their number */
+static int grid_candidates(const cand_grid* g, const float* p, int* out) {
+  if (!(isfinite(p[0]) && isfinite(p[1]) && isfinite(p[2]))) return 0; /* d2 is NaN/inf: no pass */
+  /* unclamped cell coordinates: a row far outside the grid has no candidates */
+  const float fx = floorf((p[0] - g->lo[0]) * g->inv_h), fy = floorf((p[1] - g->lo[1]) * g->inv_h),
+              fz = floorf((p[2] - g->lo[2]) * g->inv_h);
+  if (fx < -1.f || fy < -1.f || fz < -1.f || fx > (float)g->nx || fy > (float)g->ny || fz > (float)g->nz)
+    return 0;
+  const int cx = (int)fx, cy = (int)fy, cz = (int)fz;
+  int n = 0;
+  for (int dz = -1; dz <= 1; dz++) {
+    const int z = cz + dz;
+    if (z < 0 || z >= g->nz) continue;
+    for (int dy = -1; dy <= 1; dy++) {
+      const int yy = cy + dy;
+      if (yy < 0 || yy >= g->ny) continue;
+      for (int dx = -1; dx <= 1; dx++) {
+        const int x = cx + dx;
+        if (x < 0 || x >= g->nx) continue;
+        const int c = (z * g->ny + yy) * g->nx + x;
+        const int b = g->cell_start[c], e = g->cell_start[c + 1];
+        memcpy(out + n, g->items + b, sizeof(int) * (size_t)(e - b));
+        n += e - b;
+      }
+    }
+  }
+  qsort(out, (size_t)n, sizeof(int), cmp_int);
+  return n;
+}
+
 /* shared body of the two fill kernels; kernel_inv == NULL -> isotropic */
 static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
                         const oracle_cloud* tgt, const float* y_moved, int num_neighbors,
@@ -171,7 +293,29 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
   sparse_clear(A, num_neighbors);
   (void)F;
 
-#pragma omp parallel for schedule(dynamic, 16)
+  /* accelerated candidate enumeration (see above): edge = the largest cut-off radius of any row */
+  cand_grid grid;
+  int use_grid = 0;
+  if (accel_enabled() && !kernel_inv && p->is_using_geometry && a_size > 0) {
+    float dmax = 0.f;
+    int finite_rows = 1;
+    for (int i = 0; i < a_size; i++) {
+      const float* pa = src->xyz + 3 * (size_t)i;
+      const float d = sqrtf(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2]);
+      if (isfinite(d)) { if (d > dmax) dmax = d; } else finite_rows = 0;
+    }
+    (void)finite_rows; /* non-finite rows produce no candidates and no survivors either way */
+    const float lmax = range_ell(ell, dmax);
+    const float sigma2 = p->sigma * p->sigma;
+    const float thres_max = -2.0 * lmax * lmax * logf(p->sp_thres / sigma2);
+    if (thres_max > 0.f && isfinite(thres_max))
+      use_grid = grid_build(&grid, y_moved, b_size, (float)(sqrt((double)thres_max) * (1.0 + 1e-5)) + 1e-6f);
+  }
+
+#pragma omp parallel
+  {
+  int* cand = use_grid ? (int*)malloc(sizeof(int) * (size_t)(b_size > 0 ? b_size : 1)) : NULL;
+#pragma omp for schedule(dynamic, 16)
   for (int i = 0; i < a_size; i++) {
     /* CvoGPU.cu:497-501 */
     float sigma2 = p->sigma * p->sigma;
@@ -201,7 +345,9 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
     unsigned int num_inds = 0;
     float* Ai = A->mat + (size_t)i * num_neighbors;
     int* Ii = A->ind + (size_t)i * num_neighbors;
-    for (int j = 0; j < b_size; j++) {
+    const int n_visit = use_grid ? grid_candidates(&grid, pa, cand) : b_size;
+    for (int jj = 0; jj < n_visit; jj++) {
+      const int j = use_grid ? cand[jj] : jj; /* ascending j either way */
       if (num_inds == (unsigned int)num_neighbors) break; /* :526 */
       const float* pb = y_moved + 3 * (size_t)j;
       float a = 1, sk = 1, ck = 1, k = 1, geo_sim = 1;
@@ -271,6 +417,9 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
     }
     A->nonzeros[i] = num_inds; /* :592 */
   }
+  free(cand);
+  }
+  if (use_grid) grid_free(&grid);
   /* SparseKernelMat.cu:37-46 compute_nonzeros */
   unsigned long long s = 0;
   for (int i = 0; i < a_size; i++) s += A->nonzeros[i];

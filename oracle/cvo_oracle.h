@@ -103,6 +103,9 @@ float oracle_function_angle(const cvo_b200_params* p, const oracle_cloud* src,
                             const oracle_cloud* tgt, const float T[16], float ell,
                             int is_approximate);
 int oracle_num_threads(void);
+/* 1 (default): rows visit only the targets of the 27 grid cells around them, in ascending order -
+ * outputs bit-identical to the dense loop; 0 (or ORACLE_DENSE=1): the literal dense N x M loop. */
+void oracle_set_accel(int on);
 
 #ifdef __cplusplus
 }

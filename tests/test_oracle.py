@@ -218,6 +218,38 @@ def test_trajectories_are_chaotic_under_1e7_perturbation():
     assert e0 < 1e-5 and elate > 1e-2
 
 
+def test_accelerated_candidate_enumeration_is_bit_identical_to_the_dense_loop():
+    """oracle/cvo_oracle.c visits, per row, only the targets of the 27 grid cells around it (in
+    ascending order) unless ORACLE_DENSE=1: same survivors, same truncation, same float sums."""
+    cases = []
+    src, tgt, _ = synthetic_pair(1500, 1200, 1300, 11)
+    cases.append((geometric_params(), src, tgt, 0.95, 256))
+    cases.append((geometric_params(), src, tgt, 3.0, 7))      # rows cut at the cap
+    cases.append((geometric_params(), src, tgt, 0.05, 256))   # almost nothing survives
+    src5, tgt5, _ = synthetic_pair(1500, 1000, 1100, 12, F=5, C=20, geotype=True)
+    p5 = u.read_params_yaml(os.path.join(DATA, "cvo_semantic_params_img_gpu0.yaml"))
+    p5.is_using_geometric_type, p5.c_ell = 1, 0.3
+    cases.append((p5, src5, tgt5, 0.9, 64))
+    bad = u.CvoPointCloud(np.vstack([src.positions_[:50], [[np.nan, 0, 1], [np.inf, 1, 2]]]))
+    badt = u.CvoPointCloud(np.vstack([tgt.positions_[:80], [[0, np.nan, 1], [1, 2, -np.inf]]]))
+    cases.append((geometric_params(), bad, badt, 2.0, 16))
+    R = np.eye(3, dtype=np.float32).reshape(9)
+    T = np.array([0.05, -0.02, 0.1], np.float32)
+    for p, s_, t_, ell, cap in cases:
+        out = []
+        for acc in (False, True):
+            oracle.set_accel(acc)
+            tr, sp = oracle.iterate(p, to_oracle_cloud(s_), to_oracle_cloud(t_), R, T, ell, cap, want_matrix=True)
+            out.append((tr, sp))
+        oracle.set_accel(True)
+        (ta, sa), (tb, sb) = out
+        assert np.array_equal(sa["nonzeros"], sb["nonzeros"]) and sa["nonzero_sum"] == sb["nonzero_sum"]
+        for i, n in enumerate(sa["nonzeros"]):
+            assert np.array_equal(sa["ind"][i, :n], sb["ind"][i, :n])
+            assert np.array_equal(sa["mat"][i, :n], sb["mat"][i, :n])
+        assert bytes(ta) == bytes(tb)  # every number of the iteration record, bit for bit
+
+
 # ---------------------------------------------------------------- golden fixtures
 def _golden(name):
     with open(os.path.join(os.path.dirname(__file__), "golden", name)) as fh:

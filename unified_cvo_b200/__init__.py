@@ -8,7 +8,8 @@ from ._abi import AlignInfo, IterTrace, Params, load_library  # noqa: F401
 from .cvo import (Association, CvoError, CvoGPU, CvoParams, CvoPointCloud,  # noqa: F401
                   default_params, read_params_yaml)
 from . import synthetic  # noqa: F401
+from .sequence import FrameToFrameOdometry  # noqa: F401
 
 __all__ = ["CvoGPU", "CvoPointCloud", "CvoParams", "Association", "CvoError", "Params",
            "IterTrace", "AlignInfo", "default_params", "read_params_yaml", "synthetic",
-           "load_library"]
+           "load_library", "FrameToFrameOdometry"]
