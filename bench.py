@@ -364,7 +364,10 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     value = pairs / dev_s
-    h2d = (N + M) * (32 + 4 * ((F + 3) // 4 * 4) + 4 * ((C + 3) // 4 * 4) + 8) + 9000
+    # what cvo_b200_align_host copies: the caller's arrays as they are (xyz 12 B, features 4F,
+    # labels 4C, geometric type 8 B per point when present), the parameters and the 9 KB state
+    geo = 8 if src.geometric_types_ is not None else 0
+    h2d = (N + M) * (12 + 4 * F + 4 * C + geo) + 512 + 9000
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,

@@ -322,6 +322,43 @@ def test_align_exports_the_last_iterations_association():
         g.close()
 
 
+@pytest.mark.parametrize("name,ell", [("KITTI05", 1.5), ("KITTI05", 0.15), ("C4", 0.5)])
+def test_full_size_single_iterations_against_the_oracle(name, ell):
+    """BASELINE's full sizes (KITTI-05-sized 16 384 x 16 384 and C4 = 200 000 x 200 000, both
+    with 5-dim colour), one iteration at the identity and one at a displaced pose: exact nnz and
+    max row count, twist to 1e-4.  The oracle finishes in seconds at these sizes because its rows
+    enumerate candidates through a grid (bit-identical to its dense loop, test_oracle.py)."""
+    from unified_cvo_b200 import synthetic
+    d = synthetic.make_config(name)
+    src = u.CvoPointCloud(d["source"]["xyz"], d["source"]["features"], None, None)
+    tgt = u.CvoPointCloud(d["target"]["xyz"], d["target"]["features"], None, None)
+    p = u.read_params_yaml(os.path.join(DATA, "cvo_intensity_params_img_gpu0.yaml"))
+    g = u.CvoGPU(p)
+    g.set_cloud(0, src)
+    g.set_cloud(1, tgt)
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    # a pose 5 % off the true one: T_target_to_source = inverse of the true motion (synthetic.py)
+    a = np.deg2rad(2.0 * 0.95)
+    Gn = np.eye(4)
+    Gn[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+    Tr = np.eye(4)
+    Tr[:3, 3] = np.array([0.05, 0.02, 0.50]) * 0.95
+    near = np.linalg.inv(Gn @ Tr).astype(np.float32)
+    total = 0
+    for R, T in ((np.eye(3, dtype=np.float32), np.zeros(3, np.float32)),
+                 (near[:3, :3].copy(), near[:3, 3].copy())):
+        ref = oracle.iterate(p, cs, ct, R.T.reshape(9).copy(), T, ell, 256)  # column-major R
+        got = g.iterate(R, T, ell, 256)
+        total += ref.nnz
+        if ref.nnz == 0:  # nothing within reach at this pose (ell = 0.15 against a 0.5 m offset)
+            assert got.nnz == 0 and got.max_row_nnz == 0
+            continue
+        bad = compare_traces(got, ref, twist_tol=TWIST_TOL)
+        assert not bad, (name, ell, bad)
+    assert total > 1000
+    g.close()
+
+
 def test_full_size_properties_kitti_sized_colour():
     """KITTI-05-sized clouds (N=M=16384, F=5): properties that need no oracle at this size —
     source-row shards sum to the whole (the multi-GPU decomposition), determinism, and the

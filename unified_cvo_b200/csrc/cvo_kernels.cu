@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256) prep_kernel(IterArgs A) {
       float r[3];
       mat3f_vec(Ri, yv, r);  // (*R) * input, CvoGPU_impl.cu:46-50
       const float m0 = r[0] + Ti[0], m1 = r[1] + Ti[1], m2 = r[2] + Ti[2];
-      A.tgt_moved[j] = make_float4(m0, m1, m2, 0.f);
+      A.tgt_moved[j] = make_float4(m0, m1, m2, y.w);  // .w: the point's packed colour summary
       const float ux = m0 - A.cx, uy = m1 - A.cy, uz = m2 - A.cz;
       A.px[j] = ux;
       A.py[j] = uy;
@@ -402,6 +402,7 @@ __device__ __noinline__ double exp_ref(double x) { return exp(x); }
 
 struct RowCtx {
   float px[3];
+  unsigned int qa;  // packed colour summary of the source point (cvo_upload.cu)
   float l;          // range-scaled length-scale of this row
   float d2_thres;
   float ga[2];
@@ -450,6 +451,15 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
     }
   }
   if (kc.use_intensity) {
+    // lower bound of the colour distance from the 8-bit summaries: per channel
+    // |fa - fb| >= (|qa - qb| - 1) / 255 (clamping to [0,1] is 1-Lipschitz, so it only weakens the
+    // bound).  If even the bound fails the reference's test d2_color < d2_c_thres, the pair is
+    // rejected exactly as the full test would reject it - without loading the feature rows.
+    {
+      const unsigned int d = __vsubus4(__vabsdiffu4(rc.qa, __float_as_uint(pb.w)), 0x01010101u);
+      const unsigned int lb = __dp4a(d, d, 0u);
+      if ((float)lb * (0.999f / 65025.f) >= kc.d2_c_thres) return false;
+    }
     const float* fa = A.src_feat + (size_t)i_global * A.Fp;
     const float* fb = A.tv[view].feat + (size_t)j * A.Fp;
     for (int f = 0; f < A.Fp; f += 4) {
@@ -581,7 +591,7 @@ __device__ __forceinline__ float4 move_point(const float* Ri, const float* Ti, c
   const float yv[3] = {y.x, y.y, y.z};
   float r[3];
   mat3f_vec(Ri, yv, r);
-  return make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], 0.f);
+  return make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], y.w);  // .w: packed colour summary
 }
 // 21 bits -> every third bit (the host's spread21, cvo_engine.cu)
 __device__ __forceinline__ unsigned long long spread21_dev(unsigned int a) {
@@ -646,6 +656,7 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
     {
       const float4 pa = A.src_xyz[ig];
       rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
+      rc.qa = __float_as_uint(pa.w);
       if (kGrid) {
         rc.l = range_ell(ell_now, A.src_rowA[ig].w);
         rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
@@ -675,7 +686,7 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
         const float yv[3] = {y.x, y.y, y.z};
         float r[3];
         mat3f_vec(Ri, yv, r);  // same arithmetic as prep_kernel
-        pb = make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], 0.f);
+        pb = make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], y.w);
         surv = eval_pair(A, kc, rc, ig, 1, j, pb, a);
       }
       const unsigned mask = __ballot_sync(0xffffffffu, surv);
@@ -776,6 +787,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
     {
       const float4 pa = A.src_xyz[ig];
       rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
+      rc.qa = __float_as_uint(pa.w);
       if (kGrid) {  // what prep_kernel writes to row_lt (CvoGPU.cu:506-511)
         rc.l = range_ell(ell_now, A.src_rowA[ig].w);
         rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;

@@ -152,8 +152,21 @@ __global__ void cloud_gather_kernel(GatherArgs G) {
   const int i = G.perm[s];
   G.inv[i] = s;
   const float x = G.xyz3[3 * (size_t)i], y = G.xyz3[3 * (size_t)i + 1], z = G.xyz3[3 * (size_t)i + 2];
-  G.xyz[s] = make_float4(x, y, z, 0.f);
-  G.xyz_o[s] = make_float4(G.xyz3[3 * (size_t)s], G.xyz3[3 * (size_t)s + 1], G.xyz3[3 * (size_t)s + 2], 0.f);
+  // .w of a point = its first four feature channels quantised to 8 bits each (clamped to [0,1]):
+  // a 4-byte summary from which eval_pair derives a LOWER bound of the colour distance and
+  // rejects most colour mismatches without touching the 32-byte feature rows
+  auto pack_colour = [&](int idx) -> float {
+    unsigned int q = 0u;
+    for (int k = 0; k < 4 && k < G.F; k++) {
+      const float f = G.feat_in[(size_t)idx * G.F + k];
+      const float c = fminf(fmaxf(f, 0.f), 1.f);  // NaN -> 0; the full test decides then
+      q |= (unsigned int)(c * 255.f) << (8 * k);
+    }
+    return __uint_as_float(q);
+  };
+  G.xyz[s] = make_float4(x, y, z, pack_colour(i));
+  G.xyz_o[s] = make_float4(G.xyz3[3 * (size_t)s], G.xyz3[3 * (size_t)s + 1], G.xyz3[3 * (size_t)s + 2],
+                           pack_colour(s));
   const float dist = sqrtf((x * x + y * y) + z * z);
   const float cx = G.st->centroid[0], cy = G.st->centroid[1], cz = G.st->centroid[2];
   // prefilter record: a = -2 (x - c) and the reference's a_to_sensor
