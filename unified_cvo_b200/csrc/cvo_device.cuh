@@ -102,14 +102,14 @@ struct DevState {
   int qs_head, qs_size, qe_head, qe_size;
   float start_sum, end_sum;
   // scheduling scratch
-  unsigned int work_counter;
+  unsigned int work_counter;   // dynamic hand-out of row groups (flow_rows)
+  unsigned int item_counter;   // dynamic hand-out of (tile, chunk) items (pair_kernel)
   unsigned int flow_blocks_done;
   unsigned int step_blocks_done;
   unsigned int n_sat;       // view 0: rows that reached their cap (redone exactly by the flow tail)
   unsigned int n_capped;    // view 1: rows that reached their cap (keeps the run on view 1)
   unsigned int sat_total;   // running sum of n_sat + n_capped over the iterations (host policy)
   unsigned int bar_count;   // grid barrier of the persistent kernel (monotone arrival counter)
-  unsigned int pad1;
   // trace
   cvo_b200_iter_trace* trace;
   int trace_cap;

@@ -209,14 +209,23 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
   __syncwarp();
   uint32_t phase0 = 0, phase1 = 0;
 
-  // static round-robin over (tile, chunk) items: a single global work counter costs ~10^4
-  // same-address L2 atomics per launch, more than the sweep itself on 10k x 10k clouds
+  // (tile, chunk) items: the first one of every warp is static; the rest is static round-robin
+  // on small problems (a global work counter costs ~10^4 same-address L2 atomics per launch, more
+  // than the sweep itself on 10k x 10k clouds) and handed out dynamically on large ones, where
+  // sphere pruning makes the items very unequal (27 % of the 200k sweep was tail otherwise)
   const int gwarp = blockIdx.x * kPairWarps + warp;
   const int nwarps = gridDim.x * kPairWarps;
+  const bool dynamic_items = A.n_items > 8 * nwarps;
   int next_item = gwarp;
   auto fetch_item = [&]() -> int {
     const int it = next_item;
-    next_item += nwarps;
+    if (dynamic_items) {
+      int nx = 0;
+      if (lane == 0) nx = nwarps + (int)atomicAdd(&st->item_counter, 1u);
+      next_item = __shfl_sync(0xffffffffu, nx, 0);
+    } else {
+      next_item += nwarps;
+    }
     return it;
   };
   auto issue_tile = [&](int item, int buf) {
@@ -763,11 +772,11 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
   double w_nnz = 0.0, w_max = 0.0;
 
   // Row groups: the first pass is static (warp w of block b takes rows 4(b*W+w)..+3); when there
-  // are more rows than resident row slots, cell-query mode hands out the rest dynamically, four
+  // are more rows than resident row slots the rest is handed out dynamically, four
   // rows per warp from a global counter: rows differ a lot in cost in the dense regimes (a cloud's
   // boundary rows see half the neighbours) and a static split left 20 % of C4's flow phase idle.
   const int total_slots = gridDim.x * warps_per_block * kRowsPerWarp;
-  const bool dynamic_rows = kGrid && A.n_rows > total_slots;
+  const bool dynamic_rows = A.n_rows > total_slots;
   int row_base = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp;
   for (bool first_pass = true;; first_pass = false) {
     if (!first_pass) {
@@ -1547,6 +1556,7 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
       }
     }
     st->work_counter = 0u;
+    st->item_counter = 0u;
     if (finished) st->done = 1;
   }
 }
