@@ -11,8 +11,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     p = geometric_params() if F == 0 else u.read_params_yaml(os.path.join(DATA, "cvo_intensity_params_img_gpu0.yaml"))
     g = u.CvoGPU(p); g.set_cloud(0, src); g.set_cloud(1, tgt)
     g.time_iterations(np.eye(3), np.zeros(3), ell, 64, 200, pair_kernel=False)
-    best = min(g.time_iterations(np.eye(3), np.zeros(3), ell, 64, 400, pair_kernel=False)[0] for _ in range(3))
-    print(json.dumps({"us_per_iter": best / 400 * 1e3}))
+    nit = 40 if N > 50000 else 400
+    best = min(g.time_iterations(np.eye(3), np.zeros(3), ell, 256, nit, pair_kernel=False)[0] for _ in range(3))
+    print(json.dumps({"us_per_iter": best / nit * 1e3}))
 else:
     name = sys.argv[1] if len(sys.argv) > 1 else "C2"
     ell = sys.argv[2] if len(sys.argv) > 2 else "0.95"
