@@ -255,6 +255,10 @@ def run_ours(args, rank, world, local_rank):
         g.comm_init(rank, world, uid[0])
         from unified_cvo_b200.dist import shard_rows
         g.set_row_range(*shard_rows(N, world, rank))
+        if os.environ.get("CVO_B200_FUSED", "1") != "0":  # NVLink mailboxes for the persistent kernel
+            handles = [None] * world
+            dist.all_gather_object(handles, g.comm_mailbox_handle())
+            g.comm_open_peers(handles)
 
     def barrier():
         torch.cuda.synchronize()
@@ -330,8 +334,10 @@ def run_ours(args, rank, world, local_rank):
         rows_local = re_ - rb
     alg_bytes_iter = algorithmic_bytes_per_iteration(rows_local, M, F, C)
     traffic = load_traffic()
-    if grid_frac >= 0.5 and world == 1:
-        # cell-query mode on one GPU: the whole loop is ONE launch of align_grid_kernel, so the
+    fused = world > 1 and os.environ.get("CVO_B200_FUSED", "1") != "0"
+    if grid_frac >= 0.5 and (world == 1 or fused) and os.environ.get("CVO_B200_PERSIST", "1") != "0":
+        # cell-query mode (one GPU, or sharded with the NVLink mailbox exchange): the whole loop is
+        # ONE launch of align_grid_kernel per GPU, so the
         # kernel's duration is the timed region itself (registration_seconds = CUDA events around
         # that launch) and one launch processes `iterations` iterations
         kernel = "align_grid_kernel"
@@ -376,7 +382,9 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"{name}: {desc}", "N": N, "M": M, "F": F, "C": C,
                    "iterations_per_step": iters / args.steps, "l2_flush_between_steps": True,
                    "cell_query_fraction": grid_frac,
-                   "parallelism": "single GPU" if world == 1 else f"source rows sharded x{world}, NCCL all-gather",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"source rows sharded x{world}; dense-scan batches: NCCL all-gather, cell-query "
+                   f"batches: persistent kernel with NVLink mailbox exchange",
                    "timing": "CUDA events on the launching stream inside cvo_b200_align, summed over steps"},
         "e2e": {"value": e2e_pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 8800, "steps": e2e_steps,

@@ -272,6 +272,14 @@ int cvo_b200_fma_peak(cvo_b200_handle* h, int kind, int iters, double* fma_per_s
  * and all-reduce {omega,v,nnz,max} and {B,C,D,E} once each per iteration.     */
 int cvo_b200_comm_unique_id(char id[128]);
 int cvo_b200_comm_init(cvo_b200_handle* h, int rank, int world, const char id[128]);
+/* Fused exchange (optional, after comm_init): every rank publishes the CUDA IPC handle of a small
+ * mailbox in its HBM, the host plumbing all-gathers the 64-byte handles, every rank maps its
+ * peers'.  From then on the cell-query mode runs the WHOLE registration loop of a sharded job in
+ * one persistent kernel per GPU whose two per-iteration exchanges are NVLink stores into the
+ * peers' mailboxes + a spin on the own one (no NCCL call, no kernel boundary); the dense-scan mode
+ * keeps the NCCL all-gathers.  handles = world x 64 bytes, rank order.                        */
+int cvo_b200_comm_mailbox_handle(cvo_b200_handle* h, char out[64]);
+int cvo_b200_comm_open_peers(cvo_b200_handle* h, const char* handles);
 int cvo_b200_comm_destroy(cvo_b200_handle* h);
 
 #ifdef __cplusplus

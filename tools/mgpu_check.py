@@ -18,9 +18,20 @@ g = u.CvoGPU(p, device=lr)
 uid = [u.CvoGPU.comm_unique_id() if rank == 0 else None]
 dist.broadcast_object_list(uid, src=0)
 g.comm_init(rank, world, uid[0])
-per = (10000 + world - 1) // world
-g.set_row_range(rank * per, min(10000, (rank + 1) * per))
-r1, T1, i1, tr1 = g.align(src, tgt, None, trace_cap=60)
+from unified_cvo_b200.dist import shard_rows
+g.set_row_range(*shard_rows(10000, world, rank))
+r1, T1, i1, tr1 = g.align(src, tgt, None, trace_cap=60)   # NCCL all-gathers, one launch per phase
+handles = [None] * world
+dist.all_gather_object(handles, g.comm_mailbox_handle())
+g.comm_open_peers(handles)
+r2, T2, i2, tr2 = g.align(src, tgt, None, trace_cap=60)   # fused: persistent kernel + NVLink mailboxes
+l0 = g.launch_count()
+r2, T2, i2, tr2 = g.align(src, tgt, None, trace_cap=60)
+print(f"rank {rank}: launches of the fused align: {g.launch_count() - l0}")
+if os.environ.get("CVO_B200_STAMPS"):
+    g.time_iterations(np.eye(3), np.zeros(3), 0.3, 64, 200, pair_kernel=False)
+okf = all(not compare_traces(tr2[k], tr0[k]) for k in range(8))
+print(f"rank {rank}: fused x{world} iters {i2.iterations} t={i2.registration_seconds*1e3:.2f} ms | pose diff vs NCCL path {np.abs(T2-T1).max():.2e} | first-8 parity {'OK' if okf else 'FAIL'}")
 ok = True
 for k in range(8):
     bad = compare_traces(tr1[k], tr0[k])

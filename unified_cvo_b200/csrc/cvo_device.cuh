@@ -118,6 +118,10 @@ struct DevState {
   double local_flow[9];     // omega[3], v[3], a_sum, (double)nnz, (double)max_row_nnz
   double local_step[4];
   unsigned long long dbg[16];  // %globaltimer stamps of the tails (tools/gpu_tails.py)
+  // fused multi-GPU exchange: block 0 gathers the ranks' records and hands the job totals to the
+  // other blocks of its GPU here ([phase][parity], same self-validating words; tag ~0 = a peer
+  // timed out)
+  unsigned long long xll[2][2][32];
 };
 constexpr int kHot1Words = (int)(offsetof(DevState, omega) / 4);
 constexpr int kHot2Words = (int)((offsetof(DevState, omega_sum) - offsetof(DevState, omega)) / 4);
@@ -134,6 +138,19 @@ struct GridView {
   int n_finite;                    // points with a finite key
   float lo[3];                     // origin of the key lattice
   float scale;                     // lattice units per metre ((2^21 - 1) / extent)
+};
+
+// Fused multi-GPU exchange (persistent kernel, one process per GPU): every rank owns a mailbox in
+// its HBM that its peers map through CUDA IPC.  A rank all-gathers a small record by STORING it
+// into every peer's mailbox over NVLink and polling its own mailbox - no NCCL call, no kernel
+// boundary, and no memory fence either: every double travels as two self-validating 8-byte
+// words (tag << 32 | half), so a word is either the old one or completely the new one and the
+// receiver simply polls until both tags match (the LL protocol of collective libraries).
+// Slots are indexed by (phase, iteration parity, source rank); a rank cannot run two iterations
+// ahead of a peer (it needs the peer's records to advance), so two parities suffice.
+constexpr int kMaxWorld = 16;
+struct XMailbox {
+  unsigned long long ll[2][2][kMaxWorld][32];  // [phase][parity][rank][2 words per value]
 };
 
 struct TargetView {
@@ -190,6 +207,10 @@ struct IterArgs {
   int mode;        // 0 isotropic (fill_in_A_mat_gpu), 1 Mahalanobis (.._dense_mat_kernel)
   float kinv[9];   // column-major inverse kernel for mode 1
   unsigned long long* stamps;  // debug (CVO_B200_STAMPS=1): [blocks][8] %globaltimer of block phases
+  // fused multi-GPU exchange (xfused = 1): peers' mailboxes (own included), this launch's generation
+  XMailbox* xpeer[kMaxWorld];
+  unsigned long long xgen;
+  int xfused, xrank, xworld;
   int grid;        // 1: candidates come from cell queries (flow_kernel<true>; no prep/pair launch)
   GridView gv;
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective

@@ -189,6 +189,11 @@ struct cvo_b200_handle {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // fused exchange: own mailbox + the peers' (CUDA IPC), generation counter of persistent launches
+  XMailbox* mailbox = nullptr;
+  XMailbox* peers[kMaxWorld] = {};
+  bool peers_ready = false;
+  unsigned long long xgen = 0;
   std::string err;
   uint64_t launches = 0;
   // the kernel matrix left behind by the last align() (cvo_b200_align_association)
@@ -355,6 +360,11 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
     CVO_CUDA(h, h->stamps.ensure((size_t)8 * 4096));
     A.stamps = h->stamps.p;
   }
+  A.xfused = 0;
+  A.xrank = h->rank;
+  A.xworld = h->world;
+  A.xgen = 0;
+  for (int r = 0; r < kMaxWorld; r++) A.xpeer[r] = h->peers[r];
   A.grid = 0;
   A.gv.coarse = ct.coarse.p;
   A.gv.cbits = ct.cbits;
@@ -696,16 +706,28 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
   while (true) {
     // rows that reach their cap are redone exhaustively (O(M) each) by one block in the
     // Morton-ordered modes: leave cell queries while that happens a lot
-    A.grid = (grid_profitable(h, h->src, h->tgt, ell, A.n_rows) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
-    if (A.grid && h->use_persist && A.world == 1) {
-      // the whole loop in one cooperative launch (align_grid_kernel); it returns when done
+    // multi-GPU: every rank must take the same decision (a rank in the persistent kernel and a
+    // peer in the NCCL graph would wait for each other forever), so the policy only sees
+    // replicated inputs there: the nominal shard size and the (replicated) length-scale
+    const int rows_policy = A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows;
+    if (A.world > 1) sat_recent = false;
+    A.grid = (grid_profitable(h, h->src, h->tgt, ell, rows_policy) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
+    if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
+      // the whole loop in one cooperative launch (align_grid_kernel); it returns when done.
+      // world > 1: the two per-iteration exchanges are NVLink stores into the peers' mailboxes
+      A.xfused = A.world > 1 ? 1 : 0;
+      A.xgen = ++h->xgen;
       CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->stream));
       h->launches += 1;
       CVO_CUDA(h, cudaMemcpyAsync(h->h_poll, &h->d_state->iter, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CVO_CUDA(h, cudaStreamSynchronize(h->stream));
       batches++;
       grid_batches++;
-      if (h->h_poll[1] /*done*/) break;
+      if (h->h_poll[1] /*done*/) {
+        if (h->h_poll[2] /*ret*/ == CVO_B200_ERR_NCCL)
+          return fail(h, CVO_B200_ERR_NCCL, "fused exchange: a peer's record did not arrive (peer gone?)");
+        break;
+      }
       return fail(h, CVO_B200_ERR_STATE, "persistent align kernel returned without finishing");
     }
     batches++;
@@ -817,6 +839,9 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   destroy_graph(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  for (int r = 0; r < kMaxWorld; r++)
+    if (h->peers[r] && h->peers[r] != h->mailbox) cudaIpcCloseMemHandle(h->peers[r]);
+  if (h->mailbox) cudaFree(h->mailbox);
   for (CloudDev* c : {&h->src, &h->tgt}) {
     c->xyz.release(); c->rowA.release(); c->feat.release(); c->lab.release(); c->geo.release();
     c->xyz_o.release(); c->feat_o.release(); c->lab_o.release(); c->geo_o.release();
@@ -881,10 +906,13 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) return fail(h, CVO_B200_ERR_INVALID, "num_neighbors exceeds nearest_neighbors_max");
   CVO_CUDA(h, h->d_trace.ensure(1));
-  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.n_rows) ? 1 : 0;
+  // multi-GPU: replicated inputs only, so that every rank takes the same decision
+  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
-  if (A.grid && h->use_persist && A.world == 1) {
+  if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
+    A.xfused = A.world > 1 ? 1 : 0;
+    A.xgen = ++h->xgen;
     CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->stream));
     h->launches += 1;
   } else {
@@ -936,8 +964,8 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   CVO_CUDA(h, cudaEventCreate(&ev1));
   if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
     IterArgs Ag = A;
-    Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init, A.n_rows) ? 1 : 0;
-    if (!(Ag.grid && h->use_persist && A.world == 1)) {
+    Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows) ? 1 : 0;
+    if (!(Ag.grid && h->use_persist && (A.world == 1 || h->peers_ready))) {
       rc = ensure_graph(h, Ag, 32);
       if (rc != CVO_B200_OK) return rc;
     }
@@ -1211,10 +1239,15 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   if (rc != CVO_B200_OK) return rc;
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) num_neighbors = A.cap_max;
-  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.n_rows) ? 1 : 0;
+  // multi-GPU: replicated inputs only, so that every rank takes the same decision
+  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows) ? 1 : 0;
   rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
-  const bool persist = A.grid && h->use_persist && A.world == 1;
+  const bool persist = A.grid && h->use_persist && (A.world == 1 || h->peers_ready);
+  if (persist) {
+    A.xfused = A.world > 1 ? 1 : 0;
+    A.xgen = ++h->xgen;
+  }
   // per-kernel events only exist when every phase is its own launch
   const int n_ev = (ms_pair_kernel && !persist) ? iters : 0;
   std::vector<cudaEvent_t> ea((size_t)n_ev), eb((size_t)n_ev);
@@ -1351,6 +1384,41 @@ int cvo_b200_comm_init(cvo_b200_handle* h, int rank, int world, const char id[12
   return CVO_B200_OK;
 }
 
+int cvo_b200_comm_mailbox_handle(cvo_b200_handle* h, char out[64]) {
+  if (!h || !out) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  if (!h->mailbox) {
+    CVO_CUDA(h, cudaMalloc((void**)&h->mailbox, sizeof(XMailbox)));
+    CVO_CUDA(h, cudaMemset(h->mailbox, 0, sizeof(XMailbox)));
+  }
+  cudaIpcMemHandle_t hd;
+  CVO_CUDA(h, cudaIpcGetMemHandle(&hd, h->mailbox));
+  std::memcpy(out, &hd, 64);
+  return CVO_B200_OK;
+}
+
+int cvo_b200_comm_open_peers(cvo_b200_handle* h, const char* handles) {
+  if (!h || !handles) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  if (h->world < 2 || h->world > kMaxWorld) return fail(h, CVO_B200_ERR_STATE, "comm_init first (2..16 ranks)");
+  if (!h->mailbox) return fail(h, CVO_B200_ERR_STATE, "call cvo_b200_comm_mailbox_handle first");
+  cudaSetDevice(h->device);
+  for (int r = 0; r < h->world; r++) {
+    if (r == h->rank) {
+      h->peers[r] = h->mailbox;
+      continue;
+    }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    CVO_CUDA(h, cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
+    h->peers[r] = (XMailbox*)p;
+  }
+  h->peers_ready = true;
+  h->xgen = 0;
+  return CVO_B200_OK;
+}
+
 int cvo_b200_comm_destroy(cvo_b200_handle* h) {
   if (!h) return CVO_B200_ERR_INVALID;
   cudaSetDevice(h->device);
@@ -1358,6 +1426,13 @@ int cvo_b200_comm_destroy(cvo_b200_handle* h) {
   destroy_graph(h);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;
+  for (int r = 0; r < kMaxWorld; r++) {
+    if (h->peers[r] && h->peers[r] != h->mailbox) cudaIpcCloseMemHandle(h->peers[r]);
+    h->peers[r] = nullptr;
+  }
+  h->peers_ready = false;
+  if (h->mailbox) cudaFree(h->mailbox);
+  h->mailbox = nullptr;
   h->world = 1;
   h->rank = 0;
   return CVO_B200_OK;

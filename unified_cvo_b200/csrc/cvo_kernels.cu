@@ -1742,6 +1742,86 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
   }
   __syncthreads();
 }
+// ---- fused multi-GPU all-gather of one small record (see XMailbox).  tot[] is this rank's total
+// (valid on thread 0 of every block; identical in all blocks); on return it holds the sum (first
+// NSUM values) / max (rest) over all ranks, reduced in RANK ORDER on every rank and in every
+// block, so all copies of the controller state stay bit-identical across the whole job.
+// Returns false on thread 0 if a peer's record did not arrive within ~10 s (a dead peer must not
+// hang the GPU).
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// one double as two tagged words / back (polls until both halves carry `tag`; false on timeout
+// or on the poison tag)
+__device__ __forceinline__ void ll_store(unsigned long long* w, double x, unsigned int tag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+  st_volatile_u64(w, ((unsigned long long)tag << 32) | (b & 0xffffffffull));
+  st_volatile_u64(w + 1, ((unsigned long long)tag << 32) | (b >> 32));
+}
+__device__ __forceinline__ bool ll_load(const unsigned long long* w, unsigned int tag, long long t0,
+                                        long long budget, double& x) {
+  unsigned long long lo, hi;
+  while (true) {
+    lo = ld_volatile_u64(w);
+    hi = ld_volatile_u64(w + 1);
+    if ((unsigned int)(lo >> 32) == tag && (unsigned int)(hi >> 32) == tag) break;
+    if ((unsigned int)(lo >> 32) == 0xffffffffu || (budget > 0 && clock64() - t0 > budget)) return false;
+  }
+  x = __longlong_as_double((long long)((hi << 32) | (lo & 0xffffffffull)));
+  return true;
+}
+template <int NV, int NSUM>
+__device__ bool xgpu_allgather(const IterArgs& A, DevState* gst, double (&tot)[NV], int phase,
+                               unsigned long long epoch) {
+  bool ok = true;
+  if (threadIdx.x == 0) {
+    const int par = (int)(epoch & 1ull);
+    // 32-bit tag: launch generation and iteration; never 0 (fresh mailbox) or ~0 (poison)
+    const unsigned int tag = ((((unsigned int)(epoch >> 32) & 0x7fffu) + 1u) << 16) | ((unsigned int)epoch & 0xffffu);
+    if (blockIdx.x == 0) {
+      // ---- publish: 2 NV independent 8-byte stores per peer over NVLink (own mailbox included)
+      for (int r = 0; r < A.xworld; r++) {
+        unsigned long long* dst = A.xpeer[r]->ll[phase][par][A.xrank];
+#pragma unroll
+        for (int k = 0; k < NV; k++) ll_store(dst + 2 * k, tot[k], tag);
+      }
+      // ---- gather in rank order from the own mailbox
+      XMailbox* me = A.xpeer[A.xrank];
+      double acc[NV];
+#pragma unroll
+      for (int k = 0; k < NV; k++) acc[k] = 0.0;
+      const long long t0 = clock64();
+      for (int r = 0; r < A.xworld && ok; r++) {
+#pragma unroll
+        for (int k = 0; k < NV; k++) {
+          double x = 0.0;
+          ok = ok && ll_load(me->ll[phase][par][r] + 2 * k, tag, t0, 20000000000ll /* ~10 s */, x);
+          acc[k] = (k < NSUM) ? acc[k] + x : fmax(acc[k], x);
+        }
+      }
+      // ---- hand the job totals (or the failure) to the other blocks of this GPU
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        tot[k] = acc[k];
+        ll_store(gst->xll[phase][par] + 2 * k, acc[k], ok ? tag : 0xffffffffu);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NV; k++) {
+        double x = 0.0;
+        ok = ok && ll_load(gst->xll[phase][par] + 2 * k, tag, 0, 0, x);
+        tot[k] = x;
+      }
+    }
+  }
+  return ok;
+}
+
 // block partial (NV values per warp in v, valid on lane 0) -> part[k * gridDim.x + blockIdx.x]
 template <int NV, int NSUM>
 __device__ __forceinline__ void publish_block_partial(const double (&v)[NV], double* sh, double* part) {
@@ -1833,10 +1913,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs
       }
     }
     CVO_PHASE(3)
+    // ---- multi-GPU: this rank's totals -> the job's totals (NVLink stores + local spin)
+    const unsigned long long xepoch = (A.xgen << 32) | (unsigned long long)(unsigned)(s_st.iter + 1);
+    bool xok = true;
+    if (A.xfused) xok = xgpu_allgather<9, 8>(A, gst, tot, 0, xepoch);
     // ---- normalisation, omega_hat powers
     if (threadIdx.x == 0) {
       s_st.n_sat = n_sat;  // update_tf_device's bookkeeping
       finalize_flow_scalar(&s_st, tot);
+      if (!xok) {  // a peer is gone: stop this rank's loop with an error instead of spinning
+        s_st.ret = CVO_B200_ERR_NCCL;
+        s_st.stop_reason = CVO_B200_STOP_NONE;
+        s_st.done = 1;
+      }
     }
     __syncthreads();
     CVO_PHASE(4)
@@ -1854,7 +1943,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs
       double tot[4];
       block_reduce_partials<4, 4>(step_part, (int)gridDim.x, tot, sh);
       CVO_PHASE(8)
+      bool xok2 = true;
+      if (A.xfused) xok2 = xgpu_allgather<4, 4>(A, gst, tot, 1, xepoch);
       controller_step(A, &s_st, tot, &s_ctrl);
+      if (threadIdx.x == 0 && !xok2) {
+        s_st.ret = CVO_B200_ERR_NCCL;
+        s_st.done = 1;
+      }
     }
     __syncthreads();
     CVO_PHASE(9)
@@ -1862,10 +1957,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs
   if (stamping)
     for (int q = 0; q < 10; q++) A.stamps[q] = s_acc[q];
 #undef CVO_PHASE
-  // ---- block 0 hands the final state (pose, flags, counters) back
+  // ---- block 0 hands the final state (pose, flags, results) back.  The scheduling scratch
+  //      (barrier counter, work counters, exchange flags) is NOT written back: other blocks may
+  //      still be leaving their last spin loop on it.
   if (blockIdx.x == 0) {
-    for (int i = threadIdx.x; i < (int)(sizeof(DevState) / 4); i += blockDim.x)
-      reinterpret_cast<uint32_t*>(gst)[i] = reinterpret_cast<const uint32_t*>(&s_st)[i];
+    const int w0 = (int)(offsetof(DevState, work_counter) / 4), w1 = (int)(offsetof(DevState, trace) / 4),
+              w2 = (int)(offsetof(DevState, xll) / 4);
+    for (int i = threadIdx.x; i < w2; i += blockDim.x)
+      if (i < w0 || i >= w1)
+        reinterpret_cast<uint32_t*>(gst)[i] = reinterpret_cast<const uint32_t*>(&s_st)[i];
   }
 }
 

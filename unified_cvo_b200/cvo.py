@@ -389,5 +389,15 @@ class CvoGPU:
         buf = (C.c_char * 128)(*unique_id[:128])
         self._check(self._lib.cvo_b200_comm_init(self._h, int(rank), int(world), buf))
 
+    def comm_mailbox_handle(self) -> bytes:
+        """CUDA IPC handle (64 bytes) of this rank's exchange mailbox (fused multi-GPU path)."""
+        buf = (C.c_char * 64)()
+        self._check(self._lib.cvo_b200_comm_mailbox_handle(self._h, buf))
+        return bytes(buf.raw)
+
+    def comm_open_peers(self, handles):
+        """handles: the 64-byte mailbox handles of all ranks, in rank order."""
+        self._check(self._lib.cvo_b200_comm_open_peers(self._h, b"".join(bytes(x[:64]) for x in handles)))
+
     def comm_destroy(self):
         self._check(self._lib.cvo_b200_comm_destroy(self._h))

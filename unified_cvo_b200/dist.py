@@ -19,7 +19,7 @@ def shard_rows(n_rows: int, world: int, rank: int) -> tuple[int, int]:
     return begin, min(n_rows, begin + per)
 
 
-def attach(gpu, n_rows: int, rank: int, world: int, dist_module=None) -> tuple[int, int]:
+def attach(gpu, n_rows: int, rank: int, world: int, dist_module=None, fused: bool = True) -> tuple[int, int]:
     """Create the NCCL communicator of `gpu` (a CvoGPU) and set its row shard.
 
     dist_module: an initialised torch.distributed (any backend) used only to broadcast the
@@ -30,6 +30,10 @@ def attach(gpu, n_rows: int, rank: int, world: int, dist_module=None) -> tuple[i
         uid = [CvoGPU.comm_unique_id() if rank == 0 else None]
         dist_module.broadcast_object_list(uid, src=0)
         gpu.comm_init(rank, world, uid[0])
+        if fused:  # NVLink mailboxes: the persistent kernel exchanges its records itself
+            handles = [None] * world
+            dist_module.all_gather_object(handles, gpu.comm_mailbox_handle())
+            gpu.comm_open_peers(handles)
     b, e = shard_rows(n_rows, world, rank)
     gpu.set_row_range(b, e)
     return b, e
