@@ -967,7 +967,11 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
     Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows) ? 1 : 0;
     if (!(Ag.grid && h->use_persist && (A.world == 1 || h->peers_ready))) {
       rc = ensure_graph(h, Ag, 32);
-      if (rc != CVO_B200_OK) return rc;
+      if (rc != CVO_B200_OK) {
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+        return rc;
+      }
     }
   }
   cudaEventRecord(ev0, h->stream);
