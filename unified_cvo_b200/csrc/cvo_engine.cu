@@ -32,8 +32,8 @@ void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t 
 int pair_kernel_max_blocks_per_sm();
 int sparse_kernel_max_blocks_per_sm();
 int grid_kernel_max_blocks_per_sm();
-cudaError_t launch_align_grid(const IterArgs& A, int blocks, cudaStream_t s);
-int align_grid_max_blocks_per_sm();
+cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaStream_t s);
+int align_grid_max_blocks_per_sm(int threads);
 }  // namespace cvo_b200
 
 using namespace cvo_b200;
@@ -182,6 +182,7 @@ struct cvo_b200_handle {
   bool use_graph = true;
   int grid_blocks = 1;
   int persist_blocks = 1;   // cooperative grid of align_grid_kernel (all blocks co-resident)
+  int persist_threads = kPersistThreads;
   bool use_persist = true;  // CVO_B200_PERSIST=0: one launch per phase even in cell-query mode
   int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries
   // host poll buffer (pinned)
@@ -291,9 +292,11 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   if (gocc < 1) gocc = 1;
   h->grid_blocks =
       std::max(1, std::min(h->num_sms * gocc, (n_rows + rows_per_block - 1) / rows_per_block));
-  int pocc = align_grid_max_blocks_per_sm();
+  // wider blocks when the narrow ones would need a second pass over the rows (cvo_device.cuh)
+  h->persist_threads = (n_rows > h->num_sms * (kPersistThreads / 32) * 4) ? kPersistThreadsWide : kPersistThreads;
+  int pocc = align_grid_max_blocks_per_sm(h->persist_threads);
   if (pocc < 1) pocc = 1;
-  const int rows_per_pblock = (kPersistThreads / 32) * 4;
+  const int rows_per_pblock = (h->persist_threads / 32) * 4;
   h->persist_blocks =
       std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_pblock - 1) / rows_per_pblock));
   CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
@@ -717,7 +720,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
       // world > 1: the two per-iteration exchanges are NVLink stores into the peers' mailboxes
       A.xfused = A.world > 1 ? 1 : 0;
       A.xgen = ++h->xgen;
-      CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->stream));
+      CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream));
       h->launches += 1;
       CVO_CUDA(h, cudaMemcpyAsync(h->h_poll, &h->d_state->iter, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CVO_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -913,7 +916,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
     A.xfused = A.world > 1 ? 1 : 0;
     A.xgen = ++h->xgen;
-    CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->stream));
+    CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream));
     h->launches += 1;
   } else {
     rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
@@ -1264,7 +1267,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   CVO_CUDA(h, cudaEventCreate(&e1));
   cudaEventRecord(e0, h->stream);
   if (persist) {  // one launch runs all `iters` iterations; no per-kernel events
-    cudaError_t le = launch_align_grid(A, h->persist_blocks, h->stream);
+    cudaError_t le = launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream);
     if (le != cudaSuccess) rc = fail(h, CVO_B200_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(le));
     h->launches += 1;
   } else {

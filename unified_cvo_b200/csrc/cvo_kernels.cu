@@ -649,6 +649,7 @@ __device__ __forceinline__ void cell_ranges2(const GridView& G, int lvl3, bool v
 constexpr int kGroup = 8;                    // lanes per source row
 constexpr int kRowsPerWarp = 32 / kGroup;    // 4
 constexpr int kGroupList = 80;               // pending (<8) + one batch of 8 words (<=64)
+constexpr int kGridList = 48;                // cell queries: pending (<8) + one quad pass (<=32)
 
 // Exact redo of ONE source row by one warp: all targets in the caller's original order with the
 // reference's arithmetic (the literal loop of CvoGPU.cu:524-591), for rows that were cut at their
@@ -1844,9 +1845,11 @@ __device__ __forceinline__ void publish_block_partial(const double (&v)[NV], dou
   }
 }
 
-__global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs A) {
-  __shared__ double sh[(kPersistThreads / 32 + 2) * 9];
-  __shared__ uint32_t s_list[kPersistThreads / kGroup][kGroupList];
+template <int kThreads, bool kFused>
+__global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
+  __shared__ double sh[(kThreads / 32 + 2) * 9];
+  // cell queries queue at most 7 pending + 32 new candidates per row group
+  __shared__ uint32_t s_list[kThreads / kGroup][kGridList];
   __shared__ __align__(16) DevState s_st;
   __shared__ unsigned int s_nsat;
   __shared__ CtrlScratch s_ctrl;
@@ -1916,7 +1919,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs
     // ---- multi-GPU: this rank's totals -> the job's totals (NVLink stores + local spin)
     const unsigned long long xepoch = (A.xgen << 32) | (unsigned long long)(unsigned)(s_st.iter + 1);
     bool xok = true;
-    if (A.xfused) xok = xgpu_allgather<9, 8>(A, gst, tot, 0, xepoch);
+    if (kFused) xok = xgpu_allgather<9, 8>(A, gst, tot, 0, xepoch);
     // ---- normalisation, omega_hat powers
     if (threadIdx.x == 0) {
       s_st.n_sat = n_sat;  // update_tf_device's bookkeeping
@@ -1944,7 +1947,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) align_grid_kernel(IterArgs
       block_reduce_partials<4, 4>(step_part, (int)gridDim.x, tot, sh);
       CVO_PHASE(8)
       bool xok2 = true;
-      if (A.xfused) xok2 = xgpu_allgather<4, 4>(A, gst, tot, 1, xepoch);
+      if (kFused) xok2 = xgpu_allgather<4, 4>(A, gst, tot, 1, xepoch);
       controller_step(A, &s_st, tot, &s_ctrl);
       if (threadIdx.x == 0 && !xok2) {
         s_st.ret = CVO_B200_ERR_NCCL;
@@ -2069,16 +2072,27 @@ void launch_init_bound(const IterArgs& A, cudaStream_t s) { init_bound_kernel<<<
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s) {
   fma_peak_kernel<<<blocks, 256, 0, s>>>(kind, iters, sink);
 }
-cudaError_t launch_align_grid(const IterArgs& A, int blocks, cudaStream_t s) {
+// the four instantiations of the persistent kernel: narrow / wide blocks x single GPU / fused
+// multi-GPU exchange (kept out of the single-GPU code: it costs registers)
+static const void* align_grid_fn(int threads, bool fused) {
+  if (threads == kPersistThreadsWide)
+    return fused ? (const void*)align_grid_kernel<kPersistThreadsWide, true>
+                 : (const void*)align_grid_kernel<kPersistThreadsWide, false>;
+  return fused ? (const void*)align_grid_kernel<kPersistThreads, true>
+               : (const void*)align_grid_kernel<kPersistThreads, false>;
+}
+cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaStream_t s) {
   IterArgs a = A;
   void* args[] = {&a};
-  return cudaLaunchCooperativeKernel((const void*)align_grid_kernel, dim3(blocks), dim3(kPersistThreads),
-                                     args, 0, s);
+  const int t = threads == kPersistThreadsWide ? kPersistThreadsWide : kPersistThreads;
+  return cudaLaunchCooperativeKernel(align_grid_fn(t, A.xfused != 0), dim3(blocks), dim3(t), args, 0, s);
 }
-int align_grid_max_blocks_per_sm() {
-  int n = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_kernel, kPersistThreads, 0);
-  return n;
+int align_grid_max_blocks_per_sm(int threads) {
+  int n = 0, m = 0;
+  const int t = threads == kPersistThreadsWide ? kPersistThreadsWide : kPersistThreads;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_fn(t, false), t, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, align_grid_fn(t, true), t, 0);
+  return n < m ? n : m;
 }
 int pair_kernel_max_blocks_per_sm() {
   int n = 0;
