@@ -35,10 +35,13 @@ constexpr int kJBlock = 32 * kJQ;      // targets per warp sweep
 constexpr int kPairWarps = 8;          // warps per CTA of the pair kernel
 constexpr int kSparseThreads = 256;    // CTA size of the sparse kernels
 // CTA sizes of the persistent kernel: ONE block per SM, so the all-to-all reduction after a grid
-// barrier reads 148 partials.  24 warps (80 registers per thread) cover 14 208 source rows in one
-// pass; clouds with more rows use 28 warps (72 registers, some spilling): a KITTI-sized cloud
-// (16 384 rows) then still needs ONE pass instead of two (measured: 32.8 -> 28.8 us per iteration),
-// while 10 000-row clouds are 6 % faster with the 80-register variant.
+// barrier reads 148 partials.  The kernel is latency bound and register hungry, so the block is
+// as small as one pass over the source rows allows (4 rows per warp):
+//   18 warps, 96 registers   up to 10 656 rows   (C2: 28.9 -> 25.0 us per iteration vs 24 warps)
+//   24 warps, 80 registers   up to 14 208 rows
+//   28 warps, 72 registers   beyond              (KITTI-sized 16 384 rows: one pass instead of
+//                                                 two, 32.8 -> 28.5 us per iteration)
+constexpr int kPersistThreadsSmall = 576;  // 18 warps, up to 112 registers: no spilling; covers 10 656 rows
 constexpr int kPersistThreads = 768;
 constexpr int kPersistThreadsWide = 896;
 constexpr int kQueueCap = 1024;        // max indicator_window_size supported

@@ -293,7 +293,9 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   h->grid_blocks =
       std::max(1, std::min(h->num_sms * gocc, (n_rows + rows_per_block - 1) / rows_per_block));
   // wider blocks when the narrow ones would need a second pass over the rows (cvo_device.cuh)
-  h->persist_threads = (n_rows > h->num_sms * (kPersistThreads / 32) * 4) ? kPersistThreadsWide : kPersistThreads;
+  h->persist_threads = (n_rows > h->num_sms * (kPersistThreads / 32) * 4)        ? kPersistThreadsWide
+                       : (n_rows <= h->num_sms * (kPersistThreadsSmall / 32) * 4) ? kPersistThreadsSmall
+                                                                                  : kPersistThreads;
   int pocc = align_grid_max_blocks_per_sm(h->persist_threads);
   if (pocc < 1) pocc = 1;
   const int rows_per_pblock = (h->persist_threads / 32) * 4;

@@ -2075,6 +2075,9 @@ void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t 
 // the four instantiations of the persistent kernel: narrow / wide blocks x single GPU / fused
 // multi-GPU exchange (kept out of the single-GPU code: it costs registers)
 static const void* align_grid_fn(int threads, bool fused) {
+  if (threads == kPersistThreadsSmall)
+    return fused ? (const void*)align_grid_kernel<kPersistThreadsSmall, true>
+                 : (const void*)align_grid_kernel<kPersistThreadsSmall, false>;
   if (threads == kPersistThreadsWide)
     return fused ? (const void*)align_grid_kernel<kPersistThreadsWide, true>
                  : (const void*)align_grid_kernel<kPersistThreadsWide, false>;
@@ -2084,12 +2087,12 @@ static const void* align_grid_fn(int threads, bool fused) {
 cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaStream_t s) {
   IterArgs a = A;
   void* args[] = {&a};
-  const int t = threads == kPersistThreadsWide ? kPersistThreadsWide : kPersistThreads;
+  const int t = (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
   return cudaLaunchCooperativeKernel(align_grid_fn(t, A.xfused != 0), dim3(blocks), dim3(t), args, 0, s);
 }
 int align_grid_max_blocks_per_sm(int threads) {
   int n = 0, m = 0;
-  const int t = threads == kPersistThreadsWide ? kPersistThreadsWide : kPersistThreads;
+  const int t = (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_fn(t, false), t, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, align_grid_fn(t, true), t, 0);
   return n < m ? n : m;
