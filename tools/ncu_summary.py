@@ -21,6 +21,9 @@ traffic = {}
 K = hdr.index("Kernel Name")
 for r in rows[2:]:
     name = r[K].split("(")[0].replace("void ", "")
+    if name.startswith("align_grid_kernel"):
+        name = "align_grid_kernel"  # all block-size / fused instantiations are the same kernel
+    name = name.replace("<1>", "<true>").replace("<0>", "<false>")
     print(f"== {r[K]}")
     for w in want:
         if w in hdr:
