@@ -229,9 +229,24 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
     }
     return it;
   };
+  // Item k -> (source tile, target chunk) in DIAGONAL-MAJOR order.  Both clouds are Morton ordered,
+  // so tile t mostly meets the chunks around c0(t) = t * nchunks / ntiles; everything else is
+  // pruned at once.  Enumerating the diagonals c0, c0+1, c0-1, c0+2, ... tile by tile puts the
+  // heavy items first and deals them round-robin to all warps, instead of giving a warp a run of
+  // chunks of ONE tile (a few heavy, most empty).
+  const int ntiles = A.n_items / A.nchunks;
+  const long long ntiles_global = ((long long)A.n_src_total + kTileRows - 1) / kTileRows;
+  auto decode_item = [&](int item, int& rt, int& jc) {
+    rt = item % ntiles;
+    const int d = item / ntiles;
+    const int c0 = (int)(((long long)(A.row_begin / kTileRows + rt) * A.nchunks) / ntiles_global);
+    const int off = (d & 1) ? (d + 1) / 2 : -(d / 2);
+    jc = ((c0 + off) % A.nchunks + A.nchunks) % A.nchunks;
+  };
   auto issue_tile = [&](int item, int buf) {
     if (item >= A.n_items) return;
-    const int rt = item / A.nchunks;
+    int rt, jc_unused;
+    decode_item(item, rt, jc_unused);
     const int row0 = rt * kTileRows;
     const int nrows = min(kTileRows, A.n_rows - row0);
     if (lane == 0) {
@@ -249,8 +264,8 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
     const int next = fetch_item();
     issue_tile(next, buf ^ 1);  // prefetch the next source tile while this one is swept
 
-    const int rt = item / A.nchunks;
-    const int jc = item - rt * A.nchunks;
+    int rt, jc;
+    decode_item(item, rt, jc);
     const int row0 = rt * kTileRows;
     const int nrows = min(kTileRows, A.n_rows - row0);
     if (buf == 0) {
