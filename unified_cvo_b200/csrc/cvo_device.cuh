@@ -190,6 +190,7 @@ struct IterArgs {
   const float* tile_maxdist;  // [ceil(N/64)] max distance-to-sensor inside the tile
   float4* tgt_moved;
   float* px; float* py; float* pz; float* pw;
+  uint32_t* pq;    // [M_pad] packed colour summaries of the targets (view order), for the emission path
   int M;
   int Fp, Cp;      // padded feature / class dims (same for both clouds)
   float cx, cy, cz;        // prefilter centre (source centroid)
@@ -219,6 +220,7 @@ struct IterArgs {
   XMailbox* xpeer[kMaxWorld];
   unsigned long long xgen;
   int xfused, xrank, xworld;
+  int colour;      // is_using_intensity (selects the persistent kernel with the stage-1 colour cut)
   int grid;        // 1: candidates come from cell queries (flow_kernel<true>; no prep/pair launch)
   GridView gv;
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective

@@ -152,6 +152,7 @@ struct cvo_b200_handle {
   // per-iteration workspace
   DevBuf<float4> tgt_moved;
   DevBuf<float> px, py, pz, pw;
+  DevBuf<uint32_t> pq;
   DevBuf<float4> rowrec;
   DevBuf<float2> row_lt;
   DevBuf<uint32_t> sat_list;
@@ -258,6 +259,7 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   CVO_CUDA(h, h->py.ensure((size_t)M_pad));
   CVO_CUDA(h, h->pz.ensure((size_t)M_pad));
   CVO_CUDA(h, h->pw.ensure((size_t)M_pad));
+  CVO_CUDA(h, h->pq.ensure((size_t)M_pad));
   CVO_CUDA(h, h->rowrec.ensure((size_t)std::max(n_rows, 1) * 2));
   CVO_CUDA(h, h->row_lt.ensure((size_t)std::max(n_rows, 1)));
   CVO_CUDA(h, h->sat_list.ensure((size_t)std::max(n_rows, 1)));
@@ -334,6 +336,7 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.tile_maxdist = cs.tile_maxdist.p;
   A.tgt_moved = h->tgt_moved.p;
   A.px = h->px.p; A.py = h->py.p; A.pz = h->pz.p; A.pw = h->pw.p;
+  A.pq = h->pq.p;
   A.M = M;
   A.Fp = Fp;
   A.Cp = Cp;
@@ -365,6 +368,7 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
     CVO_CUDA(h, h->stamps.ensure((size_t)8 * 4096));
     A.stamps = h->stamps.p;
   }
+  A.colour = h->params.is_using_intensity ? 1 : 0;
   A.xfused = 0;
   A.xrank = h->rank;
   A.xworld = h->world;
@@ -853,7 +857,7 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
     c->blk_sphere.release(); c->tile_sphere.release(); c->tile_maxdist.release(); c->inv.release();
     c->coarse.release(); c->perm_d.release(); c->keys_d.release();
   }
-  h->tgt_moved.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
+  h->tgt_moved.release(); h->pq.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
   h->rowrec.release(); h->row_lt.release(); h->sat_list.release(); h->flow_part2.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();

@@ -147,11 +147,13 @@ __global__ void __launch_bounds__(256) prep_kernel(IterArgs A) {
       A.py[j] = uy;
       A.pz[j] = uz;
       A.pw[j] = ux * ux + uy * uy + uz * uz;
+      A.pq[j] = __float_as_uint(y.w);
     } else {
       A.px[j] = 0.f;
       A.py[j] = 0.f;
       A.pz[j] = 0.f;
       A.pw[j] = INFINITY;  // padding can never be a candidate
+      A.pq[j] = 0u;
     }
   }
   // ---- source rows: range-scaled length-scale, exact threshold, prefilter record
@@ -172,7 +174,8 @@ __global__ void __launch_bounds__(256) prep_kernel(IterArgs A) {
     }
     A.row_lt[r] = make_float2(l, d2_thres);
     A.rowrec[2 * r] = make_float4(a.x, a.x, a.y, a.y);
-    A.rowrec[2 * r + 1] = make_float4(a.z, a.z, t, t);
+    // .w: the row's packed colour summary (emission path of pair_kernel)
+    A.rowrec[2 * r + 1] = make_float4(a.z, a.z, t, A.src_xyz[A.row_begin + r].w);
   }
 }
 
@@ -199,6 +202,15 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
   PairSmemWarp& S = smem[warp];
   const int L = A.L;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // colour cut of the emission path: integer threshold on sum_k max(|qa_k - qb_k| - 1, 0)^2
+  const bool colour_cut = st->kc.use_intensity != 0;
+  unsigned int lb_thr = 0xffffffffu;
+  if (colour_cut) {
+    const float th = st->kc.d2_c_thres;
+    // d2_color >= lb / 255^2; reject when lb * 0.999 / 65025 >= th.  th <= 0 or NaN: the full test
+    // rejects every pair, so does lb >= 0.
+    lb_thr = (th > 0.f) ? (th * (65025.f / 0.999f) < 4.0e9f ? (unsigned int)ceilf(th * (65025.f / 0.999f)) : 0xffffffffu) : 0u;
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[9] = gtime();
 
   if (lane == 0) {
@@ -354,6 +366,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
       };
       // rare path: some lane of the warp holds a candidate of row r -> ordered emission
       auto emit_row = [&](int r, unsigned lanes) {
+        (void)lanes;
         const float4 ra = rec[2 * r];
         const float4 rb = rec[2 * r + 1];
         const unsigned long long AX = pack2(ra.x, ra.y), AY = pack2(ra.z, ra.w),
@@ -370,6 +383,21 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
           qmask |= (s0 < t ? 1u : 0u) << (2 * p);
           qmask |= (s1 < t ? 1u : 0u) << (2 * p + 1);
         }
+        if (colour_cut && qmask != 0u) {
+          // lower bound of the colour distance from the 8-bit summaries (see eval_pair): a target
+          // whose bound already fails d2_color < d2_c_thres is dropped here, so that it never
+          // becomes a candidate (on colour-rich clouds 99 % of the geometric candidates)
+          const unsigned int qa = __float_as_uint(rb.w);
+          const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(A.pq + jl));
+          const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(A.pq + jl + 4));
+          const unsigned int qb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const unsigned int d = __vsubus4(__vabsdiffu4(qa, qb[q]), 0x01010101u);
+            if (__dp4a(d, d, 0u) >= lb_thr) qmask &= ~(1u << q);
+          }
+        }
+        lanes = __ballot_sync(0xffffffffu, qmask != 0u);
         uint32_t c = S.cnt[r];
         const uint32_t pos = c + __popc(lanes & lt_mask);
         if (qmask != 0u && pos < (uint32_t)L)
@@ -758,13 +786,18 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
 // arithmetic -> ELL rows + per-row flow; returns the warp's partial sums in bp (valid on lane 0):
 // omega[3], v[3], a_sum, nnz, max row count.  hs = this block's shared-memory copy of the hot
 // state; st = the global state (saturation counters only).
-template <bool kGrid>
+template <bool kGrid, bool kColour = true>
 __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const DevState* hs,
                                           uint32_t* list, double (&bp)[9]) {
   const int view = kGrid ? 0 : hs->view;  // cell queries index the Morton-ordered target
   const float* s_pose = hs->Rinv;          // Rinv[9], Tinv[3] are contiguous
   const float ell_now = hs->ell;
   const float g_smax = hs->smax, g_slack = hs->grid_slack;
+  unsigned int g_lb_thr = 0xffffffffu;  // integer threshold of the colour lower bound (stage 1)
+  if (kColour && hs->kc.use_intensity) {
+    const float th = hs->kc.d2_c_thres;
+    g_lb_thr = (th > 0.f) ? (th * (65025.f / 0.999f) < 4.0e9f ? (unsigned int)ceilf(th * (65025.f / 0.999f)) : 0xffffffffu) : 0u;
+  }
 
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -1048,7 +1081,13 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
             if (!vt) return false;
             const float4 y = A.tv[0].xyz[j];
             const float dx = y.x - qx, dy = y.y - qy, dz = y.z - qz;
-            return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) <= rq2;
+            const bool near = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx)) <= rq2;
+            if constexpr (!kColour) return near;
+            if (!near) return false;
+            // the point's packed colour summary rides in .w: drop targets whose colour-distance
+            // LOWER bound already fails the reference's colour test (see eval_pair)
+            const unsigned int d = __vsubus4(__vabsdiffu4(rc.qa, __float_as_uint(y.w)), 0x01010101u);
+            return __dp4a(d, d, 0u) < g_lb_thr;
           };
           auto queue_slot = [&](uint32_t j, bool pass) {
             const unsigned bits = (__ballot_sync(0xffffffffu, pass) >> gshift) & 0xffu;
@@ -1860,7 +1899,7 @@ __device__ __forceinline__ void publish_block_partial(const double (&v)[NV], dou
   }
 }
 
-template <int kThreads, bool kFused>
+template <int kThreads, bool kFused, bool kColour>
 __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   __shared__ double sh[(kThreads / 32 + 2) * 9];
   // cell queries queue at most 7 pending + 32 new candidates per row group
@@ -1900,7 +1939,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     // ---- flow phase (fill_in_A_mat_gpu + compute_flow_gpu_no_eigen on this block's rows)
     {
       double bp[9];
-      flow_rows<true>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp);
+      flow_rows<true, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp);
       CVO_PHASE(0)
       publish_block_partial<9, 8>(bp, sh, flow_part);
       CVO_PHASE(1)
@@ -2087,29 +2126,33 @@ void launch_init_bound(const IterArgs& A, cudaStream_t s) { init_bound_kernel<<<
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s) {
   fma_peak_kernel<<<blocks, 256, 0, s>>>(kind, iters, sink);
 }
-// the four instantiations of the persistent kernel: narrow / wide blocks x single GPU / fused
-// multi-GPU exchange (kept out of the single-GPU code: it costs registers)
-static const void* align_grid_fn(int threads, bool fused) {
-  if (threads == kPersistThreadsSmall)
-    return fused ? (const void*)align_grid_kernel<kPersistThreadsSmall, true>
-                 : (const void*)align_grid_kernel<kPersistThreadsSmall, false>;
-  if (threads == kPersistThreadsWide)
-    return fused ? (const void*)align_grid_kernel<kPersistThreadsWide, true>
-                 : (const void*)align_grid_kernel<kPersistThreadsWide, false>;
-  return fused ? (const void*)align_grid_kernel<kPersistThreads, true>
-               : (const void*)align_grid_kernel<kPersistThreads, false>;
+// the instantiations of the persistent kernel: block size x single GPU / fused multi-GPU
+// exchange x colour cut in stage 1 (each kept out of the code that does not need it: the kernel is
+// register bound)
+template <int kThreads>
+static const void* align_grid_fn_t(bool fused, bool colour) {
+  if (fused)
+    return colour ? (const void*)align_grid_kernel<kThreads, true, true>
+                  : (const void*)align_grid_kernel<kThreads, true, false>;
+  return colour ? (const void*)align_grid_kernel<kThreads, false, true>
+                : (const void*)align_grid_kernel<kThreads, false, false>;
+}
+static const void* align_grid_fn(int threads, bool fused, bool colour) {
+  if (threads == kPersistThreadsSmall) return align_grid_fn_t<kPersistThreadsSmall>(fused, colour);
+  if (threads == kPersistThreadsWide) return align_grid_fn_t<kPersistThreadsWide>(fused, colour);
+  return align_grid_fn_t<kPersistThreads>(fused, colour);
 }
 cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaStream_t s) {
   IterArgs a = A;
   void* args[] = {&a};
   const int t = (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
-  return cudaLaunchCooperativeKernel(align_grid_fn(t, A.xfused != 0), dim3(blocks), dim3(t), args, 0, s);
+  return cudaLaunchCooperativeKernel(align_grid_fn(t, A.xfused != 0, A.colour != 0), dim3(blocks), dim3(t), args, 0, s);
 }
 int align_grid_max_blocks_per_sm(int threads) {
   int n = 0, m = 0;
   const int t = (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_fn(t, false), t, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, align_grid_fn(t, true), t, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_fn(t, false, true), t, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, align_grid_fn(t, true, true), t, 0);
   return n < m ? n : m;
 }
 int pair_kernel_max_blocks_per_sm() {
