@@ -21,6 +21,7 @@ pairs counted, tested or skipped).  A "step" is one full registrat
 `fp32`   pair tests/s against the measured packed-FMA peak (the meaningful bound of a dense scan).
 `frame_pairs`  frame-pairs/s on KITTI-05-sized clouds: a tracking frame (regular parameters,
          constant-velocity initial guess) and a first frame (ell_init = 1.5).
+`edge_updates`  pose-graph edge updates/s (multi-frame IRLS edge loop) on four KITTI-05-sized frames.
 `cpu_baseline` / `--impl reference`  the CPU restatement of the reference's algorithm (oracle/,
          OpenMP on all host cores) on a bounded number of leading iterations of the same job.
 """
@@ -235,6 +236,36 @@ def frame_pairs_leg(u, name, steps=5):
             "wall_ms_per_frame_pair": 1e3 * wall / steps, "max_abs_pose_error_vs_truth": err, "ret": int(ret)}
 
 
+def edge_updates_leg(u, rounds=5):
+    """Pose-graph edge updates/s: four KITTI-05-sized frames resident on the
+    device, a ring of four edges, every round = one outer IRLS iteration's edge loop
+    (BinaryStateGPU::update_inner_product per edge: both frames moved by their poses, capped
+    kernel matrix filled and copied to the host).  Wall clock, matrix read-back included."""
+    from unified_cvo_b200 import synthetic
+    src, tgt, p, _ = load_workload("KITTI05_TRACK")
+    g = u.CvoGPU(p)
+    I = np.eye(4)[:3]
+    G = np.asarray(synthetic.gt_transform(), np.float64)[:3]  # maps target points into the source frame
+    frames = [u.CvoFrameGPU(g, c, P) for c, P in ((src, I), (tgt, G), (src, I), (tgt, G))]
+    ell, cap = 0.25, int(p.multiframe_num_neighbors)
+    states = [u.BinaryStateGPU(frames[i], frames[(i + 1) % 4], cap, ell) for i in range(4)]
+    u.update_edges(states)  # warm-up: buffers grow, the caps settle
+    u.update_edges(states)
+    launches0 = g.launch_count()
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(rounds):
+        total, _ = u.update_edges(states)
+    dt = time.perf_counter() - t0
+    n_edges = rounds * len(states)
+    out = {"workload": "4 KITTI-05-sized frames (N=16384, 5-dim colour), ring of 4 edges, ell=0.25, "
+                       f"cap={cap}; one update = two posed cloud builds + capped kernel matrix + CSR to host",
+           "edge_updates_per_s": n_edges / dt, "ms_per_edge_update": 1e3 * dt / n_edges,
+           "nonzeros_per_round": int(total), "gpu_launches_per_edge_update": (g.launch_count() - launches0) / n_edges}
+    g.close()
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import unified_cvo_b200 as u
@@ -399,6 +430,7 @@ def run_ours(args, rank, world, local_rank):
     # frame-pairs/s on KITTI-05-sized clouds (north_star): a tracking frame and a first frame
     if world == 1 and args.workload is None and not args.no_frames:
         line["frame_pairs"] = [frame_pairs_leg(u, wl) for wl in ("KITTI05_TRACK", "KITTI05")]
+        line["edge_updates"] = edge_updates_leg(u)
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same registration
     if world == 1 and not args.no_cpu_baseline:
         import oracle

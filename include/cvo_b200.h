@@ -248,6 +248,36 @@ int cvo_b200_association(cvo_b200_handle* h, const float T[16], float ell,
 int cvo_b200_align_association(cvo_b200_handle* h, int64_t* nnz, int32_t* row_ptr,
                                int32_t* cols, float* vals);
 
+/* ---- pose-graph edges (multi-frame registration) ----------
+ * Frames stay resident on the device in the caller's layout (replaces the
+ * points_init_gpu_ of a CvoFrameGPU, CvoFrameGPU.cu:7-30).  `frame` is a small
+ * non-negative id chosen by the caller; setting an id again replaces its
+ * contents.  Same array conventions as cvo_b200_set_cloud.                    */
+int cvo_b200_frame_set(cvo_b200_handle* h, int frame, int n, const float* xyz, int F,
+                       const float* features, int C, const float* labels,
+                       const float* geotype);
+/* frees one frame's device arrays (frame = -1: all of them)                  */
+int cvo_b200_frame_clear(cvo_b200_handle* h, int frame);
+/* One edge of the pose graph, one outer IRLS iteration: both frames are moved
+ * by their own CURRENT poses — row-major 3x4 float, x' = P [x 1]^T (replaces
+ * CvoFrameGPU::transform_pointcloud, CvoFrameGPU.cu:44-62 ->
+ * transform_point_pose_vec, CvoGPU_impl.cu:84-150) — and the row-capped kernel
+ * matrix between the moved clouds is filled with the edge's fixed `ell` and cap
+ * `num_neighbors` and copied out (replaces BinaryStateGPU::update_inner_product,
+ * IRLS_State_GPU.cu:43-79: clear_SparseKernelMat, fill_in_A_mat_gpu,
+ * compute_nonzeros, copy_internal_SparseKernelMat_gpu_to_cpu).  Nothing but the
+ * two poses goes to the device and nothing but the matrix comes back.
+ * Rows = points of frame1, columns = points of frame2, CSR in the reference's
+ * insertion order; *max_row_nnz (may be NULL) is what max_neighbors()
+ * (SparseKernelMat.cu:48-53) returns for the caller's cap update
+ * (IRLS_State_GPU.cu:45-47).  num_neighbors may exceed nearest_neighbors_max.
+ * Two-call protocol like cvo_b200_association; the second call with the same
+ * arguments reuses the matrix still on the device.  Overwrites the handle's two
+ * cloud slots (cvo_b200_set_cloud).                                           */
+int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], int frame2,
+                         const float pose2[12], float ell, int num_neighbors, int64_t* nnz,
+                         int32_t* max_row_nnz, int32_t* row_ptr, int32_t* cols, float* vals);
+
 /* ---- measurement helpers --------------------------------------------------
  * Runs `iters` iterations back to back at a FIXED state (pose, ell, cap),
  * timed with CUDA events on the handle's stream.  ms_total = whole iteration

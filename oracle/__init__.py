@@ -87,6 +87,12 @@ def lib() -> C.CDLL:
         L.oracle_transform.restype = None
         L.oracle_transform.argtypes = [f32p, f32p, f32p, C.c_int, f32p]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_transform_pose_vec.restype = None
+        L.oracle_transform_pose_vec.argtypes = [f32p, f32p, C.c_int, f32p]
+        L.oracle_edge_update.restype = C.c_ulonglong
+        L.oracle_edge_update.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), f32p,
+                                         C.POINTER(_Cloud), f32p, C.c_float, C.c_int,
+                                         C.POINTER(_Sparse)]
         _lib = L
     return _lib
 
@@ -195,6 +201,31 @@ def inner_product(params: Params, src: Cloud, tgt: Cloud, T, ell: float, kernel3
         L.oracle_sparse_free(sp)
         return float(val), out
     return float(val)
+
+
+def transform_pose_vec(pose12, xyz):
+    """x' = P [x 1]^T, P row-major 3x4 (CvoGPU_impl.cu:84-150)."""
+    P = np.ascontiguousarray(pose12, np.float32).reshape(12)
+    x = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    out = np.empty_like(x)
+    lib().oracle_transform_pose_vec(_fp(P), _fp(x), len(x), _fp(out))
+    return out
+
+
+def edge_update(params: Params, f1: Cloud, pose1, f2: Cloud, pose2, ell: float,
+                num_neighbors: int):
+    """One edge update of the multi-frame IRLS (IRLS_State_GPU.cu:43-79 on frames moved by
+    their own poses).  Returns (nonzero_sum, sparse dict)."""
+    L = lib()
+    P1 = np.ascontiguousarray(pose1, np.float32).reshape(12)
+    P2 = np.ascontiguousarray(pose2, np.float32).reshape(12)
+    c1, c2 = f1.c_struct(), f2.c_struct()
+    sp = L.oracle_sparse_new(f1.n, max(int(num_neighbors), 1))
+    total = L.oracle_edge_update(C.byref(params), C.byref(c1), _fp(P1), C.byref(c2), _fp(P2),
+                                 C.c_float(ell), int(num_neighbors), sp)
+    out = _sparse_to_numpy(sp)
+    L.oracle_sparse_free(sp)
+    return int(total), out
 
 
 def function_angle(params: Params, src: Cloud, tgt: Cloud, T, ell: float, is_approximate=True):

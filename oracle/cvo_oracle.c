@@ -1097,6 +1097,46 @@ float oracle_inner_product(const cvo_b200_params* p, const oracle_cloud* src,
   return s;
 }
 
+/* ---------- pose-graph edge (multi-frame IRLS) ---------------------------- */
+/* CvoGPU_impl.cu:84-150 transform_point_pose_vec (xyz only matter):
+ * trans = T * [x y z 1]^T with T a row-major 3x4 float map of pose_vec.  Eigen's
+ * unrolled coefficient redux over 4 terms sums (c0 + c1) + (c2 + c3). */
+void oracle_transform_pose_vec(const float pose12[12], const float* x, int n, float* x_out) {
+  for (int i = 0; i < n; i++) {
+    const float* q = x + 3 * (size_t)i;
+    for (int r = 0; r < 3; r++) {
+      volatile float c0 = pose12[4 * r + 0] * q[0];
+      volatile float c1 = pose12[4 * r + 1] * q[1];
+      volatile float c2 = pose12[4 * r + 2] * q[2];
+      volatile float c3 = pose12[4 * r + 3] * 1.0f;
+      volatile float s01 = c0 + c1;
+      volatile float s23 = c2 + c3;
+      x_out[3 * (size_t)i + r] = s01 + s23;
+    }
+  }
+}
+
+/* IRLS.cpp:104-108 (every frame: transform_pointcloud, CvoFrameGPU.cu:44-62) followed by
+ * IRLS_State_GPU.cu:43-79 BinaryStateGPU::update_inner_product for ONE edge:
+ * clear_SparseKernelMat(num_neighbors), fill_in_A_mat_gpu on the two moved clouds with the
+ * edge's ell, compute_nonzeros.  Returns nonzero_sum.  A needs capacity >= num_neighbors. */
+unsigned long long oracle_edge_update(const cvo_b200_params* p, const oracle_cloud* f1,
+                                      const float pose1[12], const oracle_cloud* f2,
+                                      const float pose2[12], float ell, int num_neighbors,
+                                      oracle_sparse* A) {
+  float* x = (float*)malloc(sizeof(float) * 3 * (size_t)(f1->n > 0 ? f1->n : 1));
+  float* y = (float*)malloc(sizeof(float) * 3 * (size_t)(f2->n > 0 ? f2->n : 1));
+  oracle_transform_pose_vec(pose1, f1->xyz, f1->n, x);
+  oracle_transform_pose_vec(pose2, f2->xyz, f2->n, y);
+  oracle_cloud moved1 = *f1; /* features, labels, geometric types travel with the point */
+  moved1.xyz = x;
+  oracle_fill_A(p, &moved1, f2, y, num_neighbors, ell, A);
+  unsigned long long s = A->nonzero_sum;
+  free(x);
+  free(y);
+  return s;
+}
+
 float oracle_function_angle(const cvo_b200_params* p, const oracle_cloud* src,
                             const oracle_cloud* tgt, const float T[16], float ell,
                             int is_approximate) {

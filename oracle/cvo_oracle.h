@@ -102,6 +102,13 @@ float oracle_inner_product(const cvo_b200_params* p, const oracle_cloud* src,
 float oracle_function_angle(const cvo_b200_params* p, const oracle_cloud* src,
                             const oracle_cloud* tgt, const float T[16], float ell,
                             int is_approximate);
+/* CvoGPU_impl.cu:84-150 transform_point_pose_vec; pose12 = row-major 3x4 */
+void oracle_transform_pose_vec(const float pose12[12], const float* x, int n, float* x_out);
+/* CvoFrameGPU.cu:44-62 + IRLS_State_GPU.cu:43-79: one edge update of the multi-frame IRLS */
+unsigned long long oracle_edge_update(const cvo_b200_params* p, const oracle_cloud* f1,
+                                      const float pose1[12], const oracle_cloud* f2,
+                                      const float pose2[12], float ell, int num_neighbors,
+                                      oracle_sparse* A);
 int oracle_num_threads(void);
 /* 1 (default): rows visit only the targets of the 27 grid cells around them, in ascending order -
  * outputs bit-identical to the dense loop; 0 (or ORACLE_DENSE=1): the literal dense N x M loop. */

@@ -1,0 +1,186 @@
+"""Pose-graph edge update: BinaryStateGPU::update_inner_product
+(IRLS_State_GPU.cu:43-79) on frames moved by their own poses (CvoFrameGPU.cu:44-62).
+
+CPU part: the oracle's restatement against an independent numpy one.  GPU part: the C-ABI
+(cvo_b200_frame_set / cvo_b200_edge_update, through the BinaryStateGPU mirror) against the
+oracle — structure of the matrix bit-exact, values to 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+import numpy_ref
+import oracle
+import unified_cvo_b200 as u
+from helpers import DATA, geometric_params, synthetic_pair, to_oracle_cloud
+
+f32 = np.float32
+
+
+def pose_rt(rx_deg, ry_deg, rz_deg, t):
+    """Row-major 3x4 [R t] in double, as CvoFrame::pose_vec holds it."""
+    ax, ay, az = np.deg2rad([rx_deg, ry_deg, rz_deg])
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    P = np.zeros((3, 4))
+    P[:, :3] = Rz @ Ry @ Rx
+    P[:, 3] = t
+    return P.reshape(12)
+
+
+def numpy_pose_transform(pose12, xyz):
+    """T * [x y z 1]^T with Eigen's 4-term unrolled redux (c0 + c1) + (c2 + c3), float."""
+    P = np.asarray(pose12, f32).reshape(3, 4)
+    x = np.asarray(xyz, f32)
+    out = np.empty_like(x)
+    for r in range(3):
+        c0, c1, c2 = (P[r, 0] * x[:, 0]).astype(f32), (P[r, 1] * x[:, 1]).astype(f32), (P[r, 2] * x[:, 2]).astype(f32)
+        c3 = f32(P[r, 3] * f32(1.0))
+        out[:, r] = (c0 + c1).astype(f32) + (c2 + c3).astype(f32)
+    return out
+
+
+def _rows(sp):
+    return [(sp["ind"][i, : sp["nonzeros"][i]], sp["mat"][i, : sp["nonzeros"][i]])
+            for i in range(len(sp["nonzeros"]))]
+
+
+# ------------------------------------------------------------------ CPU: oracle vs numpy
+def test_oracle_pose_transform_is_bit_identical_to_numpy():
+    rng = np.random.default_rng(3)
+    x = (rng.standard_normal((500, 3)) * [8, 2, 15] + [0, 0, 16]).astype(f32)
+    P = pose_rt(1.0, -2.5, 0.7, [0.3, -0.1, 1.2]).astype(f32)
+    assert np.array_equal(oracle.transform_pose_vec(P, x), numpy_pose_transform(P, x))
+    I = np.eye(4)[:3].reshape(12).astype(f32)
+    assert np.array_equal(oracle.transform_pose_vec(I, x), x)  # the identity pose moves nothing
+
+
+@pytest.mark.parametrize("cap,ell,colour", [(40, 0.9, False), (5, 1.5, False), (12, 1.2, True)])
+def test_oracle_edge_update_matches_numpy_restatement(cap, ell, colour):
+    if colour:
+        f1, f2, _ = synthetic_pair(260, 150, 200, 5, F=5, C=4, geotype=True)
+        p = u.read_params_yaml(os.path.join(DATA, "cvo_semantic_params_img_gpu0.yaml"))
+        p.is_using_geometric_type = 1
+        p.c_ell = 0.5
+    else:
+        f1, f2, _ = synthetic_pair(300, 200, 240, 11)
+        p = geometric_params()
+    P1 = pose_rt(0.5, 1.0, -0.4, [0.1, 0.0, -0.2]).astype(f32)
+    P2 = pose_rt(0.2, 3.0, -0.1, [0.15, 0.02, 0.3]).astype(f32)
+    total, sp = oracle.edge_update(p, to_oracle_cloud(f1), P1, to_oracle_cloud(f2), P2, ell, cap)
+    x = numpy_pose_transform(P1, f1.positions_)
+    y = numpy_pose_transform(P2, f2.positions_)
+    rows = numpy_ref.fill_A(p, x, y, ell, cap, f1.features_, f2.features_, f1.labels_, f2.labels_,
+                            f1.geometric_types_, f2.geometric_types_)
+    assert total == sum(len(r[0]) for r in rows) and total > 50
+    for (gi, gv), (ri, rv) in zip(_rows(sp), rows):
+        assert np.array_equal(gi, ri)
+        np.testing.assert_allclose(gv, rv, rtol=5e-7)
+    assert sp["nonzeros"].max() <= cap
+
+
+def test_oracle_edge_update_depends_on_both_poses_not_only_on_the_relative_one():
+    """The length-scale of a row grows with the MOVED point's range (CvoGPU.cu:506-507), so the
+    same relative pose applied at another place of the world gives another matrix — which is why
+    the edge call takes two poses and not one relative transform."""
+    f1, f2, _ = synthetic_pair(300, 200, 240, 11)
+    p = geometric_params()
+    I = np.eye(4)[:3].reshape(12)
+    far = I.copy()
+    far[[3, 7, 11]] = [300.0, 0.0, 0.0]
+    a, _ = oracle.edge_update(p, to_oracle_cloud(f1), I, to_oracle_cloud(f2), I, 0.5, 64)
+    b, _ = oracle.edge_update(p, to_oracle_cloud(f1), far, to_oracle_cloud(f2), far, 0.5, 64)
+    assert b > a > 0
+
+
+# ------------------------------------------------------------------ GPU: C-ABI vs oracle
+def _check_edge(state, p, f1, f2, cap_expected=None):
+    nnz = state.update_inner_product()
+    if cap_expected is not None:
+        assert state.num_neighbors_ == cap_expected
+    total, sp = oracle.edge_update(p, to_oracle_cloud(f1.points), f1.pose_float(),
+                                   to_oracle_cloud(f2.points), f2.pose_float(), state.ell_,
+                                   state.num_neighbors_)
+    row_ptr, cols, vals = oracle.sparse_to_csr(sp)
+    A = state.A_result_cpu_
+    assert nnz == total == len(A.vals)
+    assert np.array_equal(A.row_ptr, row_ptr) and np.array_equal(A.cols, cols)
+    np.testing.assert_allclose(A.vals, vals, rtol=1e-6)
+    assert state.last_max_row_nnz == int(sp["nonzeros"].max())
+    return nnz
+
+
+@pytest.mark.gpu
+def test_edge_update_matches_oracle_geometric_and_cap_schedule():
+    """Three outer iterations of one edge with the frames' poses changing in between: every
+    matrix equals the oracle's, and the cap follows min(init, 1.1 * last max row)."""
+    c1, c2, _ = synthetic_pair(2500, 1500, 1800, 21)
+    p = geometric_params()
+    g = u.CvoGPU(p)
+    f1 = u.CvoFrameGPU(g, c1, pose_rt(0.3, 0.5, -0.2, [0.05, 0.0, -0.1]))
+    f2 = u.CvoFrameGPU(g, c2, pose_rt(0.1, 2.2, 0.0, [0.1, 0.02, 0.35]))
+    st = u.BinaryStateGPU(f1, f2, num_neighbor=48, init_ell=0.8)
+    n0 = _check_edge(st, p, f1, f2, cap_expected=48)
+    assert n0 > 1000
+    f2.pose_vec[:] = pose_rt(0.05, 2.05, 0.0, [0.06, 0.02, 0.45])  # the solver moved frame 2
+    expect = min(48, int(st.last_max_row_nnz * 1.1))
+    _check_edge(st, p, f1, f2, cap_expected=expect)
+    st.update_ell()
+    assert st.ell_ == pytest.approx(0.8 * p.multiframe_ell_decay_rate)
+    _check_edge(st, p, f1, f2)
+    assert st.iter_ == 3
+    g.close()
+
+
+@pytest.mark.gpu
+def test_edge_update_colour_semantics_geotype_and_cap_above_nearest_neighbors_max():
+    c1, c2, _ = synthetic_pair(1200, 700, 900, 5, F=5, C=20, geotype=True)
+    p = u.read_params_yaml(os.path.join(DATA, "cvo_semantic_params_img_gpu0.yaml"))
+    p.is_using_geometric_type = 1
+    p.c_ell = 0.5
+    p.nearest_neighbors_max = 16  # the edge's own cap may exceed the align() cap
+    g = u.CvoGPU(p)
+    f1 = u.CvoFrameGPU(g, c1, pose_rt(0.0, 0.4, 0.0, [0.0, 0.0, 0.05]))
+    f2 = u.CvoFrameGPU(g, c2, pose_rt(0.0, 2.4, 0.0, [0.05, 0.02, 0.55]))
+    st = u.BinaryStateGPU(f1, f2, num_neighbor=40, init_ell=1.2)
+    assert _check_edge(st, p, f1, f2, cap_expected=40) > 200
+    assert st.last_max_row_nnz > 16
+    g.close()
+
+
+@pytest.mark.gpu
+def test_edge_loop_over_a_four_frame_graph_and_edge_cases():
+    """update_edges over a ring + one loop-closure edge (IRLS.cpp:111-121): per-edge parity, frames
+    shared between edges stay intact, zero cap / empty frame / unknown frame behave."""
+    p = geometric_params()
+    g = u.CvoGPU(p)
+    clouds, frames = [], []
+    for k in range(4):
+        a, _, _ = synthetic_pair(1600, 900 + 64 * k, 900, 40)  # the same scene, ragged sizes
+        clouds.append(a)
+        frames.append(u.CvoFrameGPU(g, a, pose_rt(0.0, 0.3 * k, 0.0, [0.01 * k, 0.0, 0.02 * k])))
+    edges = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]
+    states = [u.BinaryStateGPU(frames[i], frames[j], num_neighbor=24, init_ell=0.5) for i, j in edges]
+    total, per_edge = u.update_edges(states)
+    assert total == sum(per_edge) and min(per_edge) > 100
+    for st in states:  # matrices of earlier edges were copied out before the slots were reused
+        t, sp = oracle.edge_update(p, to_oracle_cloud(st.frame1.points), st.frame1.pose_float(),
+                                   to_oracle_cloud(st.frame2.points), st.frame2.pose_float(), 0.5, 24)
+        row_ptr, cols, _ = oracle.sparse_to_csr(sp)
+        assert np.array_equal(st.A_result_cpu_.row_ptr, row_ptr)
+        assert np.array_equal(st.A_result_cpu_.cols, cols)
+    # the reference's two-cloud calls still work on the same handle afterwards
+    assert g.inner_product_gpu(clouds[0], clouds[1], np.eye(4, dtype=np.float32), 0.5) > 0
+    # zero cap: fill_in_A_mat_gpu leaves every row empty (CvoGPU.cu:522)
+    z = u.BinaryStateGPU(frames[0], frames[1], num_neighbor=0, init_ell=0.5)
+    assert z.update_inner_product() == 0 and z.A_result_cpu_.row_ptr[-1] == 0
+    # empty frame
+    e = u.CvoFrameGPU(g, u.CvoPointCloud(np.zeros((0, 3), np.float32)))
+    assert u.BinaryStateGPU(frames[0], e, 24, 0.5).update_inner_product() == 0
+    assert u.BinaryStateGPU(e, frames[0], 24, 0.5).update_inner_product() == 0
+    # a released frame is refused, loudly
+    frames[3].release()
+    with pytest.raises(u.CvoError):
+        states[2].update_inner_product()
+    g.close()

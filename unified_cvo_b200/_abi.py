@@ -170,6 +170,16 @@ SYMBOLS = {
         C.c_int,
         [C.c_void_p, C.POINTER(C.c_int64), _i32p, _i32p, _f32p],
     ),
+    "cvo_b200_frame_set": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.c_int, _f32p, C.c_int, _f32p, C.c_int, _f32p, _f32p],
+    ),
+    "cvo_b200_frame_clear": (C.c_int, [C.c_void_p, C.c_int]),
+    "cvo_b200_edge_update": (
+        C.c_int,
+        [C.c_void_p, C.c_int, _f32p, C.c_int, _f32p, C.c_float, C.c_int, C.POINTER(C.c_int64),
+         _i32p, _i32p, _i32p, _f32p],
+    ),
     "cvo_b200_time_iterations": (
         C.c_int,
         [C.c_void_p, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p],

@@ -269,7 +269,30 @@ __global__ void spheres_kernel(const float4* __restrict__ xyz, const float4* __r
     }
   }
 }
+
+// CvoFrameGPU::transform_pointcloud -> transform_point_pose_vec (CvoFrameGPU.cu:44-62,
+// CvoGPU_impl.cu:84-150): x' = P [x y z 1]^T with P a row-major 3x4 float pose.  Eigen's unrolled
+// 4-term redux sums (c0 + c1) + (c2 + c3); intrinsics keep it uncontracted whatever the flags.
+__global__ void pose_vec_transform_kernel(const float* __restrict__ in, float* __restrict__ out, int n,
+                                          PoseVec P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[3 * (size_t)i], y = in[3 * (size_t)i + 1], z = in[3 * (size_t)i + 2];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const float c0 = __fmul_rn(P.m[4 * r], x), c1 = __fmul_rn(P.m[4 * r + 1], y);
+    const float c2 = __fmul_rn(P.m[4 * r + 2], z), c3 = __fmul_rn(P.m[4 * r + 3], 1.0f);
+    out[3 * (size_t)i + r] = __fadd_rn(__fadd_rn(c0, c1), __fadd_rn(c2, c3));
+  }
+}
 }  // namespace
+
+cudaError_t pose_vec_transform_device(const float* xyz3_in, float* xyz3_out, int n, const PoseVec& P,
+                                      cudaStream_t s) {
+  if (n <= 0) return cudaSuccess;
+  pose_vec_transform_kernel<<<(n + 255) / 256, 256, 0, s>>>(xyz3_in, xyz3_out, n, P);
+  return cudaGetLastError();
+}
 
 size_t cloud_sort_temp_bytes(int n) {
   size_t bytes = 0;

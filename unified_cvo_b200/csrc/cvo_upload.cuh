@@ -35,6 +35,14 @@ struct CloudBuild {
   float4* blk_sphere; float4* tile_sphere; float* tile_maxdist;
 };
 
+// a frame pose as CvoFrame::pose_vec holds it: row-major 3x4 (CvoFrame.hpp), float on the device
+struct PoseVec {
+  float m[12];
+};
+// out = P [in 1]^T per point (n x 3 floats, packed); in and out are distinct buffers
+cudaError_t pose_vec_transform_device(const float* xyz3_in, float* xyz3_out, int n, const PoseVec& P,
+                                      cudaStream_t s);
+
 size_t cloud_sort_temp_bytes(int n);
 cudaError_t build_cloud_device(const CloudBuild& B, cudaStream_t s);
 

@@ -1,0 +1,100 @@
+"""Host mirror of the reference's pose-graph edge update.
+
+`CvoFrameGPU` = cvo::CvoFrameGPU (include/UnifiedCvo/cvo/CvoFrameGPU.hpp, CvoFrameGPU.cu:7-62):
+a point cloud kept on the device plus the frame's pose, `pose_vec`, a row-major 3x4 [R t] in
+double that the outer solver (Ceres in the reference, out of scope here) mutates in place.
+`BinaryStateGPU` = cvo::BinaryStateGPU (IRLS_State_GPU.hpp, IRLS_State_GPU.cu:16-79,
+IRLS_State_GPU.cpp:54-57): one edge of the graph; `update_inner_product()` refills the capped
+kernel matrix between the two moved frames and returns its number of non-zeros.
+`update_edges` is the edge loop of one outer iteration of CvoBatchIRLS::solve
+(IRLS.cpp:104-125) without the Ceres residuals.
+
+Everything here only marshals numpy arrays into include/cvo_b200.h; the arithmetic is in
+libcvo_b200.so (cvo_b200_frame_set / cvo_b200_edge_update).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Optional
+
+import numpy as np
+
+from .cvo import Association, CvoGPU, CvoPointCloud, _ptr
+
+
+class CvoFrameGPU:
+    """cvo::CvoFrameGPU(pts, poses[12]): uploads the cloud once; the pose stays on the host."""
+
+    def __init__(self, gpu: CvoGPU, points: CvoPointCloud, pose_vec=None):
+        self.gpu = gpu
+        self.points = points
+        p = np.eye(4)[:3] if pose_vec is None else np.asarray(pose_vec, np.float64)
+        if p.size == 16:
+            p = p.reshape(4, 4)[:3]
+        self.pose_vec = np.ascontiguousarray(p.reshape(12), np.float64)  # row-major 3x4 [R t]
+        self.frame_id = getattr(gpu, "_next_frame_id", 0)  # ids are per handle
+        gpu._next_frame_id = self.frame_id + 1
+        F, Cn = points.feature_dimensions(), points.num_classes()
+        gpu._check(gpu._lib.cvo_b200_frame_set(
+            gpu._h, self.frame_id, points.num_points(), _ptr(points.positions_), F,
+            _ptr(points.features_), Cn, _ptr(points.labels_), _ptr(points.geometric_types_)))
+
+    def pose_float(self) -> np.ndarray:
+        """CvoFrameGPU.cu:47-53: the double pose narrowed to float for the device."""
+        return np.ascontiguousarray(self.pose_vec, np.float64).astype(np.float32)
+
+    def release(self):
+        if self.gpu._h:
+            self.gpu._check(self.gpu._lib.cvo_b200_frame_clear(self.gpu._h, self.frame_id))
+
+
+class BinaryStateGPU:
+    """cvo::BinaryStateGPU(pc1, pc2, params_cpu, params_gpu, num_neighbor, init_ell)."""
+
+    def __init__(self, frame1: CvoFrameGPU, frame2: CvoFrameGPU, num_neighbor: Optional[int] = None,
+                 init_ell: Optional[float] = None):
+        assert frame1.gpu is frame2.gpu, "both frames of an edge live on one handle"
+        self.gpu = frame1.gpu
+        self.frame1, self.frame2 = frame1, frame2
+        p = self.gpu.params
+        # CvoGPU.cu:1663-1666: params.multiframe_num_neighbors, params.multiframe_ell_init
+        self.init_num_neighbors_ = int(p.multiframe_num_neighbors if num_neighbor is None else num_neighbor)
+        self.num_neighbors_ = self.init_num_neighbors_
+        self.ell_ = float(p.multiframe_ell_init if init_ell is None else init_ell)
+        self.iter_ = 0
+        self.last_max_row_nnz = 0
+        self.A_result_cpu_ = Association(shape=(frame1.points.num_points(), frame2.points.num_points()))
+        self.A_result_cpu_.row_ptr = np.zeros(frame1.points.num_points() + 1, np.int64)
+        self.A_result_cpu_.cols = np.zeros(0, np.int32)
+        self.A_result_cpu_.vals = np.zeros(0, np.float32)
+
+    def update_inner_product(self) -> int:
+        """IRLS_State_GPU.cu:43-79.  Returns nonzero_sum; the matrix is in A_result_cpu_."""
+        # :45-47 cap of this update from the LAST matrix' fullest row
+        if self.last_max_row_nnz > 0:
+            self.num_neighbors_ = min(self.init_num_neighbors_, int(self.last_max_row_nnz * 1.1))
+        g = self.gpu
+        n, m = self.frame1.points.num_points(), self.frame2.points.num_points()
+        p1, p2 = self.frame1.pose_float(), self.frame2.pose_float()
+        mx = C.c_int32(0)
+        call = lambda *a: g._lib.cvo_b200_edge_update(  # noqa: E731
+            g._h, self.frame1.frame_id, _ptr(p1), self.frame2.frame_id, _ptr(p2),
+            C.c_float(self.ell_), int(self.num_neighbors_), a[0], C.byref(mx), *a[1:])
+        g.write_params()
+        g._fill_association(self.A_result_cpu_, n, m, call)
+        self.last_max_row_nnz = int(mx.value)
+        self.iter_ += 1
+        return int(len(self.A_result_cpu_.vals))
+
+    def update_ell(self):
+        """IRLS_State_GPU.cpp:54-57."""
+        p = self.gpu.params
+        if self.ell_ > p.multiframe_ell_min:
+            self.ell_ = self.ell_ * p.multiframe_ell_decay_rate
+
+
+def update_edges(states: Iterable[BinaryStateGPU]):
+    """The edge loop of one outer iteration (IRLS.cpp:111-121): every edge refills its matrix
+    from the frames' CURRENT poses; returns (total_nonzeros, per-edge nonzeros)."""
+    per_edge = [s.update_inner_product() for s in states]
+    return int(sum(per_edge)), per_edge
