@@ -145,7 +145,17 @@ def test_edge_update_colour_semantics_geotype_and_cap_above_nearest_neighbors_ma
     f2 = u.CvoFrameGPU(g, c2, pose_rt(0.0, 2.4, 0.0, [0.05, 0.02, 0.55]))
     st = u.BinaryStateGPU(f1, f2, num_neighbor=40, init_ell=1.2)
     assert _check_edge(st, p, f1, f2, cap_expected=40) > 200
-    assert st.last_max_row_nnz > 16
+    g.close()
+    # geometry only: rows fill well beyond nearest_neighbors_max, up to the edge's own cap
+    q = geometric_params()
+    q.nearest_neighbors_max = 4
+    g = u.CvoGPU(q)
+    d1, d2, _ = synthetic_pair(1200, 700, 900, 6)
+    f1 = u.CvoFrameGPU(g, d1, pose_rt(0.0, 0.4, 0.0, [0.0, 0.0, 0.05]))
+    f2 = u.CvoFrameGPU(g, d2, pose_rt(0.0, 2.4, 0.0, [0.05, 0.02, 0.55]))
+    st = u.BinaryStateGPU(f1, f2, num_neighbor=40, init_ell=1.2)
+    _check_edge(st, q, f1, f2, cap_expected=40)
+    assert 4 < st.last_max_row_nnz <= 40
     g.close()
 
 

@@ -19,6 +19,7 @@
 
 #include "cvo_device.cuh"
 #include "cvo_upload.cuh"
+#include "cvo_export.cuh"
 
 namespace cvo_b200 {
 void launch_prep(const IterArgs& A, int blocks, cudaStream_t s);
@@ -189,6 +190,11 @@ struct cvo_b200_handle {
   DevBuf<int> idx_in;
   DevBuf<unsigned char> sort_temp;
   DevBuf<CloudStats> d_stats;
+  // CSR export scratch (cvo_export.cu)
+  DevBuf<int> csr_cnt, csr_ptr;
+  DevBuf<unsigned char> csr_temp;
+  DevBuf<int32_t> csr_cols;
+  DevBuf<float> csr_vals;
   CloudStats* h_stats = nullptr;  // pinned
   int row_begin = 0, row_end = -1;
   // launch geometry
@@ -911,6 +917,7 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
   h->raw_xyz.release(); h->raw_feat.release(); h->raw_lab.release(); h->raw_geo.release();
   h->keys_in.release(); h->idx_in.release(); h->sort_temp.release(); h->d_stats.release();
   for (FrameDev& f : h->frames) f.release();
+  h->csr_cnt.release(); h->csr_ptr.release(); h->csr_temp.release(); h->csr_cols.release(); h->csr_vals.release();
   if (h->d_params) cudaFree(h->d_params);
   if (h->d_state) cudaFree(h->d_state);
   if (h->h_poll) cudaFreeHost(h->h_poll);
@@ -1198,42 +1205,55 @@ int cvo_b200_function_angle(cvo_b200_handle* h, const float T[16], float ell, in
   return CVO_B200_OK;
 }
 
-// The ELL matrix of an exact-view (original target indices) run as CSR in the caller's row order:
-// device rows are in the source cloud's Morton order and are un-permuted here.  Two-call protocol
-// (cols/vals may be null).  Replaces gpu_association_to_cpu (CvoGPU_impl.cu:366-427).
+// The ELL matrix of an exact-view (original target indices) run as CSR in the caller's row order.
+// Device rows are in the source cloud's Morton order; un-permuting, the prefix sum and the
+// compaction happen on the device (cvo_export.cu), so only row_ptr and the nnz entries are
+// copied to the host.  Two-call protocol (cols/vals may be null).  Replaces
+// gpu_association_to_cpu (CvoGPU_impl.cu:366-427) / copy_internal_SparseKernelMat_gpu_to_cpu.
 static int export_csr(cvo_b200_handle* h, const IterArgs& A, int64_t* nnz, int32_t* max_row_nnz,
                       int32_t* row_ptr, int32_t* cols, float* vals) {
   const int n_rows = A.n_rows;
-  std::vector<uint32_t> cnt((size_t)n_rows);
-  CVO_CUDA(h, cudaMemcpy(cnt.data(), A.row_nnz, sizeof(uint32_t) * (size_t)n_rows, cudaMemcpyDeviceToHost));
-  int rc = fetch_perm(h, h->src);
-  if (rc != CVO_B200_OK) return rc;
-  const std::vector<int>& perm = h->src.perm;  // Morton position -> original row
-  std::vector<int> inv((size_t)n_rows);
-  for (int s = 0; s < n_rows; s++) inv[perm[s]] = s;
-  int64_t total = 0;
-  uint32_t mx = 0;
-  if (row_ptr) row_ptr[0] = 0;
-  for (int i = 0; i < n_rows; i++) {
-    total += cnt[inv[i]];
-    mx = std::max(mx, cnt[inv[i]]);
-    if (row_ptr) row_ptr[i + 1] = (int32_t)total;
+  cudaStream_t s = h->stream;
+  CsrExport E;
+  std::memset(&E, 0, sizeof(E));
+  E.n_rows = n_rows;
+  E.cap_max = A.cap_max;
+  E.row_nnz = A.row_nnz;
+  E.ell_idx = A.ell_idx;
+  E.ell_val = A.ell_val;
+  E.inv = h->src.inv.p;  // caller's row -> Morton position
+  E.scan_temp_bytes = csr_scan_temp_bytes(n_rows);
+  CVO_CUDA(h, h->csr_cnt.ensure((size_t)n_rows + 1));
+  CVO_CUDA(h, h->csr_ptr.ensure((size_t)n_rows + 1));
+  CVO_CUDA(h, h->csr_temp.ensure(E.scan_temp_bytes));
+  E.cnt = h->csr_cnt.p;
+  E.row_ptr = h->csr_ptr.p;
+  E.scan_temp = h->csr_temp.p;
+  CVO_CUDA(h, csr_row_ptr_device(E, s));
+  h->launches += 2;
+  std::vector<int32_t> rp_local;
+  int32_t* rp = row_ptr;
+  if (!rp) {
+    rp_local.resize((size_t)n_rows + 1);
+    rp = rp_local.data();
   }
+  CVO_CUDA(h, cudaMemcpyAsync(rp, E.row_ptr, sizeof(int32_t) * ((size_t)n_rows + 1), cudaMemcpyDeviceToHost, s));
+  CVO_CUDA(h, cudaStreamSynchronize(s));
+  const int64_t total = rp[n_rows];
+  int32_t mx = 0;
+  for (int i = 0; i < n_rows; i++) mx = std::max(mx, rp[i + 1] - rp[i]);
   *nnz = total;
-  if (max_row_nnz) *max_row_nnz = (int32_t)mx;
+  if (max_row_nnz) *max_row_nnz = mx;
   if (!cols || !vals || total == 0) return CVO_B200_OK;
-  std::vector<uint32_t> idx((size_t)n_rows * A.cap_max);
-  std::vector<float> val((size_t)n_rows * A.cap_max);
-  CVO_CUDA(h, cudaMemcpy(idx.data(), A.ell_idx, idx.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  CVO_CUDA(h, cudaMemcpy(val.data(), A.ell_val, val.size() * sizeof(float), cudaMemcpyDeviceToHost));
-  int64_t o = 0;
-  for (int i = 0; i < n_rows; i++) {
-    const int s = inv[i];
-    for (uint32_t k = 0; k < cnt[s]; k++, o++) {
-      cols[o] = (int32_t)idx[(size_t)s * A.cap_max + k];  // exact view: original target indices
-      vals[o] = val[(size_t)s * A.cap_max + k];
-    }
-  }
+  CVO_CUDA(h, h->csr_cols.ensure((size_t)total));
+  CVO_CUDA(h, h->csr_vals.ensure((size_t)total));
+  E.cols = h->csr_cols.p;
+  E.vals = h->csr_vals.p;
+  CVO_CUDA(h, csr_gather_device(E, s));
+  h->launches += 1;
+  CVO_CUDA(h, cudaMemcpyAsync(cols, E.cols, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  CVO_CUDA(h, cudaMemcpyAsync(vals, E.vals, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  CVO_CUDA(h, cudaStreamSynchronize(s));
   return CVO_B200_OK;
 }
 
