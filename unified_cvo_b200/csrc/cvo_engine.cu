@@ -151,6 +151,14 @@ struct FrameDev {
   void release() { xyz.release(); feat.release(); lab.release(); geo.release(); set = false; n = 0; }
 };
 
+// a cloud slot built from a frame at a pose (edges sharing a frame at the same pose reuse it)
+struct SlotKey {
+  bool valid = false;
+  int frame = -1;
+  unsigned long long gen = 0;
+  float pose[12] = {};
+};
+
 // what the ELL matrix holds after cvo_b200_edge_update (second call of the two-call protocol)
 struct EdgeKey {
   int f1, f2, cap;
@@ -228,6 +236,7 @@ struct cvo_b200_handle {
   unsigned long long frame_gen_next = 1;
   bool edge_valid = false;
   EdgeKey edge_key;
+  SlotKey slot_key[2];  // which posed frame each cloud slot currently holds ([0] source, [1] target)
   IterArgs edge_args;
   int cap_override = 0;  // ELL stride of the next prepare() when an edge asks for more than nearest_neighbors_max
   // the kernel matrix left behind by the last align() (cvo_b200_align_association)
@@ -675,6 +684,7 @@ int build_cloud(cvo_b200_handle* h, CloudDev& c, int n, int F, const float* d_xy
   c.n_finite = 0;
   h->last_valid = false;
   h->edge_valid = false;
+  h->slot_key[&c == &h->tgt ? 1 : 0].valid = false;
   if (n == 0) return CVO_B200_OK;
   cudaStream_t s = h->stream;
   const size_t nn = (size_t)n;
@@ -1369,13 +1379,19 @@ int cvo_b200_frame_clear(cvo_b200_handle* h, int frame) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   h->edge_valid = false;
+  h->slot_key[0].valid = h->slot_key[1].valid = false;
   for (size_t k = 0; k < h->frames.size(); k++)
     if (frame < 0 || (size_t)frame == k) h->frames[k].release();
   return CVO_B200_OK;
 }
 
 // frame `f` moved by its pose becomes cloud slot `c` (everything on the device)
-static int build_posed_frame(cvo_b200_handle* h, CloudDev& c, const FrameDev& f, const float pose[12]) {
+static int build_posed_frame(cvo_b200_handle* h, CloudDev& c, int frame, const float pose[12]) {
+  const FrameDev& f = h->frames[(size_t)frame];
+  SlotKey& key = h->slot_key[&c == &h->tgt ? 1 : 0];
+  if (key.valid && key.frame == frame && key.gen == h->frame_gen[(size_t)frame] &&
+      std::memcmp(key.pose, pose, sizeof(key.pose)) == 0)
+    return CVO_B200_OK;  // the slot already holds this frame at this pose
   if (f.n > 0) {
     CVO_CUDA(h, h->raw_xyz.ensure((size_t)f.n * 3));
     PoseVec P;
@@ -1383,8 +1399,14 @@ static int build_posed_frame(cvo_b200_handle* h, CloudDev& c, const FrameDev& f,
     CVO_CUDA(h, pose_vec_transform_device(f.xyz.p, h->raw_xyz.p, f.n, P, h->stream));
     h->launches += 1;
   }
-  return build_cloud(h, c, f.n, f.F, h->raw_xyz.p, f.F ? f.feat.p : nullptr, f.C,
-                     f.C ? f.lab.p : nullptr, f.has_geo ? f.geo.p : nullptr);
+  int rc = build_cloud(h, c, f.n, f.F, h->raw_xyz.p, f.F ? f.feat.p : nullptr, f.C,
+                       f.C ? f.lab.p : nullptr, f.has_geo ? f.geo.p : nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  key.valid = true;
+  key.frame = frame;
+  key.gen = h->frame_gen[(size_t)frame];
+  std::memcpy(key.pose, pose, sizeof(key.pose));
+  return CVO_B200_OK;
 }
 
 int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], int frame2,
@@ -1415,9 +1437,20 @@ int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], 
   key.gen2 = h->frame_gen[(size_t)frame2];
   // second call of the two-call protocol: the matrix of this very edge is still on the device
   if (!(h->edge_valid && std::memcmp(&key, &h->edge_key, sizeof(key)) == 0)) {
-    int rc = build_posed_frame(h, h->src, f1, pose1);
+    // a frame shared with the previous edge may sit in the other slot (ring / chain graphs):
+    // exchange the slots when that saves a build
+    auto holds = [&](int slot, int frame, const float* pose) {
+      const SlotKey& k = h->slot_key[slot];
+      return (k.valid && k.frame == frame && k.gen == h->frame_gen[(size_t)frame] &&
+              std::memcmp(k.pose, pose, sizeof(k.pose)) == 0) ? 1 : 0;
+    };
+    if (holds(1, frame1, pose1) + holds(0, frame2, pose2) > holds(0, frame1, pose1) + holds(1, frame2, pose2)) {
+      std::swap(h->src, h->tgt);
+      std::swap(h->slot_key[0], h->slot_key[1]);
+    }
+    int rc = build_posed_frame(h, h->src, frame1, pose1);
     if (rc != CVO_B200_OK) return rc;
-    rc = build_posed_frame(h, h->tgt, f2, pose2);
+    rc = build_posed_frame(h, h->tgt, frame2, pose2);
     if (rc != CVO_B200_OK) return rc;
     // both clouds are already where fill_in_A_mat_gpu sees them: the pairwise pass runs at the
     // identity (1*y + (0*y + 0*y) + (-0) is exact), with the edge's own cap and a fixed ell
