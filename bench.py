@@ -236,7 +236,7 @@ def frame_pairs_leg(u, name, steps=5):
             "wall_ms_per_frame_pair": 1e3 * wall / steps, "max_abs_pose_error_vs_truth": err, "ret": int(ret)}
 
 
-def edge_updates_leg(u, rounds=5):
+def edge_updates_leg(u, rounds=5, cpu=True):
     """Pose-graph edge updates/s: four KITTI-05-sized frames resident on the
     device, a ring of four edges, every round = one outer IRLS iteration's edge loop
     (BinaryStateGPU::update_inner_product per edge: both frames moved by their poses, capped
@@ -262,6 +262,20 @@ def edge_updates_leg(u, rounds=5):
                        f"cap={cap}; one update = two posed cloud builds + capped kernel matrix + CSR to host",
            "edge_updates_per_s": n_edges / dt, "ms_per_edge_update": 1e3 * dt / n_edges,
            "nonzeros_per_round": int(total), "gpu_launches_per_edge_update": (g.launch_count() - launches0) / n_edges}
+    if cpu:  # the CPU restatement of the same edge loop on the host cores (one round)
+        import oracle
+        oc = {id(f): oracle.Cloud(f.points.positions_, f.points.features_, f.points.labels_,
+                                  f.points.geometric_types_) for f in frames}
+        t0 = time.perf_counter()
+        cpu_total = 0
+        for st in states:
+            t, _ = oracle.edge_update(p, oc[id(st.frame1)], st.frame1.pose_float(), oc[id(st.frame2)],
+                                      st.frame2.pose_float(), st.ell_, st.num_neighbors_)
+            cpu_total += t
+        dt_cpu = time.perf_counter() - t0
+        out["cpu_baseline"] = {"edge_updates_per_s": len(states) / dt_cpu, "cores": oracle.num_threads(), "kind": "port",
+                               "nonzeros_per_round": int(cpu_total),
+                               "sample": "one round of the same four edges, oracle/cvo_oracle.c (grid-accelerated, OpenMP)"}
     g.close()
     return out
 
@@ -430,7 +444,7 @@ def run_ours(args, rank, world, local_rank):
     # frame-pairs/s on KITTI-05-sized clouds (north_star): a tracking frame and a first frame
     if world == 1 and args.workload is None and not args.no_frames:
         line["frame_pairs"] = [frame_pairs_leg(u, wl) for wl in ("KITTI05_TRACK", "KITTI05")]
-        line["edge_updates"] = edge_updates_leg(u)
+        line["edge_updates"] = edge_updates_leg(u, cpu=not args.no_cpu_baseline)
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same registration
     if world == 1 and not args.no_cpu_baseline:
         import oracle

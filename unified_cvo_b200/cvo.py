@@ -350,8 +350,8 @@ class CvoGPU:
         assoc.cols = cols[: nnz.value]
         assoc.vals = vals[: nnz.value]
         counts = np.diff(assoc.row_ptr)
-        assoc.source_inliers = [int(i) for i in np.nonzero(counts)[0]]
-        assoc.target_inliers = [int(j) for j in assoc.cols]
+        assoc.source_inliers = np.nonzero(counts)[0].tolist()
+        assoc.target_inliers = assoc.cols.tolist()
         return assoc
 
     # --- measurement helpers (bench.py)
