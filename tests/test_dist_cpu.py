@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from helpers import ROOT
-from unified_cvo_b200.dist import shard_rows
+from unified_cvo_b200.dist import shard_edges, shard_rows
 
 
 def test_shard_rows_partition_is_exact():
@@ -24,6 +24,16 @@ def test_shard_rows_partition_is_exact():
             assert all(0 <= b <= e <= n for b, e in spans)
     with pytest.raises(ValueError):
         shard_rows(10, 2, 2)
+
+
+def test_shard_edges_partition_is_exact():
+    for n in (0, 1, 5, 16):
+        for world in (1, 2, 3, 8):
+            parts = [shard_edges(n, world, r) for r in range(world)]
+            assert sorted(e for part in parts for e in part) == list(range(n))
+            assert max(len(x) for x in parts) - min(len(x) for x in parts) <= 1
+    with pytest.raises(ValueError):
+        shard_edges(4, 2, -1)
 
 
 WORKER = textwrap.dedent("""
@@ -56,6 +66,23 @@ WORKER = textwrap.dedent("""
     sums = [None] * world
     dist.all_gather_object(sums, tot.tobytes())
     assert all(s == sums[0] for s in sums)           # bit-identical replicated control
+    # edge-parallel pose-graph loop: every rank updates its own edges, the non-zero counts are
+    # gathered in edge order and equal the single-process loop's
+    from unified_cvo_b200.dist import shard_edges
+    I = np.eye(4, dtype=np.float32)[:3].reshape(12)
+    P = I.copy(); P[[3, 7, 11]] = [0.02, 0.0, 0.1]
+    frames = [(src, I), (tgt, P), (src, P), (tgt, I)]
+    edges = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]
+    def edge_nnz(k):
+        (a, pa), (b2, pb) = frames[edges[k][0]], frames[edges[k][1]]
+        return oracle.edge_update(p, to_oracle_cloud(a), pa, to_oracle_cloud(b2), pb, 0.9, 12)[0]
+    mine = {{k: edge_nnz(k) for k in shard_edges(len(edges), world, rank)}}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    merged = {{k: v for part in parts for k, v in part.items()}}
+    assert sorted(merged) == list(range(len(edges)))
+    assert [merged[k] for k in range(len(edges))] == [edge_nnz(k) for k in range(len(edges))]
+    assert sum(merged.values()) > 100
     # the NCCL unique-id plumbing: rank 0's 128 bytes reach every rank unchanged
     uid = [bytes(range(128)) if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)

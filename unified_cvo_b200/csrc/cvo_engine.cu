@@ -203,6 +203,7 @@ struct cvo_b200_handle {
   DevBuf<unsigned char> csr_temp;
   DevBuf<int32_t> csr_cols;
   DevBuf<float> csr_vals;
+  std::vector<int32_t> csr_rp_host;
   CloudStats* h_stats = nullptr;  // pinned
   int row_begin = 0, row_end = -1;
   // launch geometry
@@ -1221,7 +1222,7 @@ int cvo_b200_function_angle(cvo_b200_handle* h, const float T[16], float ell, in
 // copied to the host.  Two-call protocol (cols/vals may be null).  Replaces
 // gpu_association_to_cpu (CvoGPU_impl.cu:366-427) / copy_internal_SparseKernelMat_gpu_to_cpu.
 static int export_csr(cvo_b200_handle* h, const IterArgs& A, int64_t* nnz, int32_t* max_row_nnz,
-                      int32_t* row_ptr, int32_t* cols, float* vals) {
+                      int32_t* row_ptr, int32_t* cols, float* vals, bool reuse_row_ptr = false) {
   const int n_rows = A.n_rows;
   cudaStream_t s = h->stream;
   CsrExport E;
@@ -1239,16 +1240,19 @@ static int export_csr(cvo_b200_handle* h, const IterArgs& A, int64_t* nnz, int32
   E.cnt = h->csr_cnt.p;
   E.row_ptr = h->csr_ptr.p;
   E.scan_temp = h->csr_temp.p;
-  CVO_CUDA(h, csr_row_ptr_device(E, s));
-  h->launches += 2;
-  std::vector<int32_t> rp_local;
-  int32_t* rp = row_ptr;
-  if (!rp) {
-    rp_local.resize((size_t)n_rows + 1);
-    rp = rp_local.data();
+  // second call of the two-call protocol on the same matrix: the prefix sums are still on the
+  // device (csr_ptr) and on the host (csr_rp_host)
+  std::vector<int32_t>& rp_host = h->csr_rp_host;
+  if (!(reuse_row_ptr && rp_host.size() == (size_t)n_rows + 1)) {
+    CVO_CUDA(h, csr_row_ptr_device(E, s));
+    h->launches += 2;
+    rp_host.resize((size_t)n_rows + 1);
+    CVO_CUDA(h, cudaMemcpyAsync(rp_host.data(), E.row_ptr, sizeof(int32_t) * ((size_t)n_rows + 1),
+                                cudaMemcpyDeviceToHost, s));
+    CVO_CUDA(h, cudaStreamSynchronize(s));
   }
-  CVO_CUDA(h, cudaMemcpyAsync(rp, E.row_ptr, sizeof(int32_t) * ((size_t)n_rows + 1), cudaMemcpyDeviceToHost, s));
-  CVO_CUDA(h, cudaStreamSynchronize(s));
+  const int32_t* rp = rp_host.data();
+  if (row_ptr) std::memcpy(row_ptr, rp, sizeof(int32_t) * ((size_t)n_rows + 1));
   const int64_t total = rp[n_rows];
   int32_t mx = 0;
   for (int i = 0; i < n_rows; i++) mx = std::max(mx, rp[i + 1] - rp[i]);
@@ -1436,7 +1440,8 @@ int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], 
   key.gen1 = h->frame_gen[(size_t)frame1];
   key.gen2 = h->frame_gen[(size_t)frame2];
   // second call of the two-call protocol: the matrix of this very edge is still on the device
-  if (!(h->edge_valid && std::memcmp(&key, &h->edge_key, sizeof(key)) == 0)) {
+  const bool cached = h->edge_valid && std::memcmp(&key, &h->edge_key, sizeof(key)) == 0;
+  if (!cached) {
     // a frame shared with the previous edge may sit in the other slot (ring / chain graphs):
     // exchange the slots when that saves a build
     auto holds = [&](int slot, int frame, const float* pose) {
@@ -1465,7 +1470,7 @@ int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], 
     h->edge_args = A;
     h->edge_valid = true;
   }
-  return export_csr(h, h->edge_args, nnz, max_row_nnz, row_ptr, cols, vals);
+  return export_csr(h, h->edge_args, nnz, max_row_nnz, row_ptr, cols, vals, cached);
 }
 
 int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T[3], float ell,

@@ -19,6 +19,17 @@ def shard_rows(n_rows: int, world: int, rank: int) -> tuple[int, int]:
     return begin, min(n_rows, begin + per)
 
 
+def shard_edges(n_edges: int, world: int, rank: int) -> list[int]:
+    """Edge-parallel decomposition of the pose-graph edge loop (IRLS.cpp:111-121): the edges are
+    independent (each fills its own matrix from the two frames' poses), so rank r takes edges
+    r, r + world, ... and uploads only the frames those edges touch.  No data-path collective:
+    the per-edge matrices go to the host solver; only the per-edge non-zero counts are gathered
+    (host control plane) for the loop's `total_nonzeros` test."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return list(range(rank, n_edges, world))
+
+
 def attach(gpu, n_rows: int, rank: int, world: int, dist_module=None, fused: bool = True) -> tuple[int, int]:
     """Create the NCCL communicator of `gpu` (a CvoGPU) and set its row shard.
 
