@@ -1,5 +1,5 @@
 // reference_api_stub.hpp — TEST-ONLY stand-ins for the third-party and reference types that
-// shim/CvoGPU_b200.cpp touches (Eigen, PCL, cvo::CvoPointCloud/CvoParams/Association/CvoGPU).
+// shim/CvoGPU_b200.cpp and shim/IRLS_State_GPU_b200.cpp touch (Eigen, PCL, cvo::CvoPointCloud/CvoParams/Association/CvoGPU).
 // The build container has neither Eigen nor PCL, so tests/test_shim_syntax.py compiles the shim
 // against these declarations (-DCVO_SHIM_SYNTAX_CHECK -include this file) to keep it
 // syntactically and type-wise honest.  Nothing here is shipped or linked; in a real build the
@@ -90,6 +90,7 @@ struct Association {
 class CvoPointCloud {
  public:
   int num_points() const { return 0; }
+  int size() const { return 0; }
   int num_classes() const { return 0; }
   const std::vector<Eigen::Vector3f, Eigen::aligned_allocator<Eigen::Vector3f>>& positions() const { return p_; }
   const Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic>& labels() const { return l_; }
@@ -101,8 +102,76 @@ class CvoPointCloud {
   Eigen::MatrixXf f_, l_;
   std::vector<float> g_;
 };
-class CvoFrame;
-class BinaryState;
+// ---- multi-frame types (cvo/CvoFrame.hpp, cvo/CvoFrameGPU.hpp, cvo/SparseKernelMat.hpp,
+//      cvo/IRLS_State.hpp, cvo/IRLS_State_GPU.hpp), members in the reference's order
+struct CvoFrame {
+  typedef std::shared_ptr<CvoFrame> Ptr;
+  CvoFrame(const CvoPointCloud* pts, const double poses[12]);  // reference's CvoFrame.cpp
+  virtual ~CvoFrame() {}
+  const CvoPointCloud* points;
+  double pose_vec[12];
+  virtual void transform_pointcloud();
+};
+class CvoFrameGPU_Impl;
+struct CvoFrameGPU : public CvoFrame {
+  CvoFrameGPU(const CvoPointCloud* pts, const double poses[12]);
+  ~CvoFrameGPU();
+  void transform_pointcloud();
+  const CvoPoint* points_transformed_gpu() const;
+  const float* pose_vec_gpu() const;
+
+ private:
+  std::unique_ptr<CvoFrameGPU_Impl> impl;
+};
+struct SparseKernelMat {
+  int rows;
+  int cols;
+  unsigned int nonzero_sum;
+  float* mat;
+  int* ind_row2col;
+  unsigned int* nonzeros;
+};
+void clear_SparseKernelMat_cpu(SparseKernelMat* A_cpu, int num_neighbors);
+void init_internal_SparseKernelMat_cpu(int rows, int cols, SparseKernelMat* A_cpu);
+void delete_internal_SparseKernelMat_cpu(SparseKernelMat* A_cpu);
+}  // namespace cvo
+namespace ceres {
+class Problem;
+}
+namespace cvo {
+class BinaryState {
+ public:
+  typedef std::shared_ptr<BinaryState> Ptr;
+  virtual int update_inner_product() = 0;
+  virtual void add_residual_to_problem(ceres::Problem& problem) = 0;
+  virtual void update_ell() = 0;
+};
+class BinaryStateGPU : public BinaryState {
+ public:
+  typedef std::shared_ptr<BinaryStateGPU> Ptr;
+  BinaryStateGPU(std::shared_ptr<CvoFrameGPU> pc1, std::shared_ptr<CvoFrameGPU> pc2,
+                 const CvoParams* params_cpu, const CvoParams* params_gpu, unsigned int num_neighbor,
+                 float init_ell);
+  ~BinaryStateGPU();
+  virtual int update_inner_product();
+  void update_ell();                                        // reference's IRLS_State_GPU.cpp
+  void add_residual_to_problem(ceres::Problem& problem);    // reference's IRLS_State_GPU.cpp
+
+ private:
+  std::shared_ptr<CvoFrameGPU> frame1_;
+  std::shared_ptr<CvoFrameGPU> frame2_;
+  CvoFrame* frame1();
+  CvoFrame* frame2();
+  unsigned int num_neighbors_;
+  SparseKernelMat A_host_;
+  SparseKernelMat* A_device_;
+  SparseKernelMat A_result_cpu_;
+  float ell_;
+  int iter_;
+  const unsigned int init_num_neighbors_;
+  const CvoParams* params_gpu_;
+  const CvoParams* params_cpu_;
+};
 // the members of cvo::CvoGPU that the shim defines (signatures as in the reference header)
 class CvoGPU {
  private:

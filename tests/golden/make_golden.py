@@ -61,7 +61,54 @@ def run_case(c):
     return dict(iters=out, ret=ret, iterations=info.iterations, transform=[[float(x) for x in row] for row in T])
 
 
+# pose-graph edge updates (oracle.edge_update): two frames at their own poses, fixed ell and cap
+EDGE_CASES = [
+    dict(name="geometric", P=1600, N=1000, M=1200, seed=77, F=0, C=0, geotype=False, ell=0.8, cap=24,
+         pose1=[0.3, 0.5, -0.2, 0.05, 0.0, -0.1], pose2=[0.1, 2.2, 0.0, 0.1, 0.02, 0.35]),
+    dict(name="colour_semantics", P=1200, N=700, M=900, seed=5, F=5, C=20, geotype=True, ell=1.2, cap=40,
+         pose1=[0.0, 0.4, 0.0, 0.0, 0.0, 0.05], pose2=[0.0, 2.4, 0.0, 0.05, 0.02, 0.55]),
+]
+
+
+def edge_pose(v):
+    """[rx, ry, rz (deg), tx, ty, tz] -> row-major 3x4 float32 (CvoFrame::pose_vec narrowed)."""
+    ax, ay, az = np.deg2rad(v[:3])
+    Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+    Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+    Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+    P = np.zeros((3, 4))
+    P[:, :3] = Rz @ Ry @ Rx
+    P[:, 3] = v[3:]
+    return P.reshape(12).astype(np.float32)
+
+
+def edge_inputs(c):
+    import unified_cvo_b200 as u
+    from helpers import DATA
+    f1, f2, _ = synthetic_pair(c["P"], c["N"], c["M"], c["seed"], F=c["F"], C=c["C"], geotype=c["geotype"])
+    if c["F"]:
+        p = u.read_params_yaml(os.path.join(DATA, "cvo_semantic_params_img_gpu0.yaml"))
+        p.is_using_geometric_type = 1
+        p.c_ell = 0.5
+    else:
+        p = geometric_params()
+    return f1, f2, p
+
+
+def run_edge_case(c):
+    f1, f2, p = edge_inputs(c)
+    total, sp = oracle.edge_update(p, to_oracle_cloud(f1), edge_pose(c["pose1"]), to_oracle_cloud(f2),
+                                   edge_pose(c["pose2"]), c["ell"], c["cap"])
+    row_ptr, cols, vals = oracle.sparse_to_csr(sp)
+    return dict(name=c["name"], nnz=total, max_row_nnz=int(sp["nonzeros"].max()),
+                row_ptr=[int(x) for x in row_ptr], cols=[int(x) for x in cols],
+                vals=[float(x) for x in vals])
+
+
 def main():
+    with open(os.path.join(HERE, "edge_updates.json"), "w") as fh:
+        json.dump([run_edge_case(c) for c in EDGE_CASES], fh, indent=0)
+    print("edge_updates", len(EDGE_CASES), "records")
     for name, c in CASES.items():
         res = run_case(c)
         with open(os.path.join(HERE, f"{name}_iters.json"), "w") as fh:

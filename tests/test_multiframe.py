@@ -94,7 +94,41 @@ def test_oracle_edge_update_depends_on_both_poses_not_only_on_the_relative_one()
     assert b > a > 0
 
 
+def _golden_edges():
+    import json
+    with open(os.path.join(os.path.dirname(__file__), "golden", "edge_updates.json")) as fh:
+        return json.load(fh)
+
+
+def test_oracle_edge_update_reproduces_the_committed_golden():
+    from golden.make_golden import EDGE_CASES, run_edge_case
+    for c, gold in zip(EDGE_CASES, _golden_edges()):
+        got = run_edge_case(c)
+        assert got["nnz"] == gold["nnz"] > 300 and got["max_row_nnz"] == gold["max_row_nnz"]
+        assert got["row_ptr"] == gold["row_ptr"] and got["cols"] == gold["cols"]
+        np.testing.assert_allclose(got["vals"], gold["vals"], rtol=1e-6)
+
+
 # ------------------------------------------------------------------ GPU: C-ABI vs oracle
+@pytest.mark.gpu
+def test_edge_update_against_the_committed_golden():
+    """tests/golden/edge_updates.json (make_golden.py, from the oracle): no oracle call here."""
+    from golden.make_golden import EDGE_CASES, edge_inputs, edge_pose
+    for c, gold in zip(EDGE_CASES, _golden_edges()):
+        c1, c2, p = edge_inputs(c)
+        g = u.CvoGPU(p)
+        f1 = u.CvoFrameGPU(g, c1, edge_pose(c["pose1"]))
+        f2 = u.CvoFrameGPU(g, c2, edge_pose(c["pose2"]))
+        st = u.BinaryStateGPU(f1, f2, num_neighbor=c["cap"], init_ell=c["ell"])
+        assert st.update_inner_product() == gold["nnz"]
+        A = st.A_result_cpu_
+        assert st.last_max_row_nnz == gold["max_row_nnz"]
+        assert A.row_ptr.tolist() == gold["row_ptr"] and A.cols.tolist() == gold["cols"]
+        np.testing.assert_allclose(A.vals, gold["vals"], rtol=1e-6)
+        g.close()
+
+
+
 def _check_edge(state, p, f1, f2, cap_expected=None):
     nnz = state.update_inner_product()
     if cap_expected is not None:

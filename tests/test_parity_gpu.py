@@ -359,6 +359,40 @@ def test_full_size_single_iterations_against_the_oracle(name, ell):
     g.close()
 
 
+def test_full_size_c5_colour_and_20_class_semantics():
+    """BASELINE configs[4] size (TUM-fr1-sized N=M=12 800, 5-dim colour + 20-class semantic kernel,
+    C a run-time value): single iterations at the identity and near the true pose against the
+    oracle.  Parameters: cvo_semantic_params_img_gpu0.yaml — with cvo_rgbd_params.yaml's
+    sigma/c_sigma and semantics switched on, sigma^2 c_sigma^2 s_sigma^2 barely exceeds sp_thres
+    and the oracle itself keeps no pair on these clouds."""
+    from unified_cvo_b200 import synthetic
+    d = synthetic.make_config("C5")
+    src = u.CvoPointCloud(d["source"]["xyz"], d["source"]["features"], d["source"]["labels"], None)
+    tgt = u.CvoPointCloud(d["target"]["xyz"], d["target"]["features"], d["target"]["labels"], None)
+    assert src.num_classes() == 20 and src.feature_dimensions() == 5 and src.num_points() == 12_800
+    p = u.read_params_yaml(os.path.join(DATA, "cvo_semantic_params_img_gpu0.yaml"))
+    g = u.CvoGPU(p)
+    g.set_cloud(0, src)
+    g.set_cloud(1, tgt)
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    a = np.deg2rad(2.0 * 0.95)
+    Gn = np.eye(4)
+    Gn[:3, :3] = [[np.cos(a), 0, np.sin(a)], [0, 1, 0], [-np.sin(a), 0, np.cos(a)]]
+    Tr = np.eye(4)
+    Tr[:3, 3] = np.array([0.05, 0.02, 0.50]) * 0.95
+    near = np.linalg.inv(Gn @ Tr).astype(np.float32)
+    cap = int(p.nearest_neighbors_max)
+    for R, T, ell in ((np.eye(3, dtype=np.float32), np.zeros(3, np.float32), 1.0),
+                      (near[:3, :3].copy(), near[:3, 3].copy(), 0.15),
+                      (near[:3, :3].copy(), near[:3, 3].copy(), 0.5)):
+        ref = oracle.iterate(p, cs, ct, R.T.reshape(9).copy(), T, ell, cap)
+        got = g.iterate(R, T, ell, cap)
+        assert ref.nnz > 4000
+        bad = compare_traces(got, ref, twist_tol=TWIST_TOL)
+        assert not bad, (ell, bad)
+    g.close()
+
+
 def test_full_size_properties_kitti_sized_colour():
     """KITTI-05-sized clouds (N=M=16384, F=5): properties that need no oracle at this size —
     source-row shards sum to the whole (the multi-GPU decomposition), determinism, and the

@@ -24,17 +24,30 @@ def test_shim_compiles_and_links_against_the_c_abi(tmp_path):
     out = subprocess.run(common + ["-c", os.path.join(ROOT, "shim", "CvoGPU_b200.cpp"), "-o", str(obj)],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
+    # the multi-frame half: CvoFrameGPU + BinaryStateGPU forwarded to cvo_b200_frame_set / edge_update
+    obj2 = tmp_path / "irls.o"
+    out = subprocess.run(common + ["-c", os.path.join(ROOT, "shim", "IRLS_State_GPU_b200.cpp"), "-o", str(obj2)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
     # the one member the shim leaves to the reference's own CvoGPU.cpp
     rest = tmp_path / "rest.cpp"
     rest.write_text("namespace cvo { float CvoGPU::inner_product_cpu(const CvoPointCloud&, const CvoPointCloud&,"
-                    " const Eigen::Matrix4f&, float) const { return 0.f; } }\n")
+                    " const Eigen::Matrix4f&, float) const { return 0.f; }\n"
+                    # ... and the members the reference's CvoFrame.cpp / IRLS_State_GPU.cpp keep defining\n"
+                    "CvoFrame::CvoFrame(const CvoPointCloud* pts, const double poses[12]) : points(pts) {"
+                    " for (int i = 0; i < 12; i++) pose_vec[i] = poses[i]; }\n"
+                    "void CvoFrame::transform_pointcloud() {}\n"
+                    "void BinaryStateGPU::update_ell() {}\n"
+                    "void BinaryStateGPU::add_residual_to_problem(ceres::Problem&) {} }\n")
     so = tmp_path / "libshim_check.so"
-    out = subprocess.run(common + ["-shared", str(obj), str(rest), "-o", str(so), "-Wl,--no-undefined",
+    out = subprocess.run(common + ["-shared", str(obj), str(obj2), str(rest), "-o", str(so), "-Wl,--no-undefined",
                                    "-L" + os.path.dirname(lib), "-lcvo_b200",
                                    "-Wl,-rpath," + os.path.dirname(lib)],
                          capture_output=True, text=True)
     assert out.returncode == 0, out.stderr[-3000:]
     syms = subprocess.run(["nm", "-D", "--defined-only", str(so)], capture_output=True, text=True).stdout
     for member in ("CvoGPU5align", "CvoGPU14function_angle", "CvoGPU23compute_association_gpu",
-                   "CvoGPU17inner_product_gpu", "CvoGPU12write_params"):
+                   "CvoGPU17inner_product_gpu", "CvoGPU12write_params",
+                   "BinaryStateGPU20update_inner_product", "CvoFrameGPUC1", "CvoFrameGPU20transform_pointcloud",
+                   "init_internal_SparseKernelMat_cpu"):
         assert member in syms, member
