@@ -110,3 +110,56 @@ def flow(p, x, y_moved, rows):
     n = np.linalg.norm(ov.astype(np.float64))
     tw = (ov / f32(n)).astype(f32) if n > 0 else ov
     return om_sum, v_sum, tw
+
+
+def step_poly(p, x, y_moved, rows, omega, v, ell):
+    """B, C, D, E of compute_step_size_poly_coeff (CvoGPU.cu:1001-1082) by a GENERIC route, in
+    float64: the reference's hand-expanded beta..epsilon combinations are the Taylor coefficients
+    of  g(t) = sum_ij A_ij exp(q_ij(t)),  q_ij(t) = -c_i (|D_ij + sum_k t^k xi^k z_j|^2 - |D_ij|^2),
+    D_ij = x_i - y'_j, xi^k z = (xi_hat^k [y'_j; 1])_xyz (no factorials: CvoGPU.cu:953-998 feeds
+    the raw powers), c_i = 1 / (2 l_i^2).  Here q is built by polynomial multiplication and exp(q)
+    by the power-series recurrence e_n = (1/n) sum_k k q_k e_{n-k} - none of the reference's
+    formulas is restated.  Returns (B, C, D, E) = sum_ij A_ij e_1..e_4."""
+    x = np.asarray(x, np.float64)
+    ym = np.asarray(y_moved, np.float64)
+    om = np.asarray(omega, np.float64)
+    xi = np.zeros((4, 4))
+    xi[:3, :3] = [[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]]
+    xi[:3, 3] = np.asarray(v, np.float64)
+    yh = np.concatenate([ym, np.ones((len(ym), 1))], axis=1)
+    powers, M = [], np.eye(4)
+    for _ in range(4):
+        M = M @ xi
+        powers.append((yh @ M.T)[:, :3])  # xi^k z for every target point
+    out = np.zeros(4)
+    for i, (idx, val) in enumerate(rows):
+        if len(idx) == 0:
+            continue
+        l = np.float64(ell)
+        if p.is_using_range_ell:
+            l = (np.linalg.norm(x[i]) / 500.0 + 1.0) * np.float64(f32(ell))  # CvoGPU.cu:86-90
+        c = 1.0 / (2.0 * l * l)
+        d0 = x[i] - ym[idx]                                   # (k, 3)
+        coeffs = np.stack([d0] + [pw[idx] for pw in powers], axis=1)  # (k, 5, 3): t^0..t^4
+        q = np.zeros((len(idx), 9))
+        for a in range(5):
+            for b in range(5):
+                q[:, a + b] += (coeffs[:, a, :] * coeffs[:, b, :]).sum(1)
+        q[:, 0] = 0.0                                          # - |D|^2
+        q *= -c
+        e = np.zeros((len(idx), 5))
+        e[:, 0] = 1.0
+        for n in range(1, 5):
+            for k in range(1, n + 1):
+                e[:, n] += k * q[:, k] * e[:, n - k]
+            e[:, n] /= n
+        out += (np.asarray(val, np.float64)[:, None] * e[:, 1:]).sum(0)
+    return tuple(out)
+
+
+def step_from_poly(p, B, C, D, E):
+    """compute_step_size (CvoGPU.cu:1124-1158): smallest positive real root of g'(t) ~ 0, clamped."""
+    roots = np.roots([4.0 * E, 3.0 * D, 2.0 * C, B])
+    cand = [r.real for r in roots if r.real > 0 and abs(r.imag) < 1e-5]
+    t = min(cand) if cand else np.inf
+    return float(min(max(t, p.min_step), p.max_step)) if np.isfinite(t) else float(p.max_step)

@@ -61,6 +61,34 @@ def test_fill_matches_numpy_with_color_semantics_geotype_and_pose():
         np.testing.assert_allclose(gv, rv, rtol=5e-7)
 
 
+@pytest.mark.parametrize("range_ell,ell,cap", [(0, 0.9, 40), (1, 1.4, 12), (0, 2.0, 256)])
+def test_step_polynomial_is_the_taylor_series_of_the_line_search_objective(range_ell, ell, cap):
+    """B..E and the step against a route that restates none of the reference's formulas:
+    polynomial multiplication + the power-series recurrence of exp (numpy_ref.step_poly), and
+    numpy.roots for the cubic.  The oracle evaluates the per-pair terms in float like the
+    reference (CvoGPU.cu:1058-1078), hence 2e-4."""
+    src, tgt, _ = synthetic_pair(300, 200, 240, 11)
+    p = geometric_params()
+    p.is_using_range_ell = range_ell
+    a = np.deg2rad(1.0)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    T = np.array([0.03, -0.02, 0.1], np.float32)
+    tr, sp = oracle.iterate(p, to_oracle_cloud(src), to_oracle_cloud(tgt), R.T.reshape(9).copy(), T, ell, cap,
+                            want_matrix=True)
+    assert tr.nnz > 50
+    ym = numpy_ref.transform(R, T, tgt.positions_)
+    B, C, D, E = numpy_ref.step_poly(p, src.positions_, ym, _csr_rows(sp), list(tr.omega), list(tr.v), ell)
+    # scale of each coefficient: the sum of the magnitudes it is made of is not available here, so
+    # compare against the largest of |coef| t^n at the step actually taken (what the cubic sees)
+    t = max(tr.step, 1e-3)
+    got = np.array([tr.B * t, tr.C * t**2, tr.D * t**3, tr.E * t**4])
+    ref = np.array([B * t, C * t**2, D * t**3, E * t**4])
+    np.testing.assert_allclose(got, ref, rtol=2e-4, atol=2e-4 * np.abs(ref).max())
+    np.testing.assert_allclose([tr.B, tr.C], [B, C], rtol=2e-4)
+    assert tr.step == pytest.approx(numpy_ref.step_from_poly(p, tr.B, tr.C, tr.D, tr.E), rel=1e-5)
+    assert tr.step == pytest.approx(numpy_ref.step_from_poly(p, B, C, D, E), rel=2e-3)
+
+
 def test_truncation_is_first_k_in_target_order_not_top_k():
     src, tgt, _ = synthetic_pair(300, 100, 250, 3)
     p = geometric_params()
