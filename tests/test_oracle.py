@@ -89,6 +89,24 @@ def test_step_polynomial_is_the_taylor_series_of_the_line_search_objective(range
     assert tr.step == pytest.approx(numpy_ref.step_from_poly(p, B, C, D, E), rel=2e-3)
 
 
+@pytest.mark.parametrize("ell,cap", [(0.9, 40), (2.0, 256), (1.4, 12)])
+def test_flow_is_the_gradient_of_the_line_search_objective(ell, cap):
+    """Ties the flow (CvoGPU.cu:729-848) to the step polynomial (:1001-1082) analytically: the
+    slope of the line-search objective along the normalised flow is B = sum A beta =
+    (1/l^2) [omega . sum A (x x y') + v . sum A (y' - x)]; the flow sums carry 1/c and 1/d
+    (CvoGPU.cu:786-789), so with c = d and no range scaling  B l^2 = c |(omega_sum, v_sum)|."""
+    src, tgt, _ = synthetic_pair(300, 200, 240, 11)
+    p = geometric_params()
+    assert p.c == p.d and not p.is_using_range_ell
+    a = np.deg2rad(1.0)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+    T = np.array([0.03, -0.02, 0.1], np.float32)
+    tr = oracle.iterate(p, to_oracle_cloud(src), to_oracle_cloud(tgt), R.T.reshape(9).copy(), T, ell, cap)
+    grad = np.linalg.norm(list(tr.omega_sum) + list(tr.v_sum))
+    assert tr.nnz > 50 and grad > 0
+    assert tr.B * ell * ell == pytest.approx(p.c * grad, rel=1e-5)
+
+
 def test_truncation_is_first_k_in_target_order_not_top_k():
     src, tgt, _ = synthetic_pair(300, 100, 250, 3)
     p = geometric_params()
