@@ -1350,11 +1350,11 @@ int cvo_b200_frame_set(cvo_b200_handle* h, int frame, int n, const float* xyz, i
     h->frame_gen.resize((size_t)frame + 1, 0);
   }
   FrameDev& f = h->frames[(size_t)frame];
+  f.set = false;  // stays unset if an allocation or a copy below fails
   f.n = n;
   f.F = features ? F : 0;
   f.C = labels ? C : 0;
   f.has_geo = geotype != nullptr;
-  f.set = true;
   h->frame_gen[(size_t)frame] = h->frame_gen_next++;
   const size_t nn = (size_t)n;
   cudaStream_t s = h->stream;
@@ -1375,6 +1375,7 @@ int cvo_b200_frame_set(cvo_b200_handle* h, int frame, int n, const float* xyz, i
     }
     CVO_CUDA(h, cudaStreamSynchronize(s));  // the caller's arrays may be released after this call
   }
+  f.set = true;
   return CVO_B200_OK;
 }
 
