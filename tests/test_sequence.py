@@ -97,3 +97,61 @@ def test_synthetic_sequence_tracks_the_true_trajectory(tmp_path):
     odo.write_kitti(tmp_path / "seq.txt")
     assert len(open(tmp_path / "seq.txt").read().splitlines()) == 4
     cvo.close()
+
+
+# ---- KITTI odometry evaluator against the reference's OWN published numbers -----------------
+GOLD04 = os.path.join(os.path.dirname(__file__), "golden", "kitti04")
+REF = "/root/reference"
+
+
+def test_kitti_evaluator_reproduces_the_references_errors_and_stats_for_sequence_04():
+    """Golden vectors from the reference (tests/golden/kitti04/README.md): its trajectory of KITTI
+    04, the ground truth, and the per-segment errors + stats its devkit evaluator wrote
+    (devkit/cpp/evaluate_odometry.cpp:83-143, :381-408)."""
+    gt = sequence.load_kitti_poses(os.path.join(GOLD04, "gt.txt"))
+    est = sequence.load_kitti_poses(os.path.join(GOLD04, "result.txt"))
+    assert gt.shape == est.shape == (271, 4, 4)
+    errs = sequence.kitti_sequence_errors(gt, est)
+    gold = np.loadtxt(os.path.join(GOLD04, "errors.txt"))
+    assert len(errs) == len(gold) == 43
+    got = np.array(errs)
+    assert np.array_equal(got[:, 0], gold[:, 0]) and np.array_equal(got[:, 3], gold[:, 3])
+    np.testing.assert_allclose(got[:, 1], gold[:, 1], atol=1.5e-6)   # "%f": six decimals
+    np.testing.assert_allclose(got[:, 2], gold[:, 2], atol=1.5e-6)
+    np.testing.assert_allclose(got[:, 4], gold[:, 4], atol=1.5e-6)
+    t_err, r_err = sequence.kitti_stats(errs)
+    ref_t, ref_r = (float(x) for x in open(os.path.join(GOLD04, "stats.txt")).read().split())
+    assert ref_t == pytest.approx(0.038597) and ref_r == pytest.approx(0.000401)
+    assert abs(t_err - ref_t) < 1e-6 and abs(r_err - ref_r) < 1e-6
+    # a perfect trajectory has no error; a short one has no 100 m segment
+    assert sequence.kitti_stats(sequence.kitti_sequence_errors(gt, gt))[0] < 1e-6
+    assert sequence.kitti_sequence_errors(gt[:20], est[:20]) == []
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "results")), reason="reference tree not present")
+def test_kitti_evaluator_reproduces_every_published_stats_file_of_the_reference():
+    """results/cvo_intensity_img_gpu0_oct25_best/{00..10}.txt against ground_truth/: the 11
+    published (t_err, r_err) pairs of the reference's headline KITTI run, to the six decimals
+    they are printed with.  (Runs only where /root/reference exists; never on the GPU box.)"""
+    d = os.path.join(REF, "results", "cvo_intensity_img_gpu0_oct25_best")
+    checked = 0
+    for k in range(11):
+        gt = sequence.load_kitti_poses(os.path.join(REF, "ground_truth", f"{k:02d}.txt"))
+        est = sequence.load_kitti_poses(os.path.join(d, f"{k:02d}.txt"))
+        ref_t, ref_r = (float(x) for x in open(os.path.join(d, "stats", f"{k:02d}_avg.txt")).read().split())
+        t_err, r_err = sequence.kitti_stats(sequence.kitti_sequence_errors(gt, est))
+        assert abs(t_err - ref_t) < 2e-6 and abs(r_err - ref_r) < 2e-6, (k, t_err, r_err, ref_t, ref_r)
+        checked += 1
+    assert checked == 11
+
+
+def test_kitti_writer_round_trips_the_references_own_trajectory_file_verbatim():
+    """The reference writes poses with operator<< at the default precision
+    (main_cvo_gpu_align_raw_image.cpp:158-166): parsing its 04.txt and writing it back with
+    kitti_line reproduces every line of the file character by character."""
+    path = os.path.join(GOLD04, "result.txt")
+    lines = open(path).read().splitlines()
+    poses = sequence.load_kitti_poses(path)
+    assert len(lines) == len(poses) == 271
+    for line, T in zip(lines, poses):
+        assert sequence.kitti_line(T) == line.strip()

@@ -128,3 +128,64 @@ def kitti_translation_error(poses_est, poses_gt) -> float:
         length = np.linalg.norm(d_gt[:3, 3])
         errs.append(np.linalg.norm(e[:3, 3]) / max(length, 1e-9))
     return float(np.mean(errs)) if errs else 0.0
+
+
+# ---- KITTI odometry evaluation (devkit/cpp/evaluate_odometry.cpp) ------------------------------
+KITTI_LENGTHS = (100, 200, 300, 400, 500, 600, 700, 800)  # evaluate_odometry.cpp:12
+
+
+def load_kitti_poses(path: str) -> np.ndarray:
+    """loadPoses (evaluate_odometry.cpp:25-43): one row-major 3x4 pose per line -> (n, 4, 4)."""
+    rows = np.loadtxt(path, dtype=np.float64, ndmin=2)
+    poses = np.tile(np.eye(4), (len(rows), 1, 1))
+    poses[:, :3, :] = rows[:, :12].reshape(-1, 3, 4)
+    return poses
+
+
+def kitti_sequence_errors(poses_gt, poses_est, step_size: int = 10):
+    """calcSequenceErrors (evaluate_odometry.cpp:83-127): for every 10th start frame and every
+    segment length of 100..800 m (measured along the GROUND-TRUTH path), the rotation [rad/m] and
+    translation [m/m] error of the estimated relative motion.  Distances, errors and the speed are
+    float like the devkit's.  Returns rows (first_frame, r_err, t_err, len, speed)."""
+    gt = np.asarray(poses_gt, np.float64)
+    est = np.asarray(poses_est, np.float64)
+    f32 = np.float32
+    # trajectoryDistances (:45-57): float accumulation of float step lengths
+    dist = np.zeros(len(gt), f32)
+    for i in range(1, len(gt)):
+        d = (gt[i - 1, :3, 3] - gt[i, :3, 3]).astype(f32)
+        dist[i] = dist[i - 1] + f32(np.sqrt(f32(d[0] * d[0] + d[1] * d[1]) + f32(d[2] * d[2])))
+    out = []
+    for first in range(0, len(gt), step_size):
+        for length in KITTI_LENGTHS:
+            # lastFrameFromSegmentLength (:59-64)
+            later = np.nonzero(dist[first:] > dist[first] + f32(length))[0]
+            if len(later) == 0:
+                continue
+            last = first + int(later[0])
+            d_gt = np.linalg.inv(gt[first]) @ gt[last]
+            d_est = np.linalg.inv(est[first]) @ est[last]
+            err = np.linalg.inv(d_est) @ d_gt
+            # rotationError / translationError (:66-81)
+            c = f32(0.5 * (f32(err[0, 0]) + f32(err[1, 1]) + f32(err[2, 2]) - 1.0))
+            r_err = f32(np.arccos(max(min(c, f32(1.0)), f32(-1.0))))
+            t = err[:3, 3].astype(f32)
+            t_err = f32(np.sqrt(f32(t[0] * t[0] + t[1] * t[1]) + f32(t[2] * t[2])))
+            num_frames = f32(last - first + 1)
+            speed = f32(length / (0.1 * num_frames))
+            out.append((first, float(r_err / f32(length)), float(t_err / f32(length)), float(length), float(speed)))
+    return out
+
+
+def kitti_stats(errors):
+    """saveStats (evaluate_odometry.cpp:381-408): (mean t_err, mean r_err) as written to
+    stats/NN_avg.txt — translation as a fraction (x100 = %), rotation in rad/m."""
+    if not errors:
+        return 0.0, 0.0
+    t = np.float32(0)
+    r = np.float32(0)
+    for e in errors:  # float running sums like the devkit
+        t = np.float32(t + np.float32(e[2]))
+        r = np.float32(r + np.float32(e[1]))
+    n = np.float32(len(errors))
+    return float(t / n), float(r / n)
