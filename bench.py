@@ -259,7 +259,8 @@ def edge_updates_leg(u, rounds=5, cpu=True):
     dt = time.perf_counter() - t0
     n_edges = rounds * len(states)
     out = {"workload": "4 KITTI-05-sized frames (N=16384, 5-dim colour), ring of 4 edges, ell=0.25, "
-                       f"cap={cap}; one update = two posed cloud builds + capped kernel matrix + CSR to host",
+                       f"cap={cap}; one update = posed cloud build(s) on the device (a frame shared with the previous "
+                       "edge is reused) + capped kernel matrix + CSR to host",
            "edge_updates_per_s": n_edges / dt, "ms_per_edge_update": 1e3 * dt / n_edges,
            "nonzeros_per_round": int(total), "gpu_launches_per_edge_update": (g.launch_count() - launches0) / n_edges}
     if cpu:  # the CPU restatement of the same edge loop on the host cores (one round)
