@@ -228,3 +228,91 @@ def test_edge_loop_over_a_four_frame_graph_and_edge_cases():
     with pytest.raises(u.CvoError):
         states[2].update_inner_product()
     g.close()
+
+
+# ------------------------------------------------------------------ CPU: host logic of the mirror
+class _FakeEdgeLib:
+    """Stands in for libcvo_b200's two edge entry points (same two-call CSR protocol), answering
+    from the oracle, so the HOST logic of CvoFrameGPU / BinaryStateGPU (ids, pose narrowing, cap
+    schedule, CSR assembly) is exercised without a GPU.  Test-only."""
+
+    def __init__(self, params):
+        self.params, self.frames, self.calls = params, {}, []
+
+    def cvo_b200_frame_set(self, h, fid, n, xyz, F, feat, C_, lab, geo):
+        self.frames[fid] = n
+        return 0
+
+    def cvo_b200_frame_clear(self, h, fid):
+        self.frames.pop(fid, None)
+        return 0
+
+    def bind(self, clouds):
+        self.clouds = clouds  # frame id -> CvoPointCloud
+
+    def cvo_b200_edge_update(self, h, f1, p1, f2, p2, ell, cap, nnz, mx, row_ptr, cols, vals):
+        import ctypes as C
+        P1 = np.ctypeslib.as_array(p1, shape=(12,)).copy()
+        P2 = np.ctypeslib.as_array(p2, shape=(12,)).copy()
+        self.calls.append((f1, f2, float(ell.value), int(cap), cols is not None))
+        total, sp = oracle.edge_update(self.params, to_oracle_cloud(self.clouds[f1]), P1,
+                                       to_oracle_cloud(self.clouds[f2]), P2, float(ell.value), int(cap))
+        rp, cs, vs = oracle.sparse_to_csr(sp)
+        C.cast(nnz, C.POINTER(C.c_int64))[0] = total
+        C.cast(mx, C.POINTER(C.c_int32))[0] = int(sp["nonzeros"].max()) if len(sp["nonzeros"]) else 0
+        np.ctypeslib.as_array(row_ptr, shape=(len(rp),))[:] = rp
+        if cols is not None and total:
+            np.ctypeslib.as_array(cols, shape=(total,))[:] = cs
+            np.ctypeslib.as_array(vals, shape=(total,))[:] = vs
+        return 0
+
+
+class _FakeGPU:
+    def __init__(self, params):
+        self.params, self._h, self._lib = params, 1, _FakeEdgeLib(params)
+
+    def _check(self, rc):
+        assert rc == 0
+
+    def write_params(self):
+        pass
+
+    _fill_association = u.CvoGPU._fill_association
+
+
+def test_mirror_host_logic_cap_schedule_pose_narrowing_and_two_call_protocol():
+    c1, c2, _ = synthetic_pair(300, 200, 240, 11)
+    p = geometric_params()
+    p.multiframe_num_neighbors, p.multiframe_ell_init = 9, 1.5
+    p.multiframe_ell_min, p.multiframe_ell_decay_rate = 1.0, 0.7
+    g = _FakeGPU(p)
+    f1 = u.CvoFrameGPU(g, c1, pose_rt(0.3, 0.5, -0.2, [0.05, 0.0, -0.1]))
+    f2 = u.CvoFrameGPU(g, c2, np.vstack([pose_rt(0.1, 2.2, 0.0, [0.1, 0.02, 0.35]).reshape(3, 4), [0, 0, 0, 1]]))
+    assert (f1.frame_id, f2.frame_id) == (0, 1) and g._lib.frames == {0: 200, 1: 240}
+    assert f2.pose_vec.shape == (12,) and f1.pose_float().dtype == np.float32
+    g._lib.bind({0: c1, 1: c2})
+    st = u.BinaryStateGPU(f1, f2)  # CvoGPU.cu:1663-1666: cap and ell from the multiframe params
+    assert st.num_neighbors_ == 9 and st.ell_ == pytest.approx(1.5)
+    n0 = st.update_inner_product()
+    total, sp = oracle.edge_update(p, to_oracle_cloud(c1), f1.pose_float(), to_oracle_cloud(c2),
+                                   f2.pose_float(), 1.5, 9)
+    assert n0 == total > 100 and st.last_max_row_nnz == sp["nonzeros"].max()
+    assert np.array_equal(st.A_result_cpu_.cols, oracle.sparse_to_csr(sp)[1])
+    assert st.A_result_cpu_.shape == (200, 240) and st.A_result_cpu_.to_scipy().nnz == total
+    # size query first, then the entries: exactly two calls per update
+    assert [c[4] for c in g._lib.calls] == [False, True]
+    st.last_max_row_nnz = 5            # the next cap: min(9, int(5 * 1.1)) = 5  (IRLS_State_GPU.cu:45-47)
+    st.update_inner_product()
+    assert st.num_neighbors_ == 5 and g._lib.calls[-1][3] == 5
+    st.last_max_row_nnz = 100
+    st.update_inner_product()
+    assert st.num_neighbors_ == 9      # never above the initial cap
+    st.update_ell()                    # IRLS_State_GPU.cpp:54-57
+    assert st.ell_ == pytest.approx(1.05)
+    st.update_ell()
+    assert st.ell_ == pytest.approx(0.735)
+    st.update_ell()                    # 0.735 is not above ell_min = 1.0: no further decay
+    assert st.ell_ == pytest.approx(0.735)
+    assert u.update_edges([st])[0] == st.A_result_cpu_.row_ptr[-1]
+    f1.release()
+    assert 0 not in g._lib.frames
