@@ -169,6 +169,7 @@ def run_reference(args, rank, world):
         return
     import oracle
 
+    oracle.use_all_host_threads()  # torchrun exports OMP_NUM_THREADS=1 to its workers
     name = args.workload or ("C2" if world == 1 else "C4")
     src, tgt, p, desc = load_workload(name)
     N, M = src.num_points(), tgt.num_points()
@@ -265,6 +266,7 @@ def edge_updates_leg(u, rounds=5, cpu=True):
            "nonzeros_per_round": int(total), "gpu_launches_per_edge_update": (g.launch_count() - launches0) / n_edges}
     if cpu:  # the CPU restatement of the same edge loop on the host cores (one round)
         import oracle
+        oracle.use_all_host_threads()
         oc = {id(f): oracle.Cloud(f.points.positions_, f.points.features_, f.points.labels_,
                                   f.points.geometric_types_) for f in frames}
         t0 = time.perf_counter()
@@ -449,6 +451,7 @@ def run_ours(args, rank, world, local_rank):
     # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same registration
     if world == 1 and not args.no_cpu_baseline:
         import oracle
+        oracle.use_all_host_threads()
         q = p.copy()
         q.MAX_ITER = max(2, int(min(p.MAX_ITER, 2.5e11 // (N * M), 4000)))
         cs = oracle.Cloud(src.positions_, src.features_, src.labels_, src.geometric_types_)

@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         L.oracle_transform.restype = None
         L.oracle_transform.argtypes = [f32p, f32p, f32p, C.c_int, f32p]
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         L.oracle_transform_pose_vec.restype = None
         L.oracle_transform_pose_vec.argtypes = [f32p, f32p, C.c_int, f32p]
         L.oracle_edge_update.restype = C.c_ulonglong
@@ -268,3 +270,14 @@ def set_accel(on: bool) -> None:
 
 def num_threads() -> int:
     return int(lib().oracle_num_threads())
+
+
+def use_all_host_threads() -> int:
+    """OpenMP threads = the cores this process may run on, whatever OMP_NUM_THREADS says
+    (torchrun sets it to 1 for its workers).  Returns the count."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    lib().oracle_set_num_threads(int(n))
+    return num_threads()

@@ -30,6 +30,16 @@
 #include <omp.h>
 #endif
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU baseline asks for the host's cores
+ * explicitly (bench.py) instead of inheriting that. */
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -110,6 +110,7 @@ unsigned long long oracle_edge_update(const cvo_b200_params* p, const oracle_clo
                                       const float pose2[12], float ell, int num_neighbors,
                                       oracle_sparse* A);
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 /* 1 (default): rows visit only the targets of the 27 grid cells around them, in ascending order -
  * outputs bit-identical to the dense loop; 0 (or ORACLE_DENSE=1): the literal dense N x M loop. */
 void oracle_set_accel(int on);
