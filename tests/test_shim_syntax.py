@@ -51,3 +51,32 @@ def test_shim_compiles_and_links_against_the_c_abi(tmp_path):
                    "BinaryStateGPU20update_inner_product", "CvoFrameGPUC1", "CvoFrameGPU20transform_pointcloud",
                    "init_internal_SparseKernelMat_cpu"):
         assert member in syms, member
+
+
+def test_cpp_demo_driver_builds_and_fails_cleanly_without_a_gpu(tmp_path):
+    """examples/cvo_align_gpu_two_color_pcd.cpp: the reference's README demo over the C-ABI with
+    no Eigen/PCL.  It must build against libcvo_b200.so, read the demo PCDs like
+    CvoPointCloud(PointXYZRGB) does, and - on a box without a GPU - stop with the library's error
+    message and a non-zero exit code instead of a CPU fallback or an exit() inside the library."""
+    lib = os.path.join(ROOT, "unified_cvo_b200", "csrc", "libcvo_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("libcvo_b200.so not built")
+    exe = tmp_path / "demo"
+    out = subprocess.run([GXX, "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(ROOT, "include"),
+                          os.path.join(ROOT, "examples", "cvo_align_gpu_two_color_pcd.cpp"), "-o", str(exe),
+                          "-L" + os.path.dirname(lib), "-lcvo_b200", "-Wl,-rpath," + os.path.dirname(lib)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    data = os.path.join(ROOT, "tests", "data")
+    run = subprocess.run([str(exe), os.path.join(data, "source.pcd"), os.path.join(data, "target.pcd"),
+                          os.path.join(data, "cvo_outdoor_params.yaml")], capture_output=True, text=True,
+                         cwd=tmp_path, timeout=600)
+    assert "dist is 5.7598" in run.stdout  # |mean(source) - mean(target)| of the demo clouds
+    assert "write ell! ell init is 5.7598" in run.stdout
+    if run.returncode == 0:  # a GPU is present
+        assert "Transform is" in run.stdout and (tmp_path / "after_align.pcd").exists()
+    else:
+        assert run.returncode == 2 and "cvo_b200_create failed" in run.stderr
+    bad = subprocess.run([str(exe), os.path.join(data, "nope.pcd"), os.path.join(data, "target.pcd"),
+                          os.path.join(data, "cvo_outdoor_params.yaml")], capture_output=True, text=True, cwd=tmp_path)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr
