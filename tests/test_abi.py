@@ -87,3 +87,41 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(base, f), errors="replace").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "cvo_oracle" not in txt, f
+
+
+REF = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "cvo_params")), reason="reference tree not present")
+def test_yaml_reader_agrees_with_the_reference_reader_on_every_shipped_parameter_file():
+    """Every cvo_params/*.yaml of the reference through cvo_b200_params_read_yaml against an
+    independent parse: the set of keys is taken from the reference reader itself
+    (fs["key"] in CvoParams.hpp:193-303), a key the reference does not read must leave the default
+    untouched, duplicates resolve to the first occurrence (yaml-cpp), comments are stripped."""
+    hdr = open(os.path.join(REF, "include", "UnifiedCvo", "cvo", "CvoParams.hpp")).read()
+    keys = set(re.findall(r'fs\["([A-Za-z0-9_]+)"\]\.as<', hdr))
+    fields = {f[0] for f in _abi.Params._fields_}
+    assert len(keys) >= 45 and keys <= fields
+    files = sorted(f for f in os.listdir(os.path.join(REF, "cvo_params")) if f.endswith(".yaml"))
+    assert len(files) >= 16
+    checked = 0
+    for name in files:
+        path = os.path.join(REF, "cvo_params", name)
+        first = {}
+        for line in open(path):
+            line = line.split("#", 1)[0].strip()
+            if ":" not in line:
+                continue
+            k, v = (t.strip() for t in line.split(":", 1))
+            if k and v and k not in first:
+                first[k] = v
+        p, d = u.read_params_yaml(path), u.default_params()
+        for k in fields:
+            got = getattr(p, k)
+            if k in keys and k in first:
+                assert got == pytest.approx(float(first[k]), rel=1e-6), (name, k, got, first[k])
+                checked += 1
+            else:  # not in the file, or a key the reference never reads (e.g. is_ell_adaptive)
+                dv = getattr(d, k)
+                assert got == dv or (got != got and dv != dv), (name, k, got, dv)
+    assert checked > 500
