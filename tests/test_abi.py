@@ -125,3 +125,25 @@ def test_yaml_reader_agrees_with_the_reference_reader_on_every_shipped_parameter
                 dv = getattr(d, k)
                 assert got == dv or (got != got and dv != dv), (name, k, got, dv)
     assert checked > 500
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "include")), reason="reference tree not present")
+def test_defaults_and_field_order_agree_with_the_reference_header():
+    """cvo_b200_params against cvo::CvoParams as the reference header declares it: the same fields
+    in the same order (the shim reinterpret_casts one to the other) and every default of the
+    constructor's initialiser list (CvoParams.hpp:12-126)."""
+    hdr = open(os.path.join(REF, "include", "UnifiedCvo", "cvo", "CvoParams.hpp")).read()
+    body = hdr[hdr.index("struct CvoParams"):hdr.index("CvoParams() :")]
+    body = re.sub(r"//[^\n]*", "", body)
+    decl = re.findall(r"\b(float|int|double|unsigned int|bool)\s+([A-Za-z_][A-Za-z0-9_]*)\s*;", body)
+    ours = [(f[0], f[1]) for f in _abi.Params._fields_]
+    assert [n for _, n in decl] == [n for n, _ in ours]
+    ctype = {"float": C.c_float, "int": C.c_int, "double": C.c_double, "unsigned int": C.c_uint, "bool": C.c_bool}
+    for (t, n), (_, ct) in zip(decl, ours):
+        assert C.sizeof(ctype[t]) == C.sizeof(ct), (n, t, ct)
+    init = hdr[hdr.index("CvoParams() :"):hdr.index("{}", hdr.index("CvoParams() :"))]
+    defaults = dict(re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\(([-+0-9.eE]+)\)", init))
+    assert len(defaults) >= 45
+    p = u.default_params()
+    for name, val in defaults.items():
+        assert getattr(p, name) == pytest.approx(float(val), rel=1e-6), name
