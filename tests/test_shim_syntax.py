@@ -80,3 +80,58 @@ def test_cpp_demo_driver_builds_and_fails_cleanly_without_a_gpu(tmp_path):
     bad = subprocess.run([str(exe), os.path.join(data, "nope.pcd"), os.path.join(data, "target.pcd"),
                           os.path.join(data, "cvo_outdoor_params.yaml")], capture_output=True, text=True, cwd=tmp_path)
     assert bad.returncode == 1 and "cannot open" in bad.stderr
+
+
+def _member_signatures(text, cls):
+    """(name, number of parameters, const?) of every member function declared in class/struct
+    `cls` of a header: comments stripped, parentheses matched, top-level commas counted."""
+    import re
+    text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
+    text = re.sub(r"//[^\n]*", " ", text)
+    m = re.search(r"\b(?:class|struct)\s+" + cls + r"\b[^;{]*\{", text)
+    assert m, cls
+    depth, i = 1, m.end()
+    while depth:  # the class body
+        depth += {"{": 1, "}": -1}.get(text[i], 0)
+        i += 1
+    body = text[m.end():i - 1]
+    out = set()
+    for mm in re.finditer(r"(~?[A-Za-z_][A-Za-z0-9_]*)\s*\(", body):
+        name = mm.group(1)
+        if name in ("if", "for", "while", "return", "sizeof", "switch"):
+            continue
+        j, d, angle, commas, empty = mm.end(), 1, 0, 0, True
+        while d and j < len(body):
+            ch = body[j]
+            if ch == "(":
+                d += 1
+            elif ch == ")":
+                d -= 1
+            elif ch == "<":
+                angle += 1
+            elif ch == ">":
+                angle -= 1
+            elif ch == "," and d == 1 and angle == 0:
+                commas += 1
+            if d and not ch.isspace():
+                empty = False
+            j += 1
+        tail = body[j:j + 40].lstrip()
+        out.add((name, 0 if empty else commas + 1, tail.startswith("const")))
+    return out
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/include"), reason="reference tree not present")
+def test_stand_in_declarations_match_the_reference_headers():
+    """shim/stubs/reference_api_stub.hpp is what the shim is compiled against here; every member
+    it declares for CvoGPU, CvoFrameGPU, BinaryStateGPU and CvoFrame must exist in the reference's
+    own header with the same name, parameter count and const-ness, so the shim's definitions match
+    the real declarations where Eigen/PCL exist."""
+    stub = open(os.path.join(ROOT, "shim", "stubs", "reference_api_stub.hpp")).read()
+    inc = "/root/reference/include/UnifiedCvo/cvo"
+    for cls, header in (("CvoGPU", "CvoGPU.hpp"), ("CvoFrameGPU", "CvoFrameGPU.hpp"),
+                        ("BinaryStateGPU", "IRLS_State_GPU.hpp"), ("CvoFrame", "CvoFrame.hpp")):
+        ours = _member_signatures(stub, cls)
+        theirs = _member_signatures(open(os.path.join(inc, header)).read(), cls)
+        assert ours and ours <= theirs, (cls, sorted(ours - theirs))
+    # and the C-ABI calls of the multi-frame binding carry the right argument counts: compiled above
