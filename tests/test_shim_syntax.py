@@ -88,6 +88,8 @@ def _member_signatures(text, cls):
     import re
     text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
     text = re.sub(r"//[^\n]*", " ", text)
+    text = re.sub(r"^\s*#[^\n]*", " ", text, flags=re.M)          # preprocessor lines
+    text = re.sub(r"\b(?:__align__|alignas)\s*\(\s*\d+\s*\)", " ", text)
     m = re.search(r"\b(?:class|struct)\s+" + cls + r"\b[^;{]*\{", text)
     assert m, cls
     depth, i = 1, m.end()
@@ -134,4 +136,11 @@ def test_stand_in_declarations_match_the_reference_headers():
         ours = _member_signatures(stub, cls)
         theirs = _member_signatures(open(os.path.join(inc, header)).read(), cls)
         assert ours and ours <= theirs, (cls, sorted(ours - theirs))
+    # the accessors shim_pack.hpp reads a CvoPointCloud through (utils/CvoPointCloud.hpp:125-146)
+    ours = {s for s in _member_signatures(stub, "CvoPointCloud")}
+    theirs = _member_signatures(open("/root/reference/include/UnifiedCvo/utils/CvoPointCloud.hpp").read(),
+                                "CvoPointCloud")
+    assert {n for n, _, _ in ours} >= {"num_points", "num_classes", "positions", "features", "labels",
+                                       "geometric_types", "size"}
+    assert ours <= theirs, sorted(ours - theirs)
     # and the C-ABI calls of the multi-frame binding carry the right argument counts: compiled above
