@@ -95,6 +95,23 @@ def lib() -> C.CDLL:
         L.oracle_edge_update.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), f32p,
                                          C.POINTER(_Cloud), f32p, C.c_float, C.c_int,
                                          C.POINTER(_Sparse)]
+        f64p = C.POINTER(C.c_double)
+        L.oracle_flow_rows.restype = None
+        L.oracle_flow_rows.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), f32p, C.POINTER(_Sparse),
+                                       f64p, f64p]
+        L.oracle_step_rows.restype = None
+        L.oracle_step_rows.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), f32p, C.c_int,
+                                       C.POINTER(_Sparse), f32p, f32p, C.c_float, f64p]
+        L.oracle_set_device_arith.restype = None
+        L.oracle_set_device_arith.argtypes = [C.c_int]
+        L.oracle_device_arith.restype = C.c_int
+        L.oracle_fill_A.restype = None
+        L.oracle_fill_A.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
+                                    C.c_int, C.c_float, C.POINTER(_Sparse)]
+        L.oracle_fill_A_dense_kernel.restype = None
+        L.oracle_fill_A_dense_kernel.argtypes = [C.POINTER(Params), C.POINTER(_Cloud),
+                                                 C.POINTER(_Cloud), f32p, C.c_int, f32p,
+                                                 C.POINTER(_Sparse)]
         _lib = L
     return _lib
 
@@ -261,6 +278,94 @@ def se3_log_norm(dR, dT):
     t = np.ascontiguousarray(dT, np.float64).reshape(3)
     return float(L.oracle_se3_log_norm(r.ctypes.data_as(C.POINTER(C.c_double)),
                                        t.ctypes.data_as(C.POINTER(C.c_double))))
+
+
+def set_device_arith(on: bool) -> None:
+    """K1's float sums with (default) / without the FMA contractions of the reference's GPU build
+    (see cvo_oracle.c above mul_add())."""
+    lib().oracle_set_device_arith(1 if on else 0)
+
+
+def device_arith() -> bool:
+    return bool(lib().oracle_device_arith())
+
+
+def fill_A(params: Params, src: Cloud, tgt: Cloud, y_moved, num_neighbors: int, ell: float,
+           kernel_inv=None) -> dict:
+    """fill_in_A_mat_gpu (kernel_inv None) / fill_in_A_mat_gpu_dense_mat_kernel on an already
+    moved target; kernel_inv is a 3x3 (row-major numpy) inverse kernel."""
+    L = lib()
+    y = np.ascontiguousarray(y_moved, np.float32).reshape(-1, 3)
+    cs, ct = src.c_struct(), tgt.c_struct()
+    sp = L.oracle_sparse_new(src.n, max(int(num_neighbors), 1))
+    if kernel_inv is None:
+        L.oracle_fill_A(C.byref(params), C.byref(cs), C.byref(ct), _fp(y), int(num_neighbors),
+                        C.c_float(ell), sp)
+    else:
+        K = np.ascontiguousarray(np.asarray(kernel_inv, np.float32).T).reshape(9)
+        L.oracle_fill_A_dense_kernel(C.byref(params), C.byref(cs), C.byref(ct), _fp(y),
+                                     int(num_neighbors), _fp(K), sp)
+    out = _sparse_to_numpy(sp)
+    L.oracle_sparse_free(sp)
+    return out
+
+
+def transform(R, T, y):
+    """update_tf + transform_pointcloud_thrust (CvoGPU.cu:94-112, CvoGPU_impl.cu:31-82): the
+    target moved by the INVERSE of the pose (R, T); R is a 3x3 numpy matrix (row-major)."""
+    L = lib()
+    Rc = np.ascontiguousarray(np.asarray(R, np.float32).T).reshape(9)  # column-major
+    Tc = np.ascontiguousarray(T, np.float32).reshape(3)
+    Rinv = np.zeros(9, np.float32)
+    Tinv = np.zeros(3, np.float32)
+    tf = np.zeros(16, np.float32)
+    L.oracle_update_tf(_fp(Rc), _fp(Tc), _fp(Rinv), _fp(Tinv), _fp(tf))
+    yy = np.ascontiguousarray(y, np.float32).reshape(-1, 3)
+    out = np.empty_like(yy)
+    L.oracle_transform(_fp(Rinv), _fp(Tinv), _fp(yy), len(yy), _fp(out))
+    return out
+
+
+def _sparse_from_dict(L, sp: dict):
+    """An oracle_sparse holding the given matrix (stride = its column count)."""
+    rows, k = sp["mat"].shape
+    h = L.oracle_sparse_new(rows, max(k, 1))
+    s = h.contents
+    s.stride = k
+    if rows * k:
+        np.ctypeslib.as_array(s.mat, shape=(rows * k,))[:] = np.ascontiguousarray(sp["mat"], np.float32).reshape(-1)
+        np.ctypeslib.as_array(s.ind, shape=(rows * k,))[:] = np.ascontiguousarray(sp["ind"], np.int32).reshape(-1)
+    np.ctypeslib.as_array(s.nonzeros, shape=(max(rows, 1),))[:rows] = sp["nonzeros"]
+    return h
+
+
+def flow_rows(params: Params, src: Cloud, y_moved, sparse: dict):
+    """Per-row (omega_i / c, v_i / d) of compute_flow_gpu_no_eigen, [N, 3] doubles each."""
+    L = lib()
+    y = np.ascontiguousarray(y_moved, np.float32).reshape(-1, 3)
+    h = _sparse_from_dict(L, sparse)
+    om = np.zeros((src.n, 3), np.float64)
+    vv = np.zeros((src.n, 3), np.float64)
+    d = C.POINTER(C.c_double)
+    cs = src.c_struct()
+    L.oracle_flow_rows(C.byref(params), C.byref(cs), _fp(y), h, om.ctypes.data_as(d), vv.ctypes.data_as(d))
+    L.oracle_sparse_free(h)
+    return om, vv
+
+
+def step_rows(params: Params, src: Cloud, y_moved, sparse: dict, omega, v, ell: float):
+    """Per-row (B_i, C_i, D_i, E_i) of compute_step_size_xi + _poly_coeff, [N, 4] doubles."""
+    L = lib()
+    y = np.ascontiguousarray(y_moved, np.float32).reshape(-1, 3)
+    h = _sparse_from_dict(L, sparse)
+    out = np.zeros((src.n, 4), np.float64)
+    o = np.ascontiguousarray(omega, np.float32).reshape(3)
+    vv = np.ascontiguousarray(v, np.float32).reshape(3)
+    cs = src.c_struct()
+    L.oracle_step_rows(C.byref(params), C.byref(cs), _fp(y), len(y), h, _fp(o), _fp(vv), C.c_float(ell),
+                       out.ctypes.data_as(C.POINTER(C.c_double)))
+    L.oracle_sparse_free(h)
+    return out
 
 
 def set_accel(on: bool) -> None:

@@ -146,25 +146,41 @@ void oracle_transform(const float Rinv[9], const float Tinv[3], const float* y, 
 }
 
 /* ---------- kernel matrix ------------------------------------------------ */
-/* gpu_utils.cuh:24-41: serial accumulation starting from 0 */
-static inline float dot_serial(const float* a, const float* b, int dim) {
-  float result = 0;
-  for (int i = 0; i < dim; i++) result += a[i] * b[i];
-  return result;
+/* Arithmetic of the float sums of fill_in_A_mat_gpu (the Eigen-free kernel K1).
+ *   0  "as written": every multiply and every add is rounded on its own - what g++ makes of the
+ *      text on x86-64 and what nvcc makes of it with --fmad=false.  Pinned bit for bit against
+ *      oracle/_ref/libcvo_ref_host.so (the reference's own text compiled by g++).
+ *   1  (default) "as the reference's GPU computes": the reference builds Release with nvcc's
+ *      default --fmad=true (CMakeLists.txt:29,79), so nvcc contracts a*b + c into fma(a,b,c).
+ *      oracle/_ref/ref_harness.ptx (the reference's text compiled with its own flags) shows which:
+ *        result += t*t                 -> result = fma(t, t, result)     (gpu_utils.cuh:24-41,97-104)
+ *        dx*dx + dy*dy + dz*dz         -> fma(dz, dz, fma(dx, dx, dy*dy))  (gpu_utils.cuh:73-78, CvoGPU.cu:506)
+ *      everything else of K1 is products, divisions and library calls (no contraction possible).
+ *      Pinned bit for bit on a B200 against oracle/_ref/libcvo_ref_cuda.so (tests, -m gpu).
+ * The Eigen-typed kernels (transform, K2-K4) are not affected: how Eigen's fixed-size
+ * expressions contract is unknowable without Eigen itself, they keep c0 + (c1 + c2). */
+static int g_device_arith = 1;
+void oracle_set_device_arith(int on) { g_device_arith = on ? 1 : 0; }
+int oracle_device_arith(void) { return g_device_arith; }
+static inline float mul_add(int fused, float a, float b, float c) {
+  return fused ? fmaf(a, b, c) : a * b + c;
 }
-static inline float squared_dist_serial(const float* a, const float* b, int dim) {
+/* gpu_utils.cuh:73-78 squared_dist(a, b) of two points, and the norm under CvoGPU.cu:506 */
+static inline float sum_sq3(int fused, float dx, float dy, float dz) {
+  if (fused) return fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+  return dx * dx + dy * dy + dz * dz;
+}
+/* gpu_utils.cuh:24-41: serial accumulation starting from 0 */
+static inline float dot_serial(int fused, const float* a, const float* b, int dim) {
   float result = 0;
-  for (int i = 0; i < dim; i++) {
-    float tmp = (a[i] - b[i]);
-    result += tmp * tmp;
-  }
+  for (int i = 0; i < dim; i++) result = mul_add(fused, a[i], b[i], result);
   return result;
 }
 /* CvoGPU.cu:203-215 compute_geometric_type_ip */
-static inline float geometric_type_ip(const float* ga, const float* gb) {
-  float norm2_a = dot_serial(ga, ga, 2);
-  float norm2_b = dot_serial(gb, gb, 2);
-  float dot_ab = dot_serial(ga, gb, 2);
+static inline float geometric_type_ip(int fused, const float* ga, const float* gb) {
+  float norm2_a = dot_serial(fused, ga, ga, 2);
+  float norm2_b = dot_serial(fused, gb, gb, 2);
+  float dot_ab = dot_serial(fused, ga, gb, 2);
   return dot_ab * dot_ab / (norm2_a * norm2_b);
 }
 /* CvoGPU.cu:86-90 compute_range_ell */
@@ -302,6 +318,7 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
   const int Ca = src->C, Cb = tgt->C;
   sparse_clear(A, num_neighbors);
   (void)F;
+  const int fused = g_device_arith;
 
   /* accelerated candidate enumeration (see above): edge = the largest cut-off radius of any row */
   cand_grid grid;
@@ -311,7 +328,7 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
     int finite_rows = 1;
     for (int i = 0; i < a_size; i++) {
       const float* pa = src->xyz + 3 * (size_t)i;
-      const float d = sqrtf(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2]);
+      const float d = sqrtf(sum_sq3(fused, pa[0], pa[1], pa[2]));
       if (isfinite(d)) { if (d > dmax) dmax = d; } else finite_rows = 0;
     }
     (void)finite_rows; /* non-finite rows produce no candidates and no survivors either way */
@@ -335,7 +352,7 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
     float s_sigma2 = p->s_sigma * p->s_sigma;
     const float* pa = src->xyz + 3 * (size_t)i;
     /* :506-507 */
-    float a_to_sensor = sqrtf(pa[0] * pa[0] + pa[1] * pa[1] + pa[2] * pa[2]);
+    float a_to_sensor = sqrtf(sum_sq3(fused, pa[0], pa[1], pa[2]));
     float l = range_ell(ell, a_to_sensor);
     /* :509-515 (device log(float) resolves to logf, crt/math_functions.hpp) */
     float d2_thres = 1, d2_c_thres = 1, d2_s_thres = 1;
@@ -363,13 +380,13 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
       float a = 1, sk = 1, ck = 1, k = 1, geo_sim = 1;
       if (p->is_using_geometric_type) { /* :535-547 */
         const float* gb = tgt->geotype ? tgt->geotype + 2 * (size_t)j : kZero2;
-        geo_sim = geometric_type_ip(ga, gb);
+        geo_sim = geometric_type_ip(fused, ga, gb);
         if (geo_sim < 0.01) continue;
       }
       if (p->is_using_geometry) {
         if (!kernel_inv) { /* :549-554, squared_dist(*p_b,*p_a) gpu_utils.cuh:73-78 */
           float dx = pb[0] - pa[0], dy = pb[1] - pa[1], dz = pb[2] - pa[2];
-          float d2 = dx * dx + dy * dy + dz * dz;
+          float d2 = sum_sq3(fused, dx, dy, dz);
           if (d2 < d2_thres)
             k = sigma2 * exp(-d2 / (2.0 * l * l));
           else
@@ -392,7 +409,7 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
           float fa = (src->feat && f < Fa) ? src->feat[(size_t)i * Fa + f] : 0.f;
           float fb = (tgt->feat && f < Fb) ? tgt->feat[(size_t)j * Fb + f] : 0.f;
           float tmp = (fa - fb);
-          d2_color += tmp * tmp;
+          d2_color = mul_add(fused, tmp, tmp, d2_color);
         }
         if (d2_color < d2_c_thres)
           ck = c_sigma2 * exp(-d2_color / (2.0 * c2));
@@ -406,7 +423,7 @@ static void fill_A_impl(const cvo_b200_params* p, const oracle_cloud* src,
           float la = (src->labels && c < Ca) ? src->labels[(size_t)i * Ca + c] : 0.f;
           float lb = (tgt->labels && c < Cb) ? tgt->labels[(size_t)j * Cb + c] : 0.f;
           float tmp = (la - lb);
-          d2_semantic += tmp * tmp;
+          d2_semantic = mul_add(fused, tmp, tmp, d2_semantic);
         }
         if (d2_semantic < d2_s_thres) {
           if (kernel_inv) {
@@ -448,6 +465,7 @@ void oracle_fill_A_dense_kernel(const cvo_b200_params* p, const oracle_cloud* sr
 }
 
 /* ---------- flow --------------------------------------------------------- */
+static double* g_rows_out[2] = {NULL, NULL}; /* oracle_flow_rows / oracle_step_rows taps */
 void oracle_compute_flow(const cvo_b200_params* p, const oracle_cloud* src,
                          const float* y_moved, const oracle_sparse* A, double omega_sum[3],
                          double v_sum[3], float omega[3], float v[3]) {
@@ -486,6 +504,8 @@ void oracle_compute_flow(const cvo_b200_params* p, const oracle_cloud* src,
       omega_sum[k] += om_all[3 * (size_t)i + k];
       v_sum[k] += v_all[3 * (size_t)i + k];
     }
+  if (g_rows_out[0]) memcpy(g_rows_out[0], om_all, sizeof(double) * 3 * (size_t)rows);
+  if (g_rows_out[1]) memcpy(g_rows_out[1], v_all, sizeof(double) * 3 * (size_t)rows);
   free(om_all);
   free(v_all);
   /* :824-832 cast to float, joint normalisation (Eigen normalize: z>0 ? /= sqrt(z)) */
@@ -689,6 +709,7 @@ float oracle_compute_step(const cvo_b200_params* p, const oracle_cloud* src,
     D += Bv[4 * (size_t)i + 2];
     E += Bv[4 * (size_t)i + 3];
   }
+  if (g_rows_out[0]) memcpy(g_rows_out[0], Bv, sizeof(double) * 4 * (size_t)rows);
   free(Bv);
   free(xiz); free(xi2z); free(xi3z); free(xi4z);
   free(normxiz2); free(xiz_dot_xi2z); free(epsil_const);
@@ -709,6 +730,28 @@ float oracle_compute_step(const cvo_b200_params* p, const oracle_cloud* src,
   else
     step = (float)temp_step;
   return step;
+}
+
+/* per-row outputs of the two passes above (the reference keeps them in omega_gpu / v_gpu and
+ * B..E device vectors before its thrust reductions): what tests/test_ref_pin*.py compare with the
+ * reference's own K2 / K3+K4.  Not thread-safe (test taps). */
+void oracle_flow_rows(const cvo_b200_params* p, const oracle_cloud* src, const float* y_moved,
+                      const oracle_sparse* A, double* omega_rows, double* v_rows) {
+  double os[3], vs[3];
+  float o[3], v[3];
+  g_rows_out[0] = omega_rows;
+  g_rows_out[1] = v_rows;
+  oracle_compute_flow(p, src, y_moved, A, os, vs, o, v);
+  g_rows_out[0] = g_rows_out[1] = NULL;
+}
+void oracle_step_rows(const cvo_b200_params* p, const oracle_cloud* src, const float* y_moved, int m,
+                      const oracle_sparse* A, const float omega[3], const float v[3], float ell,
+                      double* bcde_rows /* rows x 4 */) {
+  double bcde[4];
+  g_rows_out[0] = bcde_rows;
+  g_rows_out[1] = NULL;
+  (void)oracle_compute_step(p, src, y_moved, m, A, omega, v, ell, bcde);
+  g_rows_out[0] = NULL;
 }
 
 /* ---------- Lie group ---------------------------------------------------- */

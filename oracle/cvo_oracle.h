@@ -5,18 +5,26 @@
  * or call this; only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, as the checker / the CPU arm.
  *
- * PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or
- * fixtures for this path and cannot be compiled in this
- * image (Eigen, Sophus, PCL, yaml-cpp, TBB absent), so this restatement could
- * not be checked against outputs of the reference itself.  It is pinned only
- * by (i) an independent numpy brute-force restatement agreeing with it
- * (tests/test_oracle.py), (ii) analytic invariants, and (iii) the committed
- * fixtures under tests/golden/ that freeze ITS outputs against regressions.
+ * PARITY: what is pinned against the reference itself, and what is not.
+ *   PINNED (tier 1): fill_in_A_mat_gpu (CvoGPU.cu:477-593) with compute_range_ell,
+ *   compute_geometric_type_ip and the gpu_utils.cuh helpers - the dominant kernel, which uses no
+ *   Eigen/PCL/thrust - is compiled FROM THE REFERENCE'S OWN TEXT by oracle/make_ref.py into
+ *   oracle/_ref/ (g++ host build, nvcc sm_100a builds); oracle_fill_A equals it bit for bit
+ *   (values, indices, counts): tests/test_ref_pin.py (CPU) and tests/test_ref_pin_gpu.py (B200).
+ *   PINNED MODULO EIGEN (tier 2): the dense-kernel variant K1b, compute_flow_gpu_no_eigen (K2),
+ *   compute_step_size_xi / _poly_coeff (K3, K4) are compiled from the reference's text too, but
+ *   against oracle/ref_mini_eigen.h, our stand-in for Eigen's fixed-size 3-vector primitives:
+ *   formulas, float/double mix and statement order are the reference's, the evaluation order
+ *   inside a 3-term product/reduction is our reading of Eigen 3.3 (c0 + (c1 + c2)).
+ *   UNPINNED: the host controller (align_impl's schedule, Exp_SEK3, the cubic via Eigen's
+ *   eigenvalue solver, Sophus' SE3 log) - needs Eigen/Sophus proper; checked only against an
+ *   independent numpy restatement, closed forms (numpy.roots, scipy expm/logm) and invariants.
  *
  * Each function cites the reference file:line it follows (paths relative to
  * /root/reference).  Arithmetic types follow the C++ promotion rules of the
  * cited lines literally (float products, double exp, double row sums, ...);
- * compile with -ffp-contract=off so no FMA contraction sneaks in.
+ * compile with -ffp-contract=off: the only fused operations are the explicit fmaf() calls of the
+ * device-arithmetic mode.
  */
 #ifndef CVO_ORACLE_H_
 #define CVO_ORACLE_H_
@@ -75,6 +83,13 @@ void oracle_compute_flow(const cvo_b200_params* p, const oracle_cloud* src,
 float oracle_compute_step(const cvo_b200_params* p, const oracle_cloud* src,
                           const float* y_moved, int m, const oracle_sparse* A,
                           const float omega[3], const float v[3], float ell, double BCDE[4]);
+/* the per-row values of the two passes above, before their reductions: omega_i/c, v_i/d
+ * (rows x 3 doubles each) and B_i, C_i, D_i, E_i (rows x 4 doubles).  Test taps. */
+void oracle_flow_rows(const cvo_b200_params* p, const oracle_cloud* src, const float* y_moved,
+                      const oracle_sparse* A, double* omega_rows, double* v_rows);
+void oracle_step_rows(const cvo_b200_params* p, const oracle_cloud* src, const float* y_moved, int m,
+                      const oracle_sparse* A, const float omega[3], const float v[3], float ell,
+                      double* bcde_rows);
 /* LieGroup.cpp:245-274 Exp_SEK3 (K=1); out = 3x4 column-major float */
 void oracle_exp_sek3(const float xi[6], float dt, float out12[12]);
 /* LieGroup.cpp:309-325 poly_solver_order3 (double overload): roots of
@@ -114,6 +129,12 @@ void oracle_set_num_threads(int n);
 /* 1 (default): rows visit only the targets of the 27 grid cells around them, in ascending order -
  * outputs bit-identical to the dense loop; 0 (or ORACLE_DENSE=1): the literal dense N x M loop. */
 void oracle_set_accel(int on);
+/* Arithmetic of K1's float sums: 1 (default) = with the FMA contractions nvcc applies to the
+ * reference's text under the reference's own flags (what its GPU path computes), 0 = every
+ * multiply/add rounded separately (the text compiled by g++ / nvcc --fmad=false).  See the
+ * comment above mul_add() in cvo_oracle.c. */
+void oracle_set_device_arith(int on);
+int oracle_device_arith(void);
 
 #ifdef __cplusplus
 }

@@ -1,9 +1,10 @@
 """Generates the committed golden fixtures from the ORACLE (oracle/cvo_oracle.c).
 
-The reference ships no golden vectors for this path and cannot be built here
-(SURVEY.md §4, §8c), so these fixtures freeze the oracle's outputs: they guard the
-oracle against regressions and give the GPU parity tests inputs/outputs that do not need
-the oracle at run time.  Regenerate with:  python tests/golden/make_golden.py
+The reference ships no golden vectors for this path, so these fixtures
+freeze the oracle's outputs (in its default arithmetic = the reference's GPU build, see
+oracle/cvo_oracle.c above mul_add(); the oracle's K1-K4 are pinned against the reference's own
+kernel text by tests/test_ref_pin*.py): they guard the oracle against regressions and give the
+GPU parity tests inputs/outputs that do not need the oracle at run time.  Regenerate with:  python tests/golden/make_golden.py
 Each fixture holds teacher-forced single iterations: the state (R, T, ell, cap) taken
 from the oracle's own align() trajectory and the iteration's outputs at that state.
 """

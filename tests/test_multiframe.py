@@ -56,6 +56,7 @@ def test_oracle_pose_transform_is_bit_identical_to_numpy():
     assert np.array_equal(oracle.transform_pose_vec(I, x), x)  # the identity pose moves nothing
 
 
+@pytest.mark.usefixtures("as_written_arithmetic")
 @pytest.mark.parametrize("cap,ell,colour", [(40, 0.9, False), (5, 1.5, False), (12, 1.2, True)])
 def test_oracle_edge_update_matches_numpy_restatement(cap, ell, colour):
     if colour:

@@ -20,6 +20,7 @@ def _csr_rows(sp):
             for i in range(len(sp["nonzeros"]))]
 
 
+@pytest.mark.usefixtures("as_written_arithmetic")
 @pytest.mark.parametrize("cap,ell", [(256, 0.95), (3, 2.5), (1, 1.5), (7, 0.4)])
 def test_fill_and_flow_match_numpy_restatement_geometric(cap, ell):
     src, tgt, _ = synthetic_pair(300, 200, 240, 11)
@@ -41,6 +42,7 @@ def test_fill_and_flow_match_numpy_restatement_geometric(cap, ell):
     assert tr.max_row_nnz <= cap
 
 
+@pytest.mark.usefixtures("as_written_arithmetic")
 def test_fill_matches_numpy_with_color_semantics_geotype_and_pose():
     src, tgt, _ = synthetic_pair(260, 150, 200, 5, F=5, C=4, geotype=True)
     p = u.read_params_yaml(os.path.join(DATA, "cvo_semantic_params_img_gpu0.yaml"))

@@ -1,0 +1,189 @@
+"""The oracle pinned against the REFERENCE'S OWN kernels (CPU half).
+
+oracle/make_ref.py compiles the reference's text of fill_in_A_mat_gpu (CvoGPU.cu:477-593) and its
+helpers — no Eigen, no PCL, no thrust in it — with g++ into oracle/_ref/libcvo_ref_host.so (the
+grid becomes a host loop).  Tier 1 below asserts oracle_fill_A ≡ that kernel BIT FOR BIT (stored
+values, column indices, per-row counts) in the oracle's "as written" arithmetic.  Tier 2 does the
+same for K1b / K2 / K3+K4, whose Eigen 3-vector primitives come from oracle/ref_mini_eigen.h (ours).
+The B200 half (nvcc builds with the reference's own flags, the CUDA product against them) is
+tests/test_ref_pin_gpu.py.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from oracle import ref
+import unified_cvo_b200 as u
+from helpers import DATA, demo_clouds, demo_params, geometric_params, synthetic_pair, to_oracle_cloud
+
+pytestmark = pytest.mark.skipif(not ref.available("host"),
+                                reason="oracle/_ref not built (python oracle/make_ref.py needs /root/reference)")
+
+
+@pytest.fixture(autouse=True)
+def as_written_arithmetic():
+    """g++ does not contract on x86-64: compare with the oracle's uncontracted mode."""
+    oracle.set_device_arith(False)
+    yield
+    oracle.set_device_arith(True)
+
+
+def assert_same_matrix(got, want, what=""):
+    """bit for bit: counts, indices (incl. the -1 fill), values (incl. the zero fill)"""
+    assert np.array_equal(got["nonzeros"], want["nonzeros"]), f"{what}: per-row counts differ"
+    assert np.array_equal(got["ind"], want["ind"]), f"{what}: column indices differ"
+    assert np.array_equal(got["mat"].view(np.uint32), want["mat"].view(np.uint32)), f"{what}: values differ"
+
+
+def rot_z(deg):
+    a = np.deg2rad(deg)
+    return np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], np.float32)
+
+
+@pytest.mark.parametrize("color", [True, False])
+def test_demo_pcds_at_the_drivers_ell_init_saturating_rows(color):
+    """config 1: demo_data at ell = |mean(src) - mean(tgt)| = 5.76 (two_color_pcd.cpp:56-60),
+    cap 256: rows saturate (the densest has 507 geometric survivors)."""
+    src, tgt = demo_clouds(color=color)
+    p = demo_params(src, tgt, color=color)
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    cap = int(p.nearest_neighbors_max)
+    want = ref.fill_A(p, cs, ct, ct.xyz, cap, float(p.ell_init))
+    got = oracle.fill_A(p, cs, ct, ct.xyz, cap, float(p.ell_init))
+    assert_same_matrix(got, want, "demo")
+    assert want["nonzero_sum"] > 5000
+    if not color:
+        assert int(want["nonzeros"].max()) == cap  # the truncation rule is exercised
+    # the literal dense loop of the oracle as well (the grid-accelerated enumeration is the default)
+    oracle.set_accel(False)
+    try:
+        assert_same_matrix(oracle.fill_A(p, cs, ct, ct.xyz, cap, float(p.ell_init)), want, "demo/dense")
+    finally:
+        oracle.set_accel(True)
+
+
+@pytest.mark.parametrize("ell,cap", [(0.95, 256), (0.3, 256), (0.95, 5), (2.0, 1)])
+def test_c2_sized_geometric(ell, cap):
+    """config 2: N = M = 10 000 synthetic, geometric kernel, a moved target."""
+    src, tgt, _ = synthetic_pair(12500, 10000, 10000, 20002)
+    p = geometric_params()
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    ym = oracle.transform(rot_z(1.0), [0.02, -0.01, 0.3], ct.xyz)
+    want = ref.fill_A(p, cs, ct, ym, cap, ell)
+    got = oracle.fill_A(p, cs, ct, ym, cap, ell)
+    assert_same_matrix(got, want, f"C2 ell={ell} cap={cap}")
+    assert want["nonzero_sum"] > 1000
+
+
+def test_colour_semantics_geotype_moved_target():
+    """all four factors of the kernel: 5-dim colour, 19-class semantics (the width the reference is
+    compiled for), geometric types; the shipped semantic KITTI parameter set."""
+    src, tgt, _ = synthetic_pair(4000, 3000, 3300, 31, F=5, C=19, geotype=True)
+    p = u.read_params_yaml(os.path.join(DATA, "cvo_semantic_params_img_gpu0.yaml"))
+    p.is_using_geometric_type = 1
+    p.c_ell = 1.0      # random colours and labels: loosen the kernels so that pairs survive them
+    p.sp_thres = 0.001
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    ym = oracle.transform(rot_z(-2.0), [0.05, 0.02, 0.5], ct.xyz)
+    for ell, cap in ((1.2, 512), (0.6, 9)):
+        want = ref.fill_A(p, cs, ct, ym, cap, ell)
+        assert_same_matrix(oracle.fill_A(p, cs, ct, ym, cap, ell), want, f"full kernel ell={ell}")
+        assert want["nonzero_sum"] > 200
+        assert int(want["nonzeros"].max()) <= cap
+
+
+def test_rgbd_parameter_set_with_semantics_stores_nothing():
+    """BASELINE config 5 verbatim: cvo_rgbd_params.yaml + is_using_semantics=1.  sigma^2 * c_sigma^2
+    * s_sigma^2 = 0.01 * 0.36 * 0.64 = 0.0023 < sp_thres = 0.003: no pair can pass a > sp_thres."""
+    src, tgt, _ = synthetic_pair(3000, 2400, 2400, 20006, F=5, C=19)
+    p = u.read_params_yaml(os.path.join(DATA, "cvo_rgbd_params.yaml"))
+    p.is_using_semantics = 1
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    want = ref.fill_A(p, cs, ct, ct.xyz, int(p.nearest_neighbors_max), float(p.ell_init))
+    got = oracle.fill_A(p, cs, ct, ct.xyz, int(p.nearest_neighbors_max), float(p.ell_init))
+    assert_same_matrix(got, want, "config 5")
+    assert want["nonzero_sum"] == 0
+
+
+def test_all_zero_geometric_types_are_nan_and_dropped():
+    """clouds built by reserve/add_point have zero geometric types: geo_sim = 0/0 = NaN, the pair is
+    not skipped (NaN < 0.01 is false) and not stored (a = NaN > sp_thres is false)."""
+    src, tgt, _ = synthetic_pair(700, 500, 600, 3)
+    p = geometric_params()
+    p.is_using_geometric_type = 1
+    cs = oracle.Cloud(src.positions_, geotype=np.zeros((500, 2), np.float32))
+    gt = np.zeros((600, 2), np.float32)
+    gt[::2] = (0.0, 1.0)  # every other target has a type: still NaN through the source's zeros
+    ct = oracle.Cloud(tgt.positions_, geotype=gt)
+    want = ref.fill_A(p, cs, ct, ct.xyz, 64, 0.95)
+    assert_same_matrix(oracle.fill_A(p, cs, ct, ct.xyz, 64, 0.95), want, "NaN geo type")
+    assert want["nonzero_sum"] == 0
+    # and a mixed case where only some rows are affected
+    gs = np.tile(np.array([[1.0, 0.0]], np.float32), (500, 1))
+    gs[100:200] = 0.0
+    gs[300:] = (0.0, 1.0)
+    cs2 = oracle.Cloud(src.positions_, geotype=gs)
+    want = ref.fill_A(p, cs2, ct, ct.xyz, 64, 0.95)
+    assert_same_matrix(oracle.fill_A(p, cs2, ct, ct.xyz, 64, 0.95), want, "mixed geo types")
+    assert 0 < want["nonzero_sum"]
+    assert want["nonzeros"][100:200].sum() == 0
+
+
+def test_ragged_and_degenerate_shapes():
+    src, tgt, _ = synthetic_pair(700, 513, 1, 9)  # 513 rows: one thread past a 512 block; one target
+    p = geometric_params()
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    for cap in (1, 4):
+        want = ref.fill_A(p, cs, ct, ct.xyz, cap, 50.0)  # ell so large that every row keeps the target
+        assert_same_matrix(oracle.fill_A(p, cs, ct, ct.xyz, cap, 50.0), want, "one target")
+        assert want["nonzero_sum"] == 513
+    # geometry switched off: every pair passes, rows hold the first `cap` targets with a = sigma^2... = 1
+    src, tgt, _ = synthetic_pair(200, 64, 90, 10)
+    p.is_using_geometry = 0
+    p.sp_thres = 0.5
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    want = ref.fill_A(p, cs, ct, ct.xyz, 7, 0.5)
+    assert_same_matrix(oracle.fill_A(p, cs, ct, ct.xyz, 7, 0.5), want, "no geometry")
+    assert np.array_equal(want["ind"][0], np.arange(7))
+
+
+# ------------------------------------------------------------------ tier 2 (Eigen stand-in)
+def test_dense_kernel_variant_k1b():
+    """fill_in_A_mat_gpu_dense_mat_kernel (CvoGPU.cu:217-327) with an anisotropic kernel."""
+    src, tgt, _ = synthetic_pair(1500, 1000, 1200, 77, F=5)
+    p = u.read_params_yaml(os.path.join(DATA, "cvo_intensity_params_img_gpu0.yaml"))
+    p.c_ell = 0.6
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    K = np.array([[0.30, 0.02, 0.00], [0.02, 0.20, 0.01], [0.00, 0.01, 0.50]], np.float32)
+    Kinv = np.linalg.inv(K.astype(np.float64)).astype(np.float32)
+    for cap in (256, 6):
+        want = ref.fill_A(p, cs, ct, ct.xyz, cap, 0.0, kernel_inv=Kinv)
+        got = oracle.fill_A(p, cs, ct, ct.xyz, cap, 0.0, kernel_inv=Kinv)
+        assert_same_matrix(got, want, f"K1b cap={cap}")
+        assert want["nonzero_sum"] > 100
+
+
+@pytest.mark.parametrize("range_ell", [0, 1])
+def test_flow_and_step_rows_k2_k3_k4(range_ell):
+    """compute_flow_gpu_no_eigen and compute_step_size_xi/_poly_coeff on a matrix produced by K1:
+    per-row outputs equal bit for bit (same formulas, same float/double mix, same order)."""
+    src, tgt, _ = synthetic_pair(3000, 2000, 2500, 123)
+    p = geometric_params()
+    p.is_using_range_ell = range_ell
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    ym = oracle.transform(rot_z(0.7), [0.01, 0.03, 0.2], ct.xyz)
+    ell, cap = 0.8, 40
+    A = ref.fill_A(p, cs, ct, ym, cap, ell)
+    om_w, v_w = ref.flow_rows(p, cs.xyz, ym, A)
+    om_g, v_g = oracle.flow_rows(p, cs, ym, A)
+    assert np.array_equal(om_g, om_w) and np.array_equal(v_g, v_w)
+    assert np.abs(om_w).sum() > 0
+    # a unit twist, as compute_flow hands it on
+    tw = np.concatenate([om_w.sum(0), v_w.sum(0)]).astype(np.float32)
+    tw /= np.linalg.norm(tw)
+    want = ref.step_rows(tw[:3], tw[3:], ell, float(p.ell_init), range_ell, cs.xyz, ym, A)
+    got = oracle.step_rows(p, cs, ym, A, tw[:3], tw[3:], ell)
+    assert np.array_equal(got, want)
+    assert np.abs(want).sum() > 0

@@ -468,6 +468,13 @@ struct RowCtx {
 __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& kc,
                                           const RowCtx& rc, int i_global, int view, int j,
                                           const float4& pb, float& a_out) {
+  // ARITHMETIC: this is the reference's kernel AS ITS GPU BUILD COMPUTES IT.  The reference compiles
+  // Release with nvcc's default --fmad=true (CMakeLists.txt:29,79), so the multiply-adds of its
+  // text are contracted; oracle/_ref/ref_harness.ptx (the reference's own text under its own
+  // flags, built by oracle/make_ref.py) shows which: `result += t*t` -> fma(t,t,result) in
+  // dot / squared_dist / square_norm, and dx*dx + dy*dy + dz*dz -> fma(dz,dz,fma(dx,dx,dy*dy)).
+  // This file is compiled with --fmad=false, so the contractions are spelled out here and nothing
+  // else is fused.  tests/test_ref_pin_gpu.py holds the result to the reference kernel bit for bit.
   // The reference interleaves tests and kernel values (geometry test -> k = exp -> colour test ->
   // ck = exp -> ...).  Every test only rejects the pair (no side effect), so all the cheap float
   // tests run first and the double-precision exps only for pairs that pass them all: the same
@@ -477,22 +484,16 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
   float d2 = 0.f, d2_color = 0.f, d2_semantic = 0.f;
   if (kc.use_geo_type && A.mode == 0) {  // mode 1 switches it off, CvoGPU.cu:1948-1949
     const float2 gb = A.tv[view].geo[j];
-    float norm2_a = 0.f;
-    norm2_a += rc.ga[0] * rc.ga[0];
-    norm2_a += rc.ga[1] * rc.ga[1];
-    float norm2_b = 0.f;
-    norm2_b += gb.x * gb.x;
-    norm2_b += gb.y * gb.y;
-    float dot_ab = 0.f;
-    dot_ab += rc.ga[0] * gb.x;
-    dot_ab += rc.ga[1] * gb.y;
+    const float norm2_a = __fmaf_rn(rc.ga[1], rc.ga[1], __fmaf_rn(rc.ga[0], rc.ga[0], 0.f));
+    const float norm2_b = __fmaf_rn(gb.y, gb.y, __fmaf_rn(gb.x, gb.x, 0.f));
+    const float dot_ab = __fmaf_rn(rc.ga[1], gb.y, __fmaf_rn(rc.ga[0], gb.x, 0.f));
     geo_sim = dot_ab * dot_ab / (norm2_a * norm2_b);
     if (geo_sim < 0.01) return false;
   }
   if (kc.use_geometry) {
     if (A.mode == 0) {
       const float dx = pb.x - rc.px[0], dy = pb.y - rc.px[1], dz = pb.z - rc.px[2];
-      d2 = dx * dx + dy * dy + dz * dz;
+      d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, dy * dy));  // gpu_utils.cuh:73-78 as nvcc contracts it
       if (!(d2 < rc.d2_thres)) return false;
     } else {
       const float dist[3] = {rc.px[0] - pb.x, rc.px[1] - pb.y, rc.px[2] - pb.z};
@@ -520,13 +521,13 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       const float4 va = *reinterpret_cast<const float4*>(fa + f);
       const float4 vb = *reinterpret_cast<const float4*>(fb + f);
       float tmp = va.x - vb.x;
-      d2_color += tmp * tmp;
+      d2_color = __fmaf_rn(tmp, tmp, d2_color);
       tmp = va.y - vb.y;
-      d2_color += tmp * tmp;
+      d2_color = __fmaf_rn(tmp, tmp, d2_color);
       tmp = va.z - vb.z;
-      d2_color += tmp * tmp;
+      d2_color = __fmaf_rn(tmp, tmp, d2_color);
       tmp = va.w - vb.w;
-      d2_color += tmp * tmp;
+      d2_color = __fmaf_rn(tmp, tmp, d2_color);
     }
     if (!(d2_color < kc.d2_c_thres)) return false;
   }
@@ -537,13 +538,13 @@ __device__ __forceinline__ bool eval_pair(const IterArgs& A, const KernConsts& k
       const float4 va = *reinterpret_cast<const float4*>(la + c);
       const float4 vb = *reinterpret_cast<const float4*>(lb + c);
       float tmp = va.x - vb.x;
-      d2_semantic += tmp * tmp;
+      d2_semantic = __fmaf_rn(tmp, tmp, d2_semantic);
       tmp = va.y - vb.y;
-      d2_semantic += tmp * tmp;
+      d2_semantic = __fmaf_rn(tmp, tmp, d2_semantic);
       tmp = va.z - vb.z;
-      d2_semantic += tmp * tmp;
+      d2_semantic = __fmaf_rn(tmp, tmp, d2_semantic);
       tmp = va.w - vb.w;
-      d2_semantic += tmp * tmp;
+      d2_semantic = __fmaf_rn(tmp, tmp, d2_semantic);
     }
     const float thr = (A.mode == 1) ? kc.d2_s_thres_dense : kc.d2_s_thres;
     if (!(d2_semantic < thr)) return false;
@@ -2056,8 +2057,22 @@ __global__ void finalize_step_kernel(IterArgs A, const double* gathered, int str
   controller_step(A, st, tot, &s_ctrl);
 }
 // host-initialised state needs the same Rinv/Tinv/bound update_tf_device computes
+// The log-dependent constants of fill_in_A_mat_gpu's prologue (CvoGPU.cu:509-515, :246-254 for the
+// dense-kernel variant) with the DEVICE overloads the reference's threads call: log(float) is
+// logf, whose device implementation is not glibc's (they may differ in the last bit), the products
+// are double.  The host (make_consts) fills everything else.
+__device__ void device_consts(KernConsts& k) {
+  k.log_geo = logf(k.sp_thres / k.sigma2);
+  k.d2_c_thres = k.d2_s_thres = k.d2_s_thres_dense = 1.f;
+  if (k.use_intensity) k.d2_c_thres = -2.0 * k.c2 * logf(k.sp_thres / k.c_sigma2);
+  if (k.use_semantics) {
+    k.d2_s_thres = -2.0 * k.s_ell * k.s_ell * logf(k.sp_thres / k.s_sigma2);
+    k.d2_s_thres_dense = -2.0 * k.s_ell_square * logf(k.sp_thres / k.s_sigma2);
+  }
+}
 __global__ void init_bound_kernel(IterArgs A) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  device_consts(A.st->kc);
   update_tf_device(A, A.st);
 }
 

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(kStatThreads) cloud_stats_kernel(const float* 
       sum[0] += x; sum[1] += y; sum[2] += z;
       cnt++;
     }
-    const float d = sqrtf((x * x + y * y) + z * z);  // a_to_sensor (CvoGPU.cu:506)
+    const float d = sqrtf(__fmaf_rn(z, z, __fmaf_rn(x, x, y * y)));  // a_to_sensor (CvoGPU.cu:506)
     if (d > md) md = d;                               // NaN compares false
   }
 #pragma unroll
@@ -167,7 +167,8 @@ __global__ void cloud_gather_kernel(GatherArgs G) {
   G.xyz[s] = make_float4(x, y, z, pack_colour(i));
   G.xyz_o[s] = make_float4(G.xyz3[3 * (size_t)s], G.xyz3[3 * (size_t)s + 1], G.xyz3[3 * (size_t)s + 2],
                            pack_colour(s));
-  const float dist = sqrtf((x * x + y * y) + z * z);
+  // CvoGPU.cu:506 as the reference's GPU build contracts it (see eval_pair, cvo_kernels.cu)
+  const float dist = sqrtf(__fmaf_rn(z, z, __fmaf_rn(x, x, y * y)));
   const float cx = G.st->centroid[0], cy = G.st->centroid[1], cz = G.st->centroid[2];
   // prefilter record: a = -2 (x - c) and the reference's a_to_sensor
   G.rowA[s] = make_float4(-2.f * (x - cx), -2.f * (y - cy), -2.f * (z - cz), dist);
