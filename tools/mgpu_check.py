@@ -31,6 +31,8 @@ print(f"rank {rank}: launches of the fused align: {g.launch_count() - l0}")
 if os.environ.get("CVO_B200_STAMPS"):
     g.time_iterations(np.eye(3), np.zeros(3), 0.3, 64, 200, pair_kernel=False)
 okf = all(not compare_traces(tr2[k], tr0[k]) for k in range(8))
+assert okf, "fused path: first 8 iterations differ from the single-GPU run"
+assert np.array_equal(T2, T1), "fused and NCCL paths end on different poses"
 print(f"rank {rank}: fused x{world} iters {i2.iterations} t={i2.registration_seconds*1e3:.2f} ms | pose diff vs NCCL path {np.abs(T2-T1).max():.2e} | first-8 parity {'OK' if okf else 'FAIL'}")
 ok = True
 for k in range(8):
@@ -39,7 +41,11 @@ for k in range(8):
 print(f"rank {rank}: single iters {i0.iterations} t={i0.registration_seconds*1e3:.2f} ms | sharded x{world} iters {i1.iterations} t={i1.registration_seconds*1e3:.2f} ms | pose diff {np.abs(T1-T0).max():.2e} | first-8 parity {'OK' if ok else 'FAIL'}")
 poses = [None] * world
 dist.all_gather_object(poses, T1.tobytes())
+assert ok, "NCCL path: first 8 iterations differ from the single-GPU run"
+assert all(b == poses[0] for b in poses), "ranks ended on different poses"
 if rank == 0:
     print("all ranks bit-identical pose:", all(b == poses[0] for b in poses))
 dist.barrier()
 g.close(); single.close()
+if rank == 0:
+    print("MGPU_CHECK_OK")
