@@ -185,8 +185,12 @@ const char* cvo_b200_last_error(const cvo_b200_handle* h);
 int cvo_b200_set_cloud(cvo_b200_handle* h, int which, int n, const float* xyz,
                        int F, const float* features, int C, const float* labels,
                        const float* geotype);
-/* Source rows [row_begin,row_end) are the ones this handle scans (multi-GPU
- * source sharding).  Default: all rows.                                      */
+/* Source rows [row_begin,row_end) are the ones this handle scans.  Default: all rows
+ * (row_end = -1).  For a single handle (tests, manual partitioning).  In a multi-GPU job
+ * (after cvo_b200_comm_init) the range is NOT taken from here: every call derives the rank's
+ * shard from (rank, world) and the size of the source cloud currently set - contiguous blocks
+ * of ceil(N / world) rows rounded up to 64 - so re-uploading a source of another size keeps
+ * the shards covering it.                                                     */
 int cvo_b200_set_row_range(cvo_b200_handle* h, int row_begin, int row_end);
 
 /* ---- the hot path --------------------------------------------------------

@@ -272,8 +272,16 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   const CloudDev& cs = S ? *S : h->src;
   const CloudDev& ct = Tg ? *Tg : h->tgt;
   const int N = cs.n, M = ct.n;
-  const int rb = sharded ? h->row_begin : 0;
-  const int re = (!sharded || h->row_end < 0 || h->row_end > N) ? N : h->row_end;
+  int rb = sharded ? h->row_begin : 0;
+  int re = (!sharded || h->row_end < 0 || h->row_end > N) ? N : h->row_end;
+  if (sharded && h->world > 1) {
+    // multi-GPU job: the shard follows (rank, world) and the CURRENT source size, so that a new
+    // source cloud of another size can neither leave rows unscanned nor make ranks disagree
+    // (contiguous blocks starting on a source tile, unified_cvo_b200/dist.py::shard_rows)
+    const int per = round_up((N + h->world - 1) / h->world, kTileRows);
+    rb = std::min(N, h->rank * per);
+    re = std::min(N, rb + per);
+  }
   if (rb < 0 || rb > re) return fail(h, CVO_B200_ERR_INVALID, "bad row range");
   const int n_rows = re - rb;
   const int Fp = std::max(cs.Fp, ct.Fp);
@@ -678,7 +686,7 @@ int build_cloud(cvo_b200_handle* h, CloudDev& c, int n, int F, const float* d_xy
   c.Fp = round_up(c.F, 4);
   c.Cp = round_up(c.C, 4);
   c.has_geo = d_geo != nullptr;
-  c.set = true;
+  c.set = (n == 0);  // a non-empty cloud counts as set only once its build has succeeded (below)
   c.perm.clear();
   c.perm_on_host = false;
   c.max_dist = 0.f;
@@ -750,6 +758,7 @@ int build_cloud(cvo_b200_handle* h, CloudDev& c, int n, int F, const float* d_xy
   }
   const double hd = st.extent / (double)(1 << db);
   c.occupied_volume = (double)st.occupied_cells * hd * hd * hd;
+  c.set = true;
   return CVO_B200_OK;
 }
 

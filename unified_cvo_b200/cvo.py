@@ -279,9 +279,17 @@ class CvoGPU:
         Ti = np.eye(4, dtype=np.float32) if T_target_to_source is None else T_target_to_source
         Ti = _colmajor16(Ti)
         To = np.zeros(16, np.float32)
+        To[[0, 5, 10, 15]] = 1.0
         info = AlignInfo()
-        F = max(source.feature_dimensions(), target.feature_dimensions())
-        Cn = max(source.num_classes(), target.num_classes())
+        if source.num_points() == 0 or target.num_points() == 0:  # CvoGPU.cu:1614-1617
+            return 0, To.reshape(4, 4).T.copy(), info
+        Fs, Ft = source.feature_dimensions(), target.feature_dimensions()
+        Cs, Ct = source.num_classes(), target.num_classes()
+        if (Fs and Ft and Fs != Ft) or (Cs and Ct and Cs != Ct):
+            # one stride is passed for both clouds: unequal widths would be read out of bounds
+            raise CvoError("source and target feature / class dimensions differ")
+        F, Cn = max(Fs, Ft), max(Cs, Ct)
+        self.write_params()
         self._check(self._lib.cvo_b200_align_host(
             self._h, source.num_points(), _ptr(source.positions_), F, _ptr(source.features_), Cn,
             _ptr(source.labels_), _ptr(source.geometric_types_), target.num_points(),
