@@ -368,6 +368,63 @@ def step_rows(params: Params, src: Cloud, y_moved, sparse: dict, omega, v, ell: 
     return out
 
 
+class _BaselineInfo(C.Structure):
+    _fields_ = [("ret", C.c_int), ("iterations", C.c_int), ("executed", C.c_int), ("threads", C.c_int),
+                ("final_ell", C.c_float), ("nnz_last", C.c_longlong), ("pairs", C.c_ulonglong),
+                ("seconds", C.c_double), ("t_transform", C.c_double), ("t_kdtree_build", C.c_double),
+                ("t_se_kernel", C.c_double), ("t_flow", C.c_double), ("t_step", C.c_double),
+                ("t_rest", C.c_double)]
+
+
+_base_lib = None
+
+
+def _baseline():
+    global _base_lib
+    if _base_lib is None:
+        if not os.path.exists(_BASE_SO):
+            build()
+        L = C.CDLL(_BASE_SO)
+        L.cpu_baseline_align.restype = C.c_int
+        L.cpu_baseline_align.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud),
+                                         C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float),
+                                         C.POINTER(_BaselineInfo)]
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        L.cpu_baseline_radius_counts.restype = None
+        L.cpu_baseline_radius_counts.argtypes = [C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float), C.c_int,
+                                                 C.c_float, C.POINTER(C.c_int)]
+        _base_lib = L
+    return _base_lib
+
+
+def cpu_baseline_radius_counts(pts, queries, r2: float):
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    q = np.ascontiguousarray(queries, np.float32).reshape(-1, 3)
+    out = np.zeros(len(q), np.int32)
+    _baseline().cpu_baseline_radius_counts(_fp(pts), len(pts), _fp(q), len(q), C.c_float(r2),
+                                           out.ctypes.data_as(C.POINTER(C.c_int)))
+    return out
+
+
+def cpu_baseline_align(params: Params, src: Cloud, tgt: Cloud, T_init=None, use_semantics: bool = False,
+                       threads: int | None = None):
+    """The restated reference CPU path cvo::cvo::align (oracle/cvo_cpu_baseline.c, Cvo.cpp:885-1089):
+    kd-tree rebuilt per iteration, no row cap, no normalisation.  Returns (ret, T 4x4, info dict)."""
+    _base_lib = _baseline()
+    if threads:
+        _base_lib.oracle_set_num_threads(int(threads))
+    Ti = None
+    if T_init is not None:
+        Ti = np.ascontiguousarray(np.asarray(T_init, np.float32).T).reshape(16)
+    To = np.zeros(16, np.float32)
+    info = _BaselineInfo()
+    cs, ct = src.c_struct(), tgt.c_struct()
+    ret = _base_lib.cpu_baseline_align(C.byref(params), C.byref(cs), C.byref(ct), _fp(Ti),
+                                       int(bool(use_semantics)), _fp(To), C.byref(info))
+    d = {k: getattr(info, k) for k, _ in _BaselineInfo._fields_}
+    return int(ret), To.reshape(4, 4).T.copy(), d
+
+
 def set_accel(on: bool) -> None:
     """Accelerated candidate enumeration on (default) / off (the literal dense loop)."""
     lib().oracle_set_accel(1 if on else 0)

@@ -12,17 +12,25 @@
 //
 // The class layout is fixed by the reference header (CvoParams* params_gpu; CvoParams params;),
 // so the device handle lives in a side table keyed by `this`.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <list>
+#include <memory>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
 
 #ifndef CVO_SHIM_SYNTAX_CHECK
 #include "cvo/CvoGPU.hpp"
+#include "cvo/CvoFrameGPU.hpp"
+#include "cvo/IRLS.hpp"
+#include "cvo/IRLS_State.hpp"
+#include "cvo/IRLS_State_CPU.hpp"
+#include "cvo/IRLS_State_GPU.hpp"
 #endif
 #include "cvo_b200.h"
 #include "shim_pack.hpp"
@@ -269,8 +277,39 @@ void CvoGPU::compute_association_gpu(const CvoPointCloud& source_points,
                      target_points.num_points(), association);
 }
 
-// The multi-frame overloads (IRLS, CvoGPU.cu:1634-1717) and inner_product_cpu (CvoGPU.cpp:96-213)
-// are outside the hot path: keep compiling the reference's own CvoGPU.cpp /
-// IRLS*.cpp for them — they use only the public API above.
+// ---- CvoGPU.cu:1637-1686: multi-frame registration from a list of frame pairs.  This overload
+// is DEFINED IN THE REPLACED CvoGPU.cu (the one taking ready-made BinaryStates lives in the kept
+// CvoGPU.cpp:261), and all main_multi_frame_irls_* / covisMap drivers call it: one edge state per
+// pair - CPU (kd-tree) or GPU (this library: shim/IRLS_State_GPU_b200.cpp) as
+// params.multiframe_using_cpu says - then the reference's own CvoBatchIRLS (IRLS.cpp, kept).
+int CvoGPU::align(std::vector<CvoFrame::Ptr>& frames, const std::vector<bool>& frames_to_hold_const,
+                  const std::list<std::pair<CvoFrame::Ptr, CvoFrame::Ptr>>& edges,
+                  double* registration_seconds) const {
+  auto start = std::chrono::system_clock::now();
+  std::list<BinaryState::Ptr> binary_states;
+  for (auto&& e : edges) {
+    const CvoFrame::Ptr& f1 = e.first;
+    const CvoFrame::Ptr& f2 = e.second;
+    if (params.multiframe_using_cpu) {
+      BinaryStateCPU::Ptr st(new BinaryStateCPU(f1, f2, &params));
+      binary_states.push_back(std::dynamic_pointer_cast<BinaryState>(st));
+    } else {
+      BinaryStateGPU::Ptr st(new BinaryStateGPU(std::dynamic_pointer_cast<CvoFrameGPU>(f1),
+                                                std::dynamic_pointer_cast<CvoFrameGPU>(f2), &params,
+                                                params_gpu, params.multiframe_num_neighbors,
+                                                params.multiframe_ell_init));
+      binary_states.push_back(std::dynamic_pointer_cast<BinaryState>(st));
+    }
+  }
+  CvoBatchIRLS batch_irls_problem(frames, frames_to_hold_const, binary_states, &params);
+  batch_irls_problem.solve();
+  auto end = std::chrono::system_clock::now();
+  std::chrono::duration<double, std::milli> t_all = end - start;
+  if (registration_seconds) *registration_seconds = (double)t_all.count() / 1000;
+  return 0;
+}
+
+// Kept with the reference's own sources (they use only the public API above): the overload taking
+// ready-made BinaryStates and inner_product_cpu (CvoGPU.cpp:261-289, :96-213), CvoPointCloud_to_pcl.
 
 }  // namespace cvo

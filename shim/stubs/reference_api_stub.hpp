@@ -172,6 +172,20 @@ class BinaryStateGPU : public BinaryState {
   const CvoParams* params_gpu_;
   const CvoParams* params_cpu_;
 };
+class BinaryStateCPU : public BinaryState {  // cvo/IRLS_State_CPU.hpp:23-26 (reference's own source)
+ public:
+  typedef std::shared_ptr<BinaryStateCPU> Ptr;
+  BinaryStateCPU(std::shared_ptr<CvoFrame> pc1, std::shared_ptr<CvoFrame> pc2, const CvoParams* params);
+  virtual int update_inner_product();
+  virtual void add_residual_to_problem(ceres::Problem& problem);
+  virtual void update_ell();
+};
+class CvoBatchIRLS {  // cvo/IRLS.hpp:23-35 (reference's own source, Ceres)
+ public:
+  CvoBatchIRLS(const std::vector<std::shared_ptr<CvoFrame>>& frames, const std::vector<bool>& pivot_flags,
+               const std::list<std::shared_ptr<BinaryState>>& states, const CvoParams* params);
+  void solve();
+};
 // the members of cvo::CvoGPU that the shim defines (signatures as in the reference header)
 class CvoGPU {
  private:
@@ -188,6 +202,12 @@ class CvoGPU {
             Association* = nullptr, double* = nullptr) const;
   int align(const pcl::PointCloud<CvoPoint>&, const pcl::PointCloud<CvoPoint>&, const Eigen::Matrix4f&,
             Eigen::Ref<Eigen::Matrix4f>, Association* = nullptr, double* = nullptr) const;
+  int align(std::vector<std::shared_ptr<CvoFrame>>& frames, const std::vector<bool>& frames_to_hold_const,
+            const std::list<std::pair<std::shared_ptr<CvoFrame>, std::shared_ptr<CvoFrame>>>& edges,
+            double* registration_seconds = nullptr) const;
+  int align(std::vector<std::shared_ptr<CvoFrame>>& frames, const std::vector<bool>& frames_to_hold_const,
+            const std::list<std::shared_ptr<BinaryState>>& edge_states,
+            double* registration_seconds = nullptr) const;  // reference's CvoGPU.cpp:261
   float function_angle(const CvoPointCloud&, const CvoPointCloud&, const Eigen::Matrix4f&, float,
                        bool is_approximate = true, bool is_gpu = true) const;
   float function_angle(const pcl::PointCloud<CvoPoint>&, const pcl::PointCloud<CvoPoint>&,
