@@ -61,6 +61,27 @@ void delete_internal_SparseKernelMat_cpu(SparseKernelMat* A_cpu) {
 namespace {
 std::mutex g_mu;
 std::unordered_map<const CvoParams*, cvo_b200_handle*> g_edge_handles;
+// frame ids per handle: released ids are reused (a sliding-window run constructs new CvoFrameGPU
+// objects for ever; the library accepts ids < 65536)
+struct IdPool {
+  int next = 0;
+  std::vector<int> free_ids;
+};
+std::unordered_map<cvo_b200_handle*, IdPool> g_ids;
+int take_id(cvo_b200_handle* h) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  IdPool& p = g_ids[h];
+  if (!p.free_ids.empty()) {
+    const int id = p.free_ids.back();
+    p.free_ids.pop_back();
+    return id;
+  }
+  return p.next++;
+}
+void give_id(cvo_b200_handle* h, int id) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_ids[h].free_ids.push_back(id);
+}
 
 [[noreturn]] void die(const cvo_b200_handle* h, const char* what, int rc) {
   std::fprintf(stderr, "[cvo_b200] %s failed (%d): %s\n", what, rc,
@@ -86,18 +107,16 @@ class CvoFrameGPU_Impl {
  public:
   explicit CvoFrameGPU_Impl(const CvoPointCloud* pts) : packed(shim::pack(*pts)) {}
   ~CvoFrameGPU_Impl() {
-    for (auto& kv : ids) cvo_b200_frame_clear(kv.first, kv.second);
+    for (auto& kv : ids) {
+      cvo_b200_frame_clear(kv.first, kv.second);
+      give_id(kv.first, kv.second);
+    }
   }
   // the frame's id on handle h; the cloud goes to that device on first use (points_init_gpu_)
   int id_on(cvo_b200_handle* h) {
     auto it = ids.find(h);
     if (it != ids.end()) return it->second;
-    int id;
-    {
-      std::lock_guard<std::mutex> lk(g_mu);
-      static std::unordered_map<cvo_b200_handle*, int> next_id;
-      id = next_id[h]++;
-    }
+    const int id = take_id(h);
     int rc = cvo_b200_frame_set(h, id, packed.n, packed.xyz.data(), packed.F, packed.p_feat(), packed.C,
                                 packed.p_lab(), packed.p_geo());
     if (rc != CVO_B200_OK) die(h, "cvo_b200_frame_set", rc);
