@@ -88,7 +88,8 @@ struct DevState {
   float grid_slack;         // absolute slack [m] of a cell query in the target's own frame
   int prune_on;             // this run may use the Morton view
   int view;                 // target view of the CURRENT iteration: 0 Morton (pruned), 1 original
-  int pad_hot;
+  unsigned int sat_base;    // persistent kernel: value of the (monotone) n_sat counter at the start of this iteration
+  unsigned int work_base;   // persistent kernel: likewise for the (monotone) work_counter
   KernConsts kc;
   // ---- hot block 2: flow result = step kernel input
   float omega[3], v[3];
@@ -161,6 +162,18 @@ struct XMailbox {
   unsigned long long ll[2][2][kMaxWorld][32];  // [phase][parity][rank][2 words per value]
 };
 
+// Barrier-free all-reduce board of the persistent kernel: every block PUBLISHES its per-block
+// values as self-validating 8-byte words (tag << 32 | half of a double, the LL protocol again) and
+// every block POLLS all blocks' words - arrival is data validity, so one reduction costs one L2
+// store + one L2 load round trip instead of fence + atomic + spin + fence + reload.  The board is
+// zeroed before every launch; tags are the reduction's sequence number (>= 1) inside the launch;
+// two parities suffice (a block cannot run two reductions ahead of another one).
+constexpr int kLLMaxBlocks = 160;  // >= the SM count of the part (B200: 148)
+constexpr int kLLValues = 11;
+struct LLBoard {
+  unsigned long long w[2][kLLMaxBlocks][2 * kLLValues];
+};
+
 struct TargetView {
   const float4* xyz;
   const float* feat;
@@ -215,6 +228,7 @@ struct IterArgs {
   // kernel variant
   int mode;        // 0 isotropic (fill_in_A_mat_gpu), 1 Mahalanobis (.._dense_mat_kernel)
   float kinv[9];   // column-major inverse kernel for mode 1
+  LLBoard* ll;     // persistent kernel: barrier-free reduction board (zeroed before every launch)
   unsigned long long* stamps;  // debug (CVO_B200_STAMPS=1): [blocks][8] %globaltimer of block phases
   // fused multi-GPU exchange (xfused = 1): peers' mailboxes (own included), this launch's generation
   XMailbox* xpeer[kMaxWorld];

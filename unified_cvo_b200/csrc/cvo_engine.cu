@@ -186,6 +186,7 @@ struct cvo_b200_handle {
   DevBuf<uint32_t> cand, cand_cnt, ell_idx, row_nnz;
   DevBuf<float> ell_val;
   DevBuf<FlowPartial> flow_part, flow_part2;
+  DevBuf<LLBoard> ll_board;  // barrier-free reductions of the persistent kernel
   DevBuf<StepPartial> step_part;
   DevBuf<float> zeros_f;    // stand-in for absent features / labels
   DevBuf<float2> zeros_g;   // stand-in for absent geometric types
@@ -356,6 +357,8 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
       std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_pblock - 1) / rows_per_pblock));
   CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
   CVO_CUDA(h, h->flow_part2.ensure((size_t)h->persist_blocks));
+  CVO_CUDA(h, h->ll_board.ensure(1));
+  if (h->persist_blocks > kLLMaxBlocks) h->persist_blocks = kLLMaxBlocks;
   CVO_CUDA(h, h->step_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
 
   std::memset(&A, 0, sizeof(A));
@@ -408,6 +411,7 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.cap_max = cap_max;
   A.flow_part = h->flow_part.p;
   A.flow_part2 = h->flow_part2.p;
+  A.ll = h->ll_board.p;
   A.step_part = h->step_part.p;
   A.mode = mode;
   if (kinv)
@@ -475,6 +479,16 @@ int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEven
     }
   }
   return CVO_B200_OK;
+}
+
+// One launch of the persistent kernel: its reduction board and its two monotone counters start
+// from zero (stream-ordered memsets, no synchronisation).
+cudaError_t launch_persistent(cvo_b200_handle* h, const IterArgs& A) {
+  cudaError_t e = cudaMemsetAsync(h->ll_board.p, 0, sizeof(LLBoard), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->work_counter, 0, sizeof(unsigned int), h->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->n_sat, 0, sizeof(unsigned int), h->stream);
+  if (e != cudaSuccess) return e;
+  return launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream);
 }
 
 void host_update_tf(const float R[9], const float T[3], float Rinv[9], float Tinv[3]) {
@@ -798,7 +812,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
       // world > 1: the two per-iteration exchanges are NVLink stores into the peers' mailboxes
       A.xfused = A.world > 1 ? 1 : 0;
       A.xgen = ++h->xgen;
-      CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream));
+      CVO_CUDA(h, launch_persistent(h, A));
       h->launches += 1;
       CVO_CUDA(h, cudaMemcpyAsync(h->h_poll, &h->d_state->iter, 4 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
       CVO_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -931,6 +945,7 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
   }
   h->tgt_moved.release(); h->pq.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
   h->rowrec.release(); h->row_lt.release(); h->sat_list.release(); h->flow_part2.release();
+  h->ll_board.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
   h->zeros_g.release(); h->d_trace.release(); h->gathered.release(); h->stamps.release();
@@ -996,7 +1011,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
     A.xfused = A.world > 1 ? 1 : 0;
     A.xgen = ++h->xgen;
-    CVO_CUDA(h, launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream));
+    CVO_CUDA(h, launch_persistent(h, A));
     h->launches += 1;
   } else {
     rc = enqueue_iteration(h, A, 3, nullptr, nullptr);
@@ -1513,7 +1528,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   CVO_CUDA(h, cudaEventCreate(&e1));
   cudaEventRecord(e0, h->stream);
   if (persist) {  // one launch runs all `iters` iterations; no per-kernel events
-    cudaError_t le = launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream);
+    cudaError_t le = launch_persistent(h, A);
     if (le != cudaSuccess) rc = fail(h, CVO_B200_ERR_CUDA, std::string("cooperative launch: ") + cudaGetErrorString(le));
     h->launches += 1;
   } else {
@@ -1553,10 +1568,21 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   if (A.stamps && persist) {  // per-phase time of block 0 / thread 0, averaged over the iterations
     unsigned long long acc[10];
     cudaMemcpy(acc, A.stamps, sizeof(acc), cudaMemcpyDeviceToHost);
-    const char* names[10] = {"flow rows", "publish", "barrier 1", "reduce", "finalize", "step rows",
-                             "publish", "barrier 2", "reduce", "controller"};
+    const char* names[10] = {"flow rows", "flow allreduce (incl. wait)", "-", "redo of cut rows", "finalize", "step rows",
+                             "step allreduce (incl. wait)", "-", "-", "controller"};
     for (int k = 0; k < 10; k++)
-      fprintf(stderr, "[phases] %-10s %7.2f us/iter\n", names[k], (double)acc[k] / 1e3 / (double)iters);
+      fprintf(stderr, "[phases] %-28s %7.2f us/iter\n", names[k], (double)acc[k] / 1e3 / (double)iters);
+    // per block: flow rows / flow reduction / step rows / step reduction (thread 0's view)
+    std::vector<unsigned long long> pb((size_t)4 * h->persist_blocks);
+    cudaMemcpy(pb.data(), A.stamps + 64, pb.size() * 8, cudaMemcpyDeviceToHost);
+    const char* bn[4] = {"flow rows", "flow allreduce", "step rows", "step allreduce"};
+    for (int q = 0; q < 4; q++) {
+      std::vector<double> v;
+      for (int b = 0; b < h->persist_blocks; b++) v.push_back((double)pb[(size_t)4 * b + q] / 1e3 / (double)iters);
+      std::sort(v.begin(), v.end());
+      fprintf(stderr, "[blocks] %-16s min %6.2f  p50 %6.2f  p90 %6.2f  max %6.2f us/iter\n", bn[q], v.front(),
+              v[v.size() / 2], v[v.size() * 9 / 10], v.back());
+    }
   }
   if (A.stamps && !persist) {  // per-block phase stamps of the LAST flow launch (ns, relative to the first block)
     const int nb = A.grid ? h->grid_blocks : h->sparse_blocks;

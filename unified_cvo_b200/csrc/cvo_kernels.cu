@@ -790,7 +790,7 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
 // state; st = the global state (saturation counters only).
 template <bool kGrid, bool kColour = true>
 __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const DevState* hs,
-                                          uint32_t* list, double (&bp)[9]) {
+                                          uint32_t* list, double (&bp)[9], double* queued = nullptr) {
   const int view = kGrid ? 0 : hs->view;  // cell queries index the Morton-ordered target
   const float* s_pose = hs->Rinv;          // Rinv[9], Tinv[3] are contiguous
   const float ell_now = hs->ell;
@@ -822,6 +822,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
 
   double w_om[3] = {0, 0, 0}, w_v[3] = {0, 0, 0}, w_asum = 0.0;  // group sums (leader lane)
   double w_nnz = 0.0, w_max = 0.0;
+  double w_sat = 0.0, w_capped = 0.0;  // rows this group queued for the exact redo / found capped
 
   // Row groups: the first pass is static (warp w of block b takes rows 4(b*W+w)..+3); when there
   // are more rows than resident row slots the rest is handed out dynamically, four
@@ -834,7 +835,8 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
     if (!first_pass) {
       if (dynamic_rows) {
         int nb = 0;
-        if (lane == 0) nb = total_slots + (int)atomicAdd(&st->work_counter, (unsigned)kRowsPerWarp);
+        if (lane == 0)
+          nb = total_slots + (int)(atomicAdd(&st->work_counter, (unsigned)kRowsPerWarp) - hs->work_base);
         row_base = __shfl_sync(0xffffffffu, nb, 0);
       } else {
         row_base += total_slots;
@@ -1206,10 +1208,13 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
     const bool capped = rvalid && count >= cap_stop && !((kGrid || view == 0) && cap == 0);
     count = min(count, cap);
     if (capped && gl == 0) {
-      if (view == 0)
-        A.sat_list[atomicAdd(&st->n_sat, 1u)] = (uint32_t)row;
-      else
+      if (view == 0) {
+        A.sat_list[atomicAdd(&st->n_sat, 1u) - hs->sat_base] = (uint32_t)row;
+        w_sat += 1.0;
+      } else {
         atomicAdd(&st->n_capped, 1u);
+        w_capped += 1.0;
+      }
     }
     if (gl == 0 && rvalid && !(capped && view == 0)) {
       A.row_nnz[row] = (uint32_t)count;
@@ -1233,6 +1238,12 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       const double x = __shfl_xor_sync(0xffffffffu, bp[k], o);
       bp[k] = (k < 8) ? bp[k] + x : fmax(bp[k], x);
     }
+    w_sat += __shfl_xor_sync(0xffffffffu, w_sat, o);
+    w_capped += __shfl_xor_sync(0xffffffffu, w_capped, o);
+  }
+  if (queued) {
+    queued[0] = w_sat;
+    queued[1] = w_capped;
   }
 }
 
@@ -1879,6 +1890,90 @@ __device__ bool xgpu_allgather(const IterArgs& A, DevState* gst, double (&tot)[N
   return ok;
 }
 
+// Barrier-free all-reduce over the cooperative grid (see LLBoard).  v: the warp's values (valid on
+// lane 0 of every warp).  On return out[] (valid on EVERY thread) holds the sum (k < NSUM) / max
+// over all blocks, reduced in block order by every block, so all blocks get bit-identical totals.
+// release: this block wrote data other blocks will read after the reduction (queued rows, redone
+// ELL rows) - the publishing lanes fence before their stores; acquire: readers fence after the
+// poll.  sh_w: >= 32 * NV doubles; sh_all: >= NV * kLLMaxBlocks doubles.
+template <int NV, int NSUM>
+__device__ __forceinline__ void ll_allreduce(LLBoard* board, unsigned int seq, const double (&v)[NV],
+                                             double* sh_w, double* sh_all, double (&out)[NV], bool release,
+                                             bool acquire) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int par = (int)(seq & 1u);
+  __syncthreads();  // sh_w / sh_all may still be read by the previous phase; orders the block's writes
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < NV; k++) sh_w[w * NV + k] = v[k];
+  }
+  __syncthreads();
+  // one warp per value: the block's warps in a fixed xor tree, lane 0 publishes
+  for (int k = w; k < NV; k += nw) {
+    double r = (lane < nw) ? sh_w[lane * NV + k] : 0.0;  // 0 is neutral for the sums and the max (>= 0)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double x = __shfl_xor_sync(0xffffffffu, r, o);
+      r = (k < NSUM) ? r + x : fmax(r, x);
+    }
+    if (lane == 0) {
+      if (release) __threadfence();
+      ll_store(&board->w[par][blockIdx.x][2 * k], r, seq);
+    }
+  }
+  // every thread fetches its share of the nblocks x NV values: all its 16-byte loads (both words
+  // of a value) are issued together, then only the values that had not arrived yet are polled
+  // again - one L2 round trip when everybody is on time.  A word is either old or complete.
+  const int total = (int)gridDim.x * NV;
+  constexpr int kPer = (kLLMaxBlocks * NV + kPersistThreadsSmall - 1) / kPersistThreadsSmall;
+  unsigned pending = 0u;
+#pragma unroll
+  for (int j = 0; j < kPer; j++)
+    if ((int)threadIdx.x + j * (int)blockDim.x < total) pending |= 1u << j;
+  while (pending) {
+    unsigned long long lo[kPer], hi[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+      if (pending & (1u << j)) {
+        const int id = (int)threadIdx.x + j * (int)blockDim.x;
+        const int b = id / NV, k = id - b * NV;
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];"
+                     : "=l"(lo[j]), "=l"(hi[j])
+                     : "l"(&board->w[par][b][2 * k])
+                     : "memory");
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kPer; j++) {
+      if ((pending & (1u << j)) && (unsigned int)(lo[j] >> 32) == seq && (unsigned int)(hi[j] >> 32) == seq) {
+        const int id = (int)threadIdx.x + j * (int)blockDim.x;
+        const int b = id / NV, k = id - b * NV;
+        sh_all[k * kLLMaxBlocks + b] =
+            __longlong_as_double((long long)((hi[j] << 32) | (lo[j] & 0xffffffffull)));
+        pending &= ~(1u << j);
+      }
+    }
+  }
+  if (acquire) __threadfence();
+  __syncthreads();
+  for (int k = w; k < NV; k += nw) {
+    double acc = 0.0;
+    for (int b = lane; b < (int)gridDim.x; b += 32) {
+      const double x = sh_all[k * kLLMaxBlocks + b];
+      acc = (k < NSUM) ? acc + x : fmax(acc, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double x = __shfl_xor_sync(0xffffffffu, acc, o);
+      acc = (k < NSUM) ? acc + x : fmax(acc, x);
+    }
+    if (lane == 0) sh_w[k] = acc;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NV; k++) out[k] = sh_w[k];
+}
+
 // block partial (NV values per warp in v, valid on lane 0) -> part[k * gridDim.x + blockIdx.x]
 template <int NV, int NSUM>
 __device__ __forceinline__ void publish_block_partial(const double (&v)[NV], double* sh, double* part) {
@@ -1903,19 +1998,34 @@ __device__ __forceinline__ void publish_block_partial(const double (&v)[NV], dou
 
 template <int kThreads, bool kFused, bool kColour>
 __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
-  __shared__ double sh[(kThreads / 32 + 2) * 9];
-  // cell queries queue at most 7 pending + 32 new candidates per row group
-  __shared__ uint32_t s_list[kThreads / kGroup][kGridList];
+  __shared__ double sh[32 * kLLValues];              // per-warp values of a reduction
+  // one buffer, two lives: the candidate queues of the flow phase (cell queries queue at most 7
+  // pending + 32 new candidates per row group) and all blocks' values of a reduction.  Every
+  // reduction starts and ends with a block barrier, the flow phase runs between two of them.
+  constexpr size_t kListBytes = sizeof(uint32_t) * (kThreads / kGroup) * kGridList;
+  constexpr size_t kAllBytes = sizeof(double) * kLLValues * kLLMaxBlocks;
+  __shared__ __align__(16) unsigned char s_raw[kListBytes > kAllBytes ? kListBytes : kAllBytes];
+  uint32_t(*s_list)[kGridList] = reinterpret_cast<uint32_t(*)[kGridList]>(s_raw);
+  double* sh_all = reinterpret_cast<double*>(s_raw);
   __shared__ __align__(16) DevState s_st;
-  __shared__ unsigned int s_nsat;
   __shared__ CtrlScratch s_ctrl;
   // debug (CVO_B200_STAMPS=1): time spent per phase by thread 0 of block 0, summed over the loop
   __shared__ unsigned long long s_acc[12];
   unsigned long long t_prev = 0ull;
   const bool stamping = A.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  // ... and, per block, the time thread 0 spent in the flow rows / the flow reduction / the step
+  // rows / the step reduction (A.stamps[64 + 4 * block ..]): who waits for whom
+  const bool bstamp = A.stamps != nullptr && threadIdx.x == 0;
+  unsigned long long b_acc[4] = {0ull, 0ull, 0ull, 0ull}, b_prev = 0ull;
   if (stamping) {
     for (int q = 0; q < 12; q++) s_acc[q] = 0ull;
     t_prev = gtime();
+  }
+#define CVO_BSTAMP(q)                      \
+  if (bstamp) {                            \
+    const unsigned long long t = gtime();  \
+    if ((q) >= 0) b_acc[(q) & 3] += t - b_prev; \
+    b_prev = t;                            \
   }
 #define CVO_PHASE(q)                    \
   if (stamping) {                       \
@@ -1927,49 +2037,68 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   for (int i = threadIdx.x; i < (int)(sizeof(DevState) / 4); i += blockDim.x)
     reinterpret_cast<uint32_t*>(&s_st)[i] = __ldcg(reinterpret_cast<const uint32_t*>(gst) + i);
   __syncthreads();
-  if (threadIdx.x == 0 && blockIdx.x != 0) s_st.trace = nullptr;  // block 0 records the trace
+  if (threadIdx.x == 0) {
+    if (blockIdx.x != 0) s_st.trace = nullptr;  // block 0 records the trace
+    s_st.sat_base = 0u;                          // the host zeroes the monotone counters per launch
+    s_st.work_base = 0u;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  unsigned int epoch = 0;
-  double* flow_part = reinterpret_cast<double*>(A.flow_part);
-  double* flow_part2 = reinterpret_cast<double*>(A.flow_part2);
-  double* step_part = reinterpret_cast<double*>(A.step_part);
+  unsigned int seq = 0;  // sequence number of the grid-wide reductions of this launch
+  // dynamic row hand-out (more rows than resident row slots): every warp ends its flow phase
+  // with exactly one failing fetch, so the monotone counter advances by a known amount
+  const int total_slots = (int)gridDim.x * warps_per_block * kRowsPerWarp;
+  const unsigned int work_per_iter =
+      A.n_rows > total_slots
+          ? (unsigned)kRowsPerWarp * (unsigned)((A.n_rows - total_slots + kRowsPerWarp - 1) / kRowsPerWarp +
+                                                (int)gridDim.x * warps_per_block)
+          : 0u;
 
   while (!s_st.done) {  // the same value in every block
     // ---- flow phase (fill_in_A_mat_gpu + compute_flow_gpu_no_eigen on this block's rows)
-    {
-      double bp[9];
-      flow_rows<true, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp);
-      CVO_PHASE(0)
-      publish_block_partial<9, 8>(bp, sh, flow_part);
-      CVO_PHASE(1)
-    }
-    grid_barrier(&gst->bar_count, epoch);
-    if (blockIdx.x == 0 && threadIdx.x == 0) gst->work_counter = 0u;  // next iteration's dynamic rows
-    CVO_PHASE(2)
-    // ---- every block: totals in a fixed order.  The number of rows cut at their cap is fetched
-    //      by an otherwise idle warp while the partials are being reduced.
     double tot[9];
-    if (threadIdx.x == 32 * 12) s_nsat = __ldcg(&gst->n_sat);
-    block_reduce_partials<9, 8>(flow_part, (int)gridDim.x, tot, sh);  // ends with a block barrier
-    const unsigned int n_sat = s_nsat;
+    unsigned int n_sat = 0u;
+    {
+      double bp[9], queued[2], v[kLLValues], r[kLLValues];
+      CVO_BSTAMP(-1)
+      flow_rows<true, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp, queued);
+      CVO_PHASE(0)
+      CVO_BSTAMP(0)
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = bp[k];
+      v[8] = queued[0];
+      v[9] = queued[1];
+      v[10] = bp[8];
+      // release only when this block queued rows for the exact redo (sat_list entries must be
+      // visible to whoever redoes them); block-uniform decision
+      const bool rel = __syncthreads_or(lane == 0 && queued[0] > 0.0) != 0;
+      ll_allreduce<kLLValues, 10>(A.ll, ++seq, v, sh, sh_all, r, rel, false);
+      CVO_PHASE(1)
+      CVO_BSTAMP(1)
+#pragma unroll
+      for (int k = 0; k < 8; k++) tot[k] = r[k];
+      tot[8] = r[10];
+      n_sat = (unsigned int)(r[8] + 0.5);
+    }
     if (n_sat > 0u) {
-      // exact redo of the cut rows, one warp per row over the whole grid, behind one more barrier
-      double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, tot2[9];
+      // exact redo of the cut rows, one warp per row over the whole grid, behind one more reduction
+      __threadfence();  // acquire: the queued row indices of the other blocks
+      __syncthreads();
+      double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, v[kLLValues], r[kLLValues];
       for (unsigned int si = blockIdx.x * warps_per_block + warp_in_block; si < n_sat;
            si += gridDim.x * warps_per_block)
         redo_row<true>(A, s_st.kc, s_st.Rinv, s_st.Tinv, s_st.ell, s_st.num_neighbors,
                        (int)__ldcg(&A.sat_list[si]), lane, f);
-      publish_block_partial<9, 8>(f, sh, flow_part2);
-      grid_barrier(&gst->bar_count, epoch);
-      block_reduce_partials<9, 8>(flow_part2, (int)gridDim.x, tot2, sh);
-      if (threadIdx.x == 0) {
-        for (int q = 0; q < 8; q++) tot[q] += tot2[q];
-        tot[8] = fmax(tot[8], tot2[8]);
-        if (blockIdx.x == 0) gst->n_sat = 0u;  // every block has read it (barrier above)
-      }
+#pragma unroll
+      for (int k = 0; k < 8; k++) v[k] = f[k];
+      v[8] = v[9] = 0.0;
+      v[10] = f[8];
+      ll_allreduce<kLLValues, 10>(A.ll, ++seq, v, sh, sh_all, r, true, true);  // redone ELL rows: release + acquire
+#pragma unroll
+      for (int k = 0; k < 8; k++) tot[k] += r[k];
+      tot[8] = fmax(tot[8], r[10]);
     }
     CVO_PHASE(3)
     // ---- multi-GPU: this rank's totals -> the job's totals (NVLink stores + local spin)
@@ -1979,6 +2108,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     // ---- normalisation, omega_hat powers
     if (threadIdx.x == 0) {
       s_st.n_sat = n_sat;  // update_tf_device's bookkeeping
+      s_st.sat_base += n_sat;
+      s_st.work_base += work_per_iter;
       finalize_flow_scalar(&s_st, tot);
       if (!xok) {  // a peer is gone: stop this rank's loop with an error instead of spinning
         s_st.ret = CVO_B200_ERR_NCCL;
@@ -1990,21 +2121,17 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     CVO_PHASE(4)
     // ---- step phase (compute_step_size_xi + _poly_coeff on this block's ELL rows)
     {
-      double w4[4];
+      double w4[4], r4[4];
+      CVO_BSTAMP(-1)
       step_rows<true>(A, &s_st, w4[0], w4[1], w4[2], w4[3]);
       CVO_PHASE(5)
-      publish_block_partial<4, 4>(w4, sh, step_part);
+      CVO_BSTAMP(2)
+      ll_allreduce<4, 4>(A.ll, ++seq, w4, sh, sh_all, r4, false, false);
       CVO_PHASE(6)
-    }
-    grid_barrier(&gst->bar_count, epoch);
-    CVO_PHASE(7)
-    {
-      double tot[4];
-      block_reduce_partials<4, 4>(step_part, (int)gridDim.x, tot, sh);
-      CVO_PHASE(8)
+      CVO_BSTAMP(3)
       bool xok2 = true;
-      if (kFused) xok2 = xgpu_allgather<4, 4>(A, gst, tot, 1, xepoch);
-      controller_step(A, &s_st, tot, &s_ctrl);
+      if (kFused) xok2 = xgpu_allgather<4, 4>(A, gst, r4, 1, xepoch);
+      controller_step(A, &s_st, r4, &s_ctrl);
       if (threadIdx.x == 0 && !xok2) {
         s_st.ret = CVO_B200_ERR_NCCL;
         s_st.done = 1;
@@ -2015,13 +2142,17 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   }
   if (stamping)
     for (int q = 0; q < 10; q++) A.stamps[q] = s_acc[q];
+  if (bstamp)
+    for (int q = 0; q < 4; q++) A.stamps[64 + 4 * blockIdx.x + q] = b_acc[q];
 #undef CVO_PHASE
+#undef CVO_BSTAMP
   // ---- block 0 hands the final state (pose, flags, results) back.  The scheduling scratch
-  //      (barrier counter, work counters, exchange flags) is NOT written back: other blocks may
-  //      still be leaving their last spin loop on it.
+  //      (work counters, exchange flags) is NOT written back: other blocks may still use it.
   if (blockIdx.x == 0) {
     const int w0 = (int)(offsetof(DevState, work_counter) / 4), w1 = (int)(offsetof(DevState, trace) / 4),
               w2 = (int)(offsetof(DevState, xll) / 4);
+    if (threadIdx.x == 0) s_st.sat_base = s_st.work_base = 0u;  // meaningful inside a launch only
+    __syncthreads();
     for (int i = threadIdx.x; i < w2; i += blockDim.x)
       if (i < w0 || i >= w1)
         reinterpret_cast<uint32_t*>(gst)[i] = reinterpret_cast<const uint32_t*>(&s_st)[i];
