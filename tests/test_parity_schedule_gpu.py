@@ -24,7 +24,7 @@ from helpers import (DATA, compare_traces, demo_clouds, demo_params, geometric_p
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["dense", "grid", "grid-launches"])
+@pytest.fixture(params=["dense", "grid", "grid-launches", "tile"])
 def candidate_mode(request, monkeypatch):
     """dense N x M scan / cell queries in the persistent kernel / cell queries as one launch per
     phase (read by cvo_b200_create): the controller exists in each launch structure."""

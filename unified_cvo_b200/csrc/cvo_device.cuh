@@ -235,7 +235,13 @@ struct IterArgs {
   unsigned long long xgen;
   int xfused, xrank, xworld;
   int colour;      // is_using_intensity (selects the persistent kernel with the stage-1 colour cut)
-  int grid;        // 1: candidates come from cell queries (flow_kernel<true>; no prep/pair launch)
+  int grid;        // 1: candidates come from cell queries (flow_kernel_t<1>; no prep/pair launch)
+  int tile;        // 1: candidates come from tile_kernel (source tile x the octree cells of the target
+                   //    its rows can reach; Morton view only; no prep launch)
+  int tile_L;      // tile mode: candidate words per (row, part) cell
+  int tile_parts;  // tile mode: warps sharing one tile (each sweeps every tile_parts-th cell group)
+  int tile_cut_bits;  // tile mode: a tile is cut where neighbouring rows' Morton keys differ above this bit
+  const unsigned long long* src_keys;  // Morton keys of the source rows (sorted; source's own lattice)
   GridView gv;
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective
   int n_items;     // pair-kernel work items = row_tiles * nchunks

@@ -24,6 +24,8 @@
 namespace cvo_b200 {
 void launch_prep(const IterArgs& A, int blocks, cudaStream_t s);
 void launch_pair(const IterArgs& A, int blocks, cudaStream_t s);
+void launch_tile(const IterArgs& A, int blocks, cudaStream_t s);
+int tile_kernel_max_blocks_per_sm();
 void launch_flow(const IterArgs& A, int blocks, cudaStream_t s);
 void launch_step(const IterArgs& A, int blocks, cudaStream_t s);
 void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride, cudaStream_t s);
@@ -211,15 +213,17 @@ struct cvo_b200_handle {
   int prep_blocks = 1, pair_blocks = 1, sparse_blocks = 1;
   // graph cache for the align loop: [0] dense scan (prep, pair, flow, step), [1] cell queries
   // (flow, step)
-  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
-  IterArgs graph_args[2];
-  int graph_batch[2] = {0, 0};
+  // (prep, pair, flow, step), [1] cell queries (flow, step), [2] tile cells (tile, flow, step)
+  cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};
+  IterArgs graph_args[3];
+  int graph_batch[3] = {0, 0, 0};
+  int tile_blocks = 1;
   bool use_graph = true;
   int grid_blocks = 1;
   int persist_blocks = 1;   // cooperative grid of align_grid_kernel (all blocks co-resident)
   int persist_threads = kPersistThreads;
   bool use_persist = true;  // CVO_B200_PERSIST=0: one launch per phase even in cell-query mode
-  int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries
+  int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries, 2 tile cells (where possible)
   // host poll buffer (pinned)
   int* h_poll = nullptr;
   // comm
@@ -304,6 +308,14 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   // keep the candidate cells within ~8 GiB
   while ((size_t)std::max(n_rows, 1) * nchunks * L * 4 > ((size_t)8 << 30) && L > 32) L /= 2;
   const int M_pad = round_up(std::max(M, 1), kJBlock);
+  if (M >= (1 << 24)) return fail(h, CVO_B200_ERR_INVALID, "target clouds of 2^24 points or more are not supported");
+  // tile mode: ONE candidate cell per row; sized for the densest rows the mode is chosen for
+  // (choose_mode), halved until the cells fit in ~4 GiB
+  // ... shared by tile_parts warps per tile (small shards: enough items to fill the machine)
+  int tile_parts = 1;
+  while (tile_parts < 8 && row_tiles * tile_parts < 2 * h->num_sms * 24) tile_parts *= 2;
+  int tile_L = 1024 / tile_parts;
+  while ((size_t)std::max(n_rows, 1) * tile_parts * tile_L * 4 > ((size_t)4 << 30) && tile_L > 32) tile_L /= 2;
 
   const size_t n_zero = (size_t)std::max(N, M) * (size_t)std::max(std::max(Fp, Cp), 1);
   CVO_CUDA(h, h->tgt_moved.ensure((size_t)M));
@@ -315,8 +327,8 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   CVO_CUDA(h, h->rowrec.ensure((size_t)std::max(n_rows, 1) * 2));
   CVO_CUDA(h, h->row_lt.ensure((size_t)std::max(n_rows, 1)));
   CVO_CUDA(h, h->sat_list.ensure((size_t)std::max(n_rows, 1)));
-  CVO_CUDA(h, h->cand.ensure((size_t)std::max(n_rows, 1) * nchunks * L));
-  CVO_CUDA(h, h->cand_cnt.ensure((size_t)std::max(n_rows, 1) * nchunks));
+  CVO_CUDA(h, h->cand.ensure(std::max((size_t)std::max(n_rows, 1) * nchunks * L, (size_t)std::max(n_rows, 1) * tile_parts * tile_L)));
+  CVO_CUDA(h, h->cand_cnt.ensure((size_t)std::max(n_rows, 1) * std::max(nchunks, tile_parts)));
   CVO_CUDA(h, h->ell_idx.ensure((size_t)std::max(n_rows, 1) * cap_max));
   CVO_CUDA(h, h->ell_val.ensure((size_t)std::max(n_rows, 1) * cap_max));
   CVO_CUDA(h, h->row_nnz.ensure((size_t)std::max(n_rows, 1)));
@@ -335,6 +347,9 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   const int n_items = row_tiles * nchunks;
   h->pair_blocks = std::max(1, std::min(h->num_sms * occ, (n_items + kPairWarps - 1) / kPairWarps));
   h->prep_blocks = std::max(1, std::min(h->num_sms * 4, (std::max(M_pad, n_rows) + 255) / 256));
+  int tocc = tile_kernel_max_blocks_per_sm();
+  if (tocc < 1) tocc = 1;
+  h->tile_blocks = std::max(1, std::min(h->num_sms * tocc, (row_tiles * tile_parts + kPairWarps - 1) / kPairWarps));
   const int warps_per_block = kSparseThreads / 32;
   int socc = sparse_kernel_max_blocks_per_sm();
   if (socc < 1) socc = 1;
@@ -420,7 +435,10 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.n_items = n_items;
   A.stamps = nullptr;
   if (getenv("CVO_B200_STAMPS")) {
-    CVO_CUDA(h, h->stamps.ensure((size_t)8 * 4096));
+    if (h->stamps.cap < (size_t)8 * 4096) {
+      CVO_CUDA(h, h->stamps.ensure((size_t)8 * 4096));
+      CVO_CUDA(h, cudaMemsetAsync(h->stamps.p, 0, (size_t)8 * 4096 * sizeof(unsigned long long), h->stream));
+    }
     A.stamps = h->stamps.p;
   }
   A.colour = h->params.is_using_intensity ? 1 : 0;
@@ -430,6 +448,18 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.xgen = 0;
   for (int r = 0; r < kMaxWorld; r++) A.xpeer[r] = h->peers[r];
   A.grid = 0;
+  A.tile = 0;
+  A.tile_L = tile_L;
+  A.tile_parts = tile_parts;
+  A.src_keys = cs.keys_d.p;
+  {
+    // cut level of the tiles: cube nodes of the source's octree of edge >= 2 tile edges
+    const double rho_s = (cs.n_finite > 0 && cs.occupied_volume > 0.0) ? (double)cs.n_finite / cs.occupied_volume : 1.0;
+    const double D = 2.0 * std::cbrt((double)kTileRows / rho_s);
+    int b = 0;
+    while (b < 21 && (double)(1u << b) < D * (double)cs.key_scale) b++;
+    A.tile_cut_bits = 3 * b;
+  }
   A.gv.coarse = ct.coarse.p;
   A.gv.cbits = ct.cbits;
   A.gv.n_finite = ct.n_finite;
@@ -452,6 +482,12 @@ int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEven
     if (!(skip & 4)) launch_flow(A, sparse_blocks, s);
     if (pair_end) cudaEventRecord(pair_end, s);
     h->launches += 1;
+  } else if (A.tile) {  // tile cells: no O(M) prep either; the targets are moved on the fly
+    if (pair_begin) cudaEventRecord(pair_begin, s);
+    if (!(skip & 2)) launch_tile(A, h->tile_blocks, s);
+    if (pair_end) cudaEventRecord(pair_end, s);
+    if (!(skip & 4)) launch_flow(A, h->sparse_blocks, s);
+    h->launches += 2;
   } else {
     if (!(skip & 1)) launch_prep(A, h->prep_blocks, s);
     if (pair_begin) cudaEventRecord(pair_begin, s);
@@ -574,7 +610,7 @@ void split_pose(const float T16[16], float R[9], float T[3]) {
 }
 
 void destroy_graph(cvo_b200_handle* h) {
-  for (int m = 0; m < 2; m++) {
+  for (int m = 0; m < 3; m++) {
     if (h->graph_exec[m]) cudaGraphExecDestroy(h->graph_exec[m]);
     h->graph_exec[m] = nullptr;
     h->graph_batch[m] = 0;
@@ -585,7 +621,7 @@ void destroy_graph(cvo_b200_handle* h) {
 // flags) live in DevState, so the graph is parameter-free and is rebuilt only when the
 // buffers or the decomposition change.
 int ensure_graph(cvo_b200_handle* h, const IterArgs& A, int batch) {
-  const int m = A.grid ? 1 : 0;
+  const int m = A.grid ? 1 : (A.tile ? 2 : 0);
   if (h->graph_exec[m] && h->graph_batch[m] == batch && std::memcmp(&h->graph_args[m], &A, sizeof(A)) == 0)
     return CVO_B200_OK;
   if (h->graph_exec[m]) cudaGraphExecDestroy(h->graph_exec[m]);
@@ -615,7 +651,7 @@ int ensure_graph(cvo_b200_handle* h, const IterArgs& A, int batch) {
 }
 
 int launches_per_iteration(const cvo_b200_handle* h, const IterArgs& A) {
-  return (A.grid ? 2 : 4) + (h->world > 1 ? 2 : 0);
+  return (A.grid ? 2 : (A.tile ? 3 : 4)) + (h->world > 1 ? 2 : 0);
 }
 
 // Candidate-generator policy: a cost model calibrated on B200 (r01: C2, KITTI-sized and 200k
@@ -654,6 +690,52 @@ bool grid_profitable(const cvo_b200_handle* h, const CloudDev& cs, const CloudDe
   const double us_grid = rows * tests_g * 2.4e-6;
   const double us_dense = rows * tests_d * 0.62e-6 + 45.0;
   return us_grid < us_dense;
+}
+
+// The third generator: tile cells (tile_kernel).  A tile of 64 Morton-consecutive rows (edge
+// ~cbrt(64 / rho_s)) is swept against the cube cells covering its box inflated by the cut-off
+// radius: tests_t = rho_t * 1.5 (e_tile + 2 r)^3 per row at ~0.3 ps each (packed FMA prefilter,
+// measured r02), three launches per iteration.  It needs the Morton view (geometry on, isotropic
+// kernel, tile-aligned shard) and rows whose candidate runs fit the per-row cell (tile_L words).
+// Sets A.grid / A.tile.  The choice never changes a result.
+void choose_mode(const cvo_b200_handle* h, IterArgs& A, const CloudDev& cs, const CloudDev& ct, float ell,
+                 int rows_policy, bool sat_recent) {
+  A.tile = 0;
+  A.grid = (grid_profitable(h, cs, ct, ell, rows_policy) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
+  if (h->force_mode == 0 || h->force_mode == 1) return;  // dense | grid forced
+  const cvo_b200_params& p = h->params;
+  if (!A.prune || !p.is_using_geometry || ct.n_finite == 0 || !(ct.occupied_volume > 0.0) || sat_recent) return;
+  const double lmax = ((double)cs.max_dist / 500.0 + 1.0) * (double)ell;
+  const double q = (double)p.sp_thres / ((double)p.sigma * (double)p.sigma);
+  if (!(q > 0.0) || !(q < 1.0)) return;
+  const double r = lmax * std::sqrt(-2.0 * std::log(q));
+  if (!(r > 0.0) || !std::isfinite(r)) return;
+  const double density = (double)ct.n_finite / ct.occupied_volume;
+  const double rho_s = (cs.n_finite > 0 && cs.occupied_volume > 0.0) ? (double)cs.n_finite / cs.occupied_volume : density;
+  const double e_tile = std::cbrt((double)kTileRows / rho_s);
+  const double box = e_tile + 2.0 * r;
+  const double tests_t = std::min((double)ct.n, density * 1.5 * box * box * box);
+  // candidate runs a row can produce: the points of its own ball, eight per run at worst one each
+  const double ball = density * 4.18879 * r * r * r;
+  if (h->force_mode != 2 && ball > 0.5 * (double)A.tile_L * (double)A.tile_parts) return;  // rows would overflow their cells
+  const double rows = (double)rows_policy;
+  const double us_tile = rows * tests_t * 0.3e-6 + 30.0;
+  double hcell = ct.extent;
+  const double hmin = ct.extent / (double)(1 << ct.cbits);
+  while (hcell * 0.5 >= r && hcell * 0.5 >= hmin) hcell *= 0.5;
+  const double tests_g = std::min((double)ct.n, 27.0 * hcell * hcell * hcell * density);
+  const double r_tile = 0.85 * e_tile, r_blk = 0.85 * std::cbrt((double)kJBlock / density);
+  const double reach = r + r_tile + r_blk;
+  const double tests_d = std::min((double)ct.n, density * 4.18879 * reach * reach * reach);
+  const double us_other = A.grid ? rows * tests_g * 2.4e-6 : rows * tests_d * 0.62e-6 + 45.0;
+  if (h->force_mode == 2 || us_tile < us_other) {
+    A.tile = 1;
+    A.grid = 0;
+  }
+  static const bool dbg = getenv("CVO_B200_DEBUG_POLICY") != nullptr;
+  if (dbg)
+    fprintf(stderr, "[policy] ell %.3f rows %d: r %.3f ball %.0f tests/row tile %.0f grid %.0f dense %.0f -> %s\n", ell,
+            rows_policy, r, ball, tests_t, tests_g, tests_d, A.tile ? "tile" : (A.grid ? "grid" : "dense"));
 }
 
 // Builds a cloud's resident representation (Morton order, SoA packing, cell table, bounding
@@ -806,7 +888,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
     // replicated inputs there: the nominal shard size and the (replicated) length-scale
     const int rows_policy = A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows;
     if (A.world > 1) sat_recent = false;
-    A.grid = (grid_profitable(h, h->src, h->tgt, ell, rows_policy) && (!sat_recent || h->force_mode == 1)) ? 1 : 0;
+    choose_mode(h, A, h->src, h->tgt, ell, rows_policy, sat_recent);
     if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
       // the whole loop in one cooperative launch (align_grid_kernel); it returns when done.
       // world > 1: the two per-iteration exchanges are NVLink stores into the peers' mailboxes
@@ -830,7 +912,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
     if (h->use_graph) {
       rc = ensure_graph(h, A, batch);
       if (rc != CVO_B200_OK) return rc;
-      CVO_CUDA(h, cudaGraphLaunch(h->graph_exec[A.grid ? 1 : 0], h->stream));
+      CVO_CUDA(h, cudaGraphLaunch(h->graph_exec[A.grid ? 1 : (A.tile ? 2 : 0)], h->stream));
       h->launches += (uint64_t)batch * launches_per_iteration(h, A);
     } else {
       for (int b = 0; b < batch; b++) {
@@ -922,6 +1004,7 @@ int cvo_b200_create(const cvo_b200_params* p, int device, cvo_b200_handle** out)
   const char* fm = getenv("CVO_B200_MODE");  // dense | grid (anything else: automatic)
   if (fm && std::strcmp(fm, "dense") == 0) h->force_mode = 0;
   if (fm && std::strcmp(fm, "grid") == 0) h->force_mode = 1;
+  if (fm && std::strcmp(fm, "tile") == 0) h->force_mode = 2;
   const char* pe = getenv("CVO_B200_PERSIST");
   h->use_persist = !(pe && pe[0] == '0');
   *out = h;
@@ -1005,7 +1088,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   if (num_neighbors > A.cap_max) return fail(h, CVO_B200_ERR_INVALID, "num_neighbors exceeds nearest_neighbors_max");
   CVO_CUDA(h, h->d_trace.ensure(1));
   // multi-GPU: replicated inputs only, so that every rank takes the same decision
-  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows) ? 1 : 0;
+  choose_mode(h, A, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
   if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
@@ -1062,7 +1145,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   CVO_CUDA(h, cudaEventCreate(&ev1));
   if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
     IterArgs Ag = A;
-    Ag.grid = grid_profitable(h, h->src, h->tgt, h->params.ell_init, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows) ? 1 : 0;
+    choose_mode(h, Ag, h->src, h->tgt, h->params.ell_init, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
     if (!(Ag.grid && h->use_persist && (A.world == 1 || h->peers_ready))) {
       rc = ensure_graph(h, Ag, 32);
       if (rc != CVO_B200_OK) {
@@ -1508,7 +1591,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   if (h->src.n == 0 || h->tgt.n == 0) return fail(h, CVO_B200_ERR_STATE, "empty cloud");
   if (num_neighbors > A.cap_max) num_neighbors = A.cap_max;
   // multi-GPU: replicated inputs only, so that every rank takes the same decision
-  A.grid = grid_profitable(h, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows) ? 1 : 0;
+  choose_mode(h, A, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
   rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
   const bool persist = A.grid && h->use_persist && (A.world == 1 || h->peers_ready);
@@ -1564,6 +1647,13 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
             (long long)(d[13] - d[6]), (long long)(d[14] - d[6]), (long long)(d[15] - d[6]), (long long)(d[7] - d[6]));
     fprintf(stderr, "[tails] flow reduce: loads done %+lld shuffles done %+lld smem done %+lld (ns after tail_begin)\n",
             (long long)(d[10] - d[1]), (long long)(d[11] - d[1]), (long long)(d[12] - d[1]));
+  }
+  if (A.stamps && A.tile) {
+    unsigned long long t3[3];
+    cudaMemcpy(t3, A.stamps + 32000, sizeof(t3), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tiles] %llu tile sweeps, targets swept per tile: mean %.0f max %llu (x 64 rows = pair tests)\n", t3[2],
+            t3[2] ? (double)t3[0] / (double)t3[2] : 0.0, t3[1]);
+    cudaMemset(A.stamps + 32000, 0, sizeof(t3));
   }
   if (A.stamps && persist) {  // per-phase time of block 0 / thread 0, averaged over the iterations
     unsigned long long acc[10];

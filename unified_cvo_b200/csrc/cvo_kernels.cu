@@ -186,10 +186,11 @@ struct __align__(16) PairSmemWarp {
   uint64_t bar[2];
 };
 
-// candidate word: (first target index of the lane's 8-group) / 8 in the high 24 bits, the
-// 8-bit mask of candidate targets inside the group in the low bits
+// candidate word: the first target index of the lane's run of 8 consecutive targets in the high
+// 24 bits (any alignment; clouds of up to 2^24 points), the 8-bit mask of candidate targets inside
+// the run in the low bits
 __device__ __forceinline__ uint32_t make_word(int j_base, uint32_t qmask) {
-  return ((uint32_t)(j_base >> 3) << 8) | qmask;
+  return ((uint32_t)j_base << 8) | qmask;
 }
 
 __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
@@ -407,7 +408,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) pair_kernel(IterArgs A) {
         __syncwarp();
         if (lane == 0) {
           S.cnt[r] = c;
-          if (c >= (uint32_t)L) {  // cell full: stop looking at this row in this chunk
+          if (c > (uint32_t)L) {  // cell overflowed (flow rescans it): stop looking at this row in this chunk
             rec[2 * r + 1].z = -INFINITY;
             rec[2 * r + 1].w = -INFINITY;
           }
@@ -679,6 +680,371 @@ __device__ __forceinline__ void cell_ranges2(const GridView& G, int lvl3, bool v
   }
 }
 
+
+// ================================================================== tile_kernel
+// Candidate generator of the dense regimes (large cut-off radius against the point spacing, e.g.
+// the 200k x 200k clouds at ell = 1.5, where a sixth of the tested pairs pass the geometric cut):
+// one warp takes a TILE of 64 Morton-consecutive source rows and tests it against exactly the
+// targets its rows can reach - the points of the octree cells of the target (in the target's OWN
+// frame, where the cell table stays valid under any pose) that intersect the ball around the tile.
+// Per tile: (1) the tile's source points are TMA-staged into shared memory (cp.async.bulk +
+// mbarrier) and turned into prefilter records in that frame (q = R x + T, conservative radius as
+// in the cell queries); every lane OWNS two rows and keeps their records in registers; (2) <= 4 x 4
+// x 4 cube cells covering the tile's bounding box are looked up as contiguous ranges of the
+// Morton-ordered target; (3) the ranges are staged through shared memory, 128 targets at a time
+// (coalesced float4 loads, centred SoA), and every lane runs its two rows past them:
+// s = w + ax*yx + ay*yy + az*yz < t_i, two TARGETS per fma.rn.f32x2 (same identity and margin
+// analysis as pair_kernel: the prefilter can only ADD candidates, flow_rows<2> re-tests them with
+// the reference's arithmetic), then the colour lower bound on the hits.  A lane appends its rows'
+// candidates itself - no ballots, no ordered emission: with one pair in six passing, pair_kernel's
+// "rare hit" path (warp votes, re-evaluation, ordered emission) ran for every row of every sweep.
+// pair_kernel also tests every 256-target block whose bounding sphere is near the tile's (6-10x
+// more points than necessary on these clouds); this kernel tests ~1.5x the points of the tile's ball.
+// Output: per row ONE candidate cell of tile_L words (target << 8 | 1) + its count; a count above
+// tile_L marks an overflowed row (exact redo).  Order inside a row is free: the Morton view counts
+// one survivor past the cap and redoes cut rows exhaustively in original order.
+constexpr int kTileChunk = 128;  // targets staged per sweep
+struct __align__(16) TileSmemWarp {
+  union {
+    float4 stage[2 * kTileRows];  // TMA destination: src_xyz[64], src_rowA[64]
+    struct {
+      float X[kTileChunk], Y[kTileChunk], Z[kTileChunk], W[kTileChunk];  // centred targets, |y~|^2
+    } t;
+  };
+  uint32_t col[kTileChunk];  // packed colour summaries of the staged targets (4 x 8 bit)
+  uint32_t nb[kTileChunk];   // their squared norms: sum of the four squared channels
+  uint32_t idx[kTileChunk];  // their Morton positions
+  uint32_t cstart[32], cend[32];  // the current group of 32 cube cells: range of Morton positions
+  uint32_t cpre[33];              // exclusive prefix of their run counts (runs of 4 targets)
+  uint64_t bar;
+};
+
+__device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs, TileSmemWarp& S,
+                                           int gwarp, int nwarps, uint32_t& bar_phase) {
+  const int lane = threadIdx.x & 31;
+  const GridView& G = A.gv;
+  const uint32_t L = (uint32_t)A.tile_L;
+  const float ell_now = hs->ell;
+  const float log_geo = hs->kc.log_geo;
+  const float g_smax = hs->smax, g_slack = hs->grid_slack;
+  const float* Rf = hs->R;
+  const float* Tf = hs->T;
+  const bool colour_cut = hs->kc.use_intensity != 0;
+  unsigned int lb_thr = 0xffffffffu;
+  if (colour_cut) {
+    const float th = hs->kc.d2_c_thres;
+    lb_thr = (th > 0.f) ? (th * (65025.f / 0.999f) < 4.0e9f ? (unsigned int)ceilf(th * (65025.f / 0.999f)) : 0xffffffffu) : 0u;
+  }
+  // The per-hit colour test of this kernel: with q the 8-bit summaries, per channel
+  // |fa - fb| >= (|dq| - 1) / 255, and max(|d| - 1, 0)^2 >= d^2 - 2|d|, sum|d| <= 2 sqrt(S) for four
+  // channels (S = sum d^2), so  65025 d2_color >= S - 4 sqrt(S).  S = |qa|^2 + |qb|^2 - 2 qa.qb is one
+  // dp4a and two adds per pair (the video-SIMD absolute differences of eval_pair's bound are
+  // emulated on this architecture, ~20 instructions).  A pair with S >= s_thr = (2 + sqrt(4 + T))^2
+  // has S - 4 sqrt(S) >= T = lb_thr, fails d2_color < d2_c_thres and never becomes a candidate.
+  unsigned int s_thr = 0xffffffffu;
+  if (colour_cut && lb_thr != 0xffffffffu) {
+    if (lb_thr == 0u) {
+      s_thr = 0u;
+    } else {
+      const double rt2 = 2.0 + sqrt(4.0 + (double)lb_thr);
+      const double v = rt2 * rt2 * (1.0 + 1e-9) + 2.0;
+      s_thr = v < 4.0e9 ? (unsigned int)v : 0xffffffffu;
+    }
+  }
+  // |y - tc| <= trad for every target (own frame, static): the prefilter's bound on |y~|
+  const float ymax2 = A.trad * A.trad * 1.000004f + 1e-12f;
+  const int ntiles = (A.n_rows + kTileRows - 1) / kTileRows;
+  const float top = 2097151.f;
+  const int csh = 3 * (21 - G.cbits);
+  // items = (tile, part): the cell groups of a tile are dealt round-robin to `tile_parts` warps, each
+  // with its own candidate cell per row, so that small shards still fill the machine
+  const int P = A.tile_parts;
+  for (int item = gwarp; item < ntiles * P; item += nwarps) {
+    const int tile = item / P, part = item - tile * P;
+    const int row0 = tile * kTileRows;
+    const int nrows = min(kTileRows, A.n_rows - row0);
+    // ---- (1) TMA-stage the tile's source points and range records
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async();
+      const uint32_t bytes = (uint32_t)nrows * (uint32_t)sizeof(float4);
+      mbar_expect_tx(&S.bar, 2u * bytes);
+      tma_bulk_g2s(S.stage, A.src_xyz + A.row_begin + row0, bytes, &S.bar);
+      tma_bulk_g2s(S.stage + kTileRows, A.src_rowA + A.row_begin + row0, bytes, &S.bar);
+    }
+    mbar_wait(&S.bar, bar_phase);
+    bar_phase ^= 1u;
+    // ---- the lane's two rows: prefilter records in registers, the row's ball in lattice units
+    float rax[2], ray[2], raz[2], rt[2], fq[2][3], frq[2];
+    unsigned int rqa[2], rna[2];
+    unsigned int cut_after = 0u;  // bit hh: the tile is cut after row lane + 32 hh (Morton key jump)
+#pragma unroll
+    for (int hh = 0; hh < 2; hh++) {
+      const int r = lane + 32 * hh;
+      rax[hh] = ray[hh] = raz[hh] = 0.f;
+      rt[hh] = -INFINITY;
+      rqa[hh] = rna[hh] = 0u;
+      frq[hh] = -1.f;
+      fq[hh][0] = fq[hh][1] = fq[hh][2] = 0.f;
+      if (r < nrows) {
+        const float4 x4 = S.stage[r];
+        const float4 a4 = S.stage[kTileRows + r];
+        const float l = range_ell(ell_now, a4.w);          // CvoGPU.cu:506-507
+        const float d2_thres = -2.0 * l * l * log_geo;     // CvoGPU.cu:511
+        if (d2_thres > 0.f) {
+          const float xv[3] = {x4.x, x4.y, x4.z};
+          float q[3];
+          mat3f_vec(Rf, xv, q);
+          q[0] += Tf[0]; q[1] += Tf[1]; q[2] += Tf[2];
+          // |y - q| <= smax |y' - x| + slack (update_tf_device); same radius as the cell queries
+          const float rq = sqrtf(d2_thres) * g_smax * 1.00001f + g_slack +
+                           2e-6f * (fabsf(xv[0]) + fabsf(xv[1]) + fabsf(xv[2]) + fabsf(q[0]) + fabsf(q[1]) + fabsf(q[2]));
+          const float th = rq * rq * 1.000001f;
+          const float4 a = make_float4(-2.f * (q[0] - A.tcx), -2.f * (q[1] - A.tcy), -2.f * (q[2] - A.tcz), 0.f);
+          const float t = prefilter_threshold(th, a, ymax2);
+          const float f0 = (q[0] - G.lo[0]) * G.scale, f1 = (q[1] - G.lo[1]) * G.scale, f2 = (q[2] - G.lo[2]) * G.scale;
+          const float fr = rq * G.scale + 2.f;  // + the float rounding of the lattice coordinates
+          // a NaN anywhere makes every comparison false: no candidates, like d2 < thres
+          const bool hit = f0 + fr >= -2.f && f1 + fr >= -2.f && f2 + fr >= -2.f && f0 - fr <= top + 2.f &&
+                           f1 - fr <= top + 2.f && f2 - fr <= top + 2.f && t > -INFINITY;
+          if (hit) {
+            rax[hh] = a.x; ray[hh] = a.y; raz[hh] = a.z;
+            rt[hh] = t;
+            rqa[hh] = __float_as_uint(x4.w);  // the row's packed colour summary
+            rna[hh] = __dp4a(rqa[hh], rqa[hh], 0u);
+            fq[hh][0] = f0; fq[hh][1] = f1; fq[hh][2] = f2;
+            frq[hh] = fr;
+          }
+        }
+        // segments: Morton-consecutive rows can be far apart (the Z curve jumps); the tile is cut
+        // wherever two neighbours lie in different cube nodes of the source's octree at the level
+        // A.tile_cut_bits (edge ~2 tile edges), so every segment is spatially compact
+        if (r + 1 < nrows) {
+          const unsigned long long k0 = __ldg(A.src_keys + A.row_begin + row0 + r);
+          const unsigned long long k1 = __ldg(A.src_keys + A.row_begin + row0 + r + 1);
+          if (((k0 ^ k1) >> A.tile_cut_bits) != 0ull) cut_after |= 1u << hh;
+        }
+      }
+    }
+    __syncwarp();  // the staging area is reused for the target chunks from here on
+    const unsigned long long cuts = (unsigned long long)__ballot_sync(0xffffffffu, cut_after & 1u) |
+                                    ((unsigned long long)__ballot_sync(0xffffffffu, cut_after & 2u) << 32);
+    // row-duplicated operands of the packed FMAs: (a, a) x (y_k, y_k+1) tests two targets at once
+    const unsigned long long AX0 = pack2(rax[0], rax[0]), AY0 = pack2(ray[0], ray[0]), AZ0 = pack2(raz[0], raz[0]);
+    const unsigned long long AX1 = pack2(rax[1], rax[1]), AY1 = pack2(ray[1], ray[1]), AZ1 = pack2(raz[1], raz[1]);
+    uint32_t cnt0 = 0u, cnt1 = 0u;
+    uint32_t* cell_a = A.cand + ((size_t)(row0 + lane) * (size_t)P + (size_t)part) * (size_t)L;
+    uint32_t* cell_b = A.cand + ((size_t)(row0 + lane + 32) * (size_t)P + (size_t)part) * (size_t)L;
+    unsigned long long n_swept = 0ull;
+    for (int seg0 = 0; seg0 < nrows;) {
+      // the segment [seg0, seg1): up to and including the first cut at or after seg0
+      const unsigned long long rest = cuts >> seg0;
+      const int seg1 = rest ? min(nrows, seg0 + __ffsll((long long)rest)) : nrows;
+      const bool act0 = lane >= seg0 && lane < seg1 && frq[0] >= 0.f;
+      const bool act1 = lane + 32 >= seg0 && lane + 32 < seg1 && frq[1] >= 0.f;
+      const float t0 = act0 ? rt[0] : -INFINITY, t1 = act1 ? rt[1] : -INFINITY;
+      // ---- the segment's box and ball in lattice units
+      float lo3[3] = {INFINITY, INFINITY, INFINITY}, hi3[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        if (act0) { lo3[k] = fminf(lo3[k], fq[0][k] - frq[0]); hi3[k] = fmaxf(hi3[k], fq[0][k] + frq[0]); }
+        if (act1) { lo3[k] = fminf(lo3[k], fq[1][k] - frq[1]); hi3[k] = fmaxf(hi3[k], fq[1][k] + frq[1]); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          lo3[k] = fminf(lo3[k], __shfl_xor_sync(0xffffffffu, lo3[k], o));
+          hi3[k] = fmaxf(hi3[k], __shfl_xor_sync(0xffffffffu, hi3[k], o));
+        }
+      }
+      seg0 = seg1;
+      if (!(hi3[0] >= lo3[0])) continue;  // no active row
+      const float c3[3] = {0.5f * (lo3[0] + hi3[0]), 0.5f * (lo3[1] + hi3[1]), 0.5f * (lo3[2] + hi3[2])};
+      float brad = 0.f;  // radius of the ball around c3 that holds every active row's ball
+      if (act0) {
+        const float dx = fq[0][0] - c3[0], dy = fq[0][1] - c3[1], dz = fq[0][2] - c3[2];
+        brad = fmaxf(brad, sqrtf(dx * dx + dy * dy + dz * dz) * 1.000001f + frq[0]);
+      }
+      if (act1) {
+        const float dx = fq[1][0] - c3[0], dy = fq[1][1] - c3[1], dz = fq[1][2] - c3[2];
+        brad = fmaxf(brad, sqrtf(dx * dx + dy * dy + dz * dz) * 1.000001f + frq[1]);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) brad = fmaxf(brad, __shfl_xor_sync(0xffffffffu, brad, o));
+      brad += 1.f;
+      const float brad2 = brad * brad * 1.00001f;
+      const int bx0 = (int)fminf(fmaxf(floorf(lo3[0]) - 1.f, 0.f), top), bx1 = (int)fminf(fmaxf(floorf(hi3[0]) + 1.f, 0.f), top);
+      const int by0 = (int)fminf(fmaxf(floorf(lo3[1]) - 1.f, 0.f), top), by1 = (int)fminf(fmaxf(floorf(hi3[1]) + 1.f, 0.f), top);
+      const int bz0 = (int)fminf(fmaxf(floorf(lo3[2]) - 1.f, 0.f), top), bz1 = (int)fminf(fmaxf(floorf(hi3[2]) + 1.f, 0.f), top);
+      // ---- (2) cube cells covering the box: <= 12 per axis, never finer than the cell table
+      int lvl = 21 - G.cbits;
+      while (((bx1 >> lvl) - (bx0 >> lvl)) > 11 || ((by1 >> lvl) - (by0 >> lvl)) > 11 ||
+             ((bz1 >> lvl) - (bz0 >> lvl)) > 11)
+        lvl++;
+      const int icx0 = bx0 >> lvl, icy0 = by0 >> lvl, icz0 = bz0 >> lvl;
+      const int nx = (bx1 >> lvl) - icx0 + 1, ny = (by1 >> lvl) - icy0 + 1, nz = (bz1 >> lvl) - icz0 + 1;
+      const int ncell = nx * ny * nz;
+      const float ch = (float)(1 << lvl);
+      for (int cbase = 32 * part; cbase < ncell; cbase += 32 * P) {
+        // one cell per lane: dropped unless the segment's ball reaches it
+        uint32_t s0 = 0u, e0 = 0u;
+        const int c = cbase + lane;
+        if (c < ncell) {
+          const int cz = c / (nx * ny), cy = (c - cz * nx * ny) / nx, cx = c - cz * nx * ny - cy * nx;
+          const float bx = (float)((icx0 + cx) << lvl), by = (float)((icy0 + cy) << lvl), bz = (float)((icz0 + cz) << lvl);
+          const float ex = fmaxf(0.f, fmaxf(bx - c3[0], c3[0] - (bx + ch)));
+          const float ey = fmaxf(0.f, fmaxf(by - c3[1], c3[1] - (by + ch)));
+          const float ez = fmaxf(0.f, fmaxf(bz - c3[2], c3[2] - (bz + ch)));
+          if ((ex * ex + ey * ey + ez * ez) <= brad2) {
+            const unsigned long long key =
+                (spread21_dev((unsigned)(icx0 + cx)) | (spread21_dev((unsigned)(icy0 + cy)) << 1) |
+                 (spread21_dev((unsigned)(icz0 + cz)) << 2))
+                << (3 * lvl);
+            s0 = __ldg(G.coarse + (key >> csh));
+            e0 = __ldg(G.coarse + ((key + (1ull << (3 * lvl))) >> csh));
+          }
+        }
+        const uint32_t nrun = (e0 - s0 + 3u) >> 2;
+        uint32_t inc = nrun;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t tt = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += tt;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        if (total == 0u) continue;
+        __syncwarp();  // the previous group's tables have been consumed
+        S.cstart[lane] = s0;
+        S.cend[lane] = e0;
+        S.cpre[lane] = inc - nrun;
+        if (lane == 0) S.cpre[32] = total;
+        __syncwarp();
+        n_swept += total;
+        // ---- (3) sweep: 128 targets per chunk (one run of 4 consecutive targets per lane), staged
+        //      in shared memory; every lane runs its two rows past them
+        for (uint32_t sb = 0; sb < total; sb += 32u) {
+          const uint32_t slot = sb + (uint32_t)lane;
+          const bool valid = slot < total;
+          int cc = 0;  // largest cell with cpre[cc] <= slot (empty cells share their successor's prefix)
+#pragma unroll
+          for (int stp = 16; stp > 0; stp >>= 1)
+            if (S.cpre[cc + stp] <= slot) cc += stp;
+          const uint32_t j0 = valid ? S.cstart[cc] + 4u * (slot - S.cpre[cc]) : 0u;
+          const uint32_t jend = valid ? S.cend[cc] : 0u;
+          __syncwarp();  // the previous chunk has been consumed
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint32_t j = j0 + (uint32_t)q;
+            const bool v = j < jend;
+            const float4 y = v ? __ldg(A.tv[0].xyz + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float ux = y.x - A.tcx, uy = y.y - A.tcy, uz = y.z - A.tcz;
+            const int k = 4 * lane + q;
+            S.t.X[k] = ux;
+            S.t.Y[k] = uy;
+            S.t.Z[k] = uz;
+            S.t.W[k] = v ? (ux * ux + uy * uy + uz * uz) : INFINITY;  // padding: never a candidate
+            S.col[k] = __float_as_uint(y.w);
+            S.nb[k] = __dp4a(__float_as_uint(y.w), __float_as_uint(y.w), 0u);
+            S.idx[k] = j;
+          }
+          __syncwarp();
+          const int kmax = (int)min((uint32_t)kTileChunk, 4u * (total - sb));
+          // geometric prefilter of the whole chunk first: 8 hit bits per step (4 targets x the
+          // lane's 2 rows) collected in registers ...
+          uint32_t hm[kTileChunk / 16];
+#pragma unroll
+          for (int wq = 0; wq < kTileChunk / 16; wq++) {
+            uint32_t acc = 0u;
+            if (16 * wq < kmax) {  // warp-uniform: a short last chunk stops early
+#pragma unroll
+              for (int it = 0; it < 4; it++) {
+                const int k = 16 * wq + 4 * it;
+                // four targets: two packed pairs per coordinate
+                const float4 x4 = *reinterpret_cast<const float4*>(&S.t.X[k]);
+                const float4 y4 = *reinterpret_cast<const float4*>(&S.t.Y[k]);
+                const float4 z4 = *reinterpret_cast<const float4*>(&S.t.Z[k]);
+                const float4 w4 = *reinterpret_cast<const float4*>(&S.t.W[k]);
+                const unsigned long long Xa = pack2(x4.x, x4.y), Xb = pack2(x4.z, x4.w);
+                const unsigned long long Ya = pack2(y4.x, y4.y), Yb = pack2(y4.z, y4.w);
+                const unsigned long long Za = pack2(z4.x, z4.y), Zb = pack2(z4.z, z4.w);
+                const unsigned long long Wa = pack2(w4.x, w4.y), Wb = pack2(w4.z, w4.w);
+                float sv[8];
+                unpack2(fma2(AZ0, Za, fma2(AY0, Ya, fma2(AX0, Xa, Wa))), sv[0], sv[1]);
+                unpack2(fma2(AZ0, Zb, fma2(AY0, Yb, fma2(AX0, Xb, Wb))), sv[2], sv[3]);
+                unpack2(fma2(AZ1, Za, fma2(AY1, Ya, fma2(AX1, Xa, Wa))), sv[4], sv[5]);
+                unpack2(fma2(AZ1, Zb, fma2(AY1, Yb, fma2(AX1, Xb, Wb))), sv[6], sv[7]);
+                unsigned int m = 0u;  // bits 0..3: row a x targets k..k+3, bits 4..7: row b
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                  m |= (sv[b] < t0 ? 1u : 0u) << b;
+                  m |= (sv[4 + b] < t1 ? 1u : 0u) << (4 + b);
+                }
+                acc |= m << (8 * it);
+              }
+            }
+            hm[wq] = acc;
+          }
+          // ... then every lane drains ITS hits: the colour lower bound from the 8-bit summaries
+          // (see eval_pair: a target whose bound already fails d2_color < d2_c_thres never becomes
+          // a candidate) and the append to the row's cell.  With one pair in six passing the
+          // geometric cut, testing colour per hit costs a third of testing it per pair, and a lane's
+          // hit count varies little over a chunk (no warp-wide "any lane hit" coupling).
+#pragma unroll
+          for (int wq = 0; wq < kTileChunk / 16; wq++) {
+            uint32_t m = hm[wq];
+            while (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1u;
+              const int kk = 16 * wq + 4 * (b >> 3) + (b & 3);
+              const bool second = (b & 4) != 0;
+              if (colour_cut) {
+                const unsigned int S2 = (second ? rna[1] : rna[0]) + S.nb[kk] -
+                                        2u * __dp4a(second ? rqa[1] : rqa[0], S.col[kk], 0u);
+                if (S2 >= s_thr) continue;
+              }
+              const uint32_t word = (S.idx[kk] << 8) | 1u;
+              if (!second) {
+                if (cnt0 < L) cell_a[cnt0] = word;
+                cnt0++;
+              } else {
+                if (cnt1 < L) cell_b[cnt1] = word;
+                cnt1++;
+              }
+            }
+          }
+        }
+      }
+    }
+    if (lane < nrows) A.cand_cnt[(size_t)(row0 + lane) * P + part] = cnt0;
+    if (lane + 32 < nrows) A.cand_cnt[(size_t)(row0 + lane + 32) * P + part] = cnt1;
+    if (A.stamps && lane == 0) {  // debug (CVO_B200_STAMPS=1): targets swept per tile
+      atomicAdd(&A.stamps[32000], n_swept * 4ull);
+      atomicMax(&A.stamps[32001], n_swept * 4ull);
+      atomicAdd(&A.stamps[32002], 1ull);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kPairWarps * 32, 3) tile_kernel(IterArgs A) {
+  DevState* st = A.st;
+  __shared__ TileSmemWarp smem[kPairWarps];
+  __shared__ uint32_t s_hot[kHot1Words];
+  for (int i = threadIdx.x; i < kHot1Words; i += blockDim.x)
+    s_hot[i] = __ldcg(reinterpret_cast<const uint32_t*>(st) + i);
+  __syncthreads();
+  const DevState* hs = reinterpret_cast<const DevState*>(s_hot);
+  if (hs->done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  TileSmemWarp& S = smem[warp];
+  if (lane == 0) {
+    mbar_init(&S.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t bar_phase = 0u;
+  // warps of one block take tiles that are far apart in the Morton order: the heavy (spread)
+  // tiles are dealt round-robin
+  tile_phase(A, hs, S, warp * gridDim.x + blockIdx.x, gridDim.x * kPairWarps, bar_phase);
+}
+
 // ================================================================== flow_kernel
 // Two candidate generators feed the same exact per-pair arithmetic:
 //   kGrid = false  the ordered candidate cells written by pair_kernel (dense scan);
@@ -701,7 +1067,7 @@ constexpr int kGridList = 48;                // cell queries: pending (<8) + one
 // cap in a Morton-ordered candidate walk.  Adds the row's contribution to f (lane 0):
 // omega[3], v[3], a_sum, nnz, max.  ELL indices are Morton positions (tgt_inv), like the rest of
 // the matrix in these modes.
-template <bool kGrid>
+template <bool kFly>
 __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc, const float* Ri,
                                          const float* Ti, float ell_now, int cap, int row, int lane,
                                          double (&f)[9]) {
@@ -713,7 +1079,7 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
       const float4 pa = A.src_xyz[ig];
       rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
       rc.qa = __float_as_uint(pa.w);
-      if (kGrid) {
+      if (kFly) {
         rc.l = range_ell(ell_now, A.src_rowA[ig].w);
         rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
       } else {
@@ -788,10 +1154,15 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
 // arithmetic -> ELL rows + per-row flow; returns the warp's partial sums in bp (valid on lane 0):
 // omega[3], v[3], a_sum, nnz, max row count.  hs = this block's shared-memory copy of the hot
 // state; st = the global state (saturation counters only).
-template <bool kGrid, bool kColour = true>
+// kGen: 0 = candidate cells of pair_kernel (moved targets / row thresholds from prep_kernel),
+//       1 = cell queries, 2 = candidate cells of tile_kernel (Morton view; moved targets and row
+//       thresholds computed on the fly like the cell queries: no prep launch)
+template <int kGen, bool kColour = true>
 __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const DevState* hs,
                                           uint32_t* list, double (&bp)[9], double* queued = nullptr) {
-  const int view = kGrid ? 0 : hs->view;  // cell queries index the Morton-ordered target
+  constexpr bool kGrid = (kGen == 1);
+  constexpr bool kFly = (kGen != 0);
+  const int view = kFly ? 0 : hs->view;  // cell queries / tile cells index the Morton-ordered target
   const float* s_pose = hs->Rinv;          // Rinv[9], Tinv[3] are contiguous
   const float ell_now = hs->ell;
   const float g_smax = hs->smax, g_slack = hs->grid_slack;
@@ -816,8 +1187,8 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
   // common when the cap has adapted down to 1.2 * max row count = a handful) from a cut one.
   const int cap_stop = (kGrid || view == 0) ? cap + 1 : cap;  // both Morton-ordered walks
   const float c_div = kc.c_div, d_div = kc.d_div;  // divisors (CvoGPU.cu:785-788)
-  const int L = A.L;
-  const int nch = A.nchunks;
+  const int L = (kGen == 2) ? A.tile_L : A.L;
+  const int nch = (kGen == 2) ? A.tile_parts : A.nchunks;
   if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[0] = gtime();
 
   double w_om[3] = {0, 0, 0}, w_v[3] = {0, 0, 0}, w_asum = 0.0;  // group sums (leader lane)
@@ -851,7 +1222,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       const float4 pa = A.src_xyz[ig];
       rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
       rc.qa = __float_as_uint(pa.w);
-      if (kGrid) {  // what prep_kernel writes to row_lt (CvoGPU.cu:506-511)
+      if (kFly) {  // what prep_kernel writes to row_lt (CvoGPU.cu:506-511)
         rc.l = range_ell(ell_now, A.src_rowA[ig].w);
         rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
       } else {
@@ -880,7 +1251,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
       bool surv = false;
       if (valid) {
-        pb = kGrid ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
+        pb = kFly ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
         surv = eval_pair(A, kc, rc, ig, view, j, pb, a);
       }
       const unsigned bits = (__ballot_sync(0xffffffffu, surv) >> gshift) & 0xffu;
@@ -932,7 +1303,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       }
       const int total = __shfl_sync(0xffffffffu, incl, kGroup - 1, kGroup);
       int off = nlist + incl - nb;
-      const int jb8 = (int)(word >> 8) << 3;
+      const int jb8 = (int)(word >> 8);
       uint32_t m = qm;
       while (m) {
         const int q = __ffs(m) - 1;
@@ -1115,6 +1486,14 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
         }
       }
     } else {
+    if (kGen == 2) {
+      // a tile cell that overflowed its word list (more candidates than tile_L): the row is
+      // handled like one cut at its cap - exact redo in original target order
+      bool ov = false;
+      if (rvalid && cap > 0)
+        for (int c = gl; c < nch; c += kGroup) ov |= cnt_row[c] > (uint32_t)L;
+      if ((__ballot_sync(0xffffffffu, ov) >> gshift) & 0xffu) count = cap_stop;
+    }
     for (int cbase = 0;; cbase += 4 * kGroup) {
       const bool wact = rvalid && cbase < nch && count < cap_stop;
       if (!__any_sync(0xffffffffu, wact)) break;
@@ -1247,8 +1626,9 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
   }
 }
 
-template <bool kGrid>
+template <int kGen>
 __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
+  constexpr bool kFly = (kGen != 0);
   DevState* st = A.st;
   __shared__ double sh[kSparseThreads * 9];
   __shared__ uint32_t s_hot[kHot1Words];  // pose, schedule, constants: one cooperative load
@@ -1263,8 +1643,8 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
   if (hs->done) return;
   if (stamp) stamp[1] = gtime();
   double bp[9];
-  flow_rows<kGrid>(A, st, hs, s_list[threadIdx.x >> 3], bp);
-  const int view = kGrid ? 0 : hs->view;
+  flow_rows<kGen>(A, st, hs, s_list[threadIdx.x >> 3], bp);
+  const int view = kFly ? 0 : hs->view;
   const float ell_now = hs->ell;
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
@@ -1313,7 +1693,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) flow_kernel_t(IterArgs A) {
 #pragma unroll
     for (int q = 0; q < 3; q++) Ti[q] = st->Tinv[q];
     for (unsigned int si = warp_in_block; si < n_sat; si += warps_per_block)
-      redo_row<kGrid>(A, kc, Ri, Ti, ell_now, cap, (int)__ldcg(&A.sat_list[si]), lane, f);
+      redo_row<kFly>(A, kc, Ri, Ti, ell_now, cap, (int)__ldcg(&A.sat_list[si]), lane, f);
     // fold the redone rows into the totals (fixed order over the warps of this block)
     __syncthreads();
     if (lane == 0) {
@@ -1438,10 +1818,11 @@ __device__ void update_tf_device(const IterArgs& A, DevState* st) {
   }
   // target view of the next iteration: leave the Morton view when many rows reach their cap
   // (each costs an O(M) exact redo), come back once no row does
-  st->last_view = st->view;
+  st->last_view = A.tile ? 0 : st->view;  // tile cells index the Morton view whatever st->view said
   st->last_grid = A.grid;
   int next_view = 1;
   if (st->prune_on) next_view = (st->view == 0) ? (st->n_sat > 16u ? 1 : 0) : (st->n_capped == 0u ? 0 : 1);
+  if (A.tile) next_view = 0;  // tile cells exist in the Morton view only; cut rows are redone exactly
   st->view = next_view;
   st->sat_total += st->n_sat + st->n_capped;
   st->n_sat = 0u;
@@ -1633,7 +2014,7 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
 // compute_step_size_xi + compute_step_size_poly_coeff (CvoGPU.cu:953-1082) over the ELL rows of
 // this block; returns the warp's B, C, D, E sums (all lanes).  Row data written by other blocks
 // (exact redo) is read past L1.
-template <bool kGrid>
+template <bool kFly>
 __device__ __forceinline__ void step_rows(const IterArgs& A, const DevState* hs, double& wB,
                                           double& wC, double& wD, double& wE) {
   const float* s_pose = hs->Rinv;  // Rinv[9], Tinv[3] are contiguous
@@ -1675,7 +2056,7 @@ __device__ __forceinline__ void step_rows(const IterArgs& A, const DevState* hs,
     for (int e = gl; e < n; e += kGroup) {
       const int j = (int)__ldcg(idx + e);
       const float A_ij = __ldcg(val + e);
-      const float4 yb = kGrid ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
+      const float4 yb = kFly ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
       const float y[3] = {yb.x, yb.y, yb.z};
       // compute_step_size_xi, CvoGPU.cu:974-983
       float z1[3], z2[3], z3[3], z4[3], t[3];
@@ -1726,7 +2107,7 @@ __device__ __forceinline__ void step_rows(const IterArgs& A, const DevState* hs,
   }
 }
 
-template <bool kGrid>
+template <bool kFly>
 __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
   DevState* st = A.st;
   __shared__ double sh[kSparseThreads * 4];
@@ -1742,7 +2123,7 @@ __global__ void __launch_bounds__(kSparseThreads, 3) step_kernel_t(IterArgs A) {
   const int warps_per_block = blockDim.x >> 5;
   if (blockIdx.x == 0 && threadIdx.x == 0) st->dbg[4] = gtime();
   double wB, wC, wD, wE;
-  step_rows<kGrid>(A, hs, wB, wC, wD, wE);
+  step_rows<kFly>(A, hs, wB, wC, wD, wE);
   if (lane == 0) {
     sh[warp_in_block * 4 + 0] = wB;
     sh[warp_in_block * 4 + 1] = wC;
@@ -2063,7 +2444,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     {
       double bp[9], queued[2], v[kLLValues], r[kLLValues];
       CVO_BSTAMP(-1)
-      flow_rows<true, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp, queued);
+      flow_rows<1, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp, queued);
       CVO_PHASE(0)
       CVO_BSTAMP(0)
 #pragma unroll
@@ -2253,15 +2634,25 @@ void launch_pair(const IterArgs& A, int blocks, cudaStream_t s) {
 }
 void launch_flow(const IterArgs& A, int blocks, cudaStream_t s) {
   if (A.grid)
-    flow_kernel_t<true><<<blocks, kSparseThreads, 0, s>>>(A);
+    flow_kernel_t<1><<<blocks, kSparseThreads, 0, s>>>(A);
+  else if (A.tile)
+    flow_kernel_t<2><<<blocks, kSparseThreads, 0, s>>>(A);
   else
-    flow_kernel_t<false><<<blocks, kSparseThreads, 0, s>>>(A);
+    flow_kernel_t<0><<<blocks, kSparseThreads, 0, s>>>(A);
 }
 void launch_step(const IterArgs& A, int blocks, cudaStream_t s) {
-  if (A.grid)
+  if (A.grid || A.tile)
     step_kernel_t<true><<<blocks, kSparseThreads, 0, s>>>(A);
   else
     step_kernel_t<false><<<blocks, kSparseThreads, 0, s>>>(A);
+}
+void launch_tile(const IterArgs& A, int blocks, cudaStream_t s) {
+  tile_kernel<<<blocks, kPairWarps * 32, 0, s>>>(A);
+}
+int tile_kernel_max_blocks_per_sm() {
+  int n = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tile_kernel, kPairWarps * 32, 0);
+  return n;
 }
 void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride, cudaStream_t s) {
   finalize_flow_kernel<<<1, 32, 0, s>>>(A, gathered, stride);
@@ -2309,13 +2700,16 @@ int pair_kernel_max_blocks_per_sm() {
 }
 int sparse_kernel_max_blocks_per_sm() {
   int a = 0, b = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel_t<false>, kSparseThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel_t<0>, kSparseThreads, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, step_kernel_t<false>, kSparseThreads, 0);
+  int c = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, flow_kernel_t<2>, kSparseThreads, 0);
+  if (c < a) a = c;
   return a < b ? a : b;
 }
 int grid_kernel_max_blocks_per_sm() {
   int a = 0, b = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel_t<true>, kSparseThreads, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_kernel_t<1>, kSparseThreads, 0);
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, step_kernel_t<true>, kSparseThreads, 0);
   return a < b ? a : b;
 }
