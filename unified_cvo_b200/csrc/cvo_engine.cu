@@ -36,7 +36,7 @@ int pair_kernel_max_blocks_per_sm();
 int sparse_kernel_max_blocks_per_sm();
 int grid_kernel_max_blocks_per_sm();
 cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaStream_t s);
-int align_grid_max_blocks_per_sm(int threads);
+int align_grid_max_blocks_per_sm(int threads, int tile);
 }  // namespace cvo_b200
 
 using namespace cvo_b200;
@@ -221,6 +221,7 @@ struct cvo_b200_handle {
   bool use_graph = true;
   int grid_blocks = 1;
   int persist_blocks = 1;   // cooperative grid of align_grid_kernel (all blocks co-resident)
+  int persist_blocks_tile = 1;  // ... of its tile-cell instantiation
   int persist_threads = kPersistThreads;
   bool use_persist = true;  // CVO_B200_PERSIST=0: one launch per phase even in cell-query mode
   int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries, 2 tile cells (where possible)
@@ -365,11 +366,13 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   h->persist_threads = (n_rows > h->num_sms * (kPersistThreads / 32) * 4)        ? kPersistThreadsWide
                        : (n_rows <= h->num_sms * (kPersistThreadsSmall / 32) * 4) ? kPersistThreadsSmall
                                                                                   : kPersistThreads;
-  int pocc = align_grid_max_blocks_per_sm(h->persist_threads);
+  int pocc = align_grid_max_blocks_per_sm(h->persist_threads, 0);
   if (pocc < 1) pocc = 1;
   const int rows_per_pblock = (h->persist_threads / 32) * 4;
   h->persist_blocks =
       std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_pblock - 1) / rows_per_pblock));
+  // tile mode: one block of kPersistThreads per SM (tile items and rows are dealt to its warps)
+  h->persist_blocks_tile = std::min(kLLMaxBlocks, h->num_sms * std::max(1, std::min(1, align_grid_max_blocks_per_sm(kPersistThreads, 1))));
   CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
   CVO_CUDA(h, h->flow_part2.ensure((size_t)h->persist_blocks));
   CVO_CUDA(h, h->ll_board.ensure(1));
@@ -524,7 +527,7 @@ cudaError_t launch_persistent(cvo_b200_handle* h, const IterArgs& A) {
   if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->work_counter, 0, sizeof(unsigned int), h->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->n_sat, 0, sizeof(unsigned int), h->stream);
   if (e != cudaSuccess) return e;
-  return launch_align_grid(A, h->persist_blocks, h->persist_threads, h->stream);
+  return launch_align_grid(A, A.tile ? h->persist_blocks_tile : h->persist_blocks, h->persist_threads, h->stream);
 }
 
 void host_update_tf(const float R[9], const float T[3], float Rinv[9], float Tinv[3]) {
@@ -717,7 +720,11 @@ void choose_mode(const cvo_b200_handle* h, IterArgs& A, const CloudDev& cs, cons
   const double tests_t = std::min((double)ct.n, density * 1.5 * box * box * box);
   // candidate runs a row can produce: the points of its own ball, eight per run at worst one each
   const double ball = density * 4.18879 * r * r * r;
-  if (h->force_mode != 2 && ball > 0.5 * (double)A.tile_L * (double)A.tile_parts) return;  // rows would overflow their cells
+  // rows whose candidates overflow their cells are redone exhaustively (O(M) each): keep them rare.
+  // With a colour cut only a fraction of the ball becomes candidates (measured: 1 % on random
+  // colours); the loop leaves the mode when rows do overflow (sat_recent).
+  const double cand_est = ball * (p.is_using_intensity ? 0.25 : 1.0);
+  if (h->force_mode != 2 && cand_est > 0.5 * (double)A.tile_L * (double)A.tile_parts) return;
   const double rows = (double)rows_policy;
   const double us_tile = rows * tests_t * 0.3e-6 + 30.0;
   double hcell = ct.extent;
@@ -889,7 +896,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
     const int rows_policy = A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows;
     if (A.world > 1) sat_recent = false;
     choose_mode(h, A, h->src, h->tgt, ell, rows_policy, sat_recent);
-    if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
+    if ((A.grid || (A.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready)) {
       // the whole loop in one cooperative launch (align_grid_kernel); it returns when done.
       // world > 1: the two per-iteration exchanges are NVLink stores into the peers' mailboxes
       A.xfused = A.world > 1 ? 1 : 0;
@@ -1091,7 +1098,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   choose_mode(h, A, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
-  if (A.grid && h->use_persist && (A.world == 1 || h->peers_ready)) {
+  if ((A.grid || (A.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready)) {
     A.xfused = A.world > 1 ? 1 : 0;
     A.xgen = ++h->xgen;
     CVO_CUDA(h, launch_persistent(h, A));
@@ -1146,7 +1153,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
     IterArgs Ag = A;
     choose_mode(h, Ag, h->src, h->tgt, h->params.ell_init, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
-    if (!(Ag.grid && h->use_persist && (A.world == 1 || h->peers_ready))) {
+    if (!((Ag.grid || (Ag.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready))) {
       rc = ensure_graph(h, Ag, 32);
       if (rc != CVO_B200_OK) {
         cudaEventDestroy(ev0);
@@ -1594,7 +1601,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   choose_mode(h, A, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
   rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
-  const bool persist = A.grid && h->use_persist && (A.world == 1 || h->peers_ready);
+  const bool persist = (A.grid || (A.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready);
   if (persist) {
     A.xfused = A.world > 1 ? 1 : 0;
     A.xgen = ++h->xgen;

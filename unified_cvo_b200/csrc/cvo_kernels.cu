@@ -716,11 +716,10 @@ struct __align__(16) TileSmemWarp {
   uint32_t idx[kTileChunk];  // their Morton positions
   uint32_t cstart[32], cend[32];  // the current group of 32 cube cells: range of Morton positions
   uint32_t cpre[33];              // exclusive prefix of their run counts (runs of 4 targets)
-  uint64_t bar;
 };
 
 __device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs, TileSmemWarp& S,
-                                           int gwarp, int nwarps, uint32_t& bar_phase) {
+                                           uint64_t* bar, int gwarp, int nwarps, uint32_t& bar_phase) {
   const int lane = threadIdx.x & 31;
   const GridView& G = A.gv;
   const uint32_t L = (uint32_t)A.tile_L;
@@ -768,11 +767,11 @@ __device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs
     if (lane == 0) {
       fence_proxy_async();
       const uint32_t bytes = (uint32_t)nrows * (uint32_t)sizeof(float4);
-      mbar_expect_tx(&S.bar, 2u * bytes);
-      tma_bulk_g2s(S.stage, A.src_xyz + A.row_begin + row0, bytes, &S.bar);
-      tma_bulk_g2s(S.stage + kTileRows, A.src_rowA + A.row_begin + row0, bytes, &S.bar);
+      mbar_expect_tx(bar, 2u * bytes);
+      tma_bulk_g2s(S.stage, A.src_xyz + A.row_begin + row0, bytes, bar);
+      tma_bulk_g2s(S.stage + kTileRows, A.src_rowA + A.row_begin + row0, bytes, bar);
     }
-    mbar_wait(&S.bar, bar_phase);
+    mbar_wait(bar, bar_phase);
     bar_phase ^= 1u;
     // ---- the lane's two rows: prefilter records in registers, the row's ball in lattice units
     float rax[2], ray[2], raz[2], rt[2], fq[2][3], frq[2];
@@ -1034,15 +1033,15 @@ __global__ void __launch_bounds__(kPairWarps * 32, 3) tile_kernel(IterArgs A) {
   if (hs->done) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   TileSmemWarp& S = smem[warp];
+  __shared__ uint64_t bars[kPairWarps];
   if (lane == 0) {
-    mbar_init(&S.bar, 1);
+    mbar_init(&bars[warp], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
   uint32_t bar_phase = 0u;
-  // warps of one block take tiles that are far apart in the Morton order: the heavy (spread)
-  // tiles are dealt round-robin
-  tile_phase(A, hs, S, warp * gridDim.x + blockIdx.x, gridDim.x * kPairWarps, bar_phase);
+  // warps of one block take tiles that are far apart in the Morton order
+  tile_phase(A, hs, S, &bars[warp], warp * gridDim.x + blockIdx.x, gridDim.x * kPairWarps, bar_phase);
 }
 
 // ================================================================== flow_kernel
@@ -2377,16 +2376,25 @@ __device__ __forceinline__ void publish_block_partial(const double (&v)[NV], dou
   }
 }
 
-template <int kThreads, bool kFused, bool kColour>
+// dynamic shared memory of the persistent kernel: one buffer, three lives - the candidate queues
+// of the flow phase (per 8-lane row group: cell queries 48 words, tile cells 80), all blocks'
+// values of a reduction, and (tile mode) the per-warp staging of the tile phase.  Every reduction
+// starts and ends with a block barrier; the phases run between two of them.
+constexpr size_t align_grid_smem_bytes(int threads, int gen) {
+  const size_t list = sizeof(uint32_t) * (size_t)(threads / kGroup) * (size_t)(gen == 2 ? kGroupList : kGridList);
+  const size_t all = sizeof(double) * kLLValues * kLLMaxBlocks;
+  const size_t tile = gen == 2 ? sizeof(TileSmemWarp) * (size_t)(threads / 32) : 0;
+  return (list > all ? (list > tile ? list : tile) : (all > tile ? all : tile)) + 16;
+}
+
+// kGen: 1 = cell queries, 2 = tile cells (a tile phase + a grid-wide hand-over in front of the flow
+// phase)
+template <int kThreads, bool kFused, bool kColour, int kGen = 1>
 __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   __shared__ double sh[32 * kLLValues];              // per-warp values of a reduction
-  // one buffer, two lives: the candidate queues of the flow phase (cell queries queue at most 7
-  // pending + 32 new candidates per row group) and all blocks' values of a reduction.  Every
-  // reduction starts and ends with a block barrier, the flow phase runs between two of them.
-  constexpr size_t kListBytes = sizeof(uint32_t) * (kThreads / kGroup) * kGridList;
-  constexpr size_t kAllBytes = sizeof(double) * kLLValues * kLLMaxBlocks;
-  __shared__ __align__(16) unsigned char s_raw[kListBytes > kAllBytes ? kListBytes : kAllBytes];
-  uint32_t(*s_list)[kGridList] = reinterpret_cast<uint32_t(*)[kGridList]>(s_raw);
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  constexpr int kListWords = (kGen == 2) ? kGroupList : kGridList;
+  uint32_t(*s_list)[kListWords] = reinterpret_cast<uint32_t(*)[kListWords]>(s_raw);
   double* sh_all = reinterpret_cast<double*>(s_raw);
   __shared__ __align__(16) DevState s_st;
   __shared__ CtrlScratch s_ctrl;
@@ -2427,6 +2435,15 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   const int lane = threadIdx.x & 31;
   const int warp_in_block = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
+  uint32_t tile_bar_phase = 0u;
+  __shared__ uint64_t s_tile_bar[kGen == 2 ? kThreads / 32 : 1];  // outside the overlaid buffer
+  if (kGen == 2) {
+    if (lane == 0) {
+      mbar_init(&s_tile_bar[warp_in_block], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   unsigned int seq = 0;  // sequence number of the grid-wide reductions of this launch
   // dynamic row hand-out (more rows than resident row slots): every warp ends its flow phase
   // with exactly one failing fetch, so the monotone counter advances by a known amount
@@ -2441,10 +2458,22 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     // ---- flow phase (fill_in_A_mat_gpu + compute_flow_gpu_no_eigen on this block's rows)
     double tot[9];
     unsigned int n_sat = 0u;
+    if (kGen == 2) {
+      // ---- tile phase: candidate cells for ALL rows of this rank, items dealt round-robin to the
+      //      warps of the grid; the rows are evaluated by other blocks, so the cells are handed
+      //      over through one grid-wide reduction with release / acquire
+      TileSmemWarp& S = reinterpret_cast<TileSmemWarp*>(s_raw)[warp_in_block];
+      tile_phase(A, &s_st, S, &s_tile_bar[kGen == 2 ? warp_in_block : 0], warp_in_block * (int)gridDim.x + (int)blockIdx.x,
+                 (int)gridDim.x * warps_per_block, tile_bar_phase);
+      CVO_PHASE(2)
+      double one[1] = {1.0}, got[1];
+      ll_allreduce<1, 1>(A.ll, ++seq, one, sh, sh_all, got, true, true);
+      CVO_PHASE(7)
+    }
     {
       double bp[9], queued[2], v[kLLValues], r[kLLValues];
       CVO_BSTAMP(-1)
-      flow_rows<1, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp, queued);
+      flow_rows<kGen, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp, queued);
       CVO_PHASE(0)
       CVO_BSTAMP(0)
 #pragma unroll
@@ -2666,7 +2695,7 @@ void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t 
 }
 // the instantiations of the persistent kernel: block size x single GPU / fused multi-GPU
 // exchange x colour cut in stage 1 (each kept out of the code that does not need it: the kernel is
-// register bound)
+// register bound) for the cell queries; one block size for the tile cells
 template <int kThreads>
 static const void* align_grid_fn_t(bool fused, bool colour) {
   if (fused)
@@ -2675,22 +2704,39 @@ static const void* align_grid_fn_t(bool fused, bool colour) {
   return colour ? (const void*)align_grid_kernel<kThreads, false, true>
                 : (const void*)align_grid_kernel<kThreads, false, false>;
 }
-static const void* align_grid_fn(int threads, bool fused, bool colour) {
+static const void* align_grid_fn(int threads, bool fused, bool colour, bool tile) {
+  if (tile)
+    return fused ? (const void*)align_grid_kernel<kPersistThreads, true, true, 2>
+                 : (const void*)align_grid_kernel<kPersistThreads, false, true, 2>;
   if (threads == kPersistThreadsSmall) return align_grid_fn_t<kPersistThreadsSmall>(fused, colour);
   if (threads == kPersistThreadsWide) return align_grid_fn_t<kPersistThreadsWide>(fused, colour);
   return align_grid_fn_t<kPersistThreads>(fused, colour);
 }
+static int align_grid_threads(int threads, bool tile) {
+  if (tile) return kPersistThreads;
+  return (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
+}
 cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaStream_t s) {
   IterArgs a = A;
   void* args[] = {&a};
-  const int t = (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
-  return cudaLaunchCooperativeKernel(align_grid_fn(t, A.xfused != 0, A.colour != 0), dim3(blocks), dim3(t), args, 0, s);
+  const bool tile = A.tile != 0;
+  const int t = align_grid_threads(threads, tile);
+  const void* fn = align_grid_fn(t, A.xfused != 0, A.colour != 0, tile);
+  const size_t smem = align_grid_smem_bytes(t, tile ? 2 : 1);
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(t), args, smem, s);
 }
-int align_grid_max_blocks_per_sm(int threads) {
+int align_grid_max_blocks_per_sm(int threads, int tile) {
   int n = 0, m = 0;
-  const int t = (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, align_grid_fn(t, false, true), t, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, align_grid_fn(t, true, true), t, 0);
+  const int t = align_grid_threads(threads, tile != 0);
+  const size_t smem = align_grid_smem_bytes(t, tile ? 2 : 1);
+  const void* f0 = align_grid_fn(t, false, true, tile != 0);
+  const void* f1 = align_grid_fn(t, true, true, tile != 0);
+  cudaFuncSetAttribute(f0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(f1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, f0, t, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, f1, t, smem);
   return n < m ? n : m;
 }
 int pair_kernel_max_blocks_per_sm() {
