@@ -5,27 +5,40 @@
 
 Metric (BASELINE.json): point-pairs/s per CVO iteration = N_src * M_tgt * iterations / time (all
 pairs counted, tested or skipped).  A "step" is one full registration
-(CvoGPU::align) of one synthetic frame pair:
-  N=1  -> workload C2  (BASELINE configs[1]: N=M=10 000, geometric kernel)
-  N>1  -> workload C4  (BASELINE configs[3]: N=M=200 000, geometry + 5-dim colour, first-frame
-          parameters, MAX_ITER capped at 50), SOURCE rows sharded across ranks, two 72/32-byte
-          NCCL all-gathers per iteration (strong scaling: the job is fixed, per-GPU work shrinks).
+(CvoGPU::align) of one synthetic frame pair.
+
+Workloads (documented choice):
+  N=1  -> C2  (BASELINE configs[1], the configuration `metric` is quoted on: N=M=10 000, geometric
+          kernel) is the headline line; the SAME line carries `scale_anchor` = C4 measured on this one
+          GPU (value, ms_per_step), so that the scaling curve has a same-workload 1-GPU point.
+  N>1  -> C4  (BASELINE configs[3]: N=M=200 000, geometry + 5-dim colour, first-frame parameters,
+          MAX_ITER capped at 50), SOURCE rows sharded across ranks (strong scaling: the job is
+          fixed).  Efficiency at N = value_N / (N * scale_anchor.value of the N=1 line).
+          `parity_vs_single`: the first iterations of the sharded run against an unsharded run of
+          the same job on rank 0's GPU, and the final pose bit-identical on every rank.
 `value`  times the loop with the clouds already resident in HBM (CUDA events on the launching
          stream, inside libcvo_b200), L2 flushed between steps.
 `e2e`    times the reference-facing call with HOST buffers (cvo_b200_align_host: upload + device-side
          build of the cloud, loop, pose read-back) by wall clock.
-`roofline`  the dominant kernel, timed live: in cell-query mode on one GPU the whole loop is ONE
-         launch of align_grid_kernel (its duration = the timed region, one launch = all the
-         iterations); otherwise the dominant per-phase kernel (pair_kernel) at the initial state.
-         `traffic` = dram bytes per launch from the committed ncu capture (profiles/traffic.json).
-`fp32`   pair tests/s against the measured packed-FMA peak (the meaningful bound of a dense scan).
-`frame_pairs`  frame-pairs/s on KITTI-05-sized clouds: a tracking frame (regular parameters,
-         constant-velocity initial guess) and a first frame (ell_init = 1.5).
-`edge_updates`  pose-graph edge updates/s (multi-frame IRLS edge loop) on four KITTI-05-sized frames.
-`cpu_baseline` / `--impl reference`  the CPU restatement of the reference's algorithm (oracle/,
-         OpenMP on all host cores) on a bounded number of leading iterations of the same job.
+`roofline`  the dominant kernel, timed live with CUDA events on the handle's stream: when the whole
+         loop is ONE launch of the persistent kernel its duration is the timed region itself;
+         otherwise the dominant per-phase kernel (tile_kernel / pair_kernel) at the initial state.
+         bound "hbm" because the contract asks for it: algorithmic bytes = (N+M)(16+4F+4C)+256 per
+         iteration — the clouds are L2-resident and the path is latency / fp32-issue
+         bound, so `frac` is tiny by construction; `traffic` = dram bytes per launch from the
+         committed ncu capture (profiles/traffic.json).
+`pipes`  what actually bounds the dominant kernel: FMA-pipe and issue utilisation from the committed
+         ncu --set full captures (profiles/pipes.json), not a derived "fraction of peak".
+`frame_pairs`  frame-pairs/s on KITTI-05-sized clouds: a tracking frame and a first frame.
+`edge_updates`  pose-graph edge updates/s (multi-frame IRLS edge loop).
+`cpu_baseline` / `--impl reference`  the restated reference CPU path cvo::cvo::align (oracle/
+         cvo_cpu_baseline.c = Cvo.cpp:885-1089: kd-tree rebuilt per iteration, no row cap, no
+         normalisation; OpenMP on all host cores), whole registrations or a bounded number of leading
+         iterations; beside it the oracle's port of the GPU-path semantics.  The reference arm never
+         imports the product (`product_library_mapped` is checked and reported).
 """
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -77,13 +90,20 @@ def tracking_init():
     return np.linalg.inv(Rm @ Tr).astype(np.float32)
 
 
-def load_workload(name):
-    import unified_cvo_b200 as u
-    from unified_cvo_b200 import synthetic
+def _synthetic_module(with_product):
+    """unified_cvo_b200/synthetic.py is pure numpy; the reference arm loads it BY PATH so that
+    nothing of the product package is imported there."""
+    if with_product:
+        from unified_cvo_b200 import synthetic
+        return synthetic
+    spec = importlib.util.spec_from_file_location("cvo_synthetic_standalone",
+                                                  os.path.join(ROOT, "unified_cvo_b200", "synthetic.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
-    cfg, yaml, over, desc = WORKLOADS[name]
-    d = synthetic.make_config(cfg)
-    p = u.read_params_yaml(os.path.join(DATA, yaml))
+
+def apply_overrides(p, over):
     for k, v in over.items():
         if k == "TRACK":
             continue
@@ -93,11 +113,42 @@ def load_workload(name):
             p.ell_decay_start = p.ell_decay_start_first_frame
         else:
             setattr(p, k, v)
+    return p
+
+
+def load_workload(name):
+    """(source, target, params, description) through the product's host mirror."""
+    import unified_cvo_b200 as u
+
+    cfg, yaml, over, desc = WORKLOADS[name]
+    d = _synthetic_module(True).make_config(cfg)
+    p = apply_overrides(u.read_params_yaml(os.path.join(DATA, yaml)), over)
 
     def cloud(c):
         return u.CvoPointCloud(c["xyz"], c["features"], c["labels"], c["geotype"])
 
     return cloud(d["source"]), cloud(d["target"]), p, desc
+
+
+def load_workload_oracle(name):
+    """The same workload for the CPU arm: oracle clouds, oracle parameter reader, no product."""
+    import oracle
+
+    cfg, yaml, over, desc = WORKLOADS[name]
+    d = _synthetic_module(False).make_config(cfg)
+    p = apply_overrides(oracle.read_params_yaml(os.path.join(DATA, yaml)), over)
+
+    def cloud(c):
+        return oracle.Cloud(c["xyz"], c["features"], c["labels"], c["geotype"])
+
+    return cloud(d["source"]), cloud(d["target"]), p, desc
+
+
+def copy_params(p):
+    import ctypes as C
+    q = type(p)()
+    C.memmove(C.byref(q), C.byref(p), C.sizeof(q))
+    return q
 
 
 class ClockSampler:
@@ -143,16 +194,14 @@ class ClockSampler:
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
-            return json.load(fh), "measured"
+            return json.load(fh), "measured (MEASURED_PEAKS.json, burst copy bandwidth)"
     except Exception:
-        return {"hbm_gbs": 6650.0}, "fallback"
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-    captures (profiles/traffic.json, written by tools/ncu_traffic.py): {"workload:kernel": bytes}."""
+def load_json(name):
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", name)) as fh:
             return json.load(fh)
     except Exception:
         return {}
@@ -163,54 +212,73 @@ def algorithmic_bytes_per_iteration(N, M, F, C):
     return (N + M) * (16 + 4 * F + 4 * C) + 256
 
 
+# ------------------------------------------------------------------------------- the CPU arm
+def cpu_port_cvo_cpp(name, max_iter=None, threads=None):
+    """The restated reference CPU path (oracle/cvo_cpu_baseline.c = cvo::cvo::align) on `name`."""
+    import oracle
+
+    src, tgt, p, desc = load_workload_oracle(name)
+    if max_iter is not None:
+        p = copy_params(p)
+        p.MAX_ITER = int(max_iter)
+    T_init = tracking_init() if WORKLOADS[name][2].get("TRACK") else None
+    ret, T, info = oracle.cpu_baseline_align(p, src, tgt, T_init, threads=threads)
+    return {"pairs": int(info["pairs"]), "seconds": float(info["seconds"]), "iterations": int(info["executed"]),
+            "threads": int(info["threads"]), "ret": int(ret), "N": src.n, "M": tgt.n,
+            "split_s": {k: round(float(info[k]), 4) for k in ("t_transform", "t_kdtree_build", "t_se_kernel",
+                                                              "t_flow", "t_step")}}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def run_reference(args, rank, world):
-    """CPU arm: the oracle's align (restated reference algorithm, OpenMP) on a bounded sample."""
+    """CPU arm: the restated reference CPU path on the arm's own workload, all host cores."""
     if rank != 0:
         return
     import oracle
 
-    oracle.use_all_host_threads()  # torchrun exports OMP_NUM_THREADS=1 to its workers
+    n_thr = host_threads()  # torchrun exports OMP_NUM_THREADS=1 to its workers
     name = args.workload or ("C2" if world == 1 else "C4")
-    src, tgt, p, desc = load_workload(name)
-    N, M = src.num_points(), tgt.num_points()
-    # bounded sample: a fixed number of leading iterations of the same registration
-    per_iter_pairs = N * M
-    # the oracle enumerates candidates through a uniform grid (bit-identical to its dense loop,
-    # oracle/cvo_oracle.c), like the reference's CPU path searches a kd-tree: ~10 ms per C2 iteration
-    sample_iters = max(2, int(min(p.MAX_ITER, 4e10 // per_iter_pairs, 400)))
-    p = p.copy()
-    p.MAX_ITER = sample_iters
-    cs = oracle.Cloud(src.positions_, src.features_, src.labels_, src.geometric_types_)
-    ct = oracle.Cloud(tgt.positions_, tgt.features_, tgt.labels_, tgt.geometric_types_)
+    N, M = (WORKLOADS[name][0] and _synthetic_module(False).CONFIGS[WORKLOADS[name][0]][1:3])
+    # bounded sample: whole registrations where they take seconds (C2: ~450 iterations, ~3 s on 8
+    # cores), a few leading iterations where one iteration takes seconds (C4)
+    max_iter = None if N * M <= 4e8 else max(2, int(2e11 // (N * M)))
     for _ in range(min(args.warmup, 1)):
-        q = p.copy()
-        q.MAX_ITER = 2
-        oracle.align(q, cs, ct)
-    times, pairs = [], 0
-    for _ in range(args.steps):
-        t0 = time.perf_counter()
-        _, _, info, _ = oracle.align(p, cs, ct)
-        times.append(time.perf_counter() - t0)
-        pairs += info.pairs_tested
-    total = sum(times)
+        cpu_port_cvo_cpp(name, max_iter=2, threads=n_thr)
+    runs = [cpu_port_cvo_cpp(name, max_iter=max_iter, threads=n_thr) for _ in range(max(1, min(args.steps, 3)))]
+    pairs = sum(r["pairs"] for r in runs)
+    total = sum(r["seconds"] for r in runs)
     value = pairs / total
-    cores = oracle.num_threads()
-    sample = f"first {sample_iters} iterations of the {name} registration per step, {args.steps} steps"
+    sample = (f"{len(runs)} x the {name} registration by the restated cvo::cvo::align "
+              f"({'whole registration' if max_iter is None else f'first {max_iter} iterations'}, "
+              f"{runs[0]['iterations']} iterations each, {total / len(runs):.2f} s each)")
+    mapped = "libcvo_b200" in open("/proc/self/maps").read()
+    imported = any(m.startswith("unified_cvo_b200") for m in sys.modules)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "steps": len(runs), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / len(runs),
         "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{name}: {desc}", "N": N, "M": M},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "note": "oracle/cvo_oracle.c with grid-accelerated candidate enumeration "
-                                 "(bit-identical to its dense N x M loop), OpenMP"},
+        "config": {"workload": f"{name}: {WORKLOADS[name][3]}", "N": int(N), "M": int(M),
+                   "iterations_per_step": runs[0]["iterations"]},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": runs[0]["threads"], "kind": "port",
+                         "port_of": "src/cvo/Cvo.cpp:885-1089 (cvo::cvo::align), oracle/cvo_cpu_baseline.c",
+                         "sample": sample, "split_s_last_run": runs[-1]["split_s"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "product_library_mapped": bool(mapped), "product_package_imported": bool(imported),
     }
+    assert not mapped and not imported, "the reference arm must not load the product"
+    assert oracle is not None
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------- our arm
 def frame_pairs_leg(u, name, steps=5):
     """frame-pairs/s = 1 / (device time of one full align) on a KITTI-05-sized synthetic pair."""
     src, tgt, p, desc = load_workload(name)
@@ -283,200 +351,273 @@ def edge_updates_leg(u, rounds=5, cpu=True):
     return out
 
 
-def run_ours(args, rank, world, local_rank):
-    import torch
-    import unified_cvo_b200 as u
-
-    name = args.workload or ("C2" if world == 1 else "C4")
-    src, tgt, p, desc = load_workload(name)
+def measure(u, torch, g, name, src, tgt, p, steps, warmup, local_rank, rank, world, dist):
+    """Timed region of one workload on the handle g (clouds already set).  Returns a dict."""
     T_init = tracking_init() if WORKLOADS[name][2].get("TRACK") else None
     N, M, F, C = src.num_points(), tgt.num_points(), src.feature_dimensions(), src.num_classes()
-    torch.cuda.set_device(local_rank)
-    g = u.CvoGPU(p, device=local_rank)
-
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("gloo", rank=rank, world_size=world)  # control plane only
-        uid = [u.CvoGPU.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        g.comm_init(rank, world, uid[0])
-        from unified_cvo_b200.dist import shard_rows
-        g.set_row_range(*shard_rows(N, world, rank))
-        if os.environ.get("CVO_B200_FUSED", "1") != "0":  # NVLink mailboxes for the persistent kernel
-            handles = [None] * world
-            dist.all_gather_object(handles, g.comm_mailbox_handle())
-            g.comm_open_peers(handles)
 
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
 
-    g.set_cloud(0, src)
-    g.set_cloud(1, tgt)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
-
     # ---- warm-up (also ramps the clocks: at least ~0.5 s of work)
     t_warm = time.perf_counter()
     w = 0
-    while w < args.warmup or time.perf_counter() - t_warm < 0.5:
+    while w < warmup or time.perf_counter() - t_warm < 0.5:
         g.align(src, tgt, T_init, resident=True)
         w += 1
-        if w > args.warmup + 50:
+        if w > warmup + 50:
             break
-
     # ---- timed region: K resident steps, device time per step, L2 flushed between steps
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     launches0 = g.launch_count()
-    dev_s, pairs, iters, grid_frac = 0.0, 0, 0, 0.0
+    dev_s, pairs, iters, persist_frac = 0.0, 0, 0, 0.0
     wall0 = time.perf_counter()
-    for _ in range(args.steps):
+    last_T = None
+    for _ in range(steps):
         flush.fill_(1)
         torch.cuda.synchronize()
-        _, _, info = g.align(src, tgt, T_init, resident=True)
+        _, last_T, info = g.align(src, tgt, T_init, resident=True)
         dev_s += info.registration_seconds
         pairs += info.pairs_tested
         iters += info.iterations + (0 if info.stop_reason == 8 else 1)
-        grid_frac += info.cell_query_fraction / args.steps
+        persist_frac += info.cell_query_fraction / steps
     barrier()
     wall = time.perf_counter() - wall0
     launches = g.launch_count() - launches0
     clocks = sampler.stop()
-
     # ---- end to end: host buffers in, pose out, through the reference-facing call
     e2e_s, e2e_pairs = 0.0, 0
-    if world == 1:
-        for _ in range(max(1, min(args.steps, 5))):
+    e2e_steps = max(1, min(steps, 5 if world == 1 else 3))
+    for _ in range(e2e_steps):
+        if world == 1:
             t0 = time.perf_counter()
             _, _, info = g.align_host(src, tgt, T_init)
-            e2e_s += time.perf_counter() - t0
-            e2e_pairs += info.pairs_tested
-        e2e_steps = max(1, min(args.steps, 5))
-    else:
-        e2e_steps = max(1, min(args.steps, 3))
-        for _ in range(e2e_steps):
+        else:
             barrier()
             t0 = time.perf_counter()
             g.set_cloud(0, src)
             g.set_cloud(1, tgt)
             _, _, info = g.align(src, tgt, T_init, resident=True)
-            e2e_s += time.perf_counter() - t0
-            e2e_pairs += info.pairs_tested
-
-    # max over ranks of the device time
-    if dist is not None:
+        e2e_s += time.perf_counter() - t0
+        e2e_pairs += info.pairs_tested
+    if dist is not None:  # max over ranks of the device time
         t = torch.tensor([dev_s, e2e_s], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_s, e2e_s = float(t[0]), float(t[1])
+    del flush
+    return dict(N=N, M=M, F=F, C=C, dev_s=dev_s, pairs=pairs, iters=iters, persist_frac=persist_frac, wall=wall,
+                launches=launches, clocks=clocks, e2e_s=e2e_s, e2e_pairs=e2e_pairs, e2e_steps=e2e_steps,
+                last_T=last_T, T_init=T_init)
 
-    # ---- roofline of the dominant kernel, measured live with CUDA events on the handle's stream
+
+def roofline_of(u, g, name, p, m, steps, rows_local, world):
+    """Contract object for the dominant kernel + the measured pipe figures."""
     peaks, peak_src = measured_peaks()
+    alg_bytes_iter = algorithmic_bytes_per_iteration(rows_local, m["M"], m["F"], m["C"])
+    traffic, pipes = load_json("traffic.json"), load_json("pipes.json")
+    persistent = m["persist_frac"] >= 0.5 and os.environ.get("CVO_B200_PERSIST", "1") != "0"
+    if persistent:
+        # the whole loop is ONE launch of the persistent kernel per GPU: its duration is the timed
+        # region itself (registration_seconds = CUDA events around that launch) and one launch
+        # processes `iterations` iterations
+        kernel = "align_grid_kernel"
+        t_kernel = m["dev_s"] / steps
+        launch_units = m["iters"] / steps
+        share = 1.0
+    else:
+        # one launch per phase: time the candidate generator of an iteration at the initial state
+        ms_tot, ms_k = g.time_iterations(np.eye(3), np.zeros(3), p.ell_init, p.nearest_neighbors_max, 20)
+        kernel = "tile_kernel|pair_kernel (the candidate generator of the dense regimes)"
+        t_kernel = max(ms_k, 1e-6) / 20 * 1e-3
+        launch_units = 1.0
+        share = ms_k / ms_tot if ms_tot > 0 else None
+    achieved = launch_units * alg_bytes_iter / t_kernel / 1e9
+    key = f"{name}:{kernel.split('|')[0]}"
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic.get(key),
+            "peak_source": peak_src, "kernel": kernel, "kernel_us": t_kernel * 1e6,
+            "iterations_per_launch": launch_units, "algorithmic_bytes_per_iteration": alg_bytes_iter,
+            "kernel_share_of_step": share, "ranks": world,
+            "note": "algorithmic bytes = (N_local+M)(16+4F+4C)+256 per iteration (SURVEY.md 8d). The clouds are "
+                    "L2-resident; the path is latency / fp32-issue bound, not HBM bound (see pipes)"}
+    pipe = pipes.get(key, {})
+    pipe_obj = {"kernel": kernel, "fma_pipe_pct": pipe.get("fma_pipe_pct"), "issue_active_pct": pipe.get("issue_active_pct"),
+                "warps_active_pct": pipe.get("warps_active_pct"), "top_stalls": pipe.get("top_stalls"),
+                "source": pipe.get("source", "no ncu capture committed for this workload/kernel"),
+                "dense_equivalent_pairs_per_s": rows_local * m["M"] * launch_units / t_kernel,
+                "note": "ncu --set full figures of the committed capture (profiles/), not derived numbers; "
+                        "dense_equivalent = N_local*M pairs per iteration / kernel time (culled pairs counted)"}
+    return roof, pipe_obj
+
+
+def parity_vs_single(u, g, name, src, tgt, p, T_init, last_T, rank, world, local_rank, dist, k=4):
+    """The first k iterations of the sharded run against an unsharded run of the same job on
+    this rank's GPU; the final pose of the sharded run bit-identical on every rank."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import compare_traces
+    q = p.copy()
+    q.MAX_ITER = k
+    g.write_params(q)
+    _, _, _, tr_sh = g.align(src, tgt, T_init, trace_cap=k, resident=True)
+    g.write_params(p)
+    out = {"iterations_compared": k}
+    if rank == 0:
+        s = u.CvoGPU(q, device=local_rank)
+        s.set_cloud(0, src)
+        s.set_cloud(1, tgt)
+        _, _, _, tr_1 = s.align(src, tgt, T_init, trace_cap=k, resident=True)
+        s.close()
+        bad = [(i, compare_traces(tr_sh[i], tr_1[i])) for i in range(min(len(tr_sh), len(tr_1)))]
+        bad = [(i, b) for i, b in bad if b]
+        tw = max(float(np.abs(np.array(list(tr_sh[i].omega) + list(tr_sh[i].v)) -
+                              np.array(list(tr_1[i].omega) + list(tr_1[i].v))).max()) for i in range(len(tr_1)))
+        out.update({"trace_ok": not bad, "mismatches": [f"iter {i}: {b}" for i, b in bad][:4],
+                    "max_abs_twist_diff": tw, "nnz_equal": all(tr_sh[i].nnz == tr_1[i].nnz for i in range(len(tr_1)))})
+    poses = [None] * world
+    dist.all_gather_object(poses, np.asarray(last_T, np.float32).tobytes())
+    out["pose_bit_identical_across_ranks"] = all(b == poses[0] for b in poses)
+    return out
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import unified_cvo_b200 as u
+
+    name = args.workload or ("C2" if world == 1 else "C4")
+    src, tgt, p, desc = load_workload(name)
+    N = src.num_points()
+    torch.cuda.set_device(local_rank)
+    g = u.CvoGPU(p, device=local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)  # control plane only
+        from unified_cvo_b200.dist import attach
+        attach(g, N, rank, world, dist, fused=os.environ.get("CVO_B200_FUSED", "1") != "0")
+    g.set_cloud(0, src)
+    g.set_cloud(1, tgt)
+    m = measure(u, torch, g, name, src, tgt, p, args.steps, args.warmup, local_rank, rank, world, dist)
     if world == 1:
         rows_local = N
     else:
         from unified_cvo_b200.dist import shard_rows
         rb, re_ = shard_rows(N, world, rank)
         rows_local = re_ - rb
-    alg_bytes_iter = algorithmic_bytes_per_iteration(rows_local, M, F, C)
-    traffic = load_traffic()
-    fused = world > 1 and os.environ.get("CVO_B200_FUSED", "1") != "0"
-    if grid_frac >= 0.5 and (world == 1 or fused) and os.environ.get("CVO_B200_PERSIST", "1") != "0":
-        # cell-query mode (one GPU, or sharded with the NVLink mailbox exchange): the whole loop is
-        # ONE launch of align_grid_kernel per GPU, so the
-        # kernel's duration is the timed region itself (registration_seconds = CUDA events around
-        # that launch) and one launch processes `iterations` iterations
-        kernel = "align_grid_kernel"
-        t_kernel = dev_s / args.steps
-        launch_units = iters / args.steps
-        share = 1.0
-    else:
-        # one launch per phase: time the dominant kernel of an iteration at the initial state
-        kernel = "pair_kernel" if grid_frac < 0.5 else "flow_kernel_t<true>"
-        ms_tot, ms_k = g.time_iterations(np.eye(3), np.zeros(3), p.ell_init, p.nearest_neighbors_max, 40)
-        t_kernel = ms_k / 40 * 1e-3
-        launch_units = 1.0
-        share = ms_k / ms_tot
-    achieved = launch_units * alg_bytes_iter / t_kernel / 1e9
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic.get(f"{name}:{kernel}"),
-            "peak_source": peak_src, "kernel": kernel, "kernel_us": t_kernel * 1e6,
-            "iterations_per_launch": launch_units, "algorithmic_bytes_per_iteration": alg_bytes_iter,
-            "kernel_share_of_step": share,
-            "note": "algorithmic bytes = (N+M)(16+4F+4C)+256 per iteration (SURVEY.md 8d): the clouds "
-                    "are L2-resident and the path is latency/fp32 bound, not HBM bound; see fp32"}
-    fma = g.fma_peak(1, 8192)
-    pair_rate = rows_local * M * launch_units / t_kernel
-    fp32 = {"pair_tests_per_s": pair_rate, "fma_peak_per_s": fma, "fma_per_pair": 3,
-            "peak_pair_tests_per_s": fma / 3.0, "frac": pair_rate / (fma / 3.0),
-            "note": "N*M pairs per iteration / kernel time against a dense scan at the measured "
-                    "packed-FMA peak (3 FMA per pair); cell queries skip most pairs, so this "
-                    "dense-equivalent fraction can exceed 1"}
-
+    roof, pipes = roofline_of(u, g, name, p, m, args.steps, rows_local, world)
+    par = None
+    if world > 1:
+        par = parity_vs_single(u, g, name, src, tgt, p, m["T_init"], m["last_T"], rank, world, local_rank, dist)
     if rank != 0:
         return
-    value = pairs / dev_s
+    value = m["pairs"] / m["dev_s"]
     # what cvo_b200_align_host copies: the caller's arrays as they are (xyz 12 B, features 4F,
     # labels 4C, geometric type 8 B per point when present), the parameters and the 9 KB state
     geo = 8 if src.geometric_types_ is not None else 0
-    h2d = (N + M) * (12 + 4 * F + 4 * C + geo) + 512 + 9000
+    h2d = (m["N"] + m["M"]) * (12 + 4 * m["F"] + 4 * m["C"] + geo) + 512 + 9000
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": 1e3 * m["dev_s"] / args.steps, "higher_is_better": True,
         "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{name}: {desc}", "N": N, "M": M, "F": F, "C": C,
-                   "iterations_per_step": iters / args.steps, "l2_flush_between_steps": True,
-                   "cell_query_fraction": grid_frac,
+        "config": {"workload": f"{name}: {desc}", "N": m["N"], "M": m["M"], "F": m["F"], "C": m["C"],
+                   "iterations_per_step": m["iters"] / args.steps, "l2_flush_between_steps": True,
+                   "persistent_kernel_fraction": m["persist_frac"],
                    "parallelism": "single GPU" if world == 1 else
-                   f"source rows sharded x{world}; dense-scan batches: NCCL all-gather, cell-query "
-                   f"batches: persistent kernel with NVLink mailbox exchange",
-                   "timing": "CUDA events on the launching stream inside cvo_b200_align, summed over steps"},
-        "e2e": {"value": e2e_pairs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 8800, "steps": e2e_steps,
+                   f"source rows sharded x{world}; the whole loop is one persistent kernel per GPU whose two "
+                   f"per-iteration exchanges are NVLink stores into the peers' mailboxes (no NCCL call, no launch "
+                   f"per iteration); NCCL all-gathers only for batches that fall back to one launch per phase",
+                   "timing": "CUDA events on the launching stream inside cvo_b200_align, summed over steps; "
+                             "max over ranks"},
+        "e2e": {"value": m["e2e_pairs"] / m["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 8800, "steps": m["e2e_steps"],
                 "note": "wall clock around cvo_b200_align_host: upload, loop, pose read-back"},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "gpu_launches": int(m["launches"]),
+        "gpu_launches_per_iteration": m["launches"] / max(m["iters"], 1),
+        "clocks": m["clocks"],
         "roofline": roof,
-        "fp32": fp32,
-        "wall_ms_per_step": 1e3 * wall / args.steps,
-        "frame_pairs_per_s": args.steps / dev_s,
+        "pipes": pipes,
+        "wall_ms_per_step": 1e3 * m["wall"] / args.steps,
+        "frame_pairs_per_s": args.steps / m["dev_s"],
     }
+    if par is not None:
+        line["parity_vs_single"] = par
+    # the same-workload anchor of the scaling curve: C4 on THIS one GPU
+    if world == 1 and args.workload is None and not args.no_anchor:
+        g.close()
+        s4, t4, p4, d4 = load_workload("C4")
+        g4 = u.CvoGPU(p4, device=local_rank)
+        g4.set_cloud(0, s4)
+        g4.set_cloud(1, t4)
+        m4 = measure(u, torch, g4, "C4", s4, t4, p4, 2, 2, local_rank, 0, 1, None)
+        roof4, pipes4 = roofline_of(u, g4, "C4", p4, m4, 2, s4.num_points(), 1)
+        line["scale_anchor"] = {
+            "workload": f"C4: {d4}", "n_gpus": 1, "value": m4["pairs"] / m4["dev_s"], "unit": UNIT, "steps": 2,
+            "ms_per_step": 1e3 * m4["dev_s"] / 2, "iterations_per_step": m4["iters"] / 2,
+            "e2e_value": m4["e2e_pairs"] / m4["e2e_s"], "gpu_launches": int(m4["launches"]), "clocks": m4["clocks"],
+            "roofline": roof4, "pipes": pipes4,
+            "note": "the N>1 lines run this workload sharded: efficiency(N) = value_N / (N * this value)"}
+        g4.close()
+        del s4, t4
+        g = None
     # frame-pairs/s on KITTI-05-sized clouds (north_star): a tracking frame and a first frame
     if world == 1 and args.workload is None and not args.no_frames:
         line["frame_pairs"] = [frame_pairs_leg(u, wl) for wl in ("KITTI05_TRACK", "KITTI05")]
         line["edge_updates"] = edge_updates_leg(u, cpu=not args.no_cpu_baseline)
-    # CPU baseline beside it (rank 0, N=1 only): bounded sample of the same registration
+    # CPU baselines beside it (rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:
         import oracle
-        oracle.use_all_host_threads()
-        q = p.copy()
-        q.MAX_ITER = max(2, int(min(p.MAX_ITER, 2.5e11 // (N * M), 4000)))
+        n_thr = oracle.use_all_host_threads()
+        base = cpu_port_cvo_cpp(name, max_iter=None if m["N"] * m["M"] <= 4e8 else max(2, int(2e11 // (m["N"] * m["M"]))),
+                                threads=n_thr)
         cs = oracle.Cloud(src.positions_, src.features_, src.labels_, src.geometric_types_)
         ct = oracle.Cloud(tgt.positions_, tgt.features_, tgt.labels_, tgt.geometric_types_)
+        q = p.copy()
+        q.MAX_ITER = max(2, int(min(p.MAX_ITER, 2.5e11 // (m["N"] * m["M"]), 4000)))
         t0 = time.perf_counter()
         _, _, info, _ = oracle.align(q, cs, ct)
         dt = time.perf_counter() - t0
         executed = info.iterations + (0 if info.stop_reason == 8 else 1)
-        # the literal dense N x M loop of the same oracle on a short sample, for context
-        oracle.set_accel(False)
-        qd = p.copy()
-        qd.MAX_ITER = max(2, int(min(p.MAX_ITER, 4e9 // (N * M), 40)))
-        t0 = time.perf_counter()
-        _, _, info_d, _ = oracle.align(qd, cs, ct)
-        dt_d = time.perf_counter() - t0
-        oracle.set_accel(True)
-        line["cpu_baseline"] = {"value": info.pairs_tested / dt, "unit": UNIT, "cores": oracle.num_threads(),
-                                "kind": "port",
-                                "sample": f"the same {name} registration, first {q.MAX_ITER} iterations at most "
-                                          f"({executed} executed; oracle/cvo_oracle.c with grid-accelerated "
-                                          f"candidate enumeration, OpenMP), {dt:.1f} s",
-                                "dense_loop_value": info_d.pairs_tested / dt_d,
-                                "dense_loop_sample": f"first {qd.MAX_ITER} iterations, literal N x M loop, {dt_d:.1f} s"}
+        line["cpu_baseline"] = {
+            "value": base["pairs"] / base["seconds"], "unit": UNIT, "cores": base["threads"], "kind": "port",
+            "port_of": "src/cvo/Cvo.cpp:885-1089 (cvo::cvo::align), oracle/cvo_cpu_baseline.c",
+            "sample": f"one whole {name} registration by the restated reference CPU path: {base['iterations']} "
+                      f"iterations, {base['seconds']:.2f} s (kd-tree rebuilt per iteration, no row cap, no "
+                      f"normalisation)",
+            "frame_pairs_per_s": 1.0 / base["seconds"], "split_s": base["split_s"],
+            "oracle_port": {"value": info.pairs_tested / dt, "unit": UNIT, "cores": oracle.num_threads(),
+                            "what": "oracle/cvo_oracle.c: CPU port of the GPU-path semantics (row cap, normalised "
+                                    "twist), grid-accelerated candidate enumeration, OpenMP",
+                            "sample": f"first {q.MAX_ITER} iterations at most ({executed} executed), {dt:.1f} s"}}
+        if args.workload is None:  # BASELINE config 1: the demo pair through the same CPU path
+            try:
+                demo = cpu_demo_registration(n_thr)
+                line["cpu_baseline"]["demo_registration"] = demo
+            except Exception as e:  # never let an auxiliary leg take the line down
+                line["cpu_baseline"]["demo_registration"] = {"error": str(e)}
     print(json.dumps(line), flush=True)
-    g.close()
+    if g is not None:
+        g.close()
+
+
+def cpu_demo_registration(n_thr):
+    """BASELINE configs[0]: demo_data/source.pcd vs target.pcd, cvo_outdoor_params.yaml, the
+    reference CPU align() (restated) on the host cores - whole-registration time."""
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import demo_clouds, demo_params, to_oracle_cloud
+    out = {}
+    for flavour, color in (("two_color_pcd (colour)", True), ("two_pcd (geometric only)", False)):
+        src, tgt = demo_clouds(color=color)
+        p = demo_params(src, tgt, color=color)
+        ret, T, info = oracle.cpu_baseline_align(p, to_oracle_cloud(src), to_oracle_cloud(tgt), threads=n_thr)
+        out[flavour] = {"seconds": float(info["seconds"]), "iterations": int(info["executed"]), "ret": int(ret),
+                        "pairs_per_s": float(info["pairs"]) / float(info["seconds"]), "cores": int(info["threads"])}
+    return out
 
 
 def main():
@@ -488,6 +629,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-frames", action="store_true", help="skip the KITTI-05-sized frame-pairs/s legs")
+    ap.add_argument("--no-anchor", action="store_true", help="skip the C4 scale anchor of the N=1 line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,8 +1,10 @@
 """Python face of the CPU oracle (oracle/cvo_oracle.c).
 
-TEST INFRASTRUCTURE ONLY — PARITY UNPINNED (see oracle/cvo_oracle.h).  Only
-tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
-legs may import this package.  The product (unified_cvo_b200) never does.
+TEST INFRASTRUCTURE ONLY (what is pinned against the reference and what is not: oracle/cvo_oracle.h).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this package.  The product (unified_cvo_b200) never does - and this package never imports
+the product: its ABI structs (abi_types.py), parameter defaults and YAML reader (params.py) are
+its own, so the reference arm of bench.py runs without libcvo_b200.so in the process.
 """
 from __future__ import annotations
 
@@ -12,7 +14,8 @@ import subprocess
 
 import numpy as np
 
-from unified_cvo_b200._abi import AlignInfo, IterTrace, Params  # type definitions only
+from .abi_types import AlignInfo, IterTrace, Params  # the oracle's own mirrors of the ABI structs
+from .params import default_params, read_params_yaml  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libcvo_oracle.so")
@@ -64,17 +67,17 @@ def lib() -> C.CDLL:
         L.oracle_sparse_new.argtypes = [C.c_int, C.c_int]
         L.oracle_sparse_free.argtypes = [C.POINTER(_Sparse)]
         L.oracle_align.restype = C.c_int
-        L.oracle_align.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
+        L.oracle_align.argtypes = [C.c_void_p, C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
                                    f32p, C.POINTER(AlignInfo), C.POINTER(IterTrace), C.c_int]
         L.oracle_iterate.restype = None
-        L.oracle_iterate.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
+        L.oracle_iterate.argtypes = [C.c_void_p, C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
                                      f32p, C.c_float, C.c_int, C.POINTER(IterTrace),
                                      C.POINTER(_Sparse)]
         L.oracle_inner_product.restype = C.c_float
-        L.oracle_inner_product.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud),
+        L.oracle_inner_product.argtypes = [C.c_void_p, C.POINTER(_Cloud), C.POINTER(_Cloud),
                                            f32p, C.c_float, f32p, C.POINTER(_Sparse)]
         L.oracle_function_angle.restype = C.c_float
-        L.oracle_function_angle.argtypes = [C.POINTER(Params), C.POINTER(_Cloud),
+        L.oracle_function_angle.argtypes = [C.c_void_p, C.POINTER(_Cloud),
                                             C.POINTER(_Cloud), f32p, C.c_float, C.c_int]
         L.oracle_cubic_roots.restype = C.c_int
         L.oracle_cubic_roots.argtypes = [C.POINTER(C.c_double)] * 3
@@ -92,24 +95,24 @@ def lib() -> C.CDLL:
         L.oracle_transform_pose_vec.restype = None
         L.oracle_transform_pose_vec.argtypes = [f32p, f32p, C.c_int, f32p]
         L.oracle_edge_update.restype = C.c_ulonglong
-        L.oracle_edge_update.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), f32p,
+        L.oracle_edge_update.argtypes = [C.c_void_p, C.POINTER(_Cloud), f32p,
                                          C.POINTER(_Cloud), f32p, C.c_float, C.c_int,
                                          C.POINTER(_Sparse)]
         f64p = C.POINTER(C.c_double)
         L.oracle_flow_rows.restype = None
-        L.oracle_flow_rows.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), f32p, C.POINTER(_Sparse),
+        L.oracle_flow_rows.argtypes = [C.c_void_p, C.POINTER(_Cloud), f32p, C.POINTER(_Sparse),
                                        f64p, f64p]
         L.oracle_step_rows.restype = None
-        L.oracle_step_rows.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), f32p, C.c_int,
+        L.oracle_step_rows.argtypes = [C.c_void_p, C.POINTER(_Cloud), f32p, C.c_int,
                                        C.POINTER(_Sparse), f32p, f32p, C.c_float, f64p]
         L.oracle_set_device_arith.restype = None
         L.oracle_set_device_arith.argtypes = [C.c_int]
         L.oracle_device_arith.restype = C.c_int
         L.oracle_fill_A.restype = None
-        L.oracle_fill_A.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
+        L.oracle_fill_A.argtypes = [C.c_void_p, C.POINTER(_Cloud), C.POINTER(_Cloud), f32p,
                                     C.c_int, C.c_float, C.POINTER(_Sparse)]
         L.oracle_fill_A_dense_kernel.restype = None
-        L.oracle_fill_A_dense_kernel.argtypes = [C.POINTER(Params), C.POINTER(_Cloud),
+        L.oracle_fill_A_dense_kernel.argtypes = [C.c_void_p, C.POINTER(_Cloud),
                                                  C.POINTER(_Cloud), f32p, C.c_int, f32p,
                                                  C.POINTER(_Sparse)]
         _lib = L
@@ -386,7 +389,7 @@ def _baseline():
             build()
         L = C.CDLL(_BASE_SO)
         L.cpu_baseline_align.restype = C.c_int
-        L.cpu_baseline_align.argtypes = [C.POINTER(Params), C.POINTER(_Cloud), C.POINTER(_Cloud),
+        L.cpu_baseline_align.argtypes = [C.c_void_p, C.POINTER(_Cloud), C.POINTER(_Cloud),
                                          C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_float),
                                          C.POINTER(_BaselineInfo)]
         L.oracle_set_num_threads.argtypes = [C.c_int]

@@ -147,3 +147,43 @@ def test_defaults_and_field_order_agree_with_the_reference_header():
     p = u.default_params()
     for name, val in defaults.items():
         assert getattr(p, name) == pytest.approx(float(val), rel=1e-6), name
+
+
+def test_oracle_owns_identical_abi_mirrors_and_does_not_import_the_product():
+    """oracle/abi_types.py and unified_cvo_b200/_abi.py describe the same three structs field for
+    field (the oracle takes the product's structs through void pointers), and importing the
+    oracle pulls in nothing of the product (bench.py's reference arm must not map libcvo_b200.so)."""
+    import subprocess
+    import sys
+
+    from oracle import abi_types as o
+
+    for name in ("Params", "IterTrace", "AlignInfo"):
+        a, b = getattr(o, name), getattr(_abi, name)
+        assert [(n, t) if not hasattr(t, "_length_") else (n, t._type_, t._length_) for n, t in a._fields_] == \
+               [(n, t) if not hasattr(t, "_length_") else (n, t._type_, t._length_) for n, t in b._fields_], name
+        assert C.sizeof(a) == C.sizeof(b)
+    code = ("import sys, oracle; oracle.lib(); "
+            "assert not [m for m in sys.modules if m.startswith('unified_cvo_b200')], 'product imported'; "
+            "assert 'libcvo_b200' not in open('/proc/self/maps').read(), 'product library mapped'; print('clean')")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and "clean" in out.stdout, out.stderr[-2000:]
+
+
+def test_oracle_yaml_reader_equals_the_products_reader(data_dir):
+    """oracle/params.py (pure Python, used by the reference arm) against cvo_b200_params_read_yaml
+    on every yaml shipped in tests/data, field by field; and the two sets of constructor defaults."""
+    import glob
+
+    import oracle
+    import unified_cvo_b200 as u
+
+    files = sorted(glob.glob(os.path.join(data_dir, "*.yaml")))
+    assert len(files) >= 5
+    d0, d1 = oracle.default_params(), u.default_params()
+    for n, _ in _abi.Params._fields_:
+        assert getattr(d0, n) == getattr(d1, n), n
+    for f in files:
+        a, b = oracle.read_params_yaml(f), u.read_params_yaml(f)
+        for n, _ in _abi.Params._fields_:
+            assert getattr(a, n) == getattr(b, n), (os.path.basename(f), n)

@@ -1662,6 +1662,12 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
             t3[2] ? (double)t3[0] / (double)t3[2] : 0.0, t3[1]);
     cudaMemset(A.stamps + 32000, 0, sizeof(t3));
   }
+  if (A.stamps && persist) {  // inside the controller of the LAST iteration (thread 0 / thread 32 stamps)
+    unsigned long long d[16];
+    cudaMemcpy(d, h->d_state->dbg, sizeof(d), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[controller] cubic done %+lld | exp+pose (t0) done %+lld | se3log (t32) done %+lld | end %+lld ns after entry\n",
+            (long long)(d[13] - d[12]), (long long)(d[14] - d[12]), (long long)(d[15] - d[12]), (long long)(d[11] - d[12]));
+  }
   if (A.stamps && persist) {  // per-phase time of block 0 / thread 0, averaged over the iterations
     unsigned long long acc[10];
     cudaMemcpy(acc, A.stamps, sizeof(acc), cudaMemcpyDeviceToHost);
@@ -1669,17 +1675,6 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
                              "step allreduce (incl. wait)", "-", "-", "controller"};
     for (int k = 0; k < 10; k++)
       fprintf(stderr, "[phases] %-28s %7.2f us/iter\n", names[k], (double)acc[k] / 1e3 / (double)iters);
-    // per block: flow rows / flow reduction / step rows / step reduction (thread 0's view)
-    std::vector<unsigned long long> pb((size_t)4 * h->persist_blocks);
-    cudaMemcpy(pb.data(), A.stamps + 64, pb.size() * 8, cudaMemcpyDeviceToHost);
-    const char* bn[4] = {"flow rows", "flow allreduce", "step rows", "step allreduce"};
-    for (int q = 0; q < 4; q++) {
-      std::vector<double> v;
-      for (int b = 0; b < h->persist_blocks; b++) v.push_back((double)pb[(size_t)4 * b + q] / 1e3 / (double)iters);
-      std::sort(v.begin(), v.end());
-      fprintf(stderr, "[blocks] %-16s min %6.2f  p50 %6.2f  p90 %6.2f  max %6.2f us/iter\n", bn[q], v.front(),
-              v[v.size() / 2], v[v.size() * 9 / 10], v.back());
-    }
   }
   if (A.stamps && !persist) {  // per-block phase stamps of the LAST flow launch (ns, relative to the first block)
     const int nb = A.grid ? h->grid_blocks : h->sparse_blocks;

@@ -2301,38 +2301,15 @@ __device__ __forceinline__ void ll_allreduce(LLBoard* board, unsigned int seq, c
       ll_store(&board->w[par][blockIdx.x][2 * k], r, seq);
     }
   }
-  // every thread fetches its share of the nblocks x NV values: all its 16-byte loads (both words
-  // of a value) are issued together, then only the values that had not arrived yet are polled
-  // again - one L2 round trip when everybody is on time.  A word is either old or complete.
+  // every thread fetches its share of the nblocks x NV values; a word is either old or complete.
+  // (Issuing a thread's loads as one batch of 16-byte loads was measured slower: +1.2 us per
+  // reduction on C2 - the values mostly arrive while the first ones are being polled.)
   const int total = (int)gridDim.x * NV;
-  constexpr int kPer = (kLLMaxBlocks * NV + kPersistThreadsSmall - 1) / kPersistThreadsSmall;
-  unsigned pending = 0u;
-#pragma unroll
-  for (int j = 0; j < kPer; j++)
-    if ((int)threadIdx.x + j * (int)blockDim.x < total) pending |= 1u << j;
-  while (pending) {
-    unsigned long long lo[kPer], hi[kPer];
-#pragma unroll
-    for (int j = 0; j < kPer; j++) {
-      if (pending & (1u << j)) {
-        const int id = (int)threadIdx.x + j * (int)blockDim.x;
-        const int b = id / NV, k = id - b * NV;
-        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];"
-                     : "=l"(lo[j]), "=l"(hi[j])
-                     : "l"(&board->w[par][b][2 * k])
-                     : "memory");
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < kPer; j++) {
-      if ((pending & (1u << j)) && (unsigned int)(lo[j] >> 32) == seq && (unsigned int)(hi[j] >> 32) == seq) {
-        const int id = (int)threadIdx.x + j * (int)blockDim.x;
-        const int b = id / NV, k = id - b * NV;
-        sh_all[k * kLLMaxBlocks + b] =
-            __longlong_as_double((long long)((hi[j] << 32) | (lo[j] & 0xffffffffull)));
-        pending &= ~(1u << j);
-      }
-    }
+  for (int id = threadIdx.x; id < total; id += blockDim.x) {
+    const int b = id / NV, k = id - b * NV;
+    double x = 0.0;
+    (void)ll_load(&board->w[par][b][2 * k], seq, 0, 0, x);
+    sh_all[k * kLLMaxBlocks + b] = x;
   }
   if (acquire) __threadfence();
   __syncthreads();
@@ -2402,19 +2379,9 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   __shared__ unsigned long long s_acc[12];
   unsigned long long t_prev = 0ull;
   const bool stamping = A.stamps != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
-  // ... and, per block, the time thread 0 spent in the flow rows / the flow reduction / the step
-  // rows / the step reduction (A.stamps[64 + 4 * block ..]): who waits for whom
-  const bool bstamp = A.stamps != nullptr && threadIdx.x == 0;
-  unsigned long long b_acc[4] = {0ull, 0ull, 0ull, 0ull}, b_prev = 0ull;
   if (stamping) {
     for (int q = 0; q < 12; q++) s_acc[q] = 0ull;
     t_prev = gtime();
-  }
-#define CVO_BSTAMP(q)                      \
-  if (bstamp) {                            \
-    const unsigned long long t = gtime();  \
-    if ((q) >= 0) b_acc[(q) & 3] += t - b_prev; \
-    b_prev = t;                            \
   }
 #define CVO_PHASE(q)                    \
   if (stamping) {                       \
@@ -2472,10 +2439,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     }
     {
       double bp[9], queued[2], v[kLLValues], r[kLLValues];
-      CVO_BSTAMP(-1)
       flow_rows<kGen, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp, queued);
       CVO_PHASE(0)
-      CVO_BSTAMP(0)
 #pragma unroll
       for (int k = 0; k < 8; k++) v[k] = bp[k];
       v[8] = queued[0];
@@ -2486,7 +2451,6 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
       const bool rel = __syncthreads_or(lane == 0 && queued[0] > 0.0) != 0;
       ll_allreduce<kLLValues, 10>(A.ll, ++seq, v, sh, sh_all, r, rel, false);
       CVO_PHASE(1)
-      CVO_BSTAMP(1)
 #pragma unroll
       for (int k = 0; k < 8; k++) tot[k] = r[k];
       tot[8] = r[10];
@@ -2532,16 +2496,15 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     // ---- step phase (compute_step_size_xi + _poly_coeff on this block's ELL rows)
     {
       double w4[4], r4[4];
-      CVO_BSTAMP(-1)
       step_rows<true>(A, &s_st, w4[0], w4[1], w4[2], w4[3]);
       CVO_PHASE(5)
-      CVO_BSTAMP(2)
       ll_allreduce<4, 4>(A.ll, ++seq, w4, sh, sh_all, r4, false, false);
       CVO_PHASE(6)
-      CVO_BSTAMP(3)
       bool xok2 = true;
       if (kFused) xok2 = xgpu_allgather<4, 4>(A, gst, r4, 1, xepoch);
+      if (stamping) s_st.dbg[12] = gtime();
       controller_step(A, &s_st, r4, &s_ctrl);
+      if (stamping) s_st.dbg[11] = gtime();
       if (threadIdx.x == 0 && !xok2) {
         s_st.ret = CVO_B200_ERR_NCCL;
         s_st.done = 1;
@@ -2552,10 +2515,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   }
   if (stamping)
     for (int q = 0; q < 10; q++) A.stamps[q] = s_acc[q];
-  if (bstamp)
-    for (int q = 0; q < 4; q++) A.stamps[64 + 4 * blockIdx.x + q] = b_acc[q];
 #undef CVO_PHASE
-#undef CVO_BSTAMP
   // ---- block 0 hands the final state (pose, flags, results) back.  The scheduling scratch
   //      (work counters, exchange flags) is NOT written back: other blocks may still use it.
   if (blockIdx.x == 0) {
