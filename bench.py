@@ -639,6 +639,10 @@ def main():
     if world != args.gpus and world == 1 and args.gpus > 1:
         print(json.dumps({"error": f"--gpus {args.gpus} needs torchrun (WORLD_SIZE={world})"}))
         sys.exit(2)
+    if rank != 0:
+        # only rank 0 writes to stdout (the JSON line); whatever libraries print on the other
+        # ranks goes to stderr
+        os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
     else:

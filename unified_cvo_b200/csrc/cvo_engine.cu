@@ -314,7 +314,8 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   // (choose_mode), halved until the cells fit in ~4 GiB
   // ... shared by tile_parts warps per tile (small shards: enough items to fill the machine)
   int tile_parts = 1;
-  while (tile_parts < 8 && row_tiles * tile_parts < 2 * h->num_sms * 24) tile_parts *= 2;
+  while (tile_parts < 8 && 2 * row_tiles * tile_parts < 3 * h->num_sms * 24) tile_parts *= 2;  // ~1.5 waves of items (measured)
+  if (const char* tp = getenv("CVO_B200_TILE_PARTS")) tile_parts = std::max(1, std::min(8, atoi(tp)));  // measurement aid
   int tile_L = 1024 / tile_parts;
   while ((size_t)std::max(n_rows, 1) * tile_parts * tile_L * 4 > ((size_t)4 << 30) && tile_L > 32) tile_L /= 2;
 
@@ -350,7 +351,9 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   h->prep_blocks = std::max(1, std::min(h->num_sms * 4, (std::max(M_pad, n_rows) + 255) / 256));
   int tocc = tile_kernel_max_blocks_per_sm();
   if (tocc < 1) tocc = 1;
-  h->tile_blocks = std::max(1, std::min(h->num_sms * tocc, (row_tiles * tile_parts + kPairWarps - 1) / kPairWarps));
+  // items are dealt to warp 0 of every block first: few items spread over all SMs instead of
+  // filling a few blocks
+  h->tile_blocks = std::max(1, std::min(h->num_sms * tocc, row_tiles * tile_parts));
   const int warps_per_block = kSparseThreads / 32;
   int socc = sparse_kernel_max_blocks_per_sm();
   if (socc < 1) socc = 1;
