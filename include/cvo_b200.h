@@ -314,6 +314,12 @@ int cvo_b200_comm_init(cvo_b200_handle* h, int rank, int world, const char id[12
  * keeps the NCCL all-gathers.  handles = world x 64 bytes, rank order.                        */
 int cvo_b200_comm_mailbox_handle(cvo_b200_handle* h, char out[64]);
 int cvo_b200_comm_open_peers(cvo_b200_handle* h, const char* handles);
+/* on != 0: cvo_b200_inner_product / cvo_b200_function_angle become COLLECTIVE calls of the job
+ * (every rank must make them with the same arguments): each rank scans its shard of the source
+ * rows, the ranks' sums of A are all-gathered and added in rank order (bit-identical result on
+ * every rank).  Default off: every rank computes all rows on its own.  Associations (the CSR
+ * exports) are never sharded.                                                             */
+int cvo_b200_comm_shard_inner_products(cvo_b200_handle* h, int on);
 int cvo_b200_comm_destroy(cvo_b200_handle* h);
 
 #ifdef __cplusplus

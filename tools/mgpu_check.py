@@ -39,6 +39,22 @@ for k in range(8):
     bad = compare_traces(tr1[k], tr0[k])
     if bad: ok = False; print(rank, "iter", k, bad)
 print(f"rank {rank}: single iters {i0.iterations} t={i0.registration_seconds*1e3:.2f} ms | sharded x{world} iters {i1.iterations} t={i1.registration_seconds*1e3:.2f} ms | pose diff {np.abs(T1-T0).max():.2e} | first-8 parity {'OK' if ok else 'FAIL'}")
+# scalar inner products: sharded (one all-gather of the ranks' sums) == every rank on its own
+Tpose = np.linalg.inv(T1).astype(np.float32)
+fa_own = g.function_angle(src, tgt, Tpose, 0.5)
+ip_own = g.inner_product_gpu(src, tgt, Tpose, 0.5)
+g.comm_shard_inner_products(True)
+fa_sh = g.function_angle(src, tgt, Tpose, 0.5)
+ip_sh = g.inner_product_gpu(src, tgt, Tpose, 0.5)
+fa_sh_exact = g.function_angle(src, tgt, Tpose, 0.5, is_approximate=False)
+g.comm_shard_inner_products(False)
+fa_own_exact = g.function_angle(src, tgt, Tpose, 0.5, is_approximate=False)
+print(f"rank {rank}: function_angle own {fa_own:.7f} sharded {fa_sh:.7f} | inner product own {ip_own:.4f} sharded {ip_sh:.4f} | exact own {fa_own_exact:.7f} sharded {fa_sh_exact:.7f}")
+assert abs(ip_sh - ip_own) <= 2e-6 * abs(ip_own) and abs(fa_sh - fa_own) <= 2e-6 * abs(fa_own), "sharded inner product differs"
+assert abs(fa_sh_exact - fa_own_exact) <= 4e-6 * abs(fa_own_exact)
+vals = [None] * world
+dist.all_gather_object(vals, (fa_sh, ip_sh))
+assert all(v == vals[0] for v in vals), "ranks disagree on the sharded inner product"
 poses = [None] * world
 dist.all_gather_object(poses, T1.tobytes())
 assert ok, "NCCL path: first 8 iterations differ from the single-GPU run"

@@ -191,6 +191,7 @@ SYMBOLS = {
     "cvo_b200_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_char * 128]),
     "cvo_b200_comm_mailbox_handle": (C.c_int, [C.c_void_p, C.c_char * 64]),
     "cvo_b200_comm_open_peers": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "cvo_b200_comm_shard_inner_products": (C.c_int, [C.c_void_p, C.c_int]),
     "cvo_b200_comm_destroy": (C.c_int, [C.c_void_p]),
 }
 

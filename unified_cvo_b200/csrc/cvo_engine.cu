@@ -230,6 +230,7 @@ struct cvo_b200_handle {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  bool shard_inner_products = false;  // cvo_b200_comm_shard_inner_products
   // fused exchange: own mailbox + the peers' (CUDA IPC), generation counter of persistent launches
   XMailbox* mailbox = nullptr;
   XMailbox* peers[kMaxWorld] = {};
@@ -1268,8 +1269,12 @@ static int inner_product_common(cvo_b200_handle* h, const float T16[16], float e
 #undef CVO_K
     mode = 1;
   }
-  // inner products / associations are never sharded: every rank computes all rows
-  int rc = prepare(h, A, mode, kernel3x3 ? kinv : nullptr, S, Tg, false);
+  // Associations are never sharded (every row is needed where the matrix is read).  Scalar
+  // inner products (inner_product_gpu / function_angle) are sharded over the ranks of a
+  // multi-GPU job when the caller opted in (cvo_b200_comm_shard_inner_products): every rank
+  // scans its rows, one all-gather of the ranks' sums of A - a COLLECTIVE call then.
+  const bool shard = h->world > 1 && h->shard_inner_products && A_out == nullptr && h->comm != nullptr;
+  int rc = prepare(h, A, mode, kernel3x3 ? kinv : nullptr, S, Tg, shard);
   if (rc != CVO_B200_OK) return rc;
   float R[9], T[3];
   split_pose(T16, R, T);
@@ -1790,6 +1795,12 @@ int cvo_b200_comm_open_peers(cvo_b200_handle* h, const char* handles) {
   }
   h->peers_ready = true;
   h->xgen = 0;
+  return CVO_B200_OK;
+}
+
+int cvo_b200_comm_shard_inner_products(cvo_b200_handle* h, int on) {
+  if (!h) return CVO_B200_ERR_INVALID;
+  h->shard_inner_products = on != 0;
   return CVO_B200_OK;
 }
 

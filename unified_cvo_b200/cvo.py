@@ -407,5 +407,10 @@ class CvoGPU:
         """handles: the 64-byte mailbox handles of all ranks, in rank order."""
         self._check(self._lib.cvo_b200_comm_open_peers(self._h, b"".join(bytes(x[:64]) for x in handles)))
 
+    def comm_shard_inner_products(self, on: bool = True):
+        """inner_product_gpu / function_angle become collective calls of the job: every rank scans
+        its shard of the source rows, one all-gather of the ranks' sums."""
+        self._check(self._lib.cvo_b200_comm_shard_inner_products(self._h, int(bool(on))))
+
     def comm_destroy(self):
         self._check(self._lib.cvo_b200_comm_destroy(self._h))
