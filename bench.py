@@ -320,17 +320,23 @@ def edge_updates_leg(u, rounds=5, cpu=True):
     states = [u.BinaryStateGPU(frames[i], frames[(i + 1) % 4], cap, ell) for i in range(4)]
     u.update_edges(states)  # warm-up: buffers grow, the caps settle
     u.update_edges(states)
-    launches0 = g.launch_count()
-    t0 = time.perf_counter()
-    total = 0
-    for _ in range(rounds):
-        total, _ = u.update_edges(states)
-    dt = time.perf_counter() - t0
+    per_call = {}
+    for batched in (False, True):  # the per-edge C-ABI call, then the whole loop as one batch call (the headline)
+        u.update_edges(states, batched=batched)
+        launches0 = g.launch_count()
+        t0 = time.perf_counter()
+        total = 0
+        for _ in range(rounds):
+            total, _ = u.update_edges(states, batched=batched)
+        dt = time.perf_counter() - t0
+        per_call[batched] = rounds * len(states) / dt
     n_edges = rounds * len(states)
     out = {"workload": "4 KITTI-05-sized frames (N=16384, 5-dim colour), ring of 4 edges, ell=0.25, "
                        f"cap={cap}; one update = posed cloud build(s) on the device (a frame shared with the previous "
                        "edge is reused) + capped kernel matrix + CSR to host",
            "edge_updates_per_s": n_edges / dt, "ms_per_edge_update": 1e3 * dt / n_edges,
+           "api": "cvo_b200_edge_update_batch (one call per round, one host wait)",
+           "edge_updates_per_s_per_edge_calls": per_call[False],
            "nonzeros_per_round": int(total), "gpu_launches_per_edge_update": (g.launch_count() - launches0) / n_edges}
     if cpu:  # the CPU restatement of the same edge loop on the host cores (one round)
         import oracle

@@ -282,6 +282,27 @@ int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], 
                          const float pose2[12], float ell, int num_neighbors, int64_t* nnz,
                          int32_t* max_row_nnz, int32_t* row_ptr, int32_t* cols, float* vals);
 
+/* All edges of one outer IRLS iteration in ONE call (the loop of CvoBatchIRLS::solve,
+ * IRLS.cpp:111-121, over BinaryStateGPU::update_inner_product): every edge's kernels are enqueued
+ * back to back - frame 1 moved by its pose, cell queries in frame 2's own cell table, CSR
+ * compaction at a device-side running offset - and the host waits ONCE for all of them.
+ * Same per-edge semantics and outputs as cvo_b200_edge_update.
+ * nnz[e], max_row_nnz[e]: per edge.  row_ptr: the edges' row pointers back to back (edge e has
+ * n(frame1_e) + 1 entries, each starting at 0).  cols / vals: the edges' entries back to back
+ * (edge e's block starts at the sum of the earlier edges' nnz).  Two-call protocol: cols == NULL
+ * computes everything and returns the sizes; the second call with the same edges copies the
+ * entries without recomputing.  Needs is_using_geometry; every edge must be evaluable by cell
+ * queries / tile cells (else CVO_B200_ERR_STATE: use cvo_b200_edge_update for that edge).     */
+typedef struct cvo_b200_edge {
+  int32_t frame1, frame2;
+  float pose1[12], pose2[12]; /* row-major 3x4 */
+  float ell;
+  int32_t num_neighbors;
+} cvo_b200_edge;
+int cvo_b200_edge_update_batch(cvo_b200_handle* h, int n_edges, const cvo_b200_edge* edges,
+                               int64_t* nnz, int32_t* max_row_nnz, int32_t* row_ptr, int32_t* cols,
+                               float* vals);
+
 /* ---- measurement helpers --------------------------------------------------
  * Runs `iters` iterations back to back at a FIXED state (pose, ell, cap),
  * timed with CUDA events on the handle's stream.  ms_total = whole iteration

@@ -231,6 +231,45 @@ def test_edge_loop_over_a_four_frame_graph_and_edge_cases():
     g.close()
 
 
+@pytest.mark.gpu
+def test_batched_edge_update_equals_the_per_edge_calls():
+    """cvo_b200_edge_update_batch (all edges of IRLS.cpp:111-121's loop in one call, one
+    synchronisation): every edge's CSR equals the per-edge call's bit for bit, with ragged frames, an
+    empty frame, a repeated edge, per-edge ell / cap, over three rounds."""
+    p = geometric_params()
+    g = u.CvoGPU(p)
+    frames = []
+    for k in range(4):
+        a, _, _ = synthetic_pair(1600, 900 + 64 * k, 900, 40)
+        frames.append(u.CvoFrameGPU(g, a, pose_rt(0.0, 0.3 * k, 0.0, [0.01 * k, 0.0, 0.02 * k])))
+    frames.append(u.CvoFrameGPU(g, u.CvoPointCloud(np.zeros((0, 3), np.float32))))
+    edges = [(0, 1, 0.5, 24), (1, 2, 0.5, 24), (2, 3, 0.8, 7), (3, 0, 0.5, 24), (0, 2, 0.3, 24), (0, 4, 0.5, 24),
+             (4, 1, 0.5, 24), (0, 1, 0.5, 24), (1, 0, 0.5, 0)]
+
+    def make():
+        return [u.BinaryStateGPU(frames[i], frames[j], num_neighbor=c, init_ell=e) for i, j, e, c in edges]
+
+    one, many = make(), make()
+    for rep in range(3):  # the caps settle after the first pass; every data call answers from the size query's device-side copy
+        total_1, per_1 = u.update_edges(one, batched=False)
+        total_n, per_n = u.update_edges(many, batched=True)
+        assert total_n == total_1 and per_n == per_1
+        for a, b in zip(one, many):
+            assert np.array_equal(a.A_result_cpu_.row_ptr, b.A_result_cpu_.row_ptr)
+            assert np.array_equal(a.A_result_cpu_.cols, b.A_result_cpu_.cols)
+            assert np.array_equal(a.A_result_cpu_.vals.view(np.uint32), b.A_result_cpu_.vals.view(np.uint32))
+            assert a.last_max_row_nnz == b.last_max_row_nnz and a.num_neighbors_ == b.num_neighbors_
+    assert per_1[5] == per_1[6] == per_1[8] == 0 and min(per_1[:5]) > 100
+    # a pose changed between the calls: the cache must not answer
+    frames[1].set_pose_vec(pose_rt(0.0, 0.31, 0.0, [0.02, 0.0, 0.02]))
+    total_1b, per_1b = u.update_edges(one, batched=False)
+    total_nb, per_nb = u.update_edges(many, batched=True)
+    assert per_nb == per_1b and per_1b != per_1
+    for a, b in zip(one, many):
+        assert np.array_equal(a.A_result_cpu_.cols, b.A_result_cpu_.cols)
+    g.close()
+
+
 # ------------------------------------------------------------------ CPU: host logic of the mirror
 class _FakeEdgeLib:
     """Stands in for libcvo_b200's two edge entry points (same two-call CSR protocol), answering
@@ -265,6 +304,27 @@ class _FakeEdgeLib:
         if cols is not None and total:
             np.ctypeslib.as_array(cols, shape=(total,))[:] = cs
             np.ctypeslib.as_array(vals, shape=(total,))[:] = vs
+        return 0
+
+
+    def cvo_b200_edge_update_batch(self, h, n, edges, nnz, mx, row_ptr, cols, vals):
+        """same protocol as include/cvo_b200.h: concatenated row pointers (each edge's own, from 0),
+        concatenated entries"""
+        ro = eo = 0
+        for k in range(n):
+            e = edges[k]
+            self.calls.append((e.frame1, e.frame2, float(e.ell), int(e.num_neighbors), cols is not None))
+            total, sp = oracle.edge_update(self.params, to_oracle_cloud(self.clouds[e.frame1]),
+                                           np.array(list(e.pose1), np.float32), to_oracle_cloud(self.clouds[e.frame2]),
+                                           np.array(list(e.pose2), np.float32), float(e.ell), int(e.num_neighbors))
+            rp, cs, vs = oracle.sparse_to_csr(sp)
+            nnz[k], mx[k] = total, int(sp["nonzeros"].max()) if len(sp["nonzeros"]) else 0
+            np.ctypeslib.as_array(row_ptr, shape=(ro + len(rp),))[ro:] = rp
+            if cols and total:
+                np.ctypeslib.as_array(cols, shape=(eo + total,))[eo:] = cs
+                np.ctypeslib.as_array(vals, shape=(eo + total,))[eo:] = vs
+            ro += len(rp)
+            eo += total
         return 0
 
 
@@ -315,5 +375,18 @@ def test_mirror_host_logic_cap_schedule_pose_narrowing_and_two_call_protocol():
     st.update_ell()                    # 0.735 is not above ell_min = 1.0: no further decay
     assert st.ell_ == pytest.approx(0.735)
     assert u.update_edges([st])[0] == st.A_result_cpu_.row_ptr[-1]
+    # the batched edge loop assembles the same per-edge matrices as the per-edge calls
+    st2 = u.BinaryStateGPU(f2, f1, 7, 1.2)
+    a, b = [u.BinaryStateGPU(f1, f2, 9, 1.5), st2], [u.BinaryStateGPU(f1, f2, 9, 1.5), u.BinaryStateGPU(f2, f1, 7, 1.2)]
+    for _ in range(2):  # the second pass runs with the caps of the first (1.1 * fullest row)
+        ta, pa = u.update_edges(a, batched=False)
+        tb, pb = u.update_edges(b, batched=True)
+        assert ta == tb > 0 and pa == pb
+        for x, y in zip(a, b):
+            assert x.num_neighbors_ == y.num_neighbors_ and x.last_max_row_nnz == y.last_max_row_nnz
+            assert np.array_equal(x.A_result_cpu_.row_ptr, y.A_result_cpu_.row_ptr)
+            assert np.array_equal(x.A_result_cpu_.cols, y.A_result_cpu_.cols)
+            assert np.array_equal(x.A_result_cpu_.vals, y.A_result_cpu_.vals)
+            assert x.A_result_cpu_.shape == y.A_result_cpu_.shape and x.iter_ == y.iter_
     f1.release()
     assert 0 not in g._lib.frames

@@ -126,6 +126,13 @@ class AlignInfo(C.Structure):
     ]
 
 
+class Edge(C.Structure):
+    """cvo_b200_edge: one pose-graph edge of a batched update."""
+
+    _fields_ = [("frame1", C.c_int32), ("frame2", C.c_int32), ("pose1", C.c_float * 12),
+                ("pose2", C.c_float * 12), ("ell", C.c_float), ("num_neighbors", C.c_int32)]
+
+
 _f32p = C.POINTER(C.c_float)
 _i32p = C.POINTER(C.c_int32)
 
@@ -179,6 +186,10 @@ SYMBOLS = {
         C.c_int,
         [C.c_void_p, C.c_int, _f32p, C.c_int, _f32p, C.c_float, C.c_int, C.POINTER(C.c_int64),
          _i32p, _i32p, _i32p, _f32p],
+    ),
+    "cvo_b200_edge_update_batch": (
+        C.c_int,
+        [C.c_void_p, C.c_int, C.POINTER(Edge), C.POINTER(C.c_int64), _i32p, _i32p, _i32p, _f32p],
     ),
     "cvo_b200_time_iterations": (
         C.c_int,

@@ -243,6 +243,12 @@ struct IterArgs {
   int tile_cut_bits;  // tile mode: a tile is cut where neighbouring rows' Morton keys differ above this bit
   const unsigned long long* src_keys;  // Morton keys of the source rows (sorted; source's own lattice)
   GridView gv;
+  // pose-graph edges evaluated in the frames' OWN cell tables (no posed cloud is rebuilt): the
+  // source rows are the posed copy of frame 1, the target is moved on the fly by frame 2's pose
+  // with the arithmetic of transform_point_pose_vec (CvoGPU_impl.cu:84-150) instead of R, T
+  int posevec;
+  float pose2[12];   // row-major 3x4
+  float edge_slack;  // extra slack of the cell queries: the state's (R, T) only approximates pose2^-1
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective
   int n_items;     // pair-kernel work items = row_tiles * nchunks
 };

@@ -31,6 +31,8 @@ void launch_step(const IterArgs& A, int blocks, cudaStream_t s);
 void launch_finalize_flow(const IterArgs& A, const double* gathered, int stride, cudaStream_t s);
 void launch_finalize_step(const IterArgs& A, const double* gathered, int stride, cudaStream_t s);
 void launch_init_bound(const IterArgs& A, cudaStream_t s);
+void launch_pose_source(const float4* xyz, int n, const float pose1[12], float4* out_xyz, float4* out_rowA,
+                        cudaStream_t s);
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s);
 int pair_kernel_max_blocks_per_sm();
 int sparse_kernel_max_blocks_per_sm();
@@ -150,7 +152,20 @@ struct FrameDev {
   int n = 0, F = 0, C = 0;
   bool has_geo = false, set = false;
   DevBuf<float> xyz, feat, lab, geo;
-  void release() { xyz.release(); feat.release(); lab.release(); geo.release(); set = false; n = 0; }
+  // the frame as a cloud in its OWN coordinates (Morton order, cell table): edges are evaluated in
+  // these tables at any pose, nothing is rebuilt per edge
+  CloudDev cloud;
+  void release() {
+    xyz.release(); feat.release(); lab.release(); geo.release();
+    CloudDev& c = cloud;
+    c.xyz.release(); c.rowA.release(); c.feat.release(); c.lab.release(); c.geo.release();
+    c.xyz_o.release(); c.feat_o.release(); c.lab_o.release(); c.geo_o.release();
+    c.blk_sphere.release(); c.tile_sphere.release(); c.tile_maxdist.release(); c.inv.release();
+    c.coarse.release(); c.perm_d.release(); c.keys_d.release();
+    c.set = false;
+    set = false;
+    n = 0;
+  }
 };
 
 // a cloud slot built from a frame at a pose (edges sharing a frame at the same pose reuse it)
@@ -242,10 +257,21 @@ struct cvo_b200_handle {
   std::vector<FrameDev> frames;
   std::vector<unsigned long long> frame_gen;
   unsigned long long frame_gen_next = 1;
+  // cvo_b200_edge_update_batch: the edges' row pointers (device + host copy) and running offsets
+  DevBuf<int> batch_ptr;
+  DevBuf<long long> batch_base;
+  std::vector<int> batch_rp_host;
+  std::vector<cvo_b200_edge> batch_edges;
+  std::vector<unsigned long long> batch_gens;
+  bool batch_valid = false;
   bool edge_valid = false;
+  bool edge_own_frame = false;            // the matrix came from the own-frame path (Morton columns)
+  const int* edge_row_inv = nullptr;
+  const int* edge_col_perm = nullptr;
   EdgeKey edge_key;
   SlotKey slot_key[2];  // which posed frame each cloud slot currently holds ([0] source, [1] target)
   IterArgs edge_args;
+  DevBuf<float4> edge_src_xyz, edge_src_rowA;  // frame 1 of the current edge at its pose
   int cap_override = 0;  // ELL stride of the next prepare() when an edge asks for more than nearest_neighbors_max
   // the kernel matrix left behind by the last align() (cvo_b200_align_association)
   bool last_valid = false;
@@ -273,9 +299,12 @@ inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 // Pick the work decomposition of the pair kernel and size every buffer.
 int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const CloudDev* S = nullptr,
             const CloudDev* Tg = nullptr, bool sharded = true) {
-  if (!h->src.set || !h->tgt.set) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
+  if ((!S && !h->src.set) || (!Tg && !h->tgt.set)) return fail(h, CVO_B200_ERR_STATE, "source/target cloud not set");
   h->last_valid = false;  // every caller of prepare() overwrites the ELL matrix
   h->edge_valid = false;
+  // (a cached batch keeps its compacted entries in csr_cols / csr_vals: any later export reuses
+  // those buffers, so the batch cache is dropped as well)
+  h->batch_valid = false;
   const CloudDev& cs = S ? *S : h->src;
   const CloudDev& ct = Tg ? *Tg : h->tgt;
   const int N = cs.n, M = ct.n;
@@ -454,6 +483,8 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   A.xworld = h->world;
   A.xgen = 0;
   for (int r = 0; r < kMaxWorld; r++) A.xpeer[r] = h->peers[r];
+  A.posevec = 0;
+  A.edge_slack = 0.f;
   A.grid = 0;
   A.tile = 0;
   A.tile_L = tile_L;
@@ -1039,7 +1070,8 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
   }
   h->tgt_moved.release(); h->pq.release(); h->px.release(); h->py.release(); h->pz.release(); h->pw.release();
   h->rowrec.release(); h->row_lt.release(); h->sat_list.release(); h->flow_part2.release();
-  h->ll_board.release();
+  h->ll_board.release(); h->edge_src_xyz.release(); h->edge_src_rowA.release();
+  h->batch_ptr.release(); h->batch_base.release();
   h->cand.release(); h->cand_cnt.release(); h->ell_idx.release(); h->row_nnz.release();
   h->ell_val.release(); h->flow_part.release(); h->step_part.release(); h->zeros_f.release();
   h->zeros_g.release(); h->d_trace.release(); h->gathered.release(); h->stamps.release();
@@ -1344,7 +1376,8 @@ int cvo_b200_function_angle(cvo_b200_handle* h, const float T[16], float ell, in
 // copied to the host.  Two-call protocol (cols/vals may be null).  Replaces
 // gpu_association_to_cpu (CvoGPU_impl.cu:366-427) / copy_internal_SparseKernelMat_gpu_to_cpu.
 static int export_csr(cvo_b200_handle* h, const IterArgs& A, int64_t* nnz, int32_t* max_row_nnz,
-                      int32_t* row_ptr, int32_t* cols, float* vals, bool reuse_row_ptr = false) {
+                      int32_t* row_ptr, int32_t* cols, float* vals, bool reuse_row_ptr = false,
+                      const int* row_inv = nullptr, const int* col_perm = nullptr) {
   const int n_rows = A.n_rows;
   cudaStream_t s = h->stream;
   CsrExport E;
@@ -1354,7 +1387,8 @@ static int export_csr(cvo_b200_handle* h, const IterArgs& A, int64_t* nnz, int32
   E.row_nnz = A.row_nnz;
   E.ell_idx = A.ell_idx;
   E.ell_val = A.ell_val;
-  E.inv = h->src.inv.p;  // caller's row -> Morton position
+  E.inv = row_inv ? row_inv : h->src.inv.p;  // caller's row -> Morton position
+  E.col_perm = col_perm;                      // Morton-view matrix: Morton position -> caller's column
   E.scan_temp_bytes = csr_scan_temp_bytes(n_rows);
   CVO_CUDA(h, h->csr_cnt.ensure((size_t)n_rows + 1));
   CVO_CUDA(h, h->csr_ptr.ensure((size_t)n_rows + 1));
@@ -1497,6 +1531,10 @@ int cvo_b200_frame_set(cvo_b200_handle* h, int frame, int n, const float* xyz, i
     }
     CVO_CUDA(h, cudaStreamSynchronize(s));  // the caller's arrays may be released after this call
   }
+  // the frame's own-frame cloud (Morton order, cell table): built once, used by every edge
+  int rc = build_cloud(h, f.cloud, n, f.F, f.xyz.p, f.F ? f.feat.p : nullptr, f.C, f.C ? f.lab.p : nullptr,
+                       f.has_geo ? f.geo.p : nullptr);
+  if (rc != CVO_B200_OK) return rc;
   f.set = true;
   return CVO_B200_OK;
 }
@@ -1536,6 +1574,53 @@ static int build_posed_frame(cvo_b200_handle* h, CloudDev& c, int frame, const f
   return CVO_B200_OK;
 }
 
+// One pose-graph edge in the frames' OWN cell tables (enqueued, not waited for): frame 1's rows are
+// moved by pose 1 (one small kernel), frame 2 stays where its table was built and its points are
+// moved by pose 2 on the fly, exactly as transform_point_pose_vec moves them; the cell queries map
+// the moved rows back with (R, T) ~ pose2^-1.  No sort, no cloud build, no O(N M) scan per edge.
+// *done = false: the edge is in a regime neither cell queries nor tile cells serve (huge
+// length-scale): nothing was enqueued, the caller takes the rebuild path.
+static int enqueue_edge_own_frame(cvo_b200_handle* h, const FrameDev& f1, const float pose1[12], const FrameDev& f2,
+                                  const float pose2[12], float ell, int num_neighbors, IterArgs& A, bool* done) {
+  *done = false;
+  h->cap_override = num_neighbors;
+  int rc = prepare(h, A, 0, nullptr, &f1.cloud, &f2.cloud, false);
+  h->cap_override = 0;
+  if (rc != CVO_B200_OK) return rc;
+  if (num_neighbors > A.cap_max) return fail(h, CVO_B200_ERR_INVALID, "num_neighbors exceeds the row stride");
+  A.posevec = 1;
+  std::memcpy(A.pose2, pose2, sizeof(A.pose2));
+  // state pose = pose2^-1 up to rounding: R = R2^T (so that Rinv = R^T = R2 exactly), T = -R2^T t2
+  float R[9], T[3];
+  double t2n = 0.0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) R[3 * j + i] = pose2[4 * j + i];  // column-major R(i,j) = R2(j,i)
+  for (int i = 0; i < 3; i++) {
+    double acc = 0.0;
+    for (int j = 0; j < 3; j++) acc -= (double)pose2[4 * j + i] * (double)pose2[4 * j + 3];
+    T[i] = (float)acc;
+    t2n += std::fabs((double)pose2[4 * i + 3]);
+  }
+  // |y - q| bound of the cell queries assumes y' = fl(R^T y - R^T T); here y' = fl(P2 [y 1]): the
+  // two differ by the rounding of T and of the 4-term sums, a few ulp of |t2| + |y| (2x safety)
+  A.edge_slack = (float)(4e-6 * (1.0 + t2n + (double)f2.cloud.radius + std::fabs((double)f2.cloud.cx) +
+                                std::fabs((double)f2.cloud.cy) + std::fabs((double)f2.cloud.cz)));
+  choose_mode(h, A, f1.cloud, f2.cloud, ell, A.n_rows, false);
+  if (!(A.grid || A.tile)) return CVO_B200_OK;
+  CVO_CUDA(h, h->edge_src_xyz.ensure((size_t)f1.n));
+  CVO_CUDA(h, h->edge_src_rowA.ensure((size_t)f1.n));
+  launch_pose_source(f1.cloud.xyz.p, f1.n, pose1, h->edge_src_xyz.p, h->edge_src_rowA.p, h->stream);
+  h->launches += 1;
+  A.src_xyz = h->edge_src_xyz.p;
+  A.src_rowA = h->edge_src_rowA.p;
+  rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, nullptr, 0, true);
+  if (rc != CVO_B200_OK) return rc;
+  rc = enqueue_iteration(h, A, 2, nullptr, nullptr);
+  if (rc != CVO_B200_OK) return rc;
+  *done = true;
+  return CVO_B200_OK;
+}
+
 int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], int frame2,
                          const float pose2[12], float ell, int num_neighbors, int64_t* nnz,
                          int32_t* max_row_nnz, int32_t* row_ptr, int32_t* cols, float* vals) {
@@ -1564,7 +1649,31 @@ int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], 
   key.gen2 = h->frame_gen[(size_t)frame2];
   // second call of the two-call protocol: the matrix of this very edge is still on the device
   const bool cached = h->edge_valid && std::memcmp(&key, &h->edge_key, sizeof(key)) == 0;
+  static const bool rebuild_env = getenv("CVO_B200_EDGE_REBUILD") && getenv("CVO_B200_EDGE_REBUILD")[0] == '1';
+  bool own_frame = !cached && !rebuild_env && h->params.is_using_geometry && !h->params.is_using_kdtree &&
+                   f1.cloud.set && f2.cloud.set;
+  if (own_frame) {
+    IterArgs A;
+    bool done = false;
+    int rc = enqueue_edge_own_frame(h, f1, pose1, f2, pose2, ell, num_neighbors, A, &done);
+    if (rc != CVO_B200_OK) return rc;
+    if (done) {
+      h->edge_key = key;
+      h->edge_args = A;
+      h->edge_valid = true;
+      h->edge_own_frame = true;
+      h->edge_row_inv = f1.cloud.inv.p;
+      h->edge_col_perm = f2.cloud.perm_d.p;
+      h->slot_key[0].valid = h->slot_key[1].valid = false;
+    } else {
+      own_frame = false;  // dense regime (huge length-scale): the rebuild path below
+    }
+  }
+  if (h->edge_valid && h->edge_own_frame && (cached || own_frame))
+    return export_csr(h, h->edge_args, nnz, max_row_nnz, row_ptr, cols, vals, cached, h->edge_row_inv,
+                      h->edge_col_perm);
   if (!cached) {
+    h->edge_own_frame = false;
     // a frame shared with the previous edge may sit in the other slot (ring / chain graphs):
     // exchange the slots when that saves a build
     auto holds = [&](int slot, int frame, const float* pose) {
@@ -1594,6 +1703,110 @@ int cvo_b200_edge_update(cvo_b200_handle* h, int frame1, const float pose1[12], 
     h->edge_valid = true;
   }
   return export_csr(h, h->edge_args, nnz, max_row_nnz, row_ptr, cols, vals, cached);
+}
+
+int cvo_b200_edge_update_batch(cvo_b200_handle* h, int n_edges, const cvo_b200_edge* edges, int64_t* nnz,
+                               int32_t* max_row_nnz, int32_t* row_ptr, int32_t* cols, float* vals) {
+  if (!h || n_edges < 0 || (n_edges > 0 && (!edges || !nnz))) return fail(h, CVO_B200_ERR_INVALID, "null argument");
+  cudaSetDevice(h->device);
+  if (!h->params.is_using_geometry || h->params.is_using_kdtree)
+    return fail(h, CVO_B200_ERR_STATE, "batched edges need the geometric kernel (use cvo_b200_edge_update)");
+  size_t rows_total = 0, worst = 0;
+  std::vector<unsigned long long> gens;
+  for (int e = 0; e < n_edges; e++) {
+    const cvo_b200_edge& ed = edges[e];
+    if (ed.frame1 < 0 || ed.frame2 < 0 || (size_t)ed.frame1 >= h->frames.size() || (size_t)ed.frame2 >= h->frames.size() ||
+        !h->frames[(size_t)ed.frame1].set || !h->frames[(size_t)ed.frame2].set || ed.num_neighbors < 0)
+      return fail(h, CVO_B200_ERR_STATE, "frame not set / negative num_neighbors");
+    rows_total += (size_t)h->frames[(size_t)ed.frame1].n + 1;
+    worst += (size_t)h->frames[(size_t)ed.frame1].n * (size_t)std::max(ed.num_neighbors, 1);
+    gens.push_back(h->frame_gen[(size_t)ed.frame1]);
+    gens.push_back(h->frame_gen[(size_t)ed.frame2]);
+  }
+  // only the SECOND call of the two-call protocol (entries wanted) may be answered from the device-side
+  // copy of the first; a size query always recomputes, so repeated rounds are never served stale
+  const bool cached = cols != nullptr && h->batch_valid && h->batch_edges.size() == (size_t)n_edges && gens == h->batch_gens &&
+                      (n_edges == 0 || std::memcmp(h->batch_edges.data(), edges, sizeof(cvo_b200_edge) * (size_t)n_edges) == 0);
+  cudaStream_t s = h->stream;
+  if (!cached) {
+    h->batch_valid = false;
+    CVO_CUDA(h, h->batch_ptr.ensure(std::max(rows_total, (size_t)1)));
+    CVO_CUDA(h, h->batch_base.ensure((size_t)n_edges + 1));
+    CVO_CUDA(h, h->csr_cols.ensure(std::max(worst, (size_t)1)));
+    CVO_CUDA(h, h->csr_vals.ensure(std::max(worst, (size_t)1)));
+    CVO_CUDA(h, cudaMemsetAsync(h->batch_base.p, 0, sizeof(long long), s));
+    size_t off = 0;
+    for (int e = 0; e < n_edges; e++) {
+      const cvo_b200_edge& ed = edges[e];
+      const FrameDev& f1 = h->frames[(size_t)ed.frame1];
+      const FrameDev& f2 = h->frames[(size_t)ed.frame2];
+      if (f1.n == 0 || f2.n == 0) {  // no entries: row pointers all zero, the running offset moves on unchanged
+        CVO_CUDA(h, cudaMemsetAsync(h->batch_ptr.p + off, 0, sizeof(int) * ((size_t)f1.n + 1), s));
+        CVO_CUDA(h, cudaMemcpyAsync(h->batch_base.p + e + 1, h->batch_base.p + e, sizeof(long long),
+                                    cudaMemcpyDeviceToDevice, s));
+        off += (size_t)f1.n + 1;
+        continue;
+      }
+      IterArgs A;
+      bool done = false;
+      int rc = enqueue_edge_own_frame(h, f1, ed.pose1, f2, ed.pose2, ed.ell, ed.num_neighbors, A, &done);
+      if (rc != CVO_B200_OK) return rc;
+      if (!done)
+        return fail(h, CVO_B200_ERR_STATE, "an edge of the batch is outside the cell-query / tile regimes: use cvo_b200_edge_update");
+      CsrExport E;
+      std::memset(&E, 0, sizeof(E));
+      E.n_rows = A.n_rows;
+      E.cap_max = A.cap_max;
+      E.row_nnz = A.row_nnz;
+      E.ell_idx = A.ell_idx;
+      E.ell_val = A.ell_val;
+      E.inv = f1.cloud.inv.p;
+      E.col_perm = f2.cloud.perm_d.p;
+      E.scan_temp_bytes = csr_scan_temp_bytes(A.n_rows);
+      CVO_CUDA(h, h->csr_cnt.ensure((size_t)A.n_rows + 1));
+      CVO_CUDA(h, h->csr_temp.ensure(E.scan_temp_bytes));
+      E.cnt = h->csr_cnt.p;
+      E.row_ptr = h->batch_ptr.p + off;
+      E.scan_temp = h->csr_temp.p;
+      E.base = h->batch_base.p + e;
+      E.base_next = h->batch_base.p + e + 1;
+      E.cols = h->csr_cols.p;
+      E.vals = h->csr_vals.p;
+      CVO_CUDA(h, csr_row_ptr_device(E, s));
+      CVO_CUDA(h, csr_gather_device(E, s));
+      h->launches += 4;
+      off += (size_t)f1.n + 1;
+    }
+    // ONE wait for the whole batch: the row pointers of every edge
+    h->batch_rp_host.resize(std::max(rows_total, (size_t)1));
+    if (rows_total)
+      CVO_CUDA(h, cudaMemcpyAsync(h->batch_rp_host.data(), h->batch_ptr.p, sizeof(int) * rows_total, cudaMemcpyDeviceToHost, s));
+    CVO_CUDA(h, cudaStreamSynchronize(s));
+    CVO_CUDA(h, cudaGetLastError());
+    h->batch_edges.assign(edges, edges + n_edges);
+    h->batch_gens = gens;
+    h->batch_valid = true;
+    h->edge_valid = false;  // the single-edge cache shares the ELL matrix
+  }
+  size_t off = 0;
+  int64_t total = 0;
+  for (int e = 0; e < n_edges; e++) {
+    const int n1 = h->frames[(size_t)edges[e].frame1].n;
+    const int* rp = h->batch_rp_host.data() + off;
+    int32_t mx = 0;
+    for (int i = 0; i < n1; i++) mx = std::max(mx, (int32_t)(rp[i + 1] - rp[i]));
+    nnz[e] = rp[n1];
+    if (max_row_nnz) max_row_nnz[e] = mx;
+    total += rp[n1];
+    off += (size_t)n1 + 1;
+  }
+  if (row_ptr && rows_total) std::memcpy(row_ptr, h->batch_rp_host.data(), sizeof(int32_t) * rows_total);
+  if (cols && vals && total > 0) {
+    CVO_CUDA(h, cudaMemcpyAsync(cols, h->csr_cols.p, sizeof(int32_t) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    CVO_CUDA(h, cudaMemcpyAsync(vals, h->csr_vals.p, sizeof(float) * (size_t)total, cudaMemcpyDeviceToHost, s));
+    CVO_CUDA(h, cudaStreamSynchronize(s));
+  }
+  return CVO_B200_OK;
 }
 
 int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T[3], float ell,

@@ -25,12 +25,25 @@ __global__ void csr_gather_kernel(CsrExport E) {
   const int warps = (gridDim.x * blockDim.x) >> 5;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < E.n_rows; i += warps) {
     const int s = E.inv[i];
-    const int n = (int)E.row_nnz[s], o = E.row_ptr[i];
+    const int n = (int)E.row_nnz[s];
+    const long long o = (E.base ? *E.base : 0ll) + (long long)E.row_ptr[i];
     const uint32_t* idx = E.ell_idx + (size_t)s * E.cap_max;
     const float* val = E.ell_val + (size_t)s * E.cap_max;
-    for (int k = lane; k < n; k += 32) {
-      E.cols[o + k] = (int32_t)idx[k];
-      E.vals[o + k] = val[k];
+    if (!E.col_perm) {
+      for (int k = lane; k < n; k += 32) {
+        E.cols[o + k] = (int32_t)idx[k];
+        E.vals[o + k] = val[k];
+      }
+    } else {
+      // Morton-view matrix: map to the caller's column indices and write every entry at its RANK
+      // (columns are unique inside a row), i.e. in ascending column order
+      for (int k = lane; k < n; k += 32) {
+        const int key = E.col_perm[idx[k]];
+        int rank = 0;
+        for (int q = 0; q < n; q++) rank += (E.col_perm[__ldg(idx + q)] < key) ? 1 : 0;
+        E.cols[o + rank] = (int32_t)key;
+        E.vals[o + rank] = val[k];
+      }
     }
   }
 }
@@ -51,9 +64,16 @@ cudaError_t csr_row_ptr_device(const CsrExport& E, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+namespace {
+__global__ void csr_base_next_kernel(CsrExport E) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *E.base_next = (E.base ? *E.base : 0ll) + (long long)E.row_ptr[E.n_rows];
+}
+}  // namespace
+
 cudaError_t csr_gather_device(const CsrExport& E, cudaStream_t s) {
   const int blocks = (E.n_rows + 7) / 8;  // 8 warps per block
   csr_gather_kernel<<<blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, s>>>(E);
+  if (E.base_next) csr_base_next_kernel<<<1, 32, 0, s>>>(E);
   return cudaGetLastError();
 }
 

@@ -13,10 +13,15 @@ struct CsrExport {
   const uint32_t* ell_idx;
   const float* ell_val;
   const int* inv;           // caller's row -> device row
+  const int* col_perm;      // null: ell_idx holds the caller's column indices in insertion order;
+                            // else: ell_idx holds Morton positions of the target in any order ->
+                            // columns = col_perm[idx], rows sorted ascending (the reference's order)
   int* cnt;                 // scratch, n_rows + 1
   int* row_ptr;             // out, n_rows + 1 (caller's row order)
   void* scan_temp;
   size_t scan_temp_bytes;
+  const long long* base;    // null or: device pointer to the offset of this matrix' block in cols / vals
+  long long* base_next;     // null or: receives *base + row_ptr[n_rows] (the next matrix' offset)
   int32_t* cols;            // out, compacted (row_ptr[n_rows] entries)
   float* vals;
 };

@@ -649,6 +649,22 @@ __device__ __forceinline__ float4 move_point(const float* Ri, const float* Ti, c
   mat3f_vec(Ri, yv, r);
   return make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], y.w);  // .w: packed colour summary
 }
+// transform_point_pose_vec (CvoGPU_impl.cu:84-150): x' = P [x y z 1]^T, P row-major 3x4; Eigen's
+// unrolled 4-term redux sums (c0 + c1) + (c2 + c3)
+__device__ __forceinline__ float4 move_point_pose(const float* P, const float4 y) {
+  float r[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float c0 = P[4 * i] * y.x, c1 = P[4 * i + 1] * y.y, c2 = P[4 * i + 2] * y.z, c3 = P[4 * i + 3] * 1.0f;
+    r[i] = (c0 + c1) + (c2 + c3);
+  }
+  return make_float4(r[0], r[1], r[2], y.w);
+}
+// the moved target point of the "on the fly" generators: by the state's inverse pose, or (pose-graph
+// edges) by frame 2's pose vector
+__device__ __forceinline__ float4 move_target(const IterArgs& A, const float* Ri, const float* Ti, const float4 y) {
+  return A.posevec ? move_point_pose(A.pose2, y) : move_point(Ri, Ti, y);
+}
 // 21 bits -> every third bit (the host's spread21, cvo_engine.cu)
 __device__ __forceinline__ unsigned long long spread21_dev(unsigned int a) {
   unsigned long long v = a & 0x1fffffull;
@@ -725,7 +741,7 @@ __device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs
   const uint32_t L = (uint32_t)A.tile_L;
   const float ell_now = hs->ell;
   const float log_geo = hs->kc.log_geo;
-  const float g_smax = hs->smax, g_slack = hs->grid_slack;
+  const float g_smax = hs->smax, g_slack = hs->grid_slack + A.edge_slack;
   const float* Rf = hs->R;
   const float* Tf = hs->T;
   const bool colour_cut = hs->kc.use_intensity != 0;
@@ -1103,11 +1119,7 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
       float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
       bool surv = false;
       if (j < A.M) {
-        const float4 y = A.tv[1].xyz[j];
-        const float yv[3] = {y.x, y.y, y.z};
-        float r[3];
-        mat3f_vec(Ri, yv, r);  // same arithmetic as prep_kernel
-        pb = make_float4(r[0] + Ti[0], r[1] + Ti[1], r[2] + Ti[2], y.w);
+        pb = move_target(A, Ri, Ti, A.tv[1].xyz[j]);  // same arithmetic as prep_kernel / the edge's pose
         surv = eval_pair(A, kc, rc, ig, 1, j, pb, a);
       }
       const unsigned mask = __ballot_sync(0xffffffffu, surv);
@@ -1164,7 +1176,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
   const int view = kFly ? 0 : hs->view;  // cell queries / tile cells index the Morton-ordered target
   const float* s_pose = hs->Rinv;          // Rinv[9], Tinv[3] are contiguous
   const float ell_now = hs->ell;
-  const float g_smax = hs->smax, g_slack = hs->grid_slack;
+  const float g_smax = hs->smax, g_slack = hs->grid_slack + A.edge_slack;
   unsigned int g_lb_thr = 0xffffffffu;  // integer threshold of the colour lower bound (stage 1)
   if (kColour && hs->kc.use_intensity) {
     const float th = hs->kc.d2_c_thres;
@@ -1250,7 +1262,7 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
       float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
       bool surv = false;
       if (valid) {
-        pb = kFly ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
+        pb = kFly ? move_target(A, s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
         surv = eval_pair(A, kc, rc, ig, view, j, pb, a);
       }
       const unsigned bits = (__ballot_sync(0xffffffffu, surv) >> gshift) & 0xffu;
@@ -2055,7 +2067,7 @@ __device__ __forceinline__ void step_rows(const IterArgs& A, const DevState* hs,
     for (int e = gl; e < n; e += kGroup) {
       const int j = (int)__ldcg(idx + e);
       const float A_ij = __ldcg(val + e);
-      const float4 yb = kFly ? move_point(s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
+      const float4 yb = kFly ? move_target(A, s_pose, s_pose + 9, A.tv[0].xyz[j]) : A.tgt_moved[j];
       const float y[3] = {yb.x, yb.y, yb.z};
       // compute_step_size_xi, CvoGPU.cu:974-983
       float z1[3], z2[3], z3[3], z4[3], t[3];
@@ -2650,6 +2662,28 @@ void launch_finalize_step(const IterArgs& A, const double* gathered, int stride,
   finalize_step_kernel<<<1, 64, 0, s>>>(A, gathered, stride);
 }
 void launch_init_bound(const IterArgs& A, cudaStream_t s) { init_bound_kernel<<<1, 32, 0, s>>>(A); }
+// Pose-graph edges: the source rows of an edge = frame 1 (Morton order of its own frame) moved by
+// its pose (transform_point_pose_vec), with the records the generators read: xyz + colour summary,
+// and rowA.w = the reference's a_to_sensor of the MOVED point (CvoGPU.cu:506, contracted as its GPU
+// build does).  The prefilter centre of pair_kernel is not used on this path.
+struct PoseArg {
+  float m[12];
+};
+__global__ void pose_source_kernel(const float4* __restrict__ xyz, int n, PoseArg P, float4* __restrict__ out_xyz,
+                                   float4* __restrict__ out_rowA) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 x = move_point_pose(P.m, xyz[i]);
+  out_xyz[i] = x;
+  const float dist = sqrtf(__fmaf_rn(x.z, x.z, __fmaf_rn(x.x, x.x, x.y * x.y)));
+  out_rowA[i] = make_float4(-2.f * x.x, -2.f * x.y, -2.f * x.z, dist);
+}
+void launch_pose_source(const float4* xyz, int n, const float pose1[12], float4* out_xyz, float4* out_rowA,
+                        cudaStream_t s) {
+  PoseArg P;
+  for (int k = 0; k < 12; k++) P.m[k] = pose1[k];
+  if (n > 0) pose_source_kernel<<<(n + 255) / 256, 256, 0, s>>>(xyz, n, P, out_xyz, out_rowA);
+}
 void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t s) {
   fma_peak_kernel<<<blocks, 256, 0, s>>>(kind, iters, sink);
 }

@@ -167,13 +167,21 @@ class CvoPointCloud:
 
 @dataclass
 class Association:
-    """cvo::Association: inlier index lists + the sparse N x M weight matrix (CSR)."""
-    source_inliers: list = field(default_factory=list)
-    target_inliers: list = field(default_factory=list)
+    """cvo::Association: inlier index lists + the sparse N x M weight matrix (CSR).  The index
+    lists are views of the CSR (rows that hold an entry; every entry's column, in row order -
+    gpu_association_to_cpu, CvoGPU_impl.cu:366-427) and are built when first read."""
     row_ptr: Optional[np.ndarray] = None
     cols: Optional[np.ndarray] = None
     vals: Optional[np.ndarray] = None
     shape: tuple = (0, 0)
+
+    @property
+    def source_inliers(self) -> list:
+        return [] if self.row_ptr is None else np.nonzero(np.diff(self.row_ptr))[0].tolist()
+
+    @property
+    def target_inliers(self) -> list:
+        return [] if self.cols is None else self.cols.tolist()
 
     def to_scipy(self):
         import scipy.sparse as sp
@@ -357,9 +365,6 @@ class CvoGPU:
         assoc.row_ptr = row_ptr.astype(np.int64)
         assoc.cols = cols[: nnz.value]
         assoc.vals = vals[: nnz.value]
-        counts = np.diff(assoc.row_ptr)
-        assoc.source_inliers = np.nonzero(counts)[0].tolist()
-        assoc.target_inliers = assoc.cols.tolist()
         return assoc
 
     # --- measurement helpers (bench.py)

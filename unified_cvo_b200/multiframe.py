@@ -28,16 +28,20 @@ class CvoFrameGPU:
     def __init__(self, gpu: CvoGPU, points: CvoPointCloud, pose_vec=None):
         self.gpu = gpu
         self.points = points
-        p = np.eye(4)[:3] if pose_vec is None else np.asarray(pose_vec, np.float64)
-        if p.size == 16:
-            p = p.reshape(4, 4)[:3]
-        self.pose_vec = np.ascontiguousarray(p.reshape(12), np.float64)  # row-major 3x4 [R t]
+        self.set_pose_vec(pose_vec)
         self.frame_id = getattr(gpu, "_next_frame_id", 0)  # ids are per handle
         gpu._next_frame_id = self.frame_id + 1
         F, Cn = points.feature_dimensions(), points.num_classes()
         gpu._check(gpu._lib.cvo_b200_frame_set(
             gpu._h, self.frame_id, points.num_points(), _ptr(points.positions_), F,
             _ptr(points.features_), Cn, _ptr(points.labels_), _ptr(points.geometric_types_)))
+
+    def set_pose_vec(self, pose_vec=None):
+        """The optimiser writes the frame's pose between outer iterations (CvoFrame::pose_vec)."""
+        p = np.eye(4)[:3] if pose_vec is None else np.asarray(pose_vec, np.float64)
+        if p.size == 16:
+            p = p.reshape(4, 4)[:3]
+        self.pose_vec = np.ascontiguousarray(p.reshape(12), np.float64)  # row-major 3x4 [R t]
 
     def pose_float(self) -> np.ndarray:
         """CvoFrameGPU.cu:47-53: the double pose narrowed to float for the device."""
@@ -93,8 +97,55 @@ class BinaryStateGPU:
             self.ell_ = self.ell_ * p.multiframe_ell_decay_rate
 
 
-def update_edges(states: Iterable[BinaryStateGPU]):
+def update_edges(states: Iterable[BinaryStateGPU], batched: bool = True):
     """The edge loop of one outer iteration (IRLS.cpp:111-121): every edge refills its matrix
-    from the frames' CURRENT poses; returns (total_nonzeros, per-edge nonzeros)."""
-    per_edge = [s.update_inner_product() for s in states]
-    return int(sum(per_edge)), per_edge
+    from the frames' CURRENT poses; returns (total_nonzeros, per-edge nonzeros).
+
+    batched (default): ONE cvo_b200_edge_update_batch call for all edges of a handle - the kernels
+    of every edge are enqueued back to back and the host waits once; same matrices as the per-edge
+    calls.  Falls back to the per-edge loop for edges the batch cannot serve."""
+    states = list(states)
+    if not batched or not states or any(s.gpu is not states[0].gpu for s in states):
+        per_edge = [s.update_inner_product() for s in states]
+        return int(sum(per_edge)), per_edge
+    from ._abi import Edge
+    g = states[0].gpu
+    g.write_params()
+    n = len(states)
+    edges = (Edge * n)()
+    for e, st in zip(edges, states):
+        if st.last_max_row_nnz > 0:  # IRLS_State_GPU.cu:45-47
+            st.num_neighbors_ = min(st.init_num_neighbors_, int(st.last_max_row_nnz * 1.1))
+        e.frame1, e.frame2 = st.frame1.frame_id, st.frame2.frame_id
+        e.pose1[:] = st.frame1.pose_float().tolist()
+        e.pose2[:] = st.frame2.pose_float().tolist()
+        e.ell, e.num_neighbors = st.ell_, int(st.num_neighbors_)
+    rows = [st.frame1.points.num_points() for st in states]
+    nnz = (C.c_int64 * n)()
+    mx = (C.c_int32 * n)()
+    row_ptr = np.zeros(sum(rows) + n, np.int32)
+    i32p = C.POINTER(C.c_int32)
+    rc = g._lib.cvo_b200_edge_update_batch(g._h, n, edges, nnz, mx, row_ptr.ctypes.data_as(i32p), None, None)
+    if rc == -5:  # CVO_B200_ERR_STATE: an edge outside the cell-query regimes
+        per_edge = [s.update_inner_product() for s in states]
+        return int(sum(per_edge)), per_edge
+    g._check(rc)
+    total = int(sum(nnz))
+    cols = np.zeros(max(total, 1), np.int32)
+    vals = np.zeros(max(total, 1), np.float32)
+    if total:
+        g._check(g._lib.cvo_b200_edge_update_batch(g._h, n, edges, nnz, mx, row_ptr.ctypes.data_as(i32p),
+                                                   cols.ctypes.data_as(i32p), _ptr(vals)))
+    per_edge, ro, eo = [], 0, 0
+    for k, st in enumerate(states):
+        a = st.A_result_cpu_
+        a.shape = (rows[k], st.frame2.points.num_points())
+        a.row_ptr = row_ptr[ro:ro + rows[k] + 1].astype(np.int64)
+        a.cols = cols[eo:eo + int(nnz[k])]  # views of the round's buffers (fresh arrays every call)
+        a.vals = vals[eo:eo + int(nnz[k])]
+        st.last_max_row_nnz = int(mx[k])
+        st.iter_ += 1
+        per_edge.append(int(nnz[k]))
+        ro += rows[k] + 1
+        eo += int(nnz[k])
+    return total, per_edge
