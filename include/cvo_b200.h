@@ -303,6 +303,10 @@ int cvo_b200_edge_update_batch(cvo_b200_handle* h, int n_edges, const cvo_b200_e
                                int64_t* nnz, int32_t* max_row_nnz, int32_t* row_ptr, int32_t* cols,
                                float* vals);
 
+/* How many iterations of the last cvo_b200_align built candidate cells (persistent tile mode: the
+ * cells are reused while the pose has drifted less than their skin; 0 in the other modes). */
+int cvo_b200_last_candidate_builds(const cvo_b200_handle* h);
+
 /* ---- measurement helpers --------------------------------------------------
  * Runs `iters` iterations back to back at a FIXED state (pose, ell, cap),
  * timed with CUDA events on the handle's stream.  ms_total = whole iteration

@@ -24,10 +24,12 @@ from helpers import (DATA, compare_traces, demo_clouds, demo_params, geometric_p
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["dense", "grid", "grid-launches", "tile"])
+@pytest.fixture(params=["dense", "grid", "grid-launches", "tile", "tile-launches"])
 def candidate_mode(request, monkeypatch):
     """dense N x M scan / cell queries in the persistent kernel / cell queries as one launch per
-    phase (read by cvo_b200_create): the controller exists in each launch structure."""
+    phase / tile cells in the persistent kernel (built with a skin and REUSED while the pose has
+    drifted less than it) / tile cells as one launch per phase (read by cvo_b200_create): the
+    controller exists in each launch structure."""
     monkeypatch.setenv("CVO_B200_MODE", request.param.split("-")[0])
     monkeypatch.setenv("CVO_B200_PERSIST", "0" if request.param.endswith("-launches") else "1")
     return request.param
@@ -172,6 +174,55 @@ def test_c4_full_size_iteration_at_the_benchmarked_ell():
     assert got.nnz == want.nnz > 10000
     assert np.abs(np.array(list(got.R)) - np.array(list(want.R))).max() <= 1e-6
     assert np.abs(np.array(list(got.T)) - np.array(list(want.T))).max() <= 1e-5
+
+
+@pytest.mark.parametrize("colour", [False, True])
+def test_reused_candidate_cells_lose_no_pair(monkeypatch, colour):
+    """Persistent tile mode keeps a row's candidate cells over several iterations (built with a skin,
+    verlet_decide in cvo_kernels.cu).  A lost pair would show as a different nnz: the free-running
+    loop must agree with the oracle record by record (nnz exactly) over a prefix that contains
+    reused iterations AND rebuilds, and end where the rebuild-every-iteration run ends."""
+    monkeypatch.setenv("CVO_B200_MODE", "tile")
+    monkeypatch.setenv("CVO_B200_PERSIST", "1")
+    if colour:
+        src, tgt, _ = synthetic_pair(5000, 4000, 4000, 20005, F=5)
+        p = u.read_params_yaml(os.path.join(DATA, "cvo_intensity_params_img_gpu0.yaml"))
+        p.ell_init, p.c_ell = 1.5, 1.0  # random colours: loosen the colour kernel so that rows fill
+    else:
+        src, tgt, _ = synthetic_pair(2500, 2000, 2000, 20002)
+        p = geometric_params(0.95)
+    p.MAX_ITER = 48
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    _, T_o, _, tr_o = oracle.align(p, cs, ct, None, trace_cap=48)
+    out = {}
+    for kappa in ("0.1", "0.02", "0"):
+        monkeypatch.setenv("CVO_B200_VERLET", kappa)
+        g = u.CvoGPU(p, device=0)
+        _, T_g, info, tr_g = g.align(src, tgt, None, trace_cap=48)
+        out[kappa] = (T_g, len(tr_g), g.last_candidate_builds(), agreeing_prefix(tr_g, tr_o), [t.nnz for t in tr_g])
+        g.close()
+    for kappa, (T_g, n_it, builds, prefix, nnz) in out.items():
+        print(f"colour {colour} kappa {kappa}: {n_it} iterations, {builds} builds, prefix {prefix}, nnz[0] {nnz[0]}")
+    base = out["0"][3]  # how long the rebuild-every-iteration run follows the oracle (the loop is chaotic)
+    assert base >= 12
+    for kappa, (T_g, n_it, builds, prefix, nnz) in out.items():
+        assert prefix >= base - 2, (kappa, prefix, base)
+        assert nnz[:prefix] == [t.nnz for t in tr_o[:prefix]] and nnz[0] > 1000
+    n_it = out["0"][1]
+    assert out["0"][2] == n_it                      # no skin: every iteration builds
+    assert 1 <= out["0.1"][2] <= (2 * n_it) // 3    # cells reused ...
+    assert out["0.1"][2] <= out["0.02"][2] <= n_it  # ... and a thinner skin is used up sooner
+    assert out["0.02"][2] >= 2                      # rebuilds happened inside the run
+    # reused iterations lie INSIDE the compared prefix: the same run stopped there built fewer times
+    # than it iterated
+    monkeypatch.setenv("CVO_B200_VERLET", "0.1")
+    p.MAX_ITER = out["0.1"][3]
+    g = u.CvoGPU(p, device=0)
+    g.align(src, tgt, None)
+    builds_in_prefix = g.last_candidate_builds()
+    g.close()
+    print(f"builds inside the agreeing prefix of {p.MAX_ITER}: {builds_in_prefix}")
+    assert 1 <= builds_in_prefix < p.MAX_ITER
 
 
 def test_two_gpus_equal_one(tmp_path):

@@ -196,6 +196,7 @@ SYMBOLS = {
         [C.c_void_p, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _f32p, _f32p],
     ),
     "cvo_b200_launch_count": (C.c_uint64, [C.c_void_p]),
+    "cvo_b200_last_candidate_builds": (C.c_int, [C.c_void_p]),
     "cvo_b200_stream": (C.c_void_p, [C.c_void_p]),
     "cvo_b200_fma_peak": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "cvo_b200_comm_unique_id": (C.c_int, [C.c_char * 128]),

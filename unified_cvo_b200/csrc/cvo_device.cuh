@@ -86,6 +86,9 @@ struct DevState {
   float ymax2_bound;        // upper bound of max_j |y'_j - c|^2 for the CURRENT Rinv/Tinv
   float smax;               // upper bound of sigma_max(Rinv) (scales block radii)
   float grid_slack;         // absolute slack [m] of a cell query in the target's own frame
+  // candidate-cell reuse (persistent tile mode): the cells are built with every row's query radius
+  // enlarged by vl_str + vl_srot |x| and stay valid while the pose has drifted less than that
+  float vl_str, vl_srot;    // translation budget [m], rotation budget [Frobenius norm of R - R_build]
   int prune_on;             // this run may use the Morton view
   int view;                 // target view of the CURRENT iteration: 0 Morton (pruned), 1 original
   unsigned int sat_base;    // persistent kernel: value of the (monotone) n_sat counter at the start of this iteration
@@ -101,6 +104,13 @@ struct DevState {
   unsigned int max_row_nnz;
   int last_grid;            // the LAST executed iteration used cell queries (Morton index space)
   int last_view;            // view the LAST executed iteration used (its ELL matrix is in that index space)
+  // candidate-cell reuse: the state the current cells were built at
+  float vl_R[9], vl_T[3];   // R, T (source -> target frame)
+  float vl_ls;              // ell * smax
+  float vl_slack;           // grid_slack
+  int vl_valid;             // cells exist for this launch
+  int tile_rebuild;         // decision of the current iteration (same in every block)
+  unsigned int tile_builds; // how many iterations built cells (statistics)
   // step
   double B, C, D, E;
   float step;
@@ -249,6 +259,8 @@ struct IterArgs {
   int posevec;
   float pose2[12];   // row-major 3x4
   float edge_slack;  // extra slack of the cell queries: the state's (R, T) only approximates pose2^-1
+  float verlet_kappa;  // candidate-cell reuse: skin as a fraction of the cut-off radius (0 = rebuild every iteration)
+  float src_rmax;      // max |x| over the source (scales the rotation budget)
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective
   int n_items;     // pair-kernel work items = row_tiles * nchunks
 };

@@ -238,7 +238,10 @@ struct cvo_b200_handle {
   int persist_blocks = 1;   // cooperative grid of align_grid_kernel (all blocks co-resident)
   int persist_blocks_tile = 1;  // ... of its tile-cell instantiation
   int persist_threads = kPersistThreads;
+  int persist_threads_tile = kPersistThreads;
   bool use_persist = true;  // CVO_B200_PERSIST=0: one launch per phase even in cell-query mode
+  int last_tile_builds = 0;   // iterations of the last align() that built candidate cells (persistent tile mode)
+  float verlet_kappa = 0.1f;  // candidate-cell reuse of the persistent tile mode: skin / cut-off radius (CVO_B200_VERLET)
   int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries, 2 tile cells (where possible)
   // host poll buffer (pinned)
   int* h_poll = nullptr;
@@ -404,8 +407,13 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   const int rows_per_pblock = (h->persist_threads / 32) * 4;
   h->persist_blocks =
       std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_pblock - 1) / rows_per_pblock));
-  // tile mode: one block of kPersistThreads per SM (tile items and rows are dealt to its warps)
-  h->persist_blocks_tile = std::min(kLLMaxBlocks, h->num_sms * std::max(1, std::min(1, align_grid_max_blocks_per_sm(kPersistThreads, 1))));
+  // tile mode: one block per SM (tile items and rows are dealt to its warps); the wide block where
+  // it saves the second pass over the rows (cells are mostly reused: the row walk is the iteration)
+  h->persist_threads_tile = (n_rows > h->num_sms * (kPersistThreads / 32) * 4 && n_rows <= h->num_sms * (kPersistThreadsWide / 32) * 4)
+                                ? kPersistThreadsWide
+                                : kPersistThreads;
+  h->persist_blocks_tile =
+      std::min(kLLMaxBlocks, h->num_sms * std::max(1, std::min(1, align_grid_max_blocks_per_sm(h->persist_threads_tile, 1))));
   CVO_CUDA(h, h->flow_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
   CVO_CUDA(h, h->flow_part2.ensure((size_t)h->persist_blocks));
   CVO_CUDA(h, h->ll_board.ensure(1));
@@ -485,6 +493,8 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   for (int r = 0; r < kMaxWorld; r++) A.xpeer[r] = h->peers[r];
   A.posevec = 0;
   A.edge_slack = 0.f;
+  A.verlet_kappa = h->verlet_kappa;
+  A.src_rmax = cs.max_dist;
   A.grid = 0;
   A.tile = 0;
   A.tile_L = tile_L;
@@ -562,7 +572,8 @@ cudaError_t launch_persistent(cvo_b200_handle* h, const IterArgs& A) {
   if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->work_counter, 0, sizeof(unsigned int), h->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->n_sat, 0, sizeof(unsigned int), h->stream);
   if (e != cudaSuccess) return e;
-  return launch_align_grid(A, A.tile ? h->persist_blocks_tile : h->persist_blocks, h->persist_threads, h->stream);
+  return launch_align_grid(A, A.tile ? h->persist_blocks_tile : h->persist_blocks,
+                           A.tile ? h->persist_threads_tile : h->persist_threads, h->stream);
 }
 
 void host_update_tf(const float R[9], const float T[3], float Rinv[9], float Tinv[3]) {
@@ -758,10 +769,16 @@ void choose_mode(const cvo_b200_handle* h, IterArgs& A, const CloudDev& cs, cons
   // rows whose candidates overflow their cells are redone exhaustively (O(M) each): keep them rare.
   // With a colour cut only a fraction of the ball becomes candidates (measured: 1 % on random
   // colours); the loop leaves the mode when rows do overflow (sat_recent).
-  const double cand_est = ball * (p.is_using_intensity ? 0.25 : 1.0);
+  // (reused cells are built with the radius enlarged by up to 2 kappa: verlet_decide)
+  const double skin = (h->use_persist && (h->world == 1 || h->peers_ready)) ? 1.0 + 1.5 * (double)h->verlet_kappa : 1.0;  // = `reuse` below
+  const double cand_est = ball * skin * skin * skin * (p.is_using_intensity ? 0.25 : 1.0);
   if (h->force_mode != 2 && cand_est > 0.5 * (double)A.tile_L * (double)A.tile_parts) return;
   const double rows = (double)rows_policy;
-  const double us_tile = rows * tests_t * 0.3e-6 + 30.0;
+  // inside the persistent kernel the cells are reused over several iterations (verlet_decide): a
+  // build is amortised (measured: 4-10 iterations per build where the mode pays off) but costs
+  // ~12 us of latency per iteration on average whatever its size
+  const bool reuse = h->use_persist && (h->world == 1 || h->peers_ready) && h->verlet_kappa > 0.f;
+  const double us_tile = reuse ? rows * tests_t * 0.3e-6 / 4.0 + 12.0 : rows * tests_t * 0.3e-6 + 30.0;
   double hcell = ct.extent;
   const double hmin = ct.extent / (double)(1 << ct.cbits);
   while (hcell * 0.5 >= r && hcell * 0.5 >= hmin) hcell *= 0.5;
@@ -931,7 +948,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
     const int rows_policy = A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows;
     if (A.world > 1) sat_recent = false;
     choose_mode(h, A, h->src, h->tgt, ell, rows_policy, sat_recent);
-    if ((A.grid || (A.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready)) {
+    if ((A.grid || A.tile) && h->use_persist && (A.world == 1 || h->peers_ready)) {
       // the whole loop in one cooperative launch (align_grid_kernel); it returns when done.
       // world > 1: the two per-iteration exchanges are NVLink stores into the peers' mailboxes
       A.xfused = A.world > 1 ? 1 : 0;
@@ -942,6 +959,14 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
       CVO_CUDA(h, cudaStreamSynchronize(h->stream));
       batches++;
       grid_batches++;
+      if (A.stamps && h->h_poll[0] > 0) {  // CVO_B200_STAMPS=1: per-phase time of block 0 / thread 0 over the whole loop
+        unsigned long long acc[10];
+        cudaMemcpy(acc, A.stamps, sizeof(acc), cudaMemcpyDeviceToHost);
+        const char* names[10] = {"flow rows", "flow allreduce (incl. wait)", "tile phase (when built)", "redo of cut rows", "finalize",
+                                 "step rows", "step allreduce (incl. wait)", "tile hand-over", "-", "controller"};
+        for (int k = 0; k < 10; k++)
+          fprintf(stderr, "[align phases] %-28s %7.2f us/iter\n", names[k], (double)acc[k] / 1e3 / (double)h->h_poll[0]);
+      }
       if (h->h_poll[1] /*done*/) {
         if (h->h_poll[2] /*ret*/ == CVO_B200_ERR_NCCL)
           return fail(h, CVO_B200_ERR_NCCL, "fused exchange: a peer's record did not arrive (peer gone?)");
@@ -1049,6 +1074,7 @@ int cvo_b200_create(const cvo_b200_params* p, int device, cvo_b200_handle** out)
   if (fm && std::strcmp(fm, "tile") == 0) h->force_mode = 2;
   const char* pe = getenv("CVO_B200_PERSIST");
   h->use_persist = !(pe && pe[0] == '0');
+  if (const char* vk = getenv("CVO_B200_VERLET")) h->verlet_kappa = std::max(0.f, std::min(1.f, (float)atof(vk)));
   *out = h;
   return CVO_B200_OK;
 }
@@ -1134,7 +1160,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   choose_mode(h, A, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
-  if ((A.grid || (A.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready)) {
+  if ((A.grid || A.tile) && h->use_persist && (A.world == 1 || h->peers_ready)) {
     A.xfused = A.world > 1 ? 1 : 0;
     A.xgen = ++h->xgen;
     CVO_CUDA(h, launch_persistent(h, A));
@@ -1189,7 +1215,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
     IterArgs Ag = A;
     choose_mode(h, Ag, h->src, h->tgt, h->params.ell_init, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
-    if (!((Ag.grid || (Ag.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready))) {
+    if (!((Ag.grid || Ag.tile) && h->use_persist && (A.world == 1 || h->peers_ready))) {
       rc = ensure_graph(h, Ag, 32);
       if (rc != CVO_B200_OK) {
         cudaEventDestroy(ev0);
@@ -1234,6 +1260,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   h->last_valid = true;
   h->last_view = hs.last_grid ? 0 : hs.last_view;
   h->last_args = A;
+  h->last_tile_builds = (int)hs.tile_builds;
   if (trace_cap > 0) {
     const int nrec = std::min(trace_cap, executed);
     CVO_CUDA(h, cudaMemcpy(trace, h->d_trace.p, sizeof(cvo_b200_iter_trace) * (size_t)nrec, cudaMemcpyDeviceToHost));
@@ -1809,6 +1836,8 @@ int cvo_b200_edge_update_batch(cvo_b200_handle* h, int n_edges, const cvo_b200_e
   return CVO_B200_OK;
 }
 
+int cvo_b200_last_candidate_builds(const cvo_b200_handle* h) { return h ? h->last_tile_builds : CVO_B200_ERR_INVALID; }
+
 int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T[3], float ell,
                              int num_neighbors, int iters, float* ms_total, float* ms_pair_kernel) {
   if (!h || !R || !T || iters <= 0) return fail(h, CVO_B200_ERR_INVALID, "bad argument");
@@ -1822,7 +1851,7 @@ int cvo_b200_time_iterations(cvo_b200_handle* h, const float R[9], const float T
   choose_mode(h, A, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
   rc = init_state(h, A, R, T, ell, num_neighbors, 2, iters, nullptr, 0);
   if (rc != CVO_B200_OK) return rc;
-  const bool persist = (A.grid || (A.tile && A.world > 1)) && h->use_persist && (A.world == 1 || h->peers_ready);
+  const bool persist = (A.grid || A.tile) && h->use_persist && (A.world == 1 || h->peers_ready);
   if (persist) {
     A.xfused = A.world > 1 ? 1 : 0;
     A.xgen = ++h->xgen;

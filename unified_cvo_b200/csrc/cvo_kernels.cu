@@ -742,6 +742,7 @@ __device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs
   const float ell_now = hs->ell;
   const float log_geo = hs->kc.log_geo;
   const float g_smax = hs->smax, g_slack = hs->grid_slack + A.edge_slack;
+  const float skin_tr = hs->vl_str, skin_rot = hs->vl_srot;
   const float* Rf = hs->R;
   const float* Tf = hs->T;
   const bool colour_cut = hs->kc.use_intensity != 0;
@@ -812,8 +813,13 @@ __device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs
           mat3f_vec(Rf, xv, q);
           q[0] += Tf[0]; q[1] += Tf[1]; q[2] += Tf[2];
           // |y - q| <= smax |y' - x| + slack (update_tf_device); same radius as the cell queries
-          const float rq = sqrtf(d2_thres) * g_smax * 1.00001f + g_slack +
-                           2e-6f * (fabsf(xv[0]) + fabsf(xv[1]) + fabsf(xv[2]) + fabsf(q[0]) + fabsf(q[1]) + fabsf(q[2]));
+          float rq = sqrtf(d2_thres) * g_smax * 1.00001f + g_slack +
+                     2e-6f * (fabsf(xv[0]) + fabsf(xv[1]) + fabsf(xv[2]) + fabsf(q[0]) + fabsf(q[1]) + fabsf(q[2]));
+          // candidate-cell reuse (verlet_decide): the cells stay valid while q has moved by less than
+          // the skin, |q - q_build| <= |R - R_build|_F |x| + |T - T_build|
+          if (skin_tr > 0.f)
+            rq += skin_tr + skin_rot * (sqrtf(xv[0] * xv[0] + xv[1] * xv[1] + xv[2] * xv[2]) * 1.000001f) +
+                  4e-6f * sqrtf(d2_thres) * g_smax;
           const float th = rq * rq * 1.000001f;
           const float4 a = make_float4(-2.f * (q[0] - A.tcx), -2.f * (q[1] - A.tcy), -2.f * (q[2] - A.tcz), 0.f);
           const float t = prefilter_threshold(th, a, ymax2);
@@ -2376,6 +2382,50 @@ constexpr size_t align_grid_smem_bytes(int threads, int gen) {
   return (list > all ? (list > tile ? list : tile) : (all > tile ? all : tile)) + 16;
 }
 
+// Candidate-cell reuse of the persistent tile mode (a Verlet list with a skin).  The cells of
+// tile_phase hold, per source row x, every target y with |y - q_b| <= rq_b(x) + skin(x), q_b = R_b x
+// + T_b the row in the target's frame at BUILD time and skin(x) = s_tr + s_rot |x| (+ a relative
+// 4e-6 of the radius).  An iteration at pose (R, T) needs every y with |y - q| <= rq(x); since
+// |q - q_b| <= |R - R_b|_F |x| + |T - T_b|, the old cells still contain them while
+//   |R - R_b|_F <= s_rot,   |T - T_b| + (slack - slack_b)+ <= s_tr,   ell smax <= ell_b smax_b (1 + 2e-6)
+// (the cut-off radius is proportional to ell * smax, CvoGPU.cu:506-511; flow_rows<2> re-tests every
+// candidate with the reference's arithmetic at the CURRENT pose, so a superset changes nothing).
+// Budgets: s_tr = kappa * (cut-off radius at range 0), s_rot = s_tr / max|x|.  Called by thread 0 of
+// every block at the top of an iteration: same inputs, same decision everywhere.
+__device__ void verlet_decide(const IterArgs& A, DevState* st) {
+  bool rebuild = st->vl_valid == 0 || st->controller_on == 2 || !(A.verlet_kappa > 0.f);
+  if (!rebuild) {
+    float dr2 = 0.f, dt2 = 0.f;
+    for (int i = 0; i < 9; i++) {
+      const float d = st->R[i] - st->vl_R[i];
+      dr2 += d * d;
+    }
+    for (int i = 0; i < 3; i++) {
+      const float d = st->T[i] - st->vl_T[i];
+      dt2 += d * d;
+    }
+    const float dr = sqrtf(dr2) * 1.0001f, dt = sqrtf(dt2) * 1.0001f + 1e-7f;
+    const float ds = fmaxf(0.f, st->grid_slack - st->vl_slack) * 1.0001f;
+    const float ls = st->ell * st->smax;
+    // (NaN anywhere: every comparison is false -> rebuild)
+    const bool keep = dr <= st->vl_srot && dt + ds <= st->vl_str && ls <= st->vl_ls * 1.000002f;
+    rebuild = !keep;
+  }
+  if (rebuild) {
+    const float r0 = sqrtf(fmaxf(0.f, (float)(-2.0 * st->ell * st->ell * st->kc.log_geo)));
+    const bool on = A.verlet_kappa > 0.f && st->controller_on != 2 && r0 > 0.f && r0 < 1e30f;
+    st->vl_str = on ? A.verlet_kappa * r0 : 0.f;
+    st->vl_srot = on ? st->vl_str / fmaxf(A.src_rmax, 1e-3f) : 0.f;
+    for (int i = 0; i < 9; i++) st->vl_R[i] = st->R[i];
+    for (int i = 0; i < 3; i++) st->vl_T[i] = st->T[i];
+    st->vl_ls = st->ell * st->smax;
+    st->vl_slack = st->grid_slack;
+    st->vl_valid = 1;
+    st->tile_builds += 1u;
+  }
+  st->tile_rebuild = rebuild ? 1 : 0;
+}
+
 // kGen: 1 = cell queries, 2 = tile cells (a tile phase + a grid-wide hand-over in front of the flow
 // phase)
 template <int kThreads, bool kFused, bool kColour, int kGen = 1>
@@ -2440,14 +2490,19 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     if (kGen == 2) {
       // ---- tile phase: candidate cells for ALL rows of this rank, items dealt round-robin to the
       //      warps of the grid; the rows are evaluated by other blocks, so the cells are handed
-      //      over through one grid-wide reduction with release / acquire
-      TileSmemWarp& S = reinterpret_cast<TileSmemWarp*>(s_raw)[warp_in_block];
-      tile_phase(A, &s_st, S, &s_tile_bar[kGen == 2 ? warp_in_block : 0], warp_in_block * (int)gridDim.x + (int)blockIdx.x,
-                 (int)gridDim.x * warps_per_block, tile_bar_phase);
-      CVO_PHASE(2)
-      double one[1] = {1.0}, got[1];
-      ll_allreduce<1, 1>(A.ll, ++seq, one, sh, sh_all, got, true, true);
-      CVO_PHASE(7)
+      //      over through one grid-wide reduction with release / acquire.  Skipped while the cells
+      //      of an earlier iteration still cover the current pose (verlet_decide).
+      if (threadIdx.x == 0) verlet_decide(A, &s_st);
+      __syncthreads();
+      if (s_st.tile_rebuild) {  // the same value in every block
+        TileSmemWarp& S = reinterpret_cast<TileSmemWarp*>(s_raw)[warp_in_block];
+        tile_phase(A, &s_st, S, &s_tile_bar[kGen == 2 ? warp_in_block : 0], warp_in_block * (int)gridDim.x + (int)blockIdx.x,
+                   (int)gridDim.x * warps_per_block, tile_bar_phase);
+        CVO_PHASE(2)
+        double one[1] = {1.0}, got[1];
+        ll_allreduce<1, 1>(A.ll, ++seq, one, sh, sh_all, got, true, true);
+        CVO_PHASE(7)
+      }
     }
     {
       double bp[9], queued[2], v[kLLValues], r[kLLValues];
@@ -2689,7 +2744,7 @@ void launch_fma_peak(int kind, int iters, int blocks, float* sink, cudaStream_t 
 }
 // the instantiations of the persistent kernel: block size x single GPU / fused multi-GPU
 // exchange x colour cut in stage 1 (each kept out of the code that does not need it: the kernel is
-// register bound) for the cell queries; one block size for the tile cells
+// register bound) for the cell queries; two block sizes for the tile cells
 template <int kThreads>
 static const void* align_grid_fn_t(bool fused, bool colour) {
   if (fused)
@@ -2699,15 +2754,19 @@ static const void* align_grid_fn_t(bool fused, bool colour) {
                 : (const void*)align_grid_kernel<kThreads, false, false>;
 }
 static const void* align_grid_fn(int threads, bool fused, bool colour, bool tile) {
-  if (tile)
+  if (tile) {
+    if (threads == kPersistThreadsWide)
+      return fused ? (const void*)align_grid_kernel<kPersistThreadsWide, true, true, 2>
+                   : (const void*)align_grid_kernel<kPersistThreadsWide, false, true, 2>;
     return fused ? (const void*)align_grid_kernel<kPersistThreads, true, true, 2>
                  : (const void*)align_grid_kernel<kPersistThreads, false, true, 2>;
+  }
   if (threads == kPersistThreadsSmall) return align_grid_fn_t<kPersistThreadsSmall>(fused, colour);
   if (threads == kPersistThreadsWide) return align_grid_fn_t<kPersistThreadsWide>(fused, colour);
   return align_grid_fn_t<kPersistThreads>(fused, colour);
 }
 static int align_grid_threads(int threads, bool tile) {
-  if (tile) return kPersistThreads;
+  if (tile) return threads == kPersistThreadsWide ? kPersistThreadsWide : kPersistThreads;
   return (threads == kPersistThreadsWide || threads == kPersistThreadsSmall) ? threads : kPersistThreads;
 }
 cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaStream_t s) {

@@ -380,6 +380,10 @@ class CvoGPU:
     def launch_count(self) -> int:
         return int(self._lib.cvo_b200_launch_count(self._h))
 
+    def last_candidate_builds(self) -> int:
+        """Iterations of the last align() that built candidate cells (persistent tile mode)."""
+        return int(self._lib.cvo_b200_last_candidate_builds(self._h))
+
     def stream(self) -> int:
         return int(self._lib.cvo_b200_stream(self._h) or 0)
 
