@@ -369,13 +369,18 @@ def measure(u, torch, g, name, src, tgt, p, steps, warmup, local_rank, rank, wor
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
     # ---- warm-up (also ramps the clocks: at least ~0.5 s of work)
+    # The NUMBER of warm-up steps must be the same on every rank (each align is a collective of the
+    # job): it is derived from the slowest rank's first step, never from a rank's own clock.
     t_warm = time.perf_counter()
-    w = 0
-    while w < warmup or time.perf_counter() - t_warm < 0.5:
+    g.align(src, tgt, T_init, resident=True)
+    first = time.perf_counter() - t_warm
+    if dist is not None:
+        firsts = [None] * world
+        dist.all_gather_object(firsts, first)
+        first = max(firsts)
+    n_warm = max(warmup, min(warmup + 50, int(0.5 / max(first, 1e-4)) + 1))
+    for _ in range(n_warm - 1):
         g.align(src, tgt, T_init, resident=True)
-        w += 1
-        if w > warmup + 50:
-            break
     # ---- timed region: K resident steps, device time per step, L2 flushed between steps
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -637,6 +642,9 @@ def main():
     ap.add_argument("--no-frames", action="store_true", help="skip the KITTI-05-sized frame-pairs/s legs")
     ap.add_argument("--no-anchor", action="store_true", help="skip the C4 scale anchor of the N=1 line")
     args = ap.parse_args()
+    if os.environ.get("BENCH_WATCHDOG"):  # debugging aid: dump every thread's stack and exit after N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BENCH_WATCHDOG"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

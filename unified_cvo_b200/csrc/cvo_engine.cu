@@ -57,6 +57,7 @@ struct NcclApi {
   int (*CommInitRank)(ncclComm_t*, int, UniqueId, int) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*CommAbort)(ncclComm_t) = nullptr;  // optional
   const char* (*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -79,6 +80,7 @@ bool load_nccl(std::string& err) {
   g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t))dlsym(
       g_nccl.lib, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.CommAbort = (int (*)(ncclComm_t))dlsym(g_nccl.lib, "ncclCommAbort");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
     err = "libnccl is missing a required symbol";
@@ -239,6 +241,7 @@ struct cvo_b200_handle {
   int persist_blocks_tile = 1;  // ... of its tile-cell instantiation
   int persist_threads = kPersistThreads;
   int persist_threads_tile = kPersistThreads;
+  bool comm_broken = false;  // a multi-GPU exchange failed: tear the communicator down without waiting for peers
   bool use_persist = true;  // CVO_B200_PERSIST=0: one launch per phase even in cell-query mode
   int last_tile_builds = 0;   // iterations of the last align() that built candidate cells (persistent tile mode)
   float verlet_kappa = 0.1f;  // candidate-cell reuse of the persistent tile mode: skin / cut-off radius (CVO_B200_VERLET)
@@ -547,6 +550,7 @@ int enqueue_iteration(cvo_b200_handle* h, const IterArgs& A, int stage, cudaEven
   if (A.world > 1) {
     DevState* st = h->d_state;
     int rc = g_nccl.AllGather(&st->local_flow[0], h->gathered.p, 9, kNcclFloat64, h->comm, s);
+    if (rc != 0) h->comm_broken = true;
     if (rc != 0) return fail(h, CVO_B200_ERR_NCCL, "ncclAllGather(flow) failed");
     launch_finalize_flow(A, h->gathered.p, 9, s);
     h->launches += 1;
@@ -968,6 +972,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
           fprintf(stderr, "[align phases] %-28s %7.2f us/iter\n", names[k], (double)acc[k] / 1e3 / (double)h->h_poll[0]);
       }
       if (h->h_poll[1] /*done*/) {
+        if (h->h_poll[2] /*ret*/ == CVO_B200_ERR_NCCL) h->comm_broken = true;
         if (h->h_poll[2] /*ret*/ == CVO_B200_ERR_NCCL)
           return fail(h, CVO_B200_ERR_NCCL, "fused exchange: a peer's record did not arrive (peer gone?)");
         break;
@@ -1084,7 +1089,9 @@ void cvo_b200_destroy(cvo_b200_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   destroy_graph(h);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  // after a failed exchange the peers may never join a collective teardown: abort instead of waiting
+  if (h->comm && h->comm_broken && g_nccl.CommAbort) g_nccl.CommAbort(h->comm);
+  else if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   for (int r = 0; r < kMaxWorld; r++)
     if (h->peers[r] && h->peers[r] != h->mailbox) cudaIpcCloseMemHandle(h->peers[r]);
   if (h->mailbox) cudaFree(h->mailbox);
@@ -2051,7 +2058,9 @@ int cvo_b200_comm_destroy(cvo_b200_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   destroy_graph(h);
-  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+  // after a failed exchange the peers may never join a collective teardown: abort instead of waiting
+  if (h->comm && h->comm_broken && g_nccl.CommAbort) g_nccl.CommAbort(h->comm);
+  else if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
   h->comm = nullptr;
   for (int r = 0; r < kMaxWorld; r++) {
     if (h->peers[r] && h->peers[r] != h->mailbox) cudaIpcCloseMemHandle(h->peers[r]);
