@@ -159,12 +159,16 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.t_mark = [], None, gpu_index, None
+
+    def mark_timed_region(self):
+        """Samples from here on lie inside the timed region (earlier ones: the warm-up steps)."""
+        self.t_mark = time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -173,7 +177,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.perf_counter()])
 
     def stop(self):
         if not self.proc:
@@ -183,12 +187,19 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) > 9 and r[1].replace(".", "").isdigit()]
+        timed = [r for r in rows if self.t_mark is not None and r[-1] >= self.t_mark]
+        # a timed region of a few tens of ms holds few 20 ms samples: then the GPU-busy warm-up steps
+        # right before it (same kernels, back to back) are reported with it, and the line says so
+        window = "timed region"
+        if len(timed) < 3:
+            timed, window = rows, "warm-up steps + timed region (timed region shorter than 3 samples)"
+        sm = [float(r[1]) for r in timed]
+        mx = [float(r[2]) for r in timed if r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) > 8 for n, v in zip(names, r[5:9]) if v == "Active"})
+        reasons = sorted({n for r in timed for n, v in zip(names, r[5:9]) if v == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons}
+                "samples": len(sm), "reasons": reasons, "window": window, "interval_ms": 20}
 
 
 def measured_peaks():
@@ -379,12 +390,13 @@ def measure(u, torch, g, name, src, tgt, p, steps, warmup, local_rank, rank, wor
         dist.all_gather_object(firsts, first)
         first = max(firsts)
     n_warm = max(warmup, min(warmup + 50, int(0.5 / max(first, 1e-4)) + 1))
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(n_warm - 1):
         g.align(src, tgt, T_init, resident=True)
     # ---- timed region: K resident steps, device time per step, L2 flushed between steps
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     barrier()
+    sampler.mark_timed_region()
     launches0 = g.launch_count()
     dev_s, pairs, iters, persist_frac = 0.0, 0, 0, 0.0
     wall0 = time.perf_counter()
@@ -397,6 +409,7 @@ def measure(u, torch, g, name, src, tgt, p, steps, warmup, local_rank, rank, wor
         pairs += info.pairs_tested
         iters += info.iterations + (0 if info.stop_reason == 8 else 1)
         persist_frac += info.cell_query_fraction / steps
+    builds = g.last_candidate_builds()  # of the last step (persistent tile mode; 0 otherwise)
     barrier()
     wall = time.perf_counter() - wall0
     launches = g.launch_count() - launches0
@@ -422,7 +435,7 @@ def measure(u, torch, g, name, src, tgt, p, steps, warmup, local_rank, rank, wor
         dev_s, e2e_s = float(t[0]), float(t[1])
     del flush
     return dict(N=N, M=M, F=F, C=C, dev_s=dev_s, pairs=pairs, iters=iters, persist_frac=persist_frac, wall=wall,
-                launches=launches, clocks=clocks, e2e_s=e2e_s, e2e_pairs=e2e_pairs, e2e_steps=e2e_steps,
+                launches=launches, clocks=clocks, builds=builds, e2e_s=e2e_s, e2e_pairs=e2e_pairs, e2e_steps=e2e_steps,
                 last_T=last_T, T_init=T_init)
 
 
@@ -538,6 +551,7 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": f"{name}: {desc}", "N": m["N"], "M": m["M"], "F": m["F"], "C": m["C"],
                    "iterations_per_step": m["iters"] / args.steps, "l2_flush_between_steps": True,
                    "persistent_kernel_fraction": m["persist_frac"],
+                   "candidate_cell_builds_per_step": m["builds"],
                    "parallelism": "single GPU" if world == 1 else
                    f"source rows sharded x{world}; the whole loop is one persistent kernel per GPU whose two "
                    f"per-iteration exchanges are NVLink stores into the peers' mailboxes (no NCCL call, no launch "
