@@ -2,8 +2,9 @@
 // shim/CvoGPU_b200.cpp and shim/IRLS_State_GPU_b200.cpp touch (Eigen, PCL, cvo::CvoPointCloud/CvoParams/Association/CvoGPU).
 // The build container has neither Eigen nor PCL, so tests/test_shim_syntax.py compiles the shim
 // against these declarations (-DCVO_SHIM_SYNTAX_CHECK -include this file) to keep it
-// syntactically and type-wise honest.  Nothing here is shipped or linked; in a real build the
-// shim includes the reference's own headers instead.
+// syntactically and type-wise honest, and tests/test_shim_runtime_gpu.py RUNS the shim against them
+// on a B200 (the containers hold real data, column-major like Eigen's).  Nothing here is shipped; in
+// a real build the shim includes the reference's own headers instead.
 #pragma once
 #include <cstddef>
 #include <cstdint>
@@ -25,24 +26,38 @@
 namespace Eigen {
 constexpr int Dynamic = -1;
 constexpr int RowMajor = 1;
+// column-major storage like Eigen's default; only what the shim and the runtime driver touch
 template <class T, int R, int C>
 struct Matrix {
   std::vector<T> d;
   int r = R > 0 ? R : 0, c = C > 0 ? C : 0;
   Matrix() : d((size_t)(R > 0 ? R : 0) * (C > 0 ? C : 0)) {}
+  Matrix(int rows, int cols) : d((size_t)rows * cols), r(rows), c(cols) {}
+  explicit Matrix(int rows) : d((size_t)rows * (C > 0 ? C : 1)), r(rows), c(C > 0 ? C : 1) {}
+  void resize(int rows, int cols) {
+    r = rows;
+    c = cols;
+    d.assign((size_t)rows * cols, T(0));
+  }
   long rows() const { return r; }
   long cols() const { return c; }
+  long size() const { return (long)d.size(); }
   T* data() { return d.data(); }
   const T* data() const { return d.data(); }
   T& operator()(int i, int j) { return d[(size_t)j * r + i]; }
   const T& operator()(int i, int j) const { return d[(size_t)j * r + i]; }
   T& operator()(int i) { return d[i]; }
   const T& operator()(int i) const { return d[i]; }
-  static Matrix Identity() { return Matrix(); }
+  static Matrix Identity() {
+    Matrix m;
+    for (int i = 0; i < m.r && i < m.c; i++) m(i, i) = T(1);
+    return m;
+  }
 };
 using Matrix4f = Matrix<float, 4, 4>;
 using Matrix3f = Matrix<float, 3, 3>;
 using Vector3f = Matrix<float, 3, 1>;
+using VectorXf = Matrix<float, Dynamic, 1>;
 using MatrixXf = Matrix<float, Dynamic, Dynamic>;
 template <class M>
 struct Ref {
@@ -56,13 +71,23 @@ struct aligned_allocator : std::allocator<T> {
 };
 template <class T>
 struct Triplet {
-  Triplet(int, int, T) {}
+  int r, c;
+  T v;
+  Triplet(int r_, int c_, T v_) : r(r_), c(c_), v(v_) {}
+  int row() const { return r; }
+  int col() const { return c; }
+  T value() const { return v; }
 };
 template <class T, int Opt>
 struct SparseMatrix {
-  void resize(int, int) {}
-  template <class It> void setFromTriplets(It, It) {}
+  int r = 0, c = 0;
+  std::vector<Triplet<T>> t;  // row-major order of insertion is what the shim produces
+  void resize(int rows, int cols) { r = rows; c = cols; t.clear(); }
+  template <class It> void setFromTriplets(It b, It e) { t.assign(b, e); }
   void makeCompressed() {}
+  long rows() const { return r; }
+  long cols() const { return c; }
+  long nonZeros() const { return (long)t.size(); }
 };
 }  // namespace Eigen
 
@@ -89,19 +114,51 @@ struct Association {
 };
 class CvoPointCloud {
  public:
-  int num_points() const { return 0; }
-  int size() const { return 0; }
-  int num_classes() const { return 0; }
+  CvoPointCloud() {}
+  CvoPointCloud(int feature_dimensions, int num_classes);
+  ~CvoPointCloud() {}
+  int num_points() const { return n_; }
+  int size() const { return n_; }
+  int num_classes() const { return nc_; }
+  int num_features() const { return nf_; }
   const std::vector<Eigen::Vector3f, Eigen::aligned_allocator<Eigen::Vector3f>>& positions() const { return p_; }
   const Eigen::Matrix<float, Eigen::Dynamic, Eigen::Dynamic>& labels() const { return l_; }
   const Eigen::MatrixXf& features() const { return f_; }
   const std::vector<float>& geometric_types() const { return g_; }
+  // the two fillers of utils/CvoPointCloud.hpp:172-173 (stand-ins for CvoPointCloud.cpp:1383-1420,
+  // defined below the class): reserve sizes every container (geometric types to 2n ZEROS),
+  // add_point writes one point
+  void reserve(int num_points, int feature_dims, int num_classes);
+  int add_point(int index, const Eigen::Vector3f& xyz, const Eigen::VectorXf& feature, const Eigen::VectorXf& label,
+                const Eigen::VectorXf& geometric_type);
 
  private:
+  int n_ = 0, nc_ = 0, nf_ = 0;
   std::vector<Eigen::Vector3f, Eigen::aligned_allocator<Eigen::Vector3f>> p_;
   Eigen::MatrixXf f_, l_;
   std::vector<float> g_;
 };
+inline CvoPointCloud::CvoPointCloud(int feature_dimensions, int num_classes)
+    : nc_(num_classes), nf_(feature_dimensions) {}
+inline void CvoPointCloud::reserve(int num_points, int feature_dims, int num_classes) {
+  n_ = num_points;
+  nf_ = feature_dims;
+  nc_ = num_classes;
+  p_.resize((size_t)n_);
+  if (nf_) f_.resize(n_, nf_);
+  if (nc_) l_.resize(n_, nc_);
+  g_.assign((size_t)n_ * 2, 0.f);
+}
+inline int CvoPointCloud::add_point(int index, const Eigen::Vector3f& xyz, const Eigen::VectorXf& feature,
+                                    const Eigen::VectorXf& label, const Eigen::VectorXf& geometric_type) {
+  if (index >= n_ || geometric_type.size() != 2) return -1;
+  p_[(size_t)index] = xyz;
+  for (int j = 0; j < nf_; j++) f_(index, j) = feature(j);
+  for (int j = 0; j < nc_; j++) l_(index, j) = label(j);
+  g_[(size_t)index * 2] = geometric_type(0);
+  g_[(size_t)index * 2 + 1] = geometric_type(1);
+  return 0;
+}
 // ---- multi-frame types (cvo/CvoFrame.hpp, cvo/CvoFrameGPU.hpp, cvo/SparseKernelMat.hpp,
 //      cvo/IRLS_State.hpp, cvo/IRLS_State_GPU.hpp), members in the reference's order
 struct CvoFrame {

@@ -223,3 +223,24 @@ def test_shim_defines_every_member_the_replaced_sources_defined(tmp_path):
     missing = {k: (n, len(defined.get(k, ()))) for k, n in wanted.items() if len(defined.get(k, ())) < n}
     # complete-object / base-object constructor and destructor variants demangle to the same text
     assert not missing, f"defined by a replaced reference source but not by the shim: {missing}"
+
+
+def test_runtime_driver_of_the_cpp_classes_builds(tmp_path):
+    """tests/shim_runtime/driver.cpp (run on a B200 by tests/test_shim_runtime_gpu.py) compiles and
+    links here against the shim sources, the stand-in headers and libcvo_b200.so."""
+    lib = os.path.join(ROOT, "unified_cvo_b200", "csrc", "libcvo_b200.so")
+    if not os.path.exists(lib):
+        pytest.skip("libcvo_b200.so not built")
+    exe = tmp_path / "shim_driver"
+    out = subprocess.run([GXX, "-std=c++17", "-fPIC", "-Wall", "-DCVO_SHIM_SYNTAX_CHECK",
+                          "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(ROOT, "shim"), "-include",
+                          os.path.join(ROOT, "shim", "stubs", "reference_api_stub.hpp"),
+                          os.path.join(ROOT, "tests", "shim_runtime", "driver.cpp"),
+                          os.path.join(ROOT, "shim", "CvoGPU_b200.cpp"),
+                          os.path.join(ROOT, "shim", "IRLS_State_GPU_b200.cpp"), "-o", str(exe),
+                          "-L" + os.path.dirname(lib), "-lcvo_b200", "-Wl,-rpath," + os.path.dirname(lib)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+    # without arguments it prints its usage and touches no GPU
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 2 and "usage" in run.stderr
