@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -32,6 +33,7 @@
 #include "utils/CvoPointCloud.hpp"
 #endif
 #include "cvo_b200.h"
+#include "cvo_b200_batch.hpp"
 #include "shim_pack.hpp"
 
 namespace cvo {
@@ -163,6 +165,20 @@ const CvoPoint* CvoFrameGPU::points_transformed_gpu() const { return nullptr; }
 const float* CvoFrameGPU::pose_vec_gpu() const { return nullptr; }
 
 // ---- BinaryStateGPU (IRLS_State_GPU.cu:16-89) ------------------------------------------------
+// The members are private in the reference's class and a free function cannot be befriended from
+// here, so every edge registers two closures (created in its constructor, i.e. with member
+// access): `describe` = what the next update will ask the device for, `accept` = take the answer.
+// update_inner_product() is describe -> cvo_b200_edge_update -> accept; update_inner_product_batch()
+// (cvo_b200_batch.hpp) is describe x n -> ONE cvo_b200_edge_update_batch -> accept x n.
+namespace {
+struct EdgeHooks {
+  std::function<cvo_b200_handle*(cvo_b200_edge&)> describe;
+  std::function<void(int64_t, int32_t, const int32_t*, const int32_t*, const float*)> accept;
+  int rows = 0;  // points of frame 1 = rows of the edge's matrix
+};
+std::unordered_map<const BinaryStateGPU*, EdgeHooks> g_hooks;
+}  // namespace
+
 BinaryStateGPU::BinaryStateGPU(std::shared_ptr<CvoFrameGPU> pc1, std::shared_ptr<CvoFrameGPU> pc2,
                                const CvoParams* params_cpu, const CvoParams* params_gpu,
                                unsigned int num_neighbor, float init_ell)
@@ -176,53 +192,134 @@ BinaryStateGPU::BinaryStateGPU(std::shared_ptr<CvoFrameGPU> pc1, std::shared_ptr
   A_host_.mat = nullptr;
   A_host_.ind_row2col = nullptr;
   A_host_.nonzeros = nullptr;
+  EdgeHooks hk;
+  hk.rows = (int)pc1->points->size();
+  hk.describe = [this](cvo_b200_edge& e) -> cvo_b200_handle* {
+    cvo_b200_handle* h = edge_handle(params_cpu_);
+    // callers mutate *params_cpu_ between solves (CvoGPU::get_params()): upload it like write_params
+    int rc = cvo_b200_write_params(h, reinterpret_cast<const cvo_b200_params*>(params_cpu_));
+    if (rc != CVO_B200_OK) die(h, "cvo_b200_write_params", rc);
+    const unsigned int last_num_neibors = A_host_.nonzero_sum;  // IRLS_State_GPU.cu:45-47
+    if (last_num_neibors > 0)
+      num_neighbors_ = std::min(init_num_neighbors_, (unsigned int)(last_num_neibors * 1.1));
+    for (int i = 0; i < 12; i++) {  // CvoFrameGPU.cu:47-53: the double pose narrowed to float
+      e.pose1[i] = static_cast<float>(frame1_->pose_vec[i]);
+      e.pose2[i] = static_cast<float>(frame2_->pose_vec[i]);
+    }
+    e.frame1 = frame_id_on(frame1_.get(), h);
+    e.frame2 = frame_id_on(frame2_.get(), h);
+    e.ell = ell_;
+    e.num_neighbors = (int32_t)num_neighbors_;
+    return h;
+  };
+  hk.accept = [this](int64_t nnz, int32_t max_row, const int32_t* row_ptr, const int32_t* cols, const float* vals) {
+    // CSR -> the row-strided layout add_residual_to_problem walks (IRLS_State_GPU.cpp:14-45:
+    // stride num_neighbors_, rows end at the first -1)
+    const int rows = A_result_cpu_.rows;
+    clear_SparseKernelMat_cpu(&A_result_cpu_, (int)num_neighbors_);
+    for (int r = 0; r < rows; r++) {
+      const int32_t b = row_ptr[r], e = row_ptr[r + 1];
+      for (int32_t k = b; k < e; k++) {
+        A_result_cpu_.mat[(size_t)r * num_neighbors_ + (k - b)] = vals[k];
+        A_result_cpu_.ind_row2col[(size_t)r * num_neighbors_ + (k - b)] = cols[k];
+      }
+      A_result_cpu_.nonzeros[r] = (unsigned int)(e - b);
+    }
+    A_result_cpu_.nonzero_sum = (unsigned int)nnz;
+    A_host_.nonzero_sum = (unsigned int)max_row;
+    iter_++;
+  };
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_hooks[this] = std::move(hk);
 }
 
-BinaryStateGPU::~BinaryStateGPU() { delete_internal_SparseKernelMat_cpu(&A_result_cpu_); }
+BinaryStateGPU::~BinaryStateGPU() {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_hooks.erase(this);
+  }
+  delete_internal_SparseKernelMat_cpu(&A_result_cpu_);
+}
+
+namespace {
+const EdgeHooks& hooks_of(const BinaryStateGPU* s) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_hooks.find(s);
+  if (it == g_hooks.end()) die(nullptr, "edge lookup (BinaryStateGPU not constructed through this library)", CVO_B200_ERR_STATE);
+  return it->second;  // entries live as long as their edge; the map is node based
+}
+}  // namespace
 
 int BinaryStateGPU::update_inner_product() {
-  cvo_b200_handle* h = edge_handle(params_cpu_);
-  // callers mutate *params_cpu_ between solves (CvoGPU::get_params()): upload it like write_params
-  int rc = cvo_b200_write_params(h, reinterpret_cast<const cvo_b200_params*>(params_cpu_));
-  if (rc != CVO_B200_OK) die(h, "cvo_b200_write_params", rc);
-  const unsigned int last_num_neibors = A_host_.nonzero_sum;  // IRLS_State_GPU.cu:45-47
-  if (last_num_neibors > 0)
-    num_neighbors_ = std::min(init_num_neighbors_, (unsigned int)(last_num_neibors * 1.1));
-  float p1[12], p2[12];  // CvoFrameGPU.cu:47-53: the double pose narrowed to float
-  for (int i = 0; i < 12; i++) {
-    p1[i] = static_cast<float>(frame1_->pose_vec[i]);
-    p2[i] = static_cast<float>(frame2_->pose_vec[i]);
-  }
-  const int id1 = frame_id_on(frame1_.get(), h), id2 = frame_id_on(frame2_.get(), h);
+  const EdgeHooks& hk = hooks_of(this);
+  cvo_b200_edge e;
+  cvo_b200_handle* h = hk.describe(e);
   const int rows = A_result_cpu_.rows;
   int64_t nnz = 0;
   int32_t max_row = 0;
   std::vector<int32_t> row_ptr((size_t)rows + 1, 0);
-  rc = cvo_b200_edge_update(h, id1, p1, id2, p2, ell_, (int)num_neighbors_, &nnz, &max_row, row_ptr.data(),
-                            nullptr, nullptr);
+  int rc = cvo_b200_edge_update(h, e.frame1, e.pose1, e.frame2, e.pose2, e.ell, e.num_neighbors, &nnz, &max_row,
+                                row_ptr.data(), nullptr, nullptr);
   if (rc != CVO_B200_OK) die(h, "cvo_b200_edge_update", rc);
   std::vector<int32_t> cols((size_t)nnz);
   std::vector<float> vals((size_t)nnz);
   if (nnz > 0) {  // same arguments: the matrix is still on the device, nothing is recomputed
-    rc = cvo_b200_edge_update(h, id1, p1, id2, p2, ell_, (int)num_neighbors_, &nnz, &max_row, row_ptr.data(),
-                              cols.data(), vals.data());
+    rc = cvo_b200_edge_update(h, e.frame1, e.pose1, e.frame2, e.pose2, e.ell, e.num_neighbors, &nnz, &max_row,
+                              row_ptr.data(), cols.data(), vals.data());
     if (rc != CVO_B200_OK) die(h, "cvo_b200_edge_update", rc);
   }
-  // CSR -> the row-strided layout add_residual_to_problem walks (IRLS_State_GPU.cpp:14-45:
-  // stride num_neighbors_, rows end at the first -1)
-  clear_SparseKernelMat_cpu(&A_result_cpu_, (int)num_neighbors_);
-  for (int r = 0; r < rows; r++) {
-    const int32_t b = row_ptr[r], e = row_ptr[r + 1];
-    for (int32_t k = b; k < e; k++) {
-      A_result_cpu_.mat[(size_t)r * num_neighbors_ + (k - b)] = vals[k];
-      A_result_cpu_.ind_row2col[(size_t)r * num_neighbors_ + (k - b)] = cols[k];
-    }
-    A_result_cpu_.nonzeros[r] = (unsigned int)(e - b);
-  }
-  A_result_cpu_.nonzero_sum = (unsigned int)nnz;
-  A_host_.nonzero_sum = (unsigned int)max_row;
-  iter_++;
+  hk.accept(nnz, max_row, row_ptr.data(), cols.data(), vals.data());
   return (int)nnz;
+}
+
+// The whole edge loop of an outer IRLS iteration (IRLS.cpp:111-121) as one device call per handle:
+// every matrix equals what update_inner_product() of that edge would have produced.
+int update_inner_product_batch(const std::vector<BinaryStateGPU*>& states) {
+  std::unordered_map<cvo_b200_handle*, std::vector<size_t>> by_handle;
+  std::vector<cvo_b200_edge> desc(states.size());
+  std::vector<const EdgeHooks*> hk(states.size());
+  for (size_t k = 0; k < states.size(); k++) {
+    hk[k] = &hooks_of(states[k]);
+    by_handle[hk[k]->describe(desc[k])].push_back(k);
+  }
+  long total_all = 0;
+  for (auto& kv : by_handle) {
+    cvo_b200_handle* h = kv.first;
+    const std::vector<size_t>& idx = kv.second;
+    std::vector<cvo_b200_edge> edges;
+    size_t rows_total = 0;
+    for (size_t k : idx) {
+      edges.push_back(desc[k]);
+      rows_total += (size_t)hk[k]->rows + 1;
+    }
+    std::vector<int64_t> nnz(idx.size(), 0);
+    std::vector<int32_t> mx(idx.size(), 0), row_ptr(rows_total, 0);
+    int rc = cvo_b200_edge_update_batch(h, (int)edges.size(), edges.data(), nnz.data(), mx.data(), row_ptr.data(),
+                                        nullptr, nullptr);
+    if (rc == CVO_B200_ERR_STATE) {  // an edge outside the batched regimes: the per-edge calls serve every case
+      for (size_t k : idx) total_all += states[k]->update_inner_product();
+      continue;
+    }
+    if (rc != CVO_B200_OK) die(h, "cvo_b200_edge_update_batch", rc);
+    int64_t total = 0;
+    for (int64_t v : nnz) total += v;
+    std::vector<int32_t> cols((size_t)std::max<int64_t>(total, 1));
+    std::vector<float> vals((size_t)std::max<int64_t>(total, 1));
+    if (total > 0) {
+      rc = cvo_b200_edge_update_batch(h, (int)edges.size(), edges.data(), nnz.data(), mx.data(), row_ptr.data(),
+                                      cols.data(), vals.data());
+      if (rc != CVO_B200_OK) die(h, "cvo_b200_edge_update_batch", rc);
+    }
+    size_t ro = 0;
+    int64_t eo = 0;
+    for (size_t j = 0; j < idx.size(); j++) {
+      hk[idx[j]]->accept(nnz[j], mx[j], row_ptr.data() + ro, cols.data() + eo, vals.data() + eo);
+      ro += (size_t)hk[idx[j]]->rows + 1;
+      eo += nnz[j];
+    }
+    total_all += (long)total;
+  }
+  return (int)total_all;
 }
 
 CvoFrame* BinaryStateGPU::frame1() { return frame1_.get(); }

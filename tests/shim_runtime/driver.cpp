@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include "cvo_b200_batch.hpp"
+
 namespace ceres {
 class Problem {
  public:
@@ -61,10 +63,17 @@ CvoBatchIRLS::CvoBatchIRLS(const std::vector<std::shared_ptr<CvoFrame>>&, const 
 // two outer iterations of IRLS.cpp:77-215 without the Ceres solve: every edge refills its matrix
 // (:111-121), hands it to the problem (:123-131) and decays its length-scale (:190-196)
 void CvoBatchIRLS::solve() {
+  const bool batched = std::getenv("SHIM_DRIVER_BATCH") != nullptr;  // the loop replaced as cvo_b200_batch.hpp shows
   for (int outer = 0; outer < 2; outer++) {
+    if (batched) {
+      std::vector<BinaryStateGPU*> gpu;
+      for (auto&& s : g_states)
+        if (auto* g = dynamic_cast<BinaryStateGPU*>(s.get())) gpu.push_back(g);
+      std::printf("batch %d total %d\n", outer, update_inner_product_batch(gpu));
+    }
     int e = 0;
     for (auto&& st : g_states) {
-      const int nnz = st->update_inner_product();
+      const int nnz = batched ? -1 : st->update_inner_product();
       ceres::Problem problem;
       st->add_residual_to_problem(problem);
       std::printf("edge %d %d nnz %d entries %ld rows %ld checksum %.17g\n", outer, e, nnz, problem.entries,

@@ -61,8 +61,9 @@ def as_reserved(pc):
     return u.CvoPointCloud(pc.positions_, pc.features_, pc.labels_, geo)
 
 
-def run(driver, *args):
-    out = subprocess.run([driver, *args], capture_output=True, text=True, timeout=300)
+def run(driver, *args, env=None):
+    out = subprocess.run([driver, *args], capture_output=True, text=True, timeout=300,
+                         env=dict(os.environ, **(env or {})))
     assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-2000:])
     rows = {}
     for line in out.stdout.splitlines():
@@ -164,3 +165,11 @@ def test_multiframe_align_through_the_cpp_classes_equals_the_python_mirror(drive
             assert float(row[9]) == pytest.approx(checksum(st.A_result_cpu_), rel=1e-12)
             st.update_ell()
     g.close()
+    # the same loop with IRLS.cpp:111-121 replaced by cvo::update_inner_product_batch (cvo_b200_batch.hpp):
+    # one device call per outer iteration, the same matrices in every edge
+    got_b = run(driver, "edges", yaml, str(tmp_path / "poses.bin"), *paths, env={"SHIM_DRIVER_BATCH": "1"})
+    assert len(got_b["batch"]) == 2
+    for outer in range(2):
+        assert int(got_b["batch"][outer][2]) == sum(int(r[5]) for r in lines[4 * outer:4 * outer + 4])
+    for a, b in zip(lines, got_b["edge"]):
+        assert a[:2] == b[:2] and a[4:] == b[4:]  # entries, rows, checksum (nnz is not returned per edge there)
