@@ -30,7 +30,8 @@ Workloads (documented choice):
 `pipes`  what actually bounds the dominant kernel: FMA-pipe and issue utilisation from the committed
          ncu --set full captures (profiles/pipes.json), not a derived "fraction of peak".
 `frame_pairs`  frame-pairs/s on KITTI-05-sized clouds: a tracking frame and a first frame.
-`edge_updates`  pose-graph edge updates/s (multi-frame IRLS edge loop).
+`edge_updates`  pose-graph edge updates/s (multi-frame IRLS edge loop); `graph16` = a 16-edge graph whose edges
+         are sharded over the ranks (same graph at every N: edge-parallel strong scaling).
 `cpu_baseline` / `--impl reference`  the restated reference CPU path cvo::cvo::align (oracle/
          cvo_cpu_baseline.c = Cvo.cpp:885-1089: kd-tree rebuilt per iteration, no row cap, no
          normalisation; OpenMP on all host cores), whole registrations or a bounded number of leading
@@ -368,6 +369,71 @@ def edge_updates_leg(u, rounds=5, cpu=True):
     return out
 
 
+def edge_graph_leg(u, local_rank, rank, world, dist, rounds=8):
+    """Edge-parallel pose graph: 8 KITTI-05-sized frames, 16 edges (ring + every
+    second-neighbour chord), the same graph at every N.  Rank r owns edges r, r + world, ... and
+    refills them with one batch call per round on its GPU; the other ranks' CSR matrices travel to
+    rank 0 (where a solver would run) over the host control plane inside the timed region.  Wall
+    clock between barriers, max over ranks; strong scaling."""
+    from unified_cvo_b200 import synthetic
+    src, tgt, p, _ = load_workload("KITTI05_TRACK")
+    g = u.CvoGPU(p, device=local_rank)
+    I = np.eye(4)[:3]
+    G = np.asarray(synthetic.gt_transform(), np.float64)[:3]
+    n_frames = 8
+    edges = [(i, (i + 1) % n_frames) for i in range(n_frames)] + [(i, (i + 2) % n_frames) for i in range(n_frames)]
+    from unified_cvo_b200.dist import shard_edges
+    mine = shard_edges(len(edges), world, rank)
+    need = sorted({f for k in mine for f in edges[k]})
+    frames = {f: u.CvoFrameGPU(g, src if f % 2 == 0 else tgt, I if f % 2 == 0 else G) for f in need}
+    cap = int(p.multiframe_num_neighbors)
+
+    class _Remote:  # an edge owned by another rank: only its host-side result slot exists here
+        def __init__(self, m):
+            self.A_result_cpu_, self.last_max_row_nnz = u.Association(), 0
+            self.frame2 = type("F", (), {"points": type("P", (), {"num_points": staticmethod(lambda: m)})()})()
+
+    states = [u.BinaryStateGPU(frames[a], frames[b], cap, 0.25) if k in mine else _Remote(tgt.num_points() if b % 2 else src.num_points())
+              for k, (a, b) in enumerate(edges)]
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    for _ in range(2):
+        u.update_edges_sharded(states, rank, world, dist)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        u.update_edges_sharded(states, rank, world, dist)
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        ts = [None] * world
+        dist.all_gather_object(ts, dt)
+        dt = max(ts)
+    total = int(sum(len(st.A_result_cpu_.vals) for st in states)) if rank == 0 else 0
+    # the same rounds with the matrices left on the ranks that computed them (no gather): what the
+    # GPUs themselves scale like
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(rounds):
+        u.update_edges_sharded(states, rank, world, dist, gather_to=None)
+    barrier()
+    dt_local = time.perf_counter() - t0
+    if dist is not None:
+        ts = [None] * world
+        dist.all_gather_object(ts, dt_local)
+        dt_local = max(ts)
+    g.close()
+    return {"workload": "8 KITTI-05-sized frames, 16 edges (ring + second-neighbour chords), ell=0.25, cap=%d; edges sharded "
+                        "round-robin over the ranks, one cvo_b200_edge_update_batch per rank and round, CSR matrices gathered "
+                        "to rank 0 over the host control plane inside the timed region" % cap,
+            "n_gpus": world, "edges": len(edges), "rounds": rounds, "edge_updates_per_s": rounds * len(edges) / dt,
+            "ms_per_round": 1e3 * dt / rounds, "nonzeros_per_round_on_rank0": total, "scaling": "strong",
+            "edge_updates_per_s_without_gather": rounds * len(edges) / dt_local}
+
+
 def measure(u, torch, g, name, src, tgt, p, steps, warmup, local_rank, rank, world, dist):
     """Timed region of one workload on the handle g (clouds already set).  Returns a dict."""
     T_init = tracking_init() if WORKLOADS[name][2].get("TRACK") else None
@@ -536,6 +602,9 @@ def run_ours(args, rank, world, local_rank):
     par = None
     if world > 1:
         par = parity_vs_single(u, g, name, src, tgt, p, m["T_init"], m["last_T"], rank, world, local_rank, dist)
+    graph = None
+    if world > 1 and args.workload is None and not args.no_frames:
+        graph = edge_graph_leg(u, local_rank, rank, world, dist)  # every rank takes part
     if rank != 0:
         return
     value = m["pairs"] / m["dev_s"]
@@ -571,6 +640,8 @@ def run_ours(args, rank, world, local_rank):
     }
     if par is not None:
         line["parity_vs_single"] = par
+    if graph is not None:
+        line["edge_updates"] = {"graph16": graph}
     # the same-workload anchor of the scaling curve: C4 on THIS one GPU
     if world == 1 and args.workload is None and not args.no_anchor:
         g.close()
@@ -593,6 +664,7 @@ def run_ours(args, rank, world, local_rank):
     if world == 1 and args.workload is None and not args.no_frames:
         line["frame_pairs"] = [frame_pairs_leg(u, wl) for wl in ("KITTI05_TRACK", "KITTI05")]
         line["edge_updates"] = edge_updates_leg(u, cpu=not args.no_cpu_baseline)
+        line["edge_updates"]["graph16"] = edge_graph_leg(u, local_rank, 0, 1, None)
     # CPU baselines beside it (rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:
         import oracle

@@ -390,3 +390,54 @@ def test_mirror_host_logic_cap_schedule_pose_narrowing_and_two_call_protocol():
             assert x.A_result_cpu_.shape == y.A_result_cpu_.shape and x.iter_ == y.iter_
     f1.release()
     assert 0 not in g._lib.frames
+
+
+def test_edge_parallel_loop_over_two_ranks_gathers_every_matrix_on_rank_0(tmp_path):
+    """update_edges_sharded on 2 gloo ranks (host logic; the device is the oracle-backed stand-in):
+    rank r refills edges r, r + 2, ..., rank 0 ends up with every edge's matrix, equal to the
+    single-process loop."""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    worker = tmp_path / "worker.py"
+    worker.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+        import numpy as np
+        import torch.distributed as dist
+        import unified_cvo_b200 as u
+        from helpers import geometric_params, synthetic_pair
+        from test_multiframe import _FakeGPU, pose_rt
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        p = geometric_params()
+        clouds = [synthetic_pair(300, 150 + 16 * k, 150, 11)[0] for k in range(4)]
+        poses = [pose_rt(0.0, 0.4 * k, 0.0, [0.02 * k, 0.0, 0.03 * k]) for k in range(4)]
+        edges = [(0, 1), (1, 2), (2, 3), (3, 0), (0, 2)]
+
+        def graph():
+            g = _FakeGPU(p)
+            frames = [u.CvoFrameGPU(g, c, P) for c, P in zip(clouds, poses)]
+            g._lib.bind({{f.frame_id: c for f, c in zip(frames, clouds)}})
+            return [u.BinaryStateGPU(frames[a], frames[b], 12, 1.2) for a, b in edges]
+
+        sharded, single = graph(), graph()
+        for _ in range(2):  # the second round runs with the caps of the first
+            total, mine = u.update_edges_sharded(sharded, rank, world, dist)
+            assert mine == list(range(rank, len(edges), world))
+            u.update_edges(single)
+        if rank == 0:
+            for a, b in zip(sharded, single):
+                assert np.array_equal(a.A_result_cpu_.row_ptr, b.A_result_cpu_.row_ptr)
+                assert np.array_equal(a.A_result_cpu_.cols, b.A_result_cpu_.cols)
+                assert np.array_equal(a.A_result_cpu_.vals, b.A_result_cpu_.vals)
+                assert a.last_max_row_nnz == b.last_max_row_nnz > 0
+            print("EDGE_SHARD_OK", sum(len(s.A_result_cpu_.vals) for s in sharded))
+        dist.barrier()
+    """))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29677", str(worker)],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
+    assert "EDGE_SHARD_OK" in out.stdout

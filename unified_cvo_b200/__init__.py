@@ -9,8 +9,8 @@ from .cvo import (Association, CvoError, CvoGPU, CvoParams, CvoPointCloud,  # no
                   default_params, read_params_yaml)
 from . import synthetic  # noqa: F401
 from .sequence import FrameToFrameOdometry  # noqa: F401
-from .multiframe import BinaryStateGPU, CvoFrameGPU, update_edges  # noqa: F401
+from .multiframe import BinaryStateGPU, CvoFrameGPU, update_edges, update_edges_sharded  # noqa: F401
 
 __all__ = ["CvoGPU", "CvoPointCloud", "CvoParams", "Association", "CvoError", "Params",
            "IterTrace", "AlignInfo", "default_params", "read_params_yaml", "synthetic",
-           "load_library", "FrameToFrameOdometry", "CvoFrameGPU", "BinaryStateGPU", "update_edges"]
+           "load_library", "FrameToFrameOdometry", "CvoFrameGPU", "BinaryStateGPU", "update_edges", "update_edges_sharded"]

@@ -149,3 +149,49 @@ def update_edges(states: Iterable[BinaryStateGPU], batched: bool = True):
         ro += rows[k] + 1
         eo += int(nnz[k])
     return total, per_edge
+
+
+def update_edges_sharded(states, rank: int, world: int, dist_module=None, gather_to: Optional[int] = 0):
+    """Edge-parallel edge loop over the GPUs of a job: the edges of a pose graph
+    are independent, so rank r refills edges r, r + world, ... on ITS GPU with one batch call and
+    there is no data-path collective.  The matrices feed a host solver (Ceres in the reference), so
+    with gather_to = k the other ranks' CSR matrices travel to rank k over the host control plane
+    (dist_module.gather_object) and are stored into its states; gather_to = None keeps them where
+    they were computed.  Every rank must hold the frames of its own edges (states of edges it does
+    not own are never touched on the device).  Returns (nonzeros of this rank's edges, their indices)."""
+    from .dist import shard_edges
+    states = list(states)
+    mine = shard_edges(len(states), world, rank)
+    total_local, _ = update_edges([states[i] for i in mine])
+    if dist_module is None or world == 1 or gather_to is None:
+        return total_local, mine
+    # one compact buffer per rank: per edge (index, rows, nnz, fullest row), then the per-row counts
+    # as uint16 (a row holds at most nearest_neighbors_max entries), the columns and the values
+    head, parts = [len(mine)], []
+    for i in mine:
+        a = states[i].A_result_cpu_
+        head += [i, len(a.row_ptr) - 1, len(a.vals), states[i].last_max_row_nnz]
+        parts += [np.diff(a.row_ptr).astype(np.uint16).tobytes(), np.ascontiguousarray(a.cols, np.int32).tobytes(),
+                  np.ascontiguousarray(a.vals, np.float32).tobytes()]
+    payload = np.asarray(head, np.int64).tobytes() + b"".join(parts)
+    gathered = [None] * world if rank == gather_to else None
+    dist_module.gather_object(payload, gathered, dst=gather_to)
+    if rank == gather_to:
+        for r, buf in enumerate(gathered):
+            if r == rank:
+                continue
+            k = int(np.frombuffer(buf, np.int64, 1)[0])
+            meta = np.frombuffer(buf, np.int64, 4 * k, 8).reshape(k, 4)
+            off = 8 * (1 + 4 * k)
+            for i, rows, nnz, mx in meta.tolist():
+                cnt = np.frombuffer(buf, np.uint16, rows, off)
+                off += 2 * rows
+                a = states[i].A_result_cpu_
+                a.row_ptr = np.concatenate([[0], np.cumsum(cnt, dtype=np.int64)])
+                a.cols = np.frombuffer(buf, np.int32, nnz, off)
+                off += 4 * nnz
+                a.vals = np.frombuffer(buf, np.float32, nnz, off)
+                off += 4 * nnz
+                a.shape = (rows, states[i].frame2.points.num_points())
+                states[i].last_max_row_nnz = int(mx)
+    return total_local, mine
