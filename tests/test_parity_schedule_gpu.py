@@ -225,6 +225,31 @@ def test_reused_candidate_cells_lose_no_pair(monkeypatch, colour):
     assert 1 <= builds_in_prefix < p.MAX_ITER
 
 
+def test_stop_test_shortcut_never_changes_the_loop(candidate_mode):
+    """The controller skips the SE3 log of the pose increment when step * |twist| is far from eps_2
+    (controller_step); with a trace attached every iteration takes the exact path.  Both loops must
+    run the same iterations, stop for the same reason and end on the same bits — on a run that ends
+    through the eps_2 test and on one that ends at MAX_ITER."""
+    src, tgt, _ = synthetic_pair(2500, 2000, 2000, 20002)
+    for max_iter, eps_2 in ((3000, 1.2e-5), (3000, 2e-4), (40, 1.2e-5)):
+        p = geometric_params(0.95)
+        p.MAX_ITER, p.eps_2 = max_iter, eps_2
+        g = u.CvoGPU(p, device=0)
+        ret_a, T_a, info_a, tr = g.align(src, tgt, None, trace_cap=max_iter)
+        ret_b, T_b, info_b = g.align(src, tgt, None)
+        g.close()
+        print(f"{candidate_mode} MAX_ITER {max_iter} eps_2 {eps_2}: {info_a.iterations} iterations, stop {info_a.stop_reason}, "
+              f"last dist {tr[-1].dist:.3e}")
+        assert (ret_a, info_a.iterations, info_a.stop_reason) == (ret_b, info_b.iterations, info_b.stop_reason)
+        assert info_a.final_ell == info_b.final_ell and info_a.final_num_neighbors == info_b.final_num_neighbors
+        assert np.array_equal(np.asarray(T_a, np.float32).view(np.uint32), np.asarray(T_b, np.float32).view(np.uint32))
+        # the recorded distances are the exact ones and agree with step * |twist| to the bound the shortcut assumes
+        for t in tr:
+            d_fast = float(t.step) * float(np.sqrt(sum(float(x) ** 2 for x in list(t.omega) + list(t.v))))
+            assert abs(t.dist - d_fast) <= 1e-6 + 5e-5 * d_fast, (t.iter, t.dist, d_fast)
+    assert info_a.stop_reason == _abi.STOP_MAX_ITER
+
+
 def test_two_gpus_equal_one(tmp_path):
     """Sharded == single GPU: the first iterations of a source-sharded align on two
     GPUs (NCCL path and fused NVLink-mailbox path) reproduce the single-GPU records, and both
