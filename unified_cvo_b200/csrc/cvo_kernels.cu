@@ -1556,8 +1556,14 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
           const uint32_t kbase = k == 0 ? 0u : (k == 1 ? q1 : (k == 2 ? q2 : q3));
           uint32_t word = 0;
           if (valid) word = cell_row[(size_t)(cbase + 4 * o + k) * (size_t)L + (rr - kbase)];
-          append_words(valid, word);
-          drain(kGroup);
+          if constexpr (kGen == 2) {
+            // a tile-cell word names exactly ONE target (target << 8 | 1): eight words are eight
+            // candidates, evaluated in place - no expansion into the group's list, no drain
+            consume8(valid, (int)(word >> 8));
+          } else {
+            append_words(valid, word);
+            drain(kGroup);
+          }
         }
       } else {
         // ---- rare: a cell overflowed its word list -> walk the window cell by cell and
