@@ -111,6 +111,7 @@ struct DevState {
   int vl_valid;             // cells exist for this launch
   int tile_rebuild;         // decision of the current iteration (same in every block)
   unsigned int tile_builds; // how many iterations built cells (statistics)
+  unsigned int tile_item_base, tile_item_next;  // value of the monotone item counter at the start of the current / next build
   // step
   double B, C, D, E;
   float step;

@@ -350,7 +350,9 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   // (choose_mode), halved until the cells fit in ~4 GiB
   // ... shared by tile_parts warps per tile (small shards: enough items to fill the machine)
   int tile_parts = 1;
-  while (tile_parts < 8 && 2 * row_tiles * tile_parts < 3 * h->num_sms * 24) tile_parts *= 2;  // ~1.5 waves of items (measured)
+  // ~3.5 items per resident warp: items differ a lot in cost and are handed out dynamically, so the
+  // build ends with its heaviest item (measured on C4: 2 parts 20.2 ms, 4 parts 19.4, 8 parts 19.7)
+  while (tile_parts < 8 && 2 * row_tiles * tile_parts < 7 * h->num_sms * 24) tile_parts *= 2;
   if (const char* tp = getenv("CVO_B200_TILE_PARTS")) tile_parts = std::max(1, std::min(8, atoi(tp)));  // measurement aid
   int tile_L = 1024 / tile_parts;
   while ((size_t)std::max(n_rows, 1) * tile_parts * tile_L * 4 > ((size_t)4 << 30) && tile_L > 32) tile_L /= 2;
@@ -575,6 +577,7 @@ cudaError_t launch_persistent(cvo_b200_handle* h, const IterArgs& A) {
   cudaError_t e = cudaMemsetAsync(h->ll_board.p, 0, sizeof(LLBoard), h->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->work_counter, 0, sizeof(unsigned int), h->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->n_sat, 0, sizeof(unsigned int), h->stream);
+  if (e == cudaSuccess && A.tile) e = cudaMemsetAsync(&h->d_state->item_counter, 0, sizeof(unsigned int), h->stream);
   if (e != cudaSuccess) return e;
   return launch_align_grid(A, A.tile ? h->persist_blocks_tile : h->persist_blocks,
                            A.tile ? h->persist_threads_tile : h->persist_threads, h->stream);

@@ -734,8 +734,13 @@ struct __align__(16) TileSmemWarp {
   uint32_t cpre[33];              // exclusive prefix of their run counts (runs of 4 targets)
 };
 
+// counter != nullptr: every warp takes item `gwarp` first and the rest from a MONOTONE global counter
+// (items differ a lot in cost: a static deal left a third of a build waiting for the slowest block);
+// over one phase the counter advances by exactly the number of items (every warp that had a first
+// item ends with one failing fetch), so the caller tracks its base without resetting it.
 __device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs, TileSmemWarp& S,
-                                           uint64_t* bar, int gwarp, int nwarps, uint32_t& bar_phase) {
+                                           uint64_t* bar, int gwarp, int nwarps, uint32_t& bar_phase,
+                                           unsigned int* counter = nullptr, unsigned int counter_base = 0u) {
   const int lane = threadIdx.x & 31;
   const GridView& G = A.gv;
   const uint32_t L = (uint32_t)A.tile_L;
@@ -775,8 +780,16 @@ __device__ __forceinline__ void tile_phase(const IterArgs& A, const DevState* hs
   // items = (tile, part): the cell groups of a tile are dealt round-robin to `tile_parts` warps, each
   // with its own candidate cell per row, so that small shards still fill the machine
   const int P = A.tile_parts;
-  for (int item = gwarp; item < ntiles * P; item += nwarps) {
-    const int tile = item / P, part = item - tile * P;
+  for (int item = gwarp; item < ntiles * P;) {
+    const int this_item = item;
+    if (counter) {  // fetch the next item now: the atomic's latency hides behind this item's work
+      unsigned int nxt = 0u;
+      if (lane == 0) nxt = atomicAdd(counter, 1u) - counter_base;
+      item = nwarps + (int)__shfl_sync(0xffffffffu, nxt, 0);
+    } else {
+      item += nwarps;
+    }
+    const int tile = this_item / P, part = this_item - tile * P;
     const int row0 = tile * kTileRows;
     const int nrows = min(kTileRows, A.n_rows - row0);
     // ---- (1) TMA-stage the tile's source points and range records
@@ -2447,6 +2460,9 @@ __device__ void verlet_decide(const IterArgs& A, DevState* st) {
     st->vl_slack = st->grid_slack;
     st->vl_valid = 1;
     st->tile_builds += 1u;
+    // dynamic hand-out of the build's (tile, part) items: tile_phase advances the counter by exactly this many
+    st->tile_item_base = st->tile_item_next;
+    st->tile_item_next += (unsigned int)(((A.n_rows + kTileRows - 1) / kTileRows) * A.tile_parts);
   }
   st->tile_rebuild = rebuild ? 1 : 0;
 }
@@ -2484,6 +2500,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
     if (blockIdx.x != 0) s_st.trace = nullptr;  // block 0 records the trace
     s_st.sat_base = 0u;                          // the host zeroes the monotone counters per launch
     s_st.work_base = 0u;
+    s_st.tile_item_base = s_st.tile_item_next = 0u;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
@@ -2522,7 +2539,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
       if (s_st.tile_rebuild) {  // the same value in every block
         TileSmemWarp& S = reinterpret_cast<TileSmemWarp*>(s_raw)[warp_in_block];
         tile_phase(A, &s_st, S, &s_tile_bar[kGen == 2 ? warp_in_block : 0], warp_in_block * (int)gridDim.x + (int)blockIdx.x,
-                   (int)gridDim.x * warps_per_block, tile_bar_phase);
+                   (int)gridDim.x * warps_per_block, tile_bar_phase, &gst->item_counter, s_st.tile_item_base);
         CVO_PHASE(2)
         double one[1] = {1.0}, got[1];
         ll_allreduce<1, 1>(A.ll, ++seq, one, sh, sh_all, got, true, true);
