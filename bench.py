@@ -167,6 +167,25 @@ class ClockSampler:
         self.t_mark = time.perf_counter()
 
     def start(self):
+        # NVML in-process (no start-up delay: nvidia-smi needs ~1 s on an 8-GPU box, longer than a
+        # short run); nvidia-smi -lms as the fallback.  Same counters as the recipe's clocks line.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+                self.nv = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+            except Exception:
+                self.nv = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.nvml, self.stop_flag = pynvml, False
+            self.nv_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.nv, pynvml.NVML_CLOCK_SM))
+            self.proc = "nvml"
+            self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
@@ -176,6 +195,21 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll_nvml(self):
+        nv, h = self.nvml, self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        while not self.stop_flag:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(h))
+                # same row layout as the nvidia-smi reader: [idx, sm, max, power, active, 4 reasons..., t]
+                self.rows.append([str(self.gpu), f"{sm:.0f}", f"{self.nv_max:.0f}", "", hex(r)] +
+                                 ["Active" if r & b else "Not Active" for _, b in bits] + [time.perf_counter()])
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")] + [time.perf_counter()])
@@ -183,11 +217,15 @@ class ClockSampler:
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.proc == "nvml":
+            self.stop_flag = True
+            self.t.join(timeout=1)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         rows = [r for r in self.rows if len(r) > 9 and r[1].replace(".", "").isdigit()]
         timed = [r for r in rows if self.t_mark is not None and r[-1] >= self.t_mark]
         # a timed region of a few tens of ms holds few 20 ms samples: then the GPU-busy warm-up steps
@@ -200,7 +238,8 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({n for r in timed for n, v in zip(names, r[5:9]) if v == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": reasons, "window": window, "interval_ms": 20}
+                "samples": len(sm), "reasons": reasons, "window": window,
+                "source": "NVML, 5 ms" if self.proc == "nvml" else "nvidia-smi -lms 20"}
 
 
 def measured_peaks():
