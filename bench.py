@@ -704,6 +704,10 @@ def run_ours(args, rank, world, local_rank):
         line["frame_pairs"] = [frame_pairs_leg(u, wl) for wl in ("KITTI05_TRACK", "KITTI05")]
         line["edge_updates"] = edge_updates_leg(u, cpu=not args.no_cpu_baseline)
         line["edge_updates"]["graph16"] = edge_graph_leg(u, local_rank, 0, 1, None)
+        try:
+            line["demo_registration"] = gpu_demo_registration(u, local_rank)
+        except Exception as e:  # never let an auxiliary leg take the line down
+            line["demo_registration"] = {"error": str(e)}
     # CPU baselines beside it (rank 0, N=1 only)
     if world == 1 and not args.no_cpu_baseline:
         import oracle
@@ -738,6 +742,28 @@ def run_ours(args, rank, world, local_rank):
     print(json.dumps(line), flush=True)
     if g is not None:
         g.close()
+
+
+def gpu_demo_registration(u, device):
+    """BASELINE configs[0] on the GPU: the README demo pair through CvoGPU::align, both flavours
+    (the drivers' ell_init = distance of the cloud means: rows are cut at their cap, so the loop is
+    523 latency-bound rows of 1 080 targets each - the worst case for this design)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import demo_clouds, demo_params
+    out = {}
+    for flavour, color in (("two_color_pcd (colour)", True), ("two_pcd (geometric only)", False)):
+        src, tgt = demo_clouds(color=color)
+        p = demo_params(src, tgt, color=color)
+        g = u.CvoGPU(p, device=device)
+        g.align_host(src, tgt)  # warm-up
+        t0 = time.perf_counter()
+        ret, T, info = g.align_host(src, tgt)
+        wall = time.perf_counter() - t0
+        it = info.iterations + (0 if info.stop_reason == 8 else 1)
+        out[flavour] = {"seconds": float(info.registration_seconds), "wall_seconds_host_buffers": wall, "iterations": int(it),
+                        "ret": int(ret), "pairs_per_s": float(info.pairs_tested) / float(info.registration_seconds)}
+        g.close()
+    return out
 
 
 def cpu_demo_registration(n_thr):
