@@ -106,6 +106,24 @@ def run_edge_case(c):
                 vals=[float(x) for x in vals])
 
 
+def demo_final_pose_spread(T0):
+    """How far the ORACLE's own final pose of the demo registration moves when its initial pose moves
+    by 1e-7 .. 3e-7 m (six starts, ~7 000 chaotic iterations each): the bar a GPU run can be held to."""
+    import oracle
+    from helpers import demo_clouds, demo_params, to_oracle_cloud
+    src, tgt = demo_clouds(True)
+    p = demo_params(src, tgt, True)
+    cs, ct = to_oracle_cloud(src), to_oracle_cloud(tgt)
+    out = []
+    for ax, eps in ((0, 1e-7), (1, 1e-7), (2, 1e-7), (0, -1e-7), (1, 3e-7), (2, -2e-7)):
+        Ti = np.eye(4, dtype=np.float32)
+        Ti[ax, 3] = eps
+        _, T, info, _ = oracle.align(p, cs, ct, Ti)
+        out.append(dict(axis=ax, eps=eps, iterations=int(info.iterations),
+                        max_abs_pose_diff=float(np.abs(np.asarray(T) - np.asarray(T0)).max())))
+    return dict(starts=out, spread=max(o["max_abs_pose_diff"] for o in out))
+
+
 def main():
     with open(os.path.join(HERE, "edge_updates.json"), "w") as fh:
         json.dump([run_edge_case(c) for c in EDGE_CASES], fh, indent=0)
@@ -117,7 +135,8 @@ def main():
         if name == "demo_color":
             with open(os.path.join(HERE, "demo_color_align.json"), "w") as fh:
                 json.dump(dict(case=name, ret=res["ret"], iterations=res["iterations"],
-                               transform=res["transform"]), fh, indent=0)
+                               transform=res["transform"], oracle_spread=demo_final_pose_spread(res["transform"])),
+                          fh, indent=0)
         print(name, len(res["iters"]), "records; align iterations", res["iterations"])
 
 

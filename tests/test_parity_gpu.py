@@ -210,12 +210,25 @@ def test_align_with_initial_guess_and_demo_final_pose():
     with open(os.path.join(os.path.dirname(__file__), "golden", "demo_color_align.json")) as fh:
         gold = json.load(fh)
     assert ret == gold["ret"]
-    # ~7000 chaotic iterations on a flat optimum (523 vs 1080 points of a partial scene): the end
-    # point is pinned to the oracle's only loosely; the tight per-iteration bar is teacher-forced
-    np.testing.assert_allclose(T, np.array(gold["transform"]), atol=4e-2)
-    # restart from the solution: converges much sooner and stays there
+    # ~7000 chaotic iterations on a flat optimum (523 vs 1080 points of a partial scene).  The
+    # oracle's OWN final pose moves by `spread` = 2.8e-3 when its initial pose moves by 1e-7 m
+    # (six starts, tests/golden/make_golden.py::demo_final_pose_spread), so north_star's 1e-3 is
+    # not defined on this problem; the GPU run is held to three times that spread (the maximum of
+    # six samples is not a bound), 5x tighter than round 1's 4e-2.  The tight per-iteration bar is
+    # teacher-forced.
+    spread = float(gold["oracle_spread"]["spread"])
+    dev = float(np.abs(T - np.array(gold["transform"])).max())
+    print(f"demo final pose: |T_gpu - T_oracle| = {dev:.2e} after {info.iterations} iterations "
+          f"(oracle: {gold['iterations']}; its own spread {spread:.2e})")
+    assert 1e-3 < spread < 5e-3
+    assert dev <= 3.0 * spread, (dev, spread)
+    # restart from the solution (the ell schedule starts over, so it runs as long): it stays in the
+    # same flat optimum - a macroscopically different start, so not the 1e-7 spread above
+    # (measured 5e-4 .. 1.2e-2 over the six modes)
     ret2, T2, info2 = g.align(src, tgt, np.linalg.inv(T))
-    np.testing.assert_allclose(T2, T, atol=4e-2)
+    dev2 = float(np.abs(T2 - T).max())
+    print(f"restart from the solution: moved by {dev2:.2e} in {info2.iterations} iterations")
+    assert dev2 <= 4e-2
     g.close()
 
 
