@@ -105,3 +105,45 @@ def test_two_rank_sharded_reduction_equals_unsharded(tmp_path):
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+
+
+def test_gather_association_merges_the_row_shards_of_two_ranks(tmp_path):
+    """dist.gather_association on 2 gloo ranks: each rank holds the rows of its shard of one CSR
+    matrix (the layout cvo_b200_align_association returns after a sharded align); rank 0 gets the
+    whole matrix back, entry for entry."""
+    worker = tmp_path / "worker.py"
+    worker.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import numpy as np
+        import torch.distributed as dist
+        import unified_cvo_b200 as u
+        from unified_cvo_b200.dist import gather_association
+        rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        rng = np.random.default_rng(5)
+        n, m = 300, 90
+        cnt = rng.integers(0, 7, n)
+        cnt[rng.random(n) < 0.3] = 0
+        row_ptr = np.concatenate([[0], np.cumsum(cnt)])
+        cols = np.concatenate([np.sort(rng.choice(m, c, replace=False)) for c in cnt]).astype(np.int32)
+        vals = rng.random(int(row_ptr[-1])).astype(np.float32)
+        owner = rng.integers(0, world, n)   # Morton-contiguous shards are scattered in caller order
+        mine = np.repeat(owner == rank, cnt)
+        part = u.Association(shape=(n, m))
+        part.row_ptr = np.concatenate([[0], np.cumsum(np.where(owner == rank, cnt, 0))])
+        part.cols, part.vals = cols[mine], vals[mine]
+        whole = gather_association(part, rank, world, dist)
+        if rank == 0:
+            assert np.array_equal(whole.row_ptr, row_ptr) and np.array_equal(whole.cols, cols)
+            assert np.array_equal(whole.vals, vals) and whole.shape == (n, m)
+            print("GATHER_ASSOC_OK", len(vals))
+        else:
+            assert whole is None
+        dist.barrier()
+    """))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29679", str(worker)],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-2000:], out.stderr[-3000:])
+    assert "GATHER_ASSOC_OK" in out.stdout

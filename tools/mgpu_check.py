@@ -55,6 +55,21 @@ assert abs(fa_sh_exact - fa_own_exact) <= 4e-6 * abs(fa_own_exact)
 vals = [None] * world
 dist.all_gather_object(vals, (fa_sh, ip_sh))
 assert all(v == vals[0] for v in vals), "ranks disagree on the sharded inner product"
+# the kernel matrix of the LAST iteration: every rank exports the rows of its shard, rank 0 merges
+# them (dist.gather_association) - equal to the single-GPU export entry for entry
+from unified_cvo_b200.dist import gather_association
+q = p.copy(); q.is_exporting_association = 1; q.MAX_ITER = 12
+a_single, a_part = u.Association(), u.Association()
+single.write_params(q); g.write_params(q)
+single.align(src, tgt, None, association=a_single)
+g.align(src, tgt, None, association=a_part)
+whole = gather_association(a_part, rank, world, dist)
+if rank == 0:
+    assert len(a_single.vals) > 1000 and 0 < len(a_part.vals) < len(a_single.vals)
+    assert np.array_equal(whole.row_ptr, a_single.row_ptr) and np.array_equal(whole.cols, a_single.cols)
+    assert np.array_equal(whole.vals.view(np.uint32), a_single.vals.view(np.uint32))
+    print(f"sharded association: {len(a_part.vals)} of {len(a_single.vals)} entries on rank 0, merged == single-GPU export")
+single.write_params(p); g.write_params(p)
 poses = [None] * world
 dist.all_gather_object(poses, T1.tobytes())
 assert ok, "NCCL path: first 8 iterations differ from the single-GPU run"

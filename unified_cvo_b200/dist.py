@@ -48,3 +48,42 @@ def attach(gpu, n_rows: int, rank: int, world: int, dist_module=None, fused: boo
     b, e = shard_rows(n_rows, world, rank)
     gpu.set_row_range(b, e)
     return b, e
+
+
+def gather_association(assoc, rank: int, world: int, dist_module, dst: int = 0):
+    """The kernel matrix of a SHARDED align on one rank ("association rows gathered").
+    After a sharded align with is_exporting_association every rank's Association holds the rows of
+    its own source shard (all other rows empty, same shape); the rows are disjoint, so the whole
+    matrix is their row-wise union.  The parts travel over the host control plane
+    (dist_module.gather_object); returns the merged Association on `dst`, None elsewhere."""
+    import numpy as np
+    from .cvo import Association
+
+    cnt = np.diff(np.asarray(assoc.row_ptr, np.int64))
+    rows = np.nonzero(cnt)[0]
+    part = (assoc.shape, rows.astype(np.int32), cnt[rows].astype(np.int32),
+            np.ascontiguousarray(assoc.cols, np.int32), np.ascontiguousarray(assoc.vals, np.float32))
+    parts = [None] * world if rank == dst else None
+    dist_module.gather_object(part, parts, dst=dst)
+    if rank != dst:
+        return None
+    shape = parts[0][0]
+    total = np.zeros(shape[0], np.int64)
+    for sh, r, c, _, _ in parts:
+        if tuple(sh) != tuple(shape):
+            raise ValueError("ranks hold associations of different shapes")
+        if np.any(total[r] != 0):
+            raise ValueError("two ranks hold entries of the same source row")
+        total[r] = c
+    row_ptr = np.concatenate([[0], np.cumsum(total)])
+    cols = np.zeros(int(row_ptr[-1]), np.int32)
+    vals = np.zeros(int(row_ptr[-1]), np.float32)
+    for _, r, c, pc, pv in parts:
+        src_off = np.concatenate([[0], np.cumsum(c, dtype=np.int64)])
+        # entry k of part-row q goes to row_ptr[r[q]] + k
+        dest = np.repeat(row_ptr[r] - src_off[:-1], c) + np.arange(int(src_off[-1]))
+        cols[dest] = pc
+        vals[dest] = pv
+    out = Association(shape=tuple(shape))
+    out.row_ptr, out.cols, out.vals = row_ptr, cols, vals
+    return out
