@@ -333,17 +333,19 @@ int cvo_b200_comm_unique_id(char id[128]);
 int cvo_b200_comm_init(cvo_b200_handle* h, int rank, int world, const char id[128]);
 /* Fused exchange (optional, after comm_init): every rank publishes the CUDA IPC handle of a small
  * mailbox in its HBM, the host plumbing all-gathers the 64-byte handles, every rank maps its
- * peers'.  From then on the cell-query mode runs the WHOLE registration loop of a sharded job in
- * one persistent kernel per GPU whose two per-iteration exchanges are NVLink stores into the
- * peers' mailboxes + a spin on the own one (no NCCL call, no kernel boundary); the dense-scan mode
- * keeps the NCCL all-gathers.  handles = world x 64 bytes, rank order.                        */
+ * peers'.  From then on the cell-query and tile-cell modes run the WHOLE registration loop of a
+ * sharded job in one persistent kernel per GPU whose two per-iteration exchanges are NVLink stores
+ * into the peers' mailboxes + a spin on the own one (no NCCL call, no kernel boundary); the
+ * dense-scan mode keeps the NCCL all-gathers.  handles = world x 64 bytes, rank order.                        */
 int cvo_b200_comm_mailbox_handle(cvo_b200_handle* h, char out[64]);
 int cvo_b200_comm_open_peers(cvo_b200_handle* h, const char* handles);
 /* on != 0: cvo_b200_inner_product / cvo_b200_function_angle become COLLECTIVE calls of the job
  * (every rank must make them with the same arguments): each rank scans its shard of the source
  * rows, the ranks' sums of A are all-gathered and added in rank order (bit-identical result on
- * every rank).  Default off: every rank computes all rows on its own.  Associations (the CSR
- * exports) are never sharded.                                                             */
+ * every rank).  Default off: every rank computes all rows on its own.  cvo_b200_association always
+ * computes all rows; cvo_b200_align_association after a sharded align returns the rows of this
+ * rank's shard (the other rows empty) - the host merges the disjoint row sets
+ * (unified_cvo_b200/dist.py::gather_association).                                          */
 int cvo_b200_comm_shard_inner_products(cvo_b200_handle* h, int on);
 int cvo_b200_comm_destroy(cvo_b200_handle* h);
 

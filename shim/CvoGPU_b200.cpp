@@ -7,8 +7,9 @@
 // cvo/CvoParams.hpp:12-128, cvo/Association.hpp:7-11), so cvo_align_gpu_two_color_pcd and the
 // KITTI / TUM drivers link unchanged.  It needs Eigen3, PCL and yaml-cpp-free: the YAML reader
 // is inside libcvo_b200 (cvo_b200_params_read_yaml).  This translation unit cannot be compiled
-// in the build container (no Eigen / PCL there); tests/test_shim_syntax.py compiles it against
-// the minimal stand-in headers under shim/stubs/ to keep it syntactically honest.
+// against the real headers in the build container (no Eigen / PCL there); tests/test_shim_syntax.py
+// compiles it against the stand-in headers under shim/stubs/ and tests/test_shim_runtime_gpu.py
+// runs it against them on a B200 (tests/shim_runtime/driver.cpp).
 //
 // The class layout is fixed by the reference header (CvoParams* params_gpu; CvoParams params;),
 // so the device handle lives in a side table keyed by `this`.

@@ -7,8 +7,9 @@
 // the pose-graph path stays the reference's: CvoFrame.cpp, IRLS.cpp (CvoBatchIRLS::solve),
 // IRLS_State_GPU.cpp (update_ell, add_residual_to_problem: Ceres) — the latter walks
 // A_result_cpu_, which update_inner_product() below fills in the layout it expects.
-// Like CvoGPU_b200.cpp this file is only syntax- and link-checked in the build container
-// (tests/test_shim_syntax.py, stand-in headers under shim/stubs/).
+// Like CvoGPU_b200.cpp this file is compiled against the stand-in headers under shim/stubs/ in the
+// build container (tests/test_shim_syntax.py) and RUN against them on a B200 by
+// tests/test_shim_runtime_gpu.py (tests/shim_runtime/driver.cpp).
 //
 // The class layouts are the reference's, so: the device handle of an edge is found through its
 // params_cpu_ pointer (one handle per CvoParams object, created on first use, alive for the
