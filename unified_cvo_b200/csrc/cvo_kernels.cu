@@ -2425,7 +2425,8 @@ constexpr size_t align_grid_smem_bytes(int threads, int gen) {
 // + T_b the row in the target's frame at BUILD time and skin(x) = s_tr + s_rot |x| (+ a relative
 // 4e-6 of the radius).  An iteration at pose (R, T) needs every y with |y - q| <= rq(x); since
 // |q - q_b| <= |R - R_b|_F |x| + |T - T_b|, the old cells still contain them while
-//   |R - R_b|_F <= s_rot,   |T - T_b| + (slack - slack_b)+ <= s_tr,   ell smax <= ell_b smax_b (1 + 2e-6)
+//   |R - R_b|_F |x| + |T - T_b| + (slack - slack_b)+ <= s_rot |x| + s_tr for every row (checked at
+//   |x| = 0 and at max|x|: the expression is linear in |x|),   ell smax <= ell_b smax_b (1 + 2e-6)
 // (the cut-off radius is proportional to ell * smax, CvoGPU.cu:506-511; flow_rows<2> re-tests every
 // candidate with the reference's arithmetic at the CURRENT pose, so a superset changes nothing).
 // Budgets: s_tr = kappa * (cut-off radius at range 0), s_rot = s_tr / max|x|.  Called by thread 0 of
@@ -2446,7 +2447,11 @@ __device__ void verlet_decide(const IterArgs& A, DevState* st) {
     const float ds = fmaxf(0.f, st->grid_slack - st->vl_slack) * 1.0001f;
     const float ls = st->ell * st->smax;
     // (NaN anywhere: every comparison is false -> rebuild)
-    const bool keep = dr <= st->vl_srot && dt + ds <= st->vl_str && ls <= st->vl_ls * 1.000002f;
+    // every row has |x| <= xm, and (dr - s_rot) |x| + (dt + ds - s_tr) is linear in |x|: it is <= 0 for
+    // all rows iff it is at |x| = 0 and at |x| = xm - rotation may use what translation left over
+    const float xm = A.src_rmax * 1.0001f;
+    const bool keep = dt + ds <= st->vl_str && dr * xm + dt + ds <= st->vl_srot * xm + st->vl_str &&
+                      ls <= st->vl_ls * 1.000002f;
     rebuild = !keep;
   }
   if (rebuild) {
