@@ -1956,7 +1956,9 @@ __device__ void controller_step(const IterArgs& A, DevState* st, const double bc
       double n2 = 0.0;
       for (int q = 0; q < 6; q++) n2 += (double)vec_joined[q] * (double)vec_joined[q];
       d_fast = (double)st->step * sqrt(n2);
-      const bool traced = st->trace != nullptr && st->iter < st->trace_cap;
+      // (trace_cap, not the trace pointer: the persistent kernel clears the pointer in every block but
+      //  block 0, and all blocks must take the same path here)
+      const bool traced = st->iter < st->trace_cap;
       const double margin = 2e-6 + 1e-4 * d_fast;
       need_exact = traced || st->controller_on != 1 || !(fabs(d_fast - (double)params->eps_2) > margin) ||
                    !(d_fast < 1.0);  // (rotation angles near pi: the log is not step*xi any more)
