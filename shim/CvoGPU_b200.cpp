@@ -160,6 +160,7 @@ CvoGPU::~CvoGPU() {
     }
   }
   cvo_b200_destroy(h);
+  shim::forget_edge_handle(&params);
 }
 
 void CvoGPU::write_params(const CvoParams* p_cpu) {

@@ -105,6 +105,11 @@ cvo_b200_handle* edge_handle(const CvoParams* params_cpu) {
 }
 }  // namespace
 
+void shim::forget_edge_handle(const void* params_cpu) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_edge_handles.erase(static_cast<const CvoParams*>(params_cpu));
+}
+
 // ---- CvoFrameGPU (CvoFrameGPU.cu:7-100) ------------------------------------------------------
 class CvoFrameGPU_Impl {
  public:

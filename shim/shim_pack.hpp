@@ -7,6 +7,12 @@
 namespace cvo {
 namespace shim {
 
+// ~CvoGPU: the pose-graph edges of a CvoGPU find their device handle through the address of its
+// CvoParams (IRLS_State_GPU_b200.cpp).  When the object dies that address may be reused by another
+// CvoGPU: the entry is dropped so the newcomer gets a handle of its own (the old handle stays alive
+// for the frames that still hold ids on it).
+void forget_edge_handle(const void* params_cpu);
+
 // CvoPointCloud (column-major Eigen matrices) -> the row-major arrays of cvo_b200_set_cloud.
 // Mirrors what CvoPointCloud_to_gpu reads (CvoGPU_impl.cu:206-263).
 struct Packed {
