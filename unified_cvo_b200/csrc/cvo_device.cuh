@@ -264,6 +264,8 @@ struct IterArgs {
   float src_rmax;      // max |x| over the source (scales the rotation budget)
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective
   int n_items;     // pair-kernel work items = row_tiles * nchunks
+  int row_spread;  // few rows: 4-row groups are dealt warp-major (group k -> block k % blocks, warp k / blocks),
+                   // so that every SM gets a few busy warps instead of the first blocks getting them all
 };
 
 }  // namespace cvo_b200

@@ -412,6 +412,13 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   const int rows_per_pblock = (h->persist_threads / 32) * 4;
   h->persist_blocks =
       std::max(1, std::min(h->num_sms * pocc, (n_rows + rows_per_pblock - 1) / rows_per_pblock));
+  // few rows (the README demo: 523): filling block after block would put all the work on a handful
+  // of SMs, 18 warps on 4 schedulers each, while the loop is a latency chain per row.  Instead the
+  // 4-row groups are dealt warp-major over blocks of 4 busy warps (one per scheduler): more blocks
+  // in the all-reduce (+ ~1 us), but the flow phase runs at a lone warp's speed
+  bool row_spread = n_rows * 2 <= h->num_sms * (kPersistThreadsSmall / 32) * 4;
+  if (const char* rs = getenv("CVO_B200_ROW_SPREAD")) row_spread = row_spread && atoi(rs) != 0;  // measurement aid
+  if (row_spread) h->persist_blocks = std::max(1, std::min(h->num_sms * pocc, ((n_rows + 3) / 4 + 3) / 4));
   // tile mode: one block per SM (tile items and rows are dealt to its warps); the wide block where
   // it saves the second pass over the rows (cells are mostly reused: the row walk is the iteration)
   h->persist_threads_tile = (n_rows > h->num_sms * (kPersistThreads / 32) * 4 && n_rows <= h->num_sms * (kPersistThreadsWide / 32) * 4)
@@ -426,6 +433,7 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   CVO_CUDA(h, h->step_part.ensure((size_t)std::max(h->sparse_blocks, std::max(h->grid_blocks, h->persist_blocks))));
 
   std::memset(&A, 0, sizeof(A));
+  A.row_spread = row_spread ? 1 : 0;
   A.params = h->d_params;
   A.st = h->d_state;
   A.src_xyz = cs.xyz.p;

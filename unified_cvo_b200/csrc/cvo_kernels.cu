@@ -1231,7 +1231,10 @@ __device__ __forceinline__ void flow_rows(const IterArgs& A, DevState* st, const
   // boundary rows see half the neighbours) and a static split left 20 % of C4's flow phase idle.
   const int total_slots = gridDim.x * warps_per_block * kRowsPerWarp;
   const bool dynamic_rows = A.n_rows > total_slots;
-  int row_base = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp;
+  // (A.row_spread: few rows - the groups are dealt warp-major, a few busy warps on every SM; step_rows
+  // uses the same map, so a warp reads back the ELL rows it wrote itself)
+  int row_base = (A.row_spread ? warp_in_block * (int)gridDim.x + (int)blockIdx.x
+                               : (int)blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp;
   for (bool first_pass = true;; first_pass = false) {
     if (!first_pass) {
       if (dynamic_rows) {
@@ -2094,7 +2097,8 @@ __device__ __forceinline__ void step_rows(const IterArgs& A, const DevState* hs,
 
   wB = wC = wD = wE = 0.0;
   // eight lanes per source row, four rows per warp (rows hold ~10 entries in tracking regimes)
-  const int slot0 = (blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp + g;
+  const int slot0 = (A.row_spread ? warp_in_block * (int)gridDim.x + (int)blockIdx.x
+                                  : (int)blockIdx.x * warps_per_block + warp_in_block) * kRowsPerWarp + g;  // flow_rows' map
   const int slot_stride = gridDim.x * warps_per_block * kRowsPerWarp;
   for (int row = slot0; row < A.n_rows; row += slot_stride) {
     const int n = (int)__ldcg(A.row_nnz + row);
@@ -2564,8 +2568,11 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
       v[10] = bp[8];
       // release only when this block queued rows for the exact redo (sat_list entries must be
       // visible to whoever redoes them); block-uniform decision
-      const bool rel = __syncthreads_or(lane == 0 && queued[0] > 0.0) != 0;
-      ll_allreduce<kLLValues, 10>(A.ll, ++seq, v, sh, sh_all, r, rel, false);
+      // ... or when rows were handed out dynamically: step_rows walks the rows by the static map, so
+      // it reads ELL rows other blocks wrote (release here, acquire after the poll)
+      const bool dyn = work_per_iter != 0u;
+      const bool rel = (__syncthreads_or(lane == 0 && queued[0] > 0.0) != 0) || dyn;
+      ll_allreduce<kLLValues, 10>(A.ll, ++seq, v, sh, sh_all, r, rel, dyn);
       CVO_PHASE(1)
 #pragma unroll
       for (int k = 0; k < 8; k++) tot[k] = r[k];
@@ -2577,8 +2584,8 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
       __threadfence();  // acquire: the queued row indices of the other blocks
       __syncthreads();
       double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, v[kLLValues], r[kLLValues];
-      for (unsigned int si = blockIdx.x * warps_per_block + warp_in_block; si < n_sat;
-           si += gridDim.x * warps_per_block)
+      for (unsigned int si = A.row_spread ? warp_in_block * gridDim.x + blockIdx.x : blockIdx.x * warps_per_block + warp_in_block;
+           si < n_sat; si += gridDim.x * warps_per_block)
         redo_row<true>(A, s_st.kc, s_st.Rinv, s_st.Tinv, s_st.ell, s_st.num_neighbors,
                        (int)__ldcg(&A.sat_list[si]), lane, f);
 #pragma unroll
