@@ -59,13 +59,14 @@ def _teacher_forced(gpu, p, src, tgt, ks, max_iter=None):
     return failures
 
 
-@pytest.fixture(scope="module", params=["dense", "grid", "grid-launches", "tile", "tile-launches", "auto"], autouse=True)
+@pytest.fixture(scope="module", params=["dense", "grid", "grid-launches", "tile", "tile-launches", "brute", "auto"], autouse=True)
 def candidate_mode(request):
     """Every test runs with the dense N x M scan (pair_kernel), with cell queries in the
     persistent cooperative kernel (align_grid_kernel), with cell queries as one launch per phase
     (flow_kernel_t<1> / step_kernel_t<true>), with tile cells inside the persistent kernel and as
-    one launch per phase (tile_kernel + flow_kernel_t<2>; wherever the Morton view applies) and
-    with the automatic choice: the candidate
+    one launch per phase (tile_kernel + flow_kernel_t<2>; wherever the Morton view applies), with
+    every row walked exactly by one warp inside the persistent kernel ("brute": what the policy
+    picks for a few hundred rows against a small target) and with the automatic choice: the candidate
     generator and the launch structure must never change a result.  Read by cvo_b200_create."""
     old = {k: os.environ.get(k) for k in ("CVO_B200_MODE", "CVO_B200_PERSIST")}
     os.environ["CVO_B200_MODE"] = request.param.split("-")[0]

@@ -24,12 +24,13 @@ from helpers import (DATA, compare_traces, demo_clouds, demo_params, geometric_p
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["dense", "grid", "grid-launches", "tile", "tile-launches"])
+@pytest.fixture(params=["dense", "grid", "grid-launches", "tile", "tile-launches", "brute"])
 def candidate_mode(request, monkeypatch):
     """dense N x M scan / cell queries in the persistent kernel / cell queries as one launch per
     phase / tile cells in the persistent kernel (built with a skin and REUSED while the pose has
-    drifted less than it) / tile cells as one launch per phase (read by cvo_b200_create): the
-    controller exists in each launch structure."""
+    drifted less than it) / tile cells as one launch per phase / every row walked exactly by one
+    warp inside the persistent kernel (read by cvo_b200_create): the controller exists in each
+    launch structure."""
     monkeypatch.setenv("CVO_B200_MODE", request.param.split("-")[0])
     monkeypatch.setenv("CVO_B200_PERSIST", "0" if request.param.endswith("-launches") else "1")
     return request.param

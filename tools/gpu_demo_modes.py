@@ -1,6 +1,6 @@
 """The README demo pair (BASELINE configs[0]) through align() with every candidate generator forced
 and with the automatic policy: seconds per registration, iterations, share of persistent batches.
-usage: gpu_demo_modes.py [modes, comma separated: auto,dense,grid,tile]"""
+usage: gpu_demo_modes.py [modes, comma separated: auto,dense,grid,tile,brute]"""
 import os
 import sys
 import time
@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import unified_cvo_b200 as u
 from helpers import demo_clouds, demo_params
 
-modes = (sys.argv[1] if len(sys.argv) > 1 else "auto,dense,grid,tile").split(",")
+modes = (sys.argv[1] if len(sys.argv) > 1 else "auto,dense,grid,tile,brute").split(",")
 for color in (True, False):
     src, tgt = demo_clouds(color=color)
     p = demo_params(src, tgt, color=color)

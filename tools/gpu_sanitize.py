@@ -5,7 +5,8 @@
     compute-sanitizer --tool synccheck python tools/gpu_sanitize.py
 
 Every candidate generator (dense scan, cell queries, tile cells) in both launch structures (the
-persistent cooperative kernel, one launch per phase), with and without colour, then the calls that
+persistent cooperative kernel, one launch per phase) and the one-warp-per-row exact walk of the
+persistent kernel ("brute"), with and without colour, then the calls that
 reuse the pairwise pass (inner product, association export in both kernels) and the pose-graph
 edge update (per edge and batched).  Sizes are chosen so that a sanitizer run (10-100x slower)
 ends within a minute; results are only printed, parity is the tests' business.
@@ -81,7 +82,10 @@ def run_edges():
 
 
 if __name__ == "__main__":
-    for mode, persist in (("dense", "1"), ("grid", "1"), ("grid", "0"), ("tile", "1"), ("tile", "0")):
+    only = os.environ.get("SANITIZE_MODES")
+    for mode, persist in (("dense", "1"), ("grid", "1"), ("grid", "0"), ("tile", "1"), ("tile", "0"), ("brute", "1")):
+        if only and mode not in only.split(","):
+            continue
         for colour in (False, True):
             run_mode(mode, persist, colour)
     run_edges()

@@ -264,6 +264,8 @@ struct IterArgs {
   float src_rmax;      // max |x| over the source (scales the rotation budget)
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective
   int n_items;     // pair-kernel work items = row_tiles * nchunks
+  int brute;       // persistent kernel: no candidate generator - one warp per row walks ALL targets in the caller's
+                   // order with the exact arithmetic (redo_row); a handful of rows against a small target
   int row_spread;  // few rows: 4-row groups are dealt warp-major (group k -> block k % blocks, warp k / blocks),
                    // so that every SM gets a few busy warps instead of the first blocks getting them all
 };

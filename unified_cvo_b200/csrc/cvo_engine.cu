@@ -239,13 +239,14 @@ struct cvo_b200_handle {
   int grid_blocks = 1;
   int persist_blocks = 1;   // cooperative grid of align_grid_kernel (all blocks co-resident)
   int persist_blocks_tile = 1;  // ... of its tile-cell instantiation
+  int persist_blocks_brute = 1;  // ... when every row takes the exact one-warp walk (IterArgs::brute)
   int persist_threads = kPersistThreads;
   int persist_threads_tile = kPersistThreads;
   bool comm_broken = false;  // a multi-GPU exchange failed: tear the communicator down without waiting for peers
   bool use_persist = true;  // CVO_B200_PERSIST=0: one launch per phase even in cell-query mode
   int last_tile_builds = 0;   // iterations of the last align() that built candidate cells (persistent tile mode)
   float verlet_kappa = 0.1f;  // candidate-cell reuse of the persistent tile mode: skin / cut-off radius (CVO_B200_VERLET)
-  int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries, 2 tile cells (where possible)
+  int force_mode = -1;  // CVO_B200_MODE: -1 auto, 0 dense scan, 1 cell queries, 2 tile cells, 3 brute rows (where possible)
   // host poll buffer (pinned)
   int* h_poll = nullptr;
   // comm
@@ -419,6 +420,8 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   bool row_spread = n_rows * 2 <= h->num_sms * (kPersistThreadsSmall / 32) * 4;
   if (const char* rs = getenv("CVO_B200_ROW_SPREAD")) row_spread = row_spread && atoi(rs) != 0;  // measurement aid
   if (row_spread) h->persist_blocks = std::max(1, std::min(h->num_sms * pocc, ((n_rows + 3) / 4 + 3) / 4));
+  // brute rows: one warp per row, 4 busy warps per block until every SM has a block
+  h->persist_blocks_brute = std::max(1, std::min(std::min(kLLMaxBlocks, h->num_sms * pocc), (n_rows + 3) / 4));
   // tile mode: one block per SM (tile items and rows are dealt to its warps); the wide block where
   // it saves the second pass over the rows (cells are mostly reused: the row walk is the iteration)
   h->persist_threads_tile = (n_rows > h->num_sms * (kPersistThreads / 32) * 4 && n_rows <= h->num_sms * (kPersistThreadsWide / 32) * 4)
@@ -587,7 +590,7 @@ cudaError_t launch_persistent(cvo_b200_handle* h, const IterArgs& A) {
   if (e == cudaSuccess) e = cudaMemsetAsync(&h->d_state->n_sat, 0, sizeof(unsigned int), h->stream);
   if (e == cudaSuccess && A.tile) e = cudaMemsetAsync(&h->d_state->item_counter, 0, sizeof(unsigned int), h->stream);
   if (e != cudaSuccess) return e;
-  return launch_align_grid(A, A.tile ? h->persist_blocks_tile : h->persist_blocks,
+  return launch_align_grid(A, A.tile ? h->persist_blocks_tile : (A.brute ? h->persist_blocks_brute : h->persist_blocks),
                            A.tile ? h->persist_threads_tile : h->persist_threads, h->stream);
 }
 
@@ -812,6 +815,24 @@ void choose_mode(const cvo_b200_handle* h, IterArgs& A, const CloudDev& cs, cons
             rows_policy, r, ball, tests_t, tests_g, tests_d, A.tile ? "tile" : (A.grid ? "grid" : "dense"));
 }
 
+// The fourth way through the flow phase, for the align loop only: a few hundred rows against a small
+// target (the README demo: 523 x 1 080, rows cut at their cap for most of the registration).  No
+// candidate generator pays off there - 8 lanes per row walk the whole target serially and the cut
+// rows are redone anyway - so the persistent kernel gives every row a whole warp that walks ALL
+// targets in the caller's order with the exact arithmetic (redo_row: the literal loop of
+// CvoGPU.cu:524-591).  Called after choose_mode; the choice never changes a result.
+void choose_brute(const cvo_b200_handle* h, IterArgs& A) {
+  A.brute = 0;
+  if (h->force_mode != -1 && h->force_mode != 3) return;
+  if (!h->use_persist || A.world > 1 || A.mode != 0 || !h->params.is_using_geometry) return;
+  const bool small = A.n_rows <= 4 * h->num_sms && A.M <= 2048;  // <= 4 busy warps per SM, <= 64 passes per row
+  if (h->force_mode == 3 || small) {
+    A.brute = 1;
+    A.grid = 1;  // launched and exported like a cell-query run (Morton column indices)
+    A.tile = 0;
+  }
+}
+
 // Builds a cloud's resident representation (Morton order, SoA packing, cell table, bounding
 // spheres: cvo_upload.cu) from raw arrays that are ALREADY on the device, laid out as the caller's
 // (xyz n x 3, features n x F, labels n x C, geotype n x 2; null = absent).  One small read-back
@@ -963,6 +984,7 @@ int run_loop(cvo_b200_handle* h, IterArgs A, int max_iter, float ell0, float* gr
     const int rows_policy = A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows;
     if (A.world > 1) sat_recent = false;
     choose_mode(h, A, h->src, h->tgt, ell, rows_policy, sat_recent);
+    choose_brute(h, A);
     if ((A.grid || A.tile) && h->use_persist && (A.world == 1 || h->peers_ready)) {
       // the whole loop in one cooperative launch (align_grid_kernel); it returns when done.
       // world > 1: the two per-iteration exchanges are NVLink stores into the peers' mailboxes
@@ -1084,10 +1106,11 @@ int cvo_b200_create(const cvo_b200_params* p, int device, cvo_b200_handle** out)
   cudaMemset(h->d_state, 0, sizeof(DevState));
   const char* ng = getenv("CVO_B200_NO_GRAPH");
   h->use_graph = !(ng && ng[0] == '1');
-  const char* fm = getenv("CVO_B200_MODE");  // dense | grid (anything else: automatic)
+  const char* fm = getenv("CVO_B200_MODE");  // dense | grid | tile | brute (anything else: automatic)
   if (fm && std::strcmp(fm, "dense") == 0) h->force_mode = 0;
   if (fm && std::strcmp(fm, "grid") == 0) h->force_mode = 1;
   if (fm && std::strcmp(fm, "tile") == 0) h->force_mode = 2;
+  if (fm && std::strcmp(fm, "brute") == 0) h->force_mode = 3;
   const char* pe = getenv("CVO_B200_PERSIST");
   h->use_persist = !(pe && pe[0] == '0');
   if (const char* vk = getenv("CVO_B200_VERLET")) h->verlet_kappa = std::max(0.f, std::min(1.f, (float)atof(vk)));
@@ -1176,6 +1199,7 @@ int cvo_b200_iterate(cvo_b200_handle* h, const float R[9], const float T[3], flo
   CVO_CUDA(h, h->d_trace.ensure(1));
   // multi-GPU: replicated inputs only, so that every rank takes the same decision
   choose_mode(h, A, h->src, h->tgt, ell, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
+  choose_brute(h, A);
   rc = init_state(h, A, R, T, ell, num_neighbors, 0, 1, h->d_trace.p, 1);
   if (rc != CVO_B200_OK) return rc;
   if ((A.grid || A.tile) && h->use_persist && (A.world == 1 || h->peers_ready)) {
@@ -1233,6 +1257,7 @@ int cvo_b200_align(cvo_b200_handle* h, const float T_init[16], float T_out[16],
   if (h->use_graph) {  // instantiate outside the timed region, like the reference's CvoState setup
     IterArgs Ag = A;
     choose_mode(h, Ag, h->src, h->tgt, h->params.ell_init, A.world > 1 ? (A.n_src_total + A.world - 1) / A.world : A.n_rows, false);
+    choose_brute(h, Ag);
     if (!((Ag.grid || Ag.tile) && h->use_persist && (A.world == 1 || h->peers_ready))) {
       rc = ensure_graph(h, Ag, 32);
       if (rc != CVO_B200_OK) {

@@ -2557,7 +2557,10 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
         CVO_PHASE(7)
       }
     }
-    {
+    // (A.brute, cell-query instantiation only: the generator is skipped and EVERY row goes through
+    //  the exact walk below, one warp per row - a few hundred rows against a small target)
+    const bool brute = (kGen == 1) && A.brute != 0;
+    if (!brute) {
       double bp[9], queued[2], v[kLLValues], r[kLLValues];
       flow_rows<kGen, kColour>(A, gst, &s_st, s_list[threadIdx.x >> 3], bp, queued);
       CVO_PHASE(0)
@@ -2578,21 +2581,29 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
       for (int k = 0; k < 8; k++) tot[k] = r[k];
       tot[8] = r[10];
       n_sat = (unsigned int)(r[8] + 0.5);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 9; k++) tot[k] = 0.0;
     }
-    if (n_sat > 0u) {
-      // exact redo of the cut rows, one warp per row over the whole grid, behind one more reduction
-      __threadfence();  // acquire: the queued row indices of the other blocks
-      __syncthreads();
+    if (brute || n_sat > 0u) {
+      // exact redo of the cut rows (brute: of every row), one warp per row over the whole grid, behind
+      // one more reduction
+      if (!brute) {
+        __threadfence();  // acquire: the queued row indices of the other blocks
+        __syncthreads();
+      }
       double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, v[kLLValues], r[kLLValues];
-      for (unsigned int si = A.row_spread ? warp_in_block * gridDim.x + blockIdx.x : blockIdx.x * warps_per_block + warp_in_block;
-           si < n_sat; si += gridDim.x * warps_per_block)
+      const unsigned int n_exact = brute ? (unsigned int)A.n_rows : n_sat;
+      for (unsigned int si = (brute || A.row_spread) ? warp_in_block * gridDim.x + blockIdx.x : blockIdx.x * warps_per_block + warp_in_block;
+           si < n_exact; si += gridDim.x * warps_per_block)
         redo_row<true>(A, s_st.kc, s_st.Rinv, s_st.Tinv, s_st.ell, s_st.num_neighbors,
-                       (int)__ldcg(&A.sat_list[si]), lane, f);
+                       brute ? (int)si : (int)__ldcg(&A.sat_list[si]), lane, f);
 #pragma unroll
       for (int k = 0; k < 8; k++) v[k] = f[k];
       v[8] = v[9] = 0.0;
       v[10] = f[8];
-      ll_allreduce<kLLValues, 10>(A.ll, ++seq, v, sh, sh_all, r, true, true);  // redone ELL rows: release + acquire
+      // redone ELL rows are read by other blocks (step_rows' static row map): release + acquire
+      ll_allreduce<kLLValues, 10>(A.ll, ++seq, v, sh, sh_all, r, true, true);
 #pragma unroll
       for (int k = 0; k < 8; k++) tot[k] += r[k];
       tot[8] = fmax(tot[8], r[10]);
