@@ -179,6 +179,7 @@ struct XMailbox {
 // store + one L2 load round trip instead of fence + atomic + spin + fence + reload.  The board is
 // zeroed before every launch; tags are the reduction's sequence number (>= 1) inside the launch;
 // two parities suffice (a block cannot run two reductions ahead of another one).
+constexpr int kBruteTeam = 4;     // warps per source row of the team walk (IterArgs::brute == 2)
 constexpr int kLLMaxBlocks = 160;  // >= the SM count of the part (B200: 148)
 constexpr int kLLValues = 11;
 struct LLBoard {
@@ -265,7 +266,9 @@ struct IterArgs {
   int world;       // >1: tails only publish local totals, finalize kernels run after the collective
   int n_items;     // pair-kernel work items = row_tiles * nchunks
   int brute;       // persistent kernel: no candidate generator - one warp per row walks ALL targets in the caller's
-                   // order with the exact arithmetic (redo_row); a handful of rows against a small target
+                   // order with the exact arithmetic (redo_row); a handful of rows against a small target.
+                   // 2: a TEAM of kBruteTeam warps per row (brute_team_rows), each warp a contiguous part of the targets
+  int brute_cap;   // brute == 2: survivor slots per warp buffer (>= min(row cap, targets per team warp))
   int row_spread;  // few rows: 4-row groups are dealt warp-major (group k -> block k % blocks, warp k / blocks),
                    // so that every SM gets a few busy warps instead of the first blocks getting them all
 };

@@ -823,6 +823,7 @@ void choose_mode(const cvo_b200_handle* h, IterArgs& A, const CloudDev& cs, cons
 // CvoGPU.cu:524-591).  Called after choose_mode; the choice never changes a result.
 void choose_brute(const cvo_b200_handle* h, IterArgs& A) {
   A.brute = 0;
+  A.brute_cap = 0;
   if (h->force_mode != -1 && h->force_mode != 3) return;
   if (!h->use_persist || A.world > 1 || A.mode != 0 || !h->params.is_using_geometry) return;
   const bool small = A.n_rows <= 4 * h->num_sms && A.M <= 2048;  // <= 4 busy warps per SM, <= 64 passes per row
@@ -830,6 +831,14 @@ void choose_brute(const cvo_b200_handle* h, IterArgs& A) {
     A.brute = 1;
     A.grid = 1;  // launched and exported like a cell-query run (Morton column indices)
     A.tile = 0;
+    // small targets: a team of warps per row (brute_team_rows) - the survivors of a team warp's part
+    // of the targets wait in shared memory, at most min(row cap, part) of them
+    const int part = ((A.M + kBruteTeam - 1) / kBruteTeam + 31) & ~31;
+    const int slots = std::min(A.cap_max, part);
+    if (A.M <= 2048 && slots > 0 && (size_t)(h->persist_threads / 32) * (size_t)slots * 8 <= (size_t)96 * 1024) {
+      A.brute = 2;
+      A.brute_cap = slots;
+    }
   }
 }
 

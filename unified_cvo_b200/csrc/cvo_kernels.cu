@@ -1180,6 +1180,129 @@ __device__ __forceinline__ void redo_row(const IterArgs& A, const KernConsts& kc
     }
 }
 
+// IterArgs::brute == 2 - the exact walk of redo_row by a TEAM of kBruteTeam warps per source row.
+// One warp's walk over all M targets is a serial chain of M / 32 passes, each ~1 us of dependent
+// double-precision latency (the three exps of a surviving pair), and on the README demo (523 rows,
+// 1 080 targets, rows cut at their cap) that chain IS the iteration.  Here warp t of a team takes
+// the t-th contiguous part of the targets (caller's order), evaluates it with the reference's
+// arithmetic and parks its survivors (target, a) in shared memory in target order; after a block
+// barrier the survivors' positions in the row follow from the team's counts, and every warp stores
+// and accumulates those of ITS survivors that are among the row's first `cap` in target order -
+// the reference's first-K truncation (CvoGPU.cu:524-526), exactly.  A warp stops early once it
+// holds `cap` survivors itself.  Every thread of the block must call it (block barriers); f (lane 0
+// of every warp) as in redo_row.  s_raw: >= 8 * brute_cap bytes per team warp; s_cnt: 32 ints.
+__device__ __forceinline__ void brute_team_rows(const IterArgs& A, const DevState* hs, unsigned char* s_raw,
+                                                int* s_cnt, double (&f)[9]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int teams = (int)(blockDim.x >> 5) / kBruteTeam;
+  const int team = w / kBruteTeam, tw = w - team * kBruteTeam;
+  const bool in_team = team < teams;
+  const int E = A.brute_cap;
+  uint32_t* buf_j = reinterpret_cast<uint32_t*>(s_raw) + (size_t)(in_team ? w : 0) * E;
+  float* buf_a = reinterpret_cast<float*>(s_raw) + (size_t)(teams * kBruteTeam) * E + (size_t)(in_team ? w : 0) * E;
+  const KernConsts& kc = hs->kc;
+  const int cap = hs->num_neighbors;
+  const float c_div = kc.c_div, d_div = kc.d_div;
+  const unsigned lt32 = (1u << lane) - 1u;
+  const int Q = ((A.M + kBruteTeam - 1) / kBruteTeam + 31) & ~31;  // targets per team warp
+  const int j0 = tw * Q, j1 = min(A.M, j0 + Q);
+  for (int base = 0; base < A.n_rows; base += (int)gridDim.x * teams) {  // block-uniform trip count
+    const int row = base + team * (int)gridDim.x + (int)blockIdx.x;
+    const bool rvalid = in_team && row < A.n_rows;
+    const int ig = A.row_begin + (rvalid ? row : 0);
+    RowCtx rc;
+    int cnt = 0;
+    if (rvalid) {
+      const float4 pa = A.src_xyz[ig];
+      rc.px[0] = pa.x; rc.px[1] = pa.y; rc.px[2] = pa.z;
+      rc.qa = __float_as_uint(pa.w);
+      rc.l = range_ell(hs->ell, A.src_rowA[ig].w);
+      rc.d2_thres = -2.0 * rc.l * rc.l * kc.log_geo;
+      rc.ga[0] = rc.ga[1] = 0.f;
+      if (kc.use_geo_type) {
+        const float2 gg = A.src_geo[ig];
+        rc.ga[0] = gg.x; rc.ga[1] = gg.y;
+      }
+      for (int jb = j0; jb < j1 && cnt < cap; jb += 32) {
+        const int j = jb + lane;
+        float a = 0.f;
+        bool surv = false;
+        if (j < j1) {
+          const float4 pb = move_target(A, hs->Rinv, hs->Tinv, A.tv[1].xyz[j]);
+          surv = eval_pair(A, kc, rc, ig, 1, j, pb, a);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, surv);
+        const int e = cnt + __popc(mask & lt32);
+        if (surv && e < cap && e < E) {
+          buf_j[e] = (uint32_t)j;
+          buf_a[e] = a;
+        }
+        cnt = min(cap, cnt + __popc(mask));
+      }
+      cnt = min(cnt, E);
+    }
+    if (lane == 0) s_cnt[w] = cnt;
+    __syncthreads();
+    if (rvalid) {
+      int prefix = 0, total = 0;
+#pragma unroll
+      for (int t = 0; t < kBruteTeam; t++) {
+        const int c = s_cnt[team * kBruteTeam + t];
+        if (t < tw) prefix += c;
+        total += c;
+      }
+      total = min(total, cap);
+      float om[3] = {0.f, 0.f, 0.f}, vv[3] = {0.f, 0.f, 0.f};
+      double asum = 0.0;
+      uint32_t* out_idx = A.ell_idx + (size_t)row * A.cap_max;
+      float* out_val = A.ell_val + (size_t)row * A.cap_max;
+      __syncwarp();  // the warp's own buffer writes
+      for (int e = lane; e < cnt; e += 32) {
+        const int pos = prefix + e;
+        if (pos < cap) {
+          const int j = (int)buf_j[e];
+          const float a = buf_a[e];
+          const float4 pb = move_target(A, hs->Rinv, hs->Tinv, A.tv[1].xyz[j]);
+          out_idx[pos] = (uint32_t)A.tgt_inv[j];  // Morton positions, like the rest of the matrix
+          out_val[pos] = a;
+          const float py[3] = {pb.x, pb.y, pb.z};
+          float cr[3];
+          cross3f(rc.px, py, cr);  // compute_flow_gpu_no_eigen, CvoGPU.cu:765-781
+#pragma unroll
+          for (int q = 0; q < 3; q++) {
+            om[q] = om[q] + cr[q] * a;
+            vv[q] = vv[q] + (py[q] - rc.px[q]) * a;
+          }
+          asum += (double)a;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          om[q] += __shfl_xor_sync(0xffffffffu, om[q], o);
+          vv[q] += __shfl_xor_sync(0xffffffffu, vv[q], o);
+        }
+        asum += __shfl_xor_sync(0xffffffffu, asum, o);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+          f[q] += (double)(om[q] / c_div);
+          f[3 + q] += (double)(vv[q] / d_div);
+        }
+        f[6] += asum;
+        if (tw == 0) {
+          A.row_nnz[row] = (uint32_t)total;
+          f[7] += (double)total;
+          f[8] = fmax(f[8], (double)total);
+        }
+      }
+    }
+    __syncthreads();  // buffers and counts are reused by the next round
+  }
+}
+
 // The source rows of this block (grid-stride over 8-lane row groups): candidates -> exact pair
 // arithmetic -> ELL rows + per-row flow; returns the warp's partial sums in bp (valid on lane 0):
 // omega[3], v[3], a_sum, nnz, max row count.  hs = this block's shared-memory copy of the hot
@@ -2489,6 +2612,7 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
   double* sh_all = reinterpret_cast<double*>(s_raw);
   __shared__ __align__(16) DevState s_st;
   __shared__ CtrlScratch s_ctrl;
+  __shared__ int s_team_cnt[32];  // brute_team_rows: survivors per warp
   // debug (CVO_B200_STAMPS=1): time spent per phase by thread 0 of block 0, summed over the loop
   __shared__ unsigned long long s_acc[12];
   unsigned long long t_prev = 0ull;
@@ -2593,11 +2717,15 @@ __global__ void __launch_bounds__(kThreads, 1) align_grid_kernel(IterArgs A) {
         __syncthreads();
       }
       double f[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, v[kLLValues], r[kLLValues];
-      const unsigned int n_exact = brute ? (unsigned int)A.n_rows : n_sat;
-      for (unsigned int si = (brute || A.row_spread) ? warp_in_block * gridDim.x + blockIdx.x : blockIdx.x * warps_per_block + warp_in_block;
-           si < n_exact; si += gridDim.x * warps_per_block)
-        redo_row<true>(A, s_st.kc, s_st.Rinv, s_st.Tinv, s_st.ell, s_st.num_neighbors,
-                       brute ? (int)si : (int)__ldcg(&A.sat_list[si]), lane, f);
+      if (brute && A.brute == 2) {  // block-uniform: teams of warps per row (block barriers inside)
+        brute_team_rows(A, &s_st, s_raw, s_team_cnt, f);
+      } else {
+        const unsigned int n_exact = brute ? (unsigned int)A.n_rows : n_sat;
+        for (unsigned int si = (brute || A.row_spread) ? warp_in_block * gridDim.x + blockIdx.x : blockIdx.x * warps_per_block + warp_in_block;
+             si < n_exact; si += gridDim.x * warps_per_block)
+          redo_row<true>(A, s_st.kc, s_st.Rinv, s_st.Tinv, s_st.ell, s_st.num_neighbors,
+                         brute ? (int)si : (int)__ldcg(&A.sat_list[si]), lane, f);
+      }
 #pragma unroll
       for (int k = 0; k < 8; k++) v[k] = f[k];
       v[8] = v[9] = 0.0;
@@ -2842,7 +2970,11 @@ cudaError_t launch_align_grid(const IterArgs& A, int blocks, int threads, cudaSt
   const bool tile = A.tile != 0;
   const int t = align_grid_threads(threads, tile);
   const void* fn = align_grid_fn(t, A.xfused != 0, A.colour != 0, tile);
-  const size_t smem = align_grid_smem_bytes(t, tile ? 2 : 1);
+  size_t smem = align_grid_smem_bytes(t, tile ? 2 : 1);
+  if (A.brute == 2) {  // the team walk parks (target, a) per survivor: 8 bytes x brute_cap per warp
+    const size_t need = (size_t)(t / 32) * (size_t)A.brute_cap * 8 + 16;
+    if (need > smem) smem = need;
+  }
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(t), args, smem, s);
