@@ -229,8 +229,7 @@ struct cvo_b200_handle {
   // launch geometry
   int prep_blocks = 1, pair_blocks = 1, sparse_blocks = 1;
   // graph cache for the align loop: [0] dense scan (prep, pair, flow, step), [1] cell queries
-  // (flow, step)
-  // (prep, pair, flow, step), [1] cell queries (flow, step), [2] tile cells (tile, flow, step)
+  // (flow, step), [2] tile cells (tile, flow, step)
   cudaGraphExec_t graph_exec[3] = {nullptr, nullptr, nullptr};
   IterArgs graph_args[3];
   int graph_batch[3] = {0, 0, 0};
