@@ -416,7 +416,10 @@ int prepare(cvo_b200_handle* h, IterArgs& A, int mode, const float* kinv, const 
   // of SMs, 18 warps on 4 schedulers each, while the loop is a latency chain per row.  Instead the
   // 4-row groups are dealt warp-major over blocks of 4 busy warps (one per scheduler): more blocks
   // in the all-reduce (+ ~1 us), but the flow phase runs at a lone warp's speed
-  bool row_spread = n_rows * 2 <= h->num_sms * (kPersistThreadsSmall / 32) * 4;
+  // (measured on the demo's 523 rows only: 8 -> 33 blocks costs +0.4 us per all-reduce and buys 4 us
+  // of flow phase; with thousands of rows the extra blocks of the all-reduce would cost more than the
+  // lighter SMs buy, so the spread stops at 8 rows per SM)
+  bool row_spread = n_rows <= 8 * h->num_sms;
   if (const char* rs = getenv("CVO_B200_ROW_SPREAD")) row_spread = row_spread && atoi(rs) != 0;  // measurement aid
   if (row_spread) h->persist_blocks = std::max(1, std::min(h->num_sms * pocc, ((n_rows + 3) / 4 + 3) / 4));
   // brute rows: one warp per row, 4 busy warps per block until every SM has a block
