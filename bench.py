@@ -26,7 +26,7 @@ Workloads (documented choice):
          bound "hbm" because the contract asks for it: algorithmic bytes = (N+M)(16+4F+4C)+256 per
          iteration — the clouds are L2-resident and the path is latency / fp32-issue
          bound, so `frac` is tiny by construction; `traffic` = dram bytes per launch from the
-         committed ncu capture (profiles/traffic.json).
+         committed ncu capture (profiles/traffic.json); null in N>1 lines (captures are 1-GPU runs).
 `pipes`  what actually bounds the dominant kernel: FMA-pipe and issue utilisation from the committed
          ncu --set full captures (profiles/pipes.json), not a derived "fraction of peak".
 `frame_pairs`  frame-pairs/s on KITTI-05-sized clouds: a tracking frame and a first frame.
@@ -568,18 +568,22 @@ def roofline_of(u, g, name, p, m, steps, rows_local, world):
     achieved = launch_units * alg_bytes_iter / t_kernel / 1e9
     key = f"{name}:{kernel.split('|')[0]}"
     roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic.get(key),
+            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic.get(key) if world == 1 else None,
             "peak_source": peak_src, "kernel": kernel, "kernel_us": t_kernel * 1e6,
             "iterations_per_launch": launch_units, "algorithmic_bytes_per_iteration": alg_bytes_iter,
             "kernel_share_of_step": share, "ranks": world,
             "note": "algorithmic bytes = (N_local+M)(16+4F+4C)+256 per iteration (SURVEY.md 8d). The clouds are "
                     "L2-resident; the path is latency / fp32-issue bound, not HBM bound (see pipes)"}
+    if world > 1:  # ncu captures are one-GPU runs: there is no per-rank DRAM figure of a sharded job
+        roof["traffic_note"] = ("null: no per-rank capture (ncu is never run on a multi-rank command); the 1-GPU launch of "
+                                f"the same workload moves {traffic.get(key)} bytes (profiles/traffic.json)")
     pipe = pipes.get(key, {})
     pipe_obj = {"kernel": kernel, "fma_pipe_pct": pipe.get("fma_pipe_pct"), "issue_active_pct": pipe.get("issue_active_pct"),
                 "warps_active_pct": pipe.get("warps_active_pct"), "top_stalls": pipe.get("top_stalls"),
                 "source": pipe.get("source", "no ncu capture committed for this workload/kernel"),
                 "dense_equivalent_pairs_per_s": rows_local * m["M"] * launch_units / t_kernel,
-                "note": "ncu --set full figures of the committed capture (profiles/), not derived numbers; "
+                "note": ("1-GPU capture of the same workload; " if world > 1 else "") +
+                        "ncu --set full figures of the committed capture (profiles/), not derived numbers; "
                         "dense_equivalent = N_local*M pairs per iteration / kernel time (culled pairs counted)"}
     return roof, pipe_obj
 
