@@ -74,3 +74,19 @@ def test_reference_arm_line_on_a_bounded_sample():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
     assert d["product_library_mapped"] is False and d["product_package_imported"] is False
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """N > 1: launched like the product arm; rank 0 alone runs the CPU path (on the N > 1 workload,
+    C4), the other ranks exit 0 without work."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "bench.py"),
+                          "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["config"]["N"] == 200_000 and d["config"]["M"] == 200_000  # BASELINE configs[3]
+    assert d["cpu_baseline"]["sample"] and d["gpu_launches"] == 0
