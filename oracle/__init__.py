@@ -83,6 +83,8 @@ def lib() -> C.CDLL:
         L.oracle_cubic_roots.argtypes = [C.POINTER(C.c_double)] * 3
         L.oracle_exp_sek3.restype = None
         L.oracle_exp_sek3.argtypes = [f32p, C.c_float, f32p]
+        L.oracle_indicator_sequence.restype = None
+        L.oracle_indicator_sequence.argtypes = [C.c_void_p, C.c_int, f32p, C.POINTER(C.c_int), f32p, f32p]
         L.oracle_se3_log_norm.restype = C.c_double
         L.oracle_se3_log_norm.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.oracle_update_tf.restype = None
@@ -273,6 +275,18 @@ def exp_sek3(xi, dt):
     out = np.zeros(12, np.float32)
     L.oracle_exp_sek3(_fp(x), C.c_float(dt), _fp(out))
     return out.reshape(4, 3).T.copy()  # 3x4
+
+
+def indicator_sequence(params: Params, indicators):
+    """A_sparsity_indicator_ell_update (CvoGPU.cu:1167-1285) over a sequence, queues empty at entry:
+    (decisions, start sums, end sums) after every call."""
+    L = lib()
+    x = np.ascontiguousarray(indicators, np.float32)
+    n = int(x.size)
+    dec = np.zeros(n, np.int32)
+    s0, s1 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    L.oracle_indicator_sequence(C.byref(params), n, _fp(x), dec.ctypes.data_as(C.POINTER(C.c_int)), _fp(s0), _fp(s1))
+    return dec, s0, s1
 
 
 def se3_log_norm(dR, dT):

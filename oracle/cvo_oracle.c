@@ -910,6 +910,23 @@ static int sparsity_indicator_ell_update(fqueue* start_q, fqueue* end_q, float* 
   return decrease;
 }
 
+/* Test tap: the queues of one align() (both empty, sums 0 at entry, CvoGPU.cu:1377-1380) fed with
+ * a sequence of indicator values; per call the decision and the two running sums after it. */
+void oracle_indicator_sequence(const cvo_b200_params* params, int n, const float* indicators,
+                               int* decrease, float* start_sums, float* end_sums) {
+  fqueue start_q, end_q;
+  fq_init(&start_q, params->indicator_window_size + 2);
+  fq_init(&end_q, params->indicator_window_size + 2);
+  float start_sum = 0, end_sum = 0;
+  for (int k = 0; k < n; k++) {
+    decrease[k] = sparsity_indicator_ell_update(&start_q, &end_q, &start_sum, &end_sum, indicators[k], params);
+    start_sums[k] = start_sum;
+    end_sums[k] = end_sum;
+  }
+  fq_free(&start_q);
+  fq_free(&end_q);
+}
+
 /* ---------- one iteration / align ---------------------------------------- */
 static double sparse_sum_double(const oracle_sparse* A) {
   double s = 0;

@@ -96,6 +96,10 @@ void oracle_exp_sek3(const float xi[6], float dt, float out12[12]);
  * c0 t^3 + c1 t^2 + c2 t + c3; returns 0 and fills re/im, or -1 if the
  * companion matrix is not finite (Eigen would return NaNs). */
 int oracle_cubic_roots(const double coef[4], double re[3], double im[3]);
+/* CvoGPU.cu:1167-1285 A_sparsity_indicator_ell_update over a sequence of indicators, the queues
+ * empty at entry like in align_impl (:1377-1380); per call: decision, start sum, end sum.  Test tap. */
+void oracle_indicator_sequence(const cvo_b200_params* params, int n, const float* indicators,
+                               int* decrease, float* start_sums, float* end_sums);
 /* Sophus::SE3d(dRT).log().norm(), call site CvoGPU.cu:1473-1476 */
 double oracle_se3_log_norm(const double dR[9], const double dT[3]);
 

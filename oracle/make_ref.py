@@ -16,6 +16,7 @@ Tier 1 (no third-party arithmetic at all, reference text verbatim):
   compute_range_ell                     src/cvo/CvoGPU.cu:86-90
   compute_geometric_type_ip             src/cvo/CvoGPU.cu:203-215
   fill_in_A_mat_gpu  (K1)               src/cvo/CvoGPU.cu:477-593
+  A_sparsity_indicator_ell_update       src/cvo/CvoGPU.cu:1167-1285   (host code: std::queue only; host build)
 Tier 2 (reference text verbatim, but its Eigen fixed-size 3-vector / 3x3 primitives are supplied
 by oracle/ref_mini_eigen.h, OUR stand-in — sum order c0+(c1+c2), documented there):
   skew_gpu                              include/UnifiedCvo/cvo/gpu_utils.cuh:8-15
@@ -24,6 +25,9 @@ by oracle/ref_mini_eigen.h, OUR stand-in — sum order c0+(c1+c2), documented th
   compute_flow_gpu_no_eigen  (K2)       src/cvo/CvoGPU.cu:729-790
   compute_step_size_xi       (K3)       src/cvo/CvoGPU.cu:953-998
   compute_step_size_poly_coeff (K4)     src/cvo/CvoGPU.cu:1001-1082
+  skew<T, RC_MAJOR>                     src/cvo/LieGroup.cpp:11-19    (host build only)
+  Exp_SEK3 (float)                      src/cvo/LieGroup.cpp:245-274  (host build only: the pose
+                                        increment of align_impl, CvoGPU.cu:1462)
 
 Three builds (outputs only under oracle/_ref/):
   libcvo_ref_host.so         g++ -O2 -ffp-contract=off; __global__ -> plain function, the grid is a
@@ -58,12 +62,16 @@ WANTED = [
     ("src/cvo/CvoGPU.cu", r"^\s*float compute_range_ell\(", 86, 1, "compute_range_ell"),
     ("src/cvo/CvoGPU.cu", r"^\s*float compute_geometric_type_ip\(", 204, 1, "compute_geometric_type_ip"),
     ("src/cvo/CvoGPU.cu", r"^\s*void fill_in_A_mat_gpu\(const CvoParams \* cvo_params,", 478, 1, "fill_in_A_mat_gpu"),
+    ("src/cvo/CvoGPU.cu", r"^\s*static bool A_sparsity_indicator_ell_update\(std::queue<float> & indicator_start_queue,", 1167, 1,
+     "A_sparsity_indicator_ell_update"),
     ("include/UnifiedCvo/cvo/gpu_utils.cuh", r"^\s*void skew_gpu\(", 10, 2, "skew_gpu"),
     ("src/cvo/CvoGPU.cu", r"^\s*float mahananobis_distance\(", 152, 2, "mahananobis_distance"),
     ("src/cvo/CvoGPU.cu", r"^\s*void fill_in_A_mat_gpu_dense_mat_kernel\(", 218, 2, "fill_in_A_mat_gpu_dense_mat_kernel"),
     ("src/cvo/CvoGPU.cu", r"^\s*__global__ void compute_flow_gpu_no_eigen\(", 729, 2, "compute_flow_gpu_no_eigen"),
     ("src/cvo/CvoGPU.cu", r"^\s*__global__ void compute_step_size_xi\(", 953, 2, "compute_step_size_xi"),
     ("src/cvo/CvoGPU.cu", r"^\s*__global__ void compute_step_size_poly_coeff\(", 1001, 2, "compute_step_size_poly_coeff"),
+    ("src/cvo/LieGroup.cpp", r"^\s*Eigen::Matrix<T, 3, 3, RC_MAJOR> skew\(const Eigen::Matrix<T, 3, 1>& v\) \{", 12, 2, "skew"),
+    ("src/cvo/LieGroup.cpp", r"^\s*Eigen::Matrix<float, 3, 4> Exp_SEK3\(const Eigen::Matrix<float, 6,1>& v, float dt\) \{", 245, 2, "Exp_SEK3"),
 ]
 
 

@@ -51,6 +51,11 @@ def lib(kind: str = "host") -> C.CDLL:
         L.cvo_ref_step_rows.restype = C.c_int
         L.cvo_ref_step_rows.argtypes = [f32p, f32p, C.c_float, C.c_float, C.c_int, C.c_int, f32p,
                                         C.c_int, f32p, C.c_int, f32p, i32p, f64p, f64p, f64p, f64p]
+        if kind == "host":  # host code of the reference (LieGroup.cpp): host build only
+            L.cvo_ref_indicator_sequence.restype = C.c_int
+            L.cvo_ref_indicator_sequence.argtypes = [C.c_void_p, C.c_int, f32p, i32p, f32p, f32p]
+            L.cvo_ref_exp_sek3.restype = C.c_int
+            L.cvo_ref_exp_sek3.argtypes = [f32p, C.c_float, f32p]
         assert L.cvo_ref_num_classes() == NUM_CLASSES and L.cvo_ref_feature_dimensions() == FEATURE_DIMENSIONS
         _libs[kind] = L
     return _libs[kind]
@@ -160,3 +165,26 @@ def step_rows(omega, v, ell: float, ell_init: float, is_using_range_ell: int, sr
     if rc != 0:
         raise RuntimeError(f"cvo_ref_step_rows failed: {rc}")
     return np.stack(outs, axis=1)
+
+
+def exp_sek3(xi, dt: float):
+    """The reference's Exp_SEK3(v, dt) (LieGroup.cpp:245-274, tier 2: over oracle/ref_mini_eigen.h),
+    3x4 [R | t]."""
+    x = np.ascontiguousarray(xi, np.float32).reshape(6)
+    out = np.zeros(12, np.float32)
+    rc = lib("host").cvo_ref_exp_sek3(_f(x), C.c_float(dt), _f(out))
+    assert rc == 0
+    return out.reshape(4, 3).T.copy()
+
+
+def indicator_sequence(params, indicators):
+    """The reference's A_sparsity_indicator_ell_update (CvoGPU.cu:1167-1285, tier 1: std::queue
+    only) fed with a sequence of indicators, queues empty at entry: (decisions, start sums, end sums)."""
+    x = np.ascontiguousarray(indicators, np.float32)
+    n = int(x.size)
+    dec = np.zeros(n, np.int32)
+    s0, s1 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    rc = lib("host").cvo_ref_indicator_sequence(C.byref(params), n, _f(x), dec.ctypes.data_as(C.POINTER(C.c_int)),
+                                                _f(s0), _f(s1))
+    assert rc == 0
+    return dec, s0, s1

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <queue>
 #include <vector>
 
 #include "../include/cvo_b200.h"
@@ -85,6 +86,16 @@ static_assert(sizeof(CvoParams) == sizeof(cvo_b200_params), "cvo_b200_params mir
 #include "compute_flow_gpu_no_eigen.inc"
 #include "compute_step_size_xi.inc"
 #include "compute_step_size_poly_coeff.inc"
+#ifdef CVO_REF_HOST_BUILD
+// ---- tier 1, host code of the reference: the indicator queues of align_impl (std::queue only)
+#include "A_sparsity_indicator_ell_update.inc"
+#endif
+#ifdef CVO_REF_HOST_BUILD
+// ---- tier 2, host code of the reference: the pose increment of align_impl (CvoGPU.cu:1462)
+const float TOLERANCE = 1e-6;  // LieGroup.cpp:9
+#include "skew.inc"
+#include "Exp_SEK3.inc"
+#endif
 }  // namespace cvo
 
 using cvo::CvoParams;
@@ -239,6 +250,37 @@ int cvo_ref_build_kind(void) {
   return 2;
 #endif
 }
+#ifdef CVO_REF_HOST_BUILD
+// The reference's A_sparsity_indicator_ell_update (CvoGPU.cu:1167-1285) over a sequence of
+// indicators with the state align_impl gives it (:1377-1380: both queues empty, both sums 0).
+int cvo_ref_indicator_sequence(const cvo_b200_params* params, int n, const float* indicators, int* decrease,
+                               float* start_sums, float* end_sums) {
+  CvoParams p;
+  memcpy(&p, params, sizeof(p));
+  std::queue<float> indicator_start_queue, indicator_end_queue;
+  float indicator_start_sum = 0, indicator_end_sum = 0;
+  for (int k = 0; k < n; k++) {
+    decrease[k] = cvo::A_sparsity_indicator_ell_update(indicator_start_queue, indicator_end_queue, indicator_start_sum,
+                                                       indicator_end_sum, indicators[k], p)
+                      ? 1
+                      : 0;
+    start_sums[k] = indicator_start_sum;
+    end_sums[k] = indicator_end_sum;
+  }
+  return 0;
+}
+#endif
+#ifdef CVO_REF_HOST_BUILD
+// The reference's Exp_SEK3(v, dt) (LieGroup.cpp:245-274): out12 = the 3x4 result, column-major
+// (R's columns, then the translation).
+int cvo_ref_exp_sek3(const float xi[6], float dt, float out12[12]) {
+  Eigen::Matrix<float, 6, 1> v;
+  for (int i = 0; i < 6; i++) v[i] = xi[i];
+  const Eigen::Matrix<float, 3, 4> X = cvo::Exp_SEK3(v, dt);
+  for (int i = 0; i < 12; i++) out12[i] = X.d[i];
+  return 0;
+}
+#endif
 int cvo_ref_num_classes(void) { return NUM_CLASSES; }
 int cvo_ref_feature_dimensions(void) { return FEATURE_DIMENSIONS; }
 int cvo_ref_sizeof_point(void) { return (int)sizeof(CvoPoint); }

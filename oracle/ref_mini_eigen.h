@@ -1,5 +1,6 @@
 // ref_mini_eigen.h — OUR stand-in for the handful of Eigen fixed-size operations that the
-// reference's kernels K1b, K2, K3, K4 use (oracle/make_ref.py, tier 2).  TEST INFRASTRUCTURE.
+// reference's kernels K1b, K2, K3, K4 and its host function Exp_SEK3 use (oracle/make_ref.py,
+// tier 2).  TEST INFRASTRUCTURE.
 //
 // Eigen 3.3.9 (README.md:28 of the reference) is not in this image, so the tier-2 pin compiles the
 // reference's own statements against this header instead.  What that pins: every formula, the
@@ -40,8 +41,22 @@ struct redux_tree<T, N, Start, 1> {
   ME_HD static T run(const F& f) { return f(Start); }
 };
 
-template <typename T, int R, int C>
+enum { ColMajor = 0, RowMajor = 1 };  // Eigen/src/Core/util/Constants.h; only ColMajor is instantiated here
+
+template <typename T, int R, int C, int Opt = ColMajor>
 struct Matrix;
+
+// X.block<BR, BC>(i, j) = M  (Exp_SEK3, LieGroup.cpp:266-269)
+template <typename T, int R, int C, int BR, int BC>
+struct BlockRef {
+  Matrix<T, R, C>* m;
+  int i0, j0;
+  ME_HD BlockRef& operator=(const Matrix<T, BR, BC>& o) {
+    for (int j = 0; j < BC; j++)
+      for (int i = 0; i < BR; i++) (*m)(i0 + i, j0 + j) = o(i, j);
+    return *this;
+  }
+};
 
 template <typename T, int R, int C>
 struct CommaInit {
@@ -53,8 +68,9 @@ struct CommaInit {
   }
 };
 
-template <typename T, int R, int C>
+template <typename T, int R, int C, int Opt>
 struct Matrix {
+  static_assert(Opt == ColMajor, "the stand-in stores column-major only");
   T d[R * C];  // column-major (vectors: contiguous)
   ME_HD Matrix() {}
   ME_HD Matrix(T a, T b, T c) { d[0] = a; d[1] = b; d[2] = c; }
@@ -62,6 +78,27 @@ struct Matrix {
     Matrix m;
     for (int i = 0; i < R * C; i++) m.d[i] = T(0);
     return m;
+  }
+  ME_HD static Matrix Identity() {
+    Matrix m = Zero();
+    for (int i = 0; i < (R < C ? R : C); i++) m.d[i * R + i] = T(1);
+    return m;
+  }
+  // v.head(3), v.segment<3>(k), X.block<3, 3>(i, j) = ... as Exp_SEK3 uses them (LieGroup.cpp:249-269)
+  ME_HD Matrix<T, 3, 1> head(int n) const {
+    Matrix<T, 3, 1> r;
+    for (int i = 0; i < 3; i++) r.d[i] = (n == 3) ? d[i] : T(NAN);
+    return r;
+  }
+  template <int N>
+  ME_HD Matrix<T, N, 1> segment(int start) const {
+    Matrix<T, N, 1> r;
+    for (int i = 0; i < N; i++) r.d[i] = d[start + i];
+    return r;
+  }
+  template <int BR, int BC>
+  ME_HD BlockRef<T, R, C, BR, BC> block(int i, int j) {
+    return BlockRef<T, R, C, BR, BC>{this, i, j};
   }
   ME_HD T& operator()(int i, int j) { return d[j * R + i]; }
   ME_HD const T& operator()(int i, int j) const { return d[j * R + i]; }

@@ -187,3 +187,60 @@ def test_flow_and_step_rows_k2_k3_k4(range_ell):
     got = oracle.step_rows(p, cs, ym, A, tw[:3], tw[3:], ell)
     assert np.array_equal(got, want)
     assert np.abs(want).sum() > 0
+
+
+def test_exp_sek3_pose_increment_matches_the_reference_text():
+    """a11: oracle_exp_sek3 == the reference's Exp_SEK3 (LieGroup.cpp:245-274, called at
+    CvoGPU.cu:1462) compiled from its own text over the mini-Eigen, bit for bit: the small-angle
+    branch (theta < 1e-6), unit twists at the step sizes the loop takes, large rotations."""
+    rng = np.random.default_rng(20011)
+    cases = []
+    for _ in range(300):  # what align_impl passes: the jointly normalised twist, a small step
+        xi = rng.normal(size=6).astype(np.float32)
+        xi /= np.float32(np.linalg.norm(xi))
+        cases.append((xi, float(np.float32(10.0 ** rng.uniform(-6, -0.1)))))
+    for _ in range(100):  # arbitrary twists and steps, up to several turns
+        cases.append((rng.normal(scale=3.0, size=6).astype(np.float32), float(np.float32(rng.uniform(0, 2.5)))))
+    for scale in (0.0, 1e-9, 5e-7, 0.99e-6, 1.01e-6, 1e-5):  # around TOLERANCE
+        xi = np.array([scale, 0, 0, 0.3, -0.2, 0.9], np.float32)
+        cases.append((xi, 0.8))
+        xi = np.concatenate([(rng.normal(size=3) * scale).astype(np.float32), rng.normal(size=3).astype(np.float32)])
+        cases.append((xi, 0.37))
+    worst = 0
+    for xi, dt in cases:
+        got = oracle.exp_sek3(xi, dt)
+        want = ref.exp_sek3(xi, dt)
+        assert got.shape == want.shape == (3, 4)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (xi, dt, got, want)
+        # and it is a rigid motion to float accuracy (not a tautology of two equal mistakes)
+        R = want[:, :3].astype(np.float64)
+        worst = max(worst, float(np.abs(R @ R.T - np.eye(3)).max()))
+    assert worst < 5e-6
+
+
+@pytest.mark.parametrize("window", [1, 2, 3, 10, 15, 50])
+def test_indicator_queues_match_the_reference_text(window):
+    """a12: the oracle's indicator queues == the reference's A_sparsity_indicator_ell_update
+    (CvoGPU.cu:1167-1285) compiled from its own text (std::queue only, tier 1) - decisions and both
+    running float sums after every call, bit for bit, over sequences that plateau (decays fire and
+    clear the queues), drift, jump and contain zeros."""
+    rng = np.random.default_rng(7000 + window)
+    p = geometric_params()
+    p.indicator_window_size = window
+    fired = 0
+    for thr in (0.001, 0.01, 0.02, 0.2):
+        p.indicator_stable_threshold = thr
+        n = 40 * window + 60
+        plateau = np.full(n, 3.25, np.float32) * (1 + rng.normal(scale=thr / 4, size=n)).astype(np.float32)
+        drift = (5.0 * np.exp(-np.arange(n) / (3.0 * window + 5))).astype(np.float32) + np.float32(0.5)
+        jumps = plateau.copy()
+        jumps[:: 2 * window + 3] *= np.float32(1.0 + 4 * thr)
+        sparse = np.where(rng.random(n) < 0.3, 0.0, rng.random(n)).astype(np.float32)
+        for seq in (plateau, drift, jumps, sparse, np.concatenate([drift, plateau])):
+            got = oracle.indicator_sequence(p, seq)
+            want = ref.indicator_sequence(p, seq)
+            assert np.array_equal(got[0], want[0])
+            for a, b in zip(got[1:], want[1:]):
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+            fired += int(want[0].sum())
+    assert fired > 0  # the clear-on-decay branch ran
