@@ -54,6 +54,8 @@ def lib(kind: str = "host") -> C.CDLL:
         if kind == "host":  # host code of the reference (LieGroup.cpp): host build only
             L.cvo_ref_indicator_sequence.restype = C.c_int
             L.cvo_ref_indicator_sequence.argtypes = [C.c_void_p, C.c_int, f32p, i32p, f32p, f32p]
+            L.cvo_ref_update_tf_and_transform.restype = C.c_int
+            L.cvo_ref_update_tf_and_transform.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_int, f32p, f32p]
             L.cvo_ref_exp_sek3.restype = C.c_int
             L.cvo_ref_exp_sek3.argtypes = [f32p, C.c_float, f32p]
         assert L.cvo_ref_num_classes() == NUM_CLASSES and L.cvo_ref_feature_dimensions() == FEATURE_DIMENSIONS
@@ -188,3 +190,17 @@ def indicator_sequence(params, indicators):
                                                 _f(s0), _f(s1))
     assert rc == 0
     return dec, s0, s1
+
+
+def update_tf_and_transform(R, T, xyz):
+    """The reference's update_tf (CvoGPU.cu:94-112) and, with the inverse pose it uploads, its point
+    transform transform_point_R_T (CvoGPU_impl.cu:31-82) on xyz (tier 2: over the mini-Eigen).
+    R 3x3, T 3; returns (Rinv 3x3, Tinv 3, transform 4x4, moved n x 3)."""
+    r = np.ascontiguousarray(np.asarray(R, np.float32).T).reshape(9)  # column-major
+    t = np.ascontiguousarray(T, np.float32).reshape(3)
+    y = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    rinv, tinv, tf = np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(16, np.float32)
+    out = np.zeros_like(y)
+    rc = lib("host").cvo_ref_update_tf_and_transform(_f(r), _f(t), _f(rinv), _f(tinv), _f(tf), int(y.shape[0]), _f(y), _f(out))
+    assert rc == 0
+    return rinv.reshape(3, 3).T.copy(), tinv, tf.reshape(4, 4).T.copy(), out

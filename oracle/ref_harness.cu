@@ -91,6 +91,29 @@ static_assert(sizeof(CvoParams) == sizeof(cvo_b200_params), "cvo_b200_params mir
 #include "A_sparsity_indicator_ell_update.inc"
 #endif
 #ifdef CVO_REF_HOST_BUILD
+}  // namespace cvo
+namespace thrust {
+template <typename Arg, typename Res>
+struct unary_function {};
+}  // namespace thrust
+namespace cvo {
+// ---- tier 2: the inverse pose (update_tf, a3) and the point transform (transform_point_R_T, a4)
+typedef Eigen::Matrix<float, 3, 3> Mat33f;  // utils/data_type.hpp:95
+typedef Eigen::Matrix<float, 3, 1> Vec3f;   // :98
+typedef Eigen::Matrix<float, 4, 4> Mat44f;  // :137
+struct CvoState {  // the two members update_tf writes (cvo/CvoState.cuh:50-51)
+  Eigen::Matrix3f* R_gpu;
+  Eigen::Vector3f* T_gpu;
+};
+enum { cudaMemcpyHostToDevice = 1 };
+static inline int cudaMemcpy(void* dst, const void* src, size_t n, int) {
+  memcpy(dst, src, n);
+  return 0;
+}
+#include "update_tf.inc"
+#include "transform_point_R_T.inc"
+#endif
+#ifdef CVO_REF_HOST_BUILD
 // ---- tier 2, host code of the reference: the pose increment of align_impl (CvoGPU.cu:1462)
 const float TOLERANCE = 1e-6;  // LieGroup.cpp:9
 #include "skew.inc"
@@ -266,6 +289,37 @@ int cvo_ref_indicator_sequence(const cvo_b200_params* params, int n, const float
                       : 0;
     start_sums[k] = indicator_start_sum;
     end_sums[k] = indicator_end_sum;
+  }
+  return 0;
+}
+#endif
+#ifdef CVO_REF_HOST_BUILD
+// The reference's update_tf (CvoGPU.cu:94-112) followed by its point transform
+// (transform_point_R_T, CvoGPU_impl.cu:31-82, as transform_pointcloud_thrust applies it at
+// CvoGPU.cu:1404 with update_normal_and_cov = false): R, out_Rinv column-major 3x3, transform16
+// column-major 4x4, xyz / out n x 3.
+int cvo_ref_update_tf_and_transform(const float R[9], const float T[3], float out_Rinv[9], float out_Tinv[3],
+                                    float transform16[16], int n, const float* xyz, float* out) {
+  cvo::Mat33f Rm, Rg;
+  cvo::Vec3f Tm, Tg;
+  for (int i = 0; i < 9; i++) Rm.d[i] = R[i];
+  for (int i = 0; i < 3; i++) Tm.d[i] = T[i];
+  cvo::CvoState st{&Rg, &Tg};
+  cvo::Mat44f tf = cvo::Mat44f::Zero();
+  cvo::update_tf(Rm, Tm, &st, tf);
+  for (int i = 0; i < 9; i++) out_Rinv[i] = Rg.d[i];
+  for (int i = 0; i < 3; i++) out_Tinv[i] = Tg.d[i];
+  for (int i = 0; i < 16; i++) transform16[i] = tf.d[i];
+  cvo::transform_point_R_T f(&Rg, &Tg, false);
+  for (int j = 0; j < n; j++) {
+    CvoPoint p;
+    p.x = xyz[3 * j];
+    p.y = xyz[3 * j + 1];
+    p.z = xyz[3 * j + 2];
+    const CvoPoint q = f(p);
+    out[3 * j] = q.x;
+    out[3 * j + 1] = q.y;
+    out[3 * j + 2] = q.z;
   }
   return 0;
 }

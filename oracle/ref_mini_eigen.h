@@ -1,6 +1,6 @@
 // ref_mini_eigen.h — OUR stand-in for the handful of Eigen fixed-size operations that the
-// reference's kernels K1b, K2, K3, K4 and its host function Exp_SEK3 use (oracle/make_ref.py,
-// tier 2).  TEST INFRASTRUCTURE.
+// reference's kernels K1b, K2, K3, K4, its point transform and its host functions update_tf and
+// Exp_SEK3 use (oracle/make_ref.py, tier 2).  TEST INFRASTRUCTURE.
 //
 // Eigen 3.3.9 (README.md:28 of the reference) is not in this image, so the tier-2 pin compiles the
 // reference's own statements against this header instead.  What that pins: every formula, the
@@ -46,7 +46,19 @@ enum { ColMajor = 0, RowMajor = 1 };  // Eigen/src/Core/util/Constants.h; only C
 template <typename T, int R, int C, int Opt = ColMajor>
 struct Matrix;
 
-// X.block<BR, BC>(i, j) = M  (Exp_SEK3, LieGroup.cpp:266-269)
+// X.block<BR, BC>(i, j) = M  (Exp_SEK3, LieGroup.cpp:266-269; update_tf, CvoGPU.cu:102-103) and
+// X.block<BR, BC>(i, j) << a, b, ...  (update_tf, CvoGPU.cu:104: row-major fill of the block)
+template <typename T, int R, int C, int BR, int BC>
+struct BlockRef;
+template <typename T, int R, int C, int BR, int BC>
+struct BlockComma {
+  BlockRef<T, R, C, BR, BC>* b;
+  int k;
+  ME_HD BlockComma& operator,(T v) {
+    b->set_rowmajor(k++, v);
+    return *this;
+  }
+};
 template <typename T, int R, int C, int BR, int BC>
 struct BlockRef {
   Matrix<T, R, C>* m;
@@ -56,7 +68,16 @@ struct BlockRef {
       for (int i = 0; i < BR; i++) (*m)(i0 + i, j0 + j) = o(i, j);
     return *this;
   }
+  ME_HD void set_rowmajor(int k, T v) { (*m)(i0 + k / BC, j0 + k % BC) = v; }
+  ME_HD BlockComma<T, R, C, BR, BC> operator<<(T v) {
+    set_rowmajor(0, v);
+    return BlockComma<T, R, C, BR, BC>{this, 1};
+  }
 };
+
+// Eigen::Ref<M> as a by-value function parameter (update_tf): a writable view of the caller's matrix
+template <typename M>
+using Ref = M&;
 
 template <typename T, int R, int C>
 struct CommaInit {
@@ -159,6 +180,7 @@ struct Matrix {
       }
     return r;
   }
+  ME_HD Matrix eval() const { return *this; }
   ME_HD T value() const {
     static_assert(R == 1 && C == 1, "value() needs a 1x1 expression");
     return d[0];

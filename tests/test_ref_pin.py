@@ -244,3 +244,36 @@ def test_indicator_queues_match_the_reference_text(window):
                 assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
             fired += int(want[0].sum())
     assert fired > 0  # the clear-on-decay branch ran
+
+
+def test_inverse_pose_and_point_transform_match_the_reference_text():
+    """a3 / a4: oracle_update_tf + oracle_transform == the reference's update_tf (CvoGPU.cu:94-112)
+    and transform_point_R_T (CvoGPU_impl.cu:31-82) compiled from their own text over the
+    mini-Eigen, bit for bit: the inverse pose it uploads, the 4x4 it returns, and the moved target."""
+    import ctypes as C
+
+    rng = np.random.default_rng(94112)
+    L = oracle.lib()
+    f32p = C.POINTER(C.c_float)
+    y = np.concatenate([rng.normal(scale=10.0, size=(2000, 3)), rng.normal(scale=1e-3, size=(50, 3)),
+                        np.zeros((1, 3))]).astype(np.float32)
+    for k in range(40):
+        # rotations as the loop leaves them: products of float matrices, not re-orthogonalised
+        R = np.eye(3, dtype=np.float32)
+        for _ in range(1 + k % 5):
+            w = rng.normal(scale=0.3, size=3)
+            th = np.linalg.norm(w)
+            K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]) / th
+            R = (R.astype(np.float64) @ (np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K)).astype(np.float32)
+        T = rng.normal(scale=[0.1, 1.0, 20.0][k % 3], size=3).astype(np.float32)
+        rinv_w, tinv_w, tf_w, moved_w = ref.update_tf_and_transform(R, T, y)
+        Rc = np.ascontiguousarray(R.T).reshape(9)
+        rinv, tinv, tf = np.zeros(9, np.float32), np.zeros(3, np.float32), np.zeros(16, np.float32)
+        L.oracle_update_tf(Rc.ctypes.data_as(f32p), T.ctypes.data_as(f32p), rinv.ctypes.data_as(f32p),
+                           tinv.ctypes.data_as(f32p), tf.ctypes.data_as(f32p))
+        assert np.array_equal(rinv.reshape(3, 3).T.view(np.uint32), rinv_w.view(np.uint32))
+        assert np.array_equal(tinv.view(np.uint32), tinv_w.view(np.uint32))
+        assert np.array_equal(tf.reshape(4, 4).T.view(np.uint32), tf_w.view(np.uint32))
+        moved = oracle.transform(R, T, y)
+        assert np.array_equal(moved.view(np.uint32), moved_w.view(np.uint32))
+        assert np.abs(moved.astype(np.float64) - (y.astype(np.float64) - T) @ R.astype(np.float64)).max() < 1e-3
