@@ -27,6 +27,8 @@ by oracle/ref_mini_eigen.h, OUR stand-in — sum order c0+(c1+c2), documented th
   compute_step_size_poly_coeff (K4)     src/cvo/CvoGPU.cu:1001-1082
   update_tf (the 4-argument overload)   src/cvo/CvoGPU.cu:94-112      (host build only; cudaMemcpy -> memcpy)
   transform_point_R_T                   src/cvo/CvoGPU_impl.cu:31-82  (host build only)
+  transform_point_pose_vec              src/cvo/CvoGPU_impl.cu:84-150 (host build only; the frames of the
+                                        multi-frame edge update)
   skew<T, RC_MAJOR>                     src/cvo/LieGroup.cpp:11-19    (host build only)
   Exp_SEK3 (float)                      src/cvo/LieGroup.cpp:245-274  (host build only: the pose
                                         increment of align_impl, CvoGPU.cu:1462)
@@ -75,6 +77,8 @@ WANTED = [
     ("src/cvo/CvoGPU.cu", r"^\s*void update_tf\(const Mat33f & R, const Vec3f & T,\s*$", 94, 2, "update_tf"),
     ("src/cvo/CvoGPU_impl.cu", r"^\s*struct transform_point_R_T : public thrust::unary_function<CvoPoint,CvoPoint>", 31, 2,
      "transform_point_R_T"),
+    ("src/cvo/CvoGPU_impl.cu", r"^\s*struct transform_point_pose_vec : public thrust::unary_function<CvoPoint,CvoPoint>", 84, 2,
+     "transform_point_pose_vec"),
     ("src/cvo/LieGroup.cpp", r"^\s*Eigen::Matrix<T, 3, 3, RC_MAJOR> skew\(const Eigen::Matrix<T, 3, 1>& v\) \{", 12, 2, "skew"),
     ("src/cvo/LieGroup.cpp", r"^\s*Eigen::Matrix<float, 3, 4> Exp_SEK3\(const Eigen::Matrix<float, 6,1>& v, float dt\) \{", 245, 2, "Exp_SEK3"),
 ]

@@ -56,6 +56,8 @@ def lib(kind: str = "host") -> C.CDLL:
             L.cvo_ref_indicator_sequence.argtypes = [C.c_void_p, C.c_int, f32p, i32p, f32p, f32p]
             L.cvo_ref_update_tf_and_transform.restype = C.c_int
             L.cvo_ref_update_tf_and_transform.argtypes = [f32p, f32p, f32p, f32p, f32p, C.c_int, f32p, f32p]
+            L.cvo_ref_transform_pose_vec.restype = C.c_int
+            L.cvo_ref_transform_pose_vec.argtypes = [f32p, C.c_int, f32p, f32p]
             L.cvo_ref_exp_sek3.restype = C.c_int
             L.cvo_ref_exp_sek3.argtypes = [f32p, C.c_float, f32p]
         assert L.cvo_ref_num_classes() == NUM_CLASSES and L.cvo_ref_feature_dimensions() == FEATURE_DIMENSIONS
@@ -204,3 +206,14 @@ def update_tf_and_transform(R, T, xyz):
     rc = lib("host").cvo_ref_update_tf_and_transform(_f(r), _f(t), _f(rinv), _f(tinv), _f(tf), int(y.shape[0]), _f(y), _f(out))
     assert rc == 0
     return rinv.reshape(3, 3).T.copy(), tinv, tf.reshape(4, 4).T.copy(), out
+
+
+def transform_pose_vec(pose12, xyz):
+    """The reference's transform_point_pose_vec (CvoGPU_impl.cu:84-150, tier 2: over the mini-Eigen):
+    x' = P [x 1]^T with P the frame's row-major 3x4 pose."""
+    P = np.ascontiguousarray(pose12, np.float32).reshape(12)
+    x = np.ascontiguousarray(xyz, np.float32).reshape(-1, 3)
+    out = np.zeros_like(x)
+    rc = lib("host").cvo_ref_transform_pose_vec(_f(P), int(x.shape[0]), _f(x), _f(out))
+    assert rc == 0
+    return out

@@ -112,6 +112,7 @@ static inline int cudaMemcpy(void* dst, const void* src, size_t n, int) {
 }
 #include "update_tf.inc"
 #include "transform_point_R_T.inc"
+#include "transform_point_pose_vec.inc"
 #endif
 #ifdef CVO_REF_HOST_BUILD
 // ---- tier 2, host code of the reference: the pose increment of align_impl (CvoGPU.cu:1462)
@@ -311,6 +312,26 @@ int cvo_ref_update_tf_and_transform(const float R[9], const float T[3], float ou
   for (int i = 0; i < 3; i++) out_Tinv[i] = Tg.d[i];
   for (int i = 0; i < 16; i++) transform16[i] = tf.d[i];
   cvo::transform_point_R_T f(&Rg, &Tg, false);
+  for (int j = 0; j < n; j++) {
+    CvoPoint p;
+    p.x = xyz[3 * j];
+    p.y = xyz[3 * j + 1];
+    p.z = xyz[3 * j + 2];
+    const CvoPoint q = f(p);
+    out[3 * j] = q.x;
+    out[3 * j + 1] = q.y;
+    out[3 * j + 2] = q.z;
+  }
+  return 0;
+}
+#endif
+#ifdef CVO_REF_HOST_BUILD
+// The reference's transform_point_pose_vec (CvoGPU_impl.cu:84-150; CvoFrameGPU::transform_pointcloud
+// applies it with the frame's row-major 3x4 pose): xyz / out n x 3.
+int cvo_ref_transform_pose_vec(const float pose12[12], int n, const float* xyz, float* out) {
+  float pose[12];
+  memcpy(pose, pose12, sizeof(pose));
+  cvo::transform_point_pose_vec f(pose, false);
   for (int j = 0; j < n; j++) {
     CvoPoint p;
     p.x = xyz[3 * j];

@@ -41,37 +41,61 @@ struct redux_tree<T, N, Start, 1> {
   ME_HD static T run(const F& f) { return f(Start); }
 };
 
-enum { ColMajor = 0, RowMajor = 1 };  // Eigen/src/Core/util/Constants.h; only ColMajor is instantiated here
+enum { ColMajor = 0, RowMajor = 1 };  // Eigen/src/Core/util/Constants.h
 
 template <typename T, int R, int C, int Opt = ColMajor>
 struct Matrix;
 
-// X.block<BR, BC>(i, j) = M  (Exp_SEK3, LieGroup.cpp:266-269; update_tf, CvoGPU.cu:102-103) and
-// X.block<BR, BC>(i, j) << a, b, ...  (update_tf, CvoGPU.cu:104: row-major fill of the block)
-template <typename T, int R, int C, int BR, int BC>
+// X.block<BR, BC>(i, j) = M  (Exp_SEK3, LieGroup.cpp:266-269; update_tf, CvoGPU.cu:102-103),
+// X.block<BR, BC>(i, j) << a, b, ...  (update_tf, CvoGPU.cu:104: row-major fill of the block) and
+// Matrix<...> R = T.block<3, 3>(0, 0)  (transform_point_pose_vec, CvoGPU_impl.cu:141).  P = the
+// parent matrix type.
+template <typename P, int BR, int BC>
 struct BlockRef;
-template <typename T, int R, int C, int BR, int BC>
+template <typename P, int BR, int BC>
 struct BlockComma {
-  BlockRef<T, R, C, BR, BC>* b;
+  BlockRef<P, BR, BC>* b;
   int k;
-  ME_HD BlockComma& operator,(T v) {
+  ME_HD BlockComma& operator,(typename P::Scalar v) {
     b->set_rowmajor(k++, v);
     return *this;
   }
 };
-template <typename T, int R, int C, int BR, int BC>
+template <typename P, int BR, int BC>
 struct BlockRef {
-  Matrix<T, R, C>* m;
+  typedef typename P::Scalar T;
+  P* m;
   int i0, j0;
-  ME_HD BlockRef& operator=(const Matrix<T, BR, BC>& o) {
+  template <int O>
+  ME_HD BlockRef& operator=(const Matrix<T, BR, BC, O>& o) {
     for (int j = 0; j < BC; j++)
       for (int i = 0; i < BR; i++) (*m)(i0 + i, j0 + j) = o(i, j);
     return *this;
   }
+  template <int O>
+  ME_HD operator Matrix<T, BR, BC, O>() const {
+    Matrix<T, BR, BC, O> r;
+    for (int j = 0; j < BC; j++)
+      for (int i = 0; i < BR; i++) r(i, j) = (*m)(i0 + i, j0 + j);
+    return r;
+  }
   ME_HD void set_rowmajor(int k, T v) { (*m)(i0 + k / BC, j0 + k % BC) = v; }
-  ME_HD BlockComma<T, R, C, BR, BC> operator<<(T v) {
+  ME_HD BlockComma<P, BR, BC> operator<<(T v) {
     set_rowmajor(0, v);
-    return BlockComma<T, R, C, BR, BC>{this, 1};
+    return BlockComma<P, BR, BC>{this, 1};
+  }
+};
+
+// Eigen::Map<M>(ptr): the caller's array viewed as an M in M's own storage order
+// (transform_point_pose_vec, CvoGPU_impl.cu:117-119: a row-major 3x4 pose)
+template <typename M>
+struct Map {
+  typename M::Scalar* p;
+  ME_HD explicit Map(typename M::Scalar* q) : p(q) {}
+  ME_HD operator M() const {
+    M m;
+    for (int i = 0; i < M::Size; i++) m.d[i] = p[i];
+    return m;
   }
 };
 
@@ -91,8 +115,9 @@ struct CommaInit {
 
 template <typename T, int R, int C, int Opt>
 struct Matrix {
-  static_assert(Opt == ColMajor, "the stand-in stores column-major only");
-  T d[R * C];  // column-major (vectors: contiguous)
+  typedef T Scalar;
+  enum { Size = R * C };
+  T d[R * C];  // in the storage order Opt names (vectors: contiguous)
   ME_HD Matrix() {}
   ME_HD Matrix(T a, T b, T c) { d[0] = a; d[1] = b; d[2] = c; }
   ME_HD static Matrix Zero() {
@@ -102,7 +127,7 @@ struct Matrix {
   }
   ME_HD static Matrix Identity() {
     Matrix m = Zero();
-    for (int i = 0; i < (R < C ? R : C); i++) m.d[i * R + i] = T(1);
+    for (int i = 0; i < (R < C ? R : C); i++) m(i, i) = T(1);
     return m;
   }
   // v.head(3), v.segment<3>(k), X.block<3, 3>(i, j) = ... as Exp_SEK3 uses them (LieGroup.cpp:249-269)
@@ -118,11 +143,11 @@ struct Matrix {
     return r;
   }
   template <int BR, int BC>
-  ME_HD BlockRef<T, R, C, BR, BC> block(int i, int j) {
-    return BlockRef<T, R, C, BR, BC>{this, i, j};
+  ME_HD BlockRef<Matrix, BR, BC> block(int i, int j) {
+    return BlockRef<Matrix, BR, BC>{this, i, j};
   }
-  ME_HD T& operator()(int i, int j) { return d[j * R + i]; }
-  ME_HD const T& operator()(int i, int j) const { return d[j * R + i]; }
+  ME_HD T& operator()(int i, int j) { return d[Opt == RowMajor ? i * C + j : j * R + i]; }
+  ME_HD const T& operator()(int i, int j) const { return d[Opt == RowMajor ? i * C + j : j * R + i]; }
   ME_HD T& operator()(int i) { return d[i]; }
   ME_HD const T& operator()(int i) const { return d[i]; }
   ME_HD T& operator[](int i) { return d[i]; }
@@ -170,8 +195,8 @@ struct Matrix {
     for (int i = 0; i < R * C; i++) r.d[i] = d[i] / st;
     return r;
   }
-  template <int C2>
-  ME_HD Matrix<T, R, C2> operator*(const Matrix<T, C, C2>& o) const {
+  template <int C2, int O2>
+  ME_HD Matrix<T, R, C2> operator*(const Matrix<T, C, C2, O2>& o) const {
     Matrix<T, R, C2> r;
     for (int i = 0; i < R; i++)
       for (int j = 0; j < C2; j++) {
@@ -224,6 +249,7 @@ ME_HD Matrix<T, R, C> operator*(int s, const Matrix<T, R, C>& m) { return m * s;
 typedef Matrix<float, 3, 1> Vector3f;
 typedef Matrix<double, 3, 1> Vector3d;
 typedef Matrix<float, 3, 3> Matrix3f;
+typedef Matrix<float, 4, 1> Vector4f;
 typedef Matrix<float, 1, 3> Vector3f_row;  // CvoState.cuh:12 of the reference
 
 }  // namespace Eigen

@@ -277,3 +277,21 @@ def test_inverse_pose_and_point_transform_match_the_reference_text():
         moved = oracle.transform(R, T, y)
         assert np.array_equal(moved.view(np.uint32), moved_w.view(np.uint32))
         assert np.abs(moved.astype(np.float64) - (y.astype(np.float64) - T) @ R.astype(np.float64)).max() < 1e-3
+
+
+def test_frame_pose_transform_matches_the_reference_text():
+    """N3: oracle_transform_pose_vec == the reference's transform_point_pose_vec
+    (CvoGPU_impl.cu:84-150: a row-major 3x4 pose mapped onto [x y z 1]) compiled from its own text
+    over the mini-Eigen, bit for bit."""
+    rng = np.random.default_rng(84150)
+    x = np.concatenate([rng.normal(scale=12.0, size=(3000, 3)), np.zeros((1, 3)),
+                        rng.normal(scale=1e-4, size=(20, 3))]).astype(np.float32)
+    for k in range(30):
+        q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+        pose = np.concatenate([q * (1 + 1e-4 * rng.normal()), rng.normal(scale=[0.05, 2.0, 30.0][k % 3], size=(3, 1))],
+                              axis=1).astype(np.float32)
+        got = oracle.transform_pose_vec(pose, x)
+        want = ref.transform_pose_vec(pose, x)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+        exact = x.astype(np.float64) @ pose[:, :3].astype(np.float64).T + pose[:, 3].astype(np.float64)
+        assert np.abs(want - exact).max() < 1e-4
